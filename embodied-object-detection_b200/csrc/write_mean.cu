@@ -1,0 +1,546 @@
+// Memory write, mean mode.
+//
+//   pre-pass   eod_frame_count      n_c  = #sampled pixels per cell (+ visibility bit)      [index plane only]
+//   main pass  eod_write_mean       sums[c] += (sum over the cell's sampled pixels of f_p) / n_c
+//   post-pass  eod_finalize_counts  counts[c] += 1 for every visible cell ; scratch := 0
+//
+// The main pass streams the per-pixel feature tensor exactly once (N*C*4 bytes per frame - the term that
+// bounds the whole path) and is written for HBM bandwidth:
+//   * CHW features (the reference's (1,C,480,640) layout): a persistent CTA per SM walks 32-pixel tiles;
+//     a producer warp issues ONE 3-D TMA box load (32 px x C channels, 128B-swizzled) + a 128 B bulk copy
+//     of the tile's cell indices per stage into a 3..6-deep mbarrier ring; consumer thread c owns channel
+//     c, reads its 32 pixels with conflict-free LDS.128, and accumulates runs of equal cell id in a
+//     register (neighbouring pixels fall into the same map cell); per run the C-vector is staged in shared
+//     memory (in place, same swizzle) and flushed with 128-bit red.global.add.v4.f32 - one L2 atomic
+//     transaction per four channels per run instead of one per pixel.
+//   * an LDG-staged variant of the same algorithm (padded smem tile) handles shapes the TMA path does
+//     not (HW % 32 != 0) and is the bring-up comparator (variant = EOD_WRITE_LDG).
+//   * HWC features: a warp walks a strip of pixels, lanes own float4 channel groups, runs accumulate in
+//     registers and flush straight from registers.
+#include <cuda.h>
+
+#include "eod_common.cuh"
+
+namespace {
+
+constexpr int TILE_PX = 32;
+
+// ------------------------------------------------------------------------------------------------------
+// pre-pass / post-pass: one thread per pixel, warp-level run aggregation of the cell id
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) frame_count_kernel(const int32_t *__restrict__ idx, const uint8_t *__restrict__ samp,
+                                                          int HW, int64_t n_cells, uint32_t *__restrict__ frame_cnt)
+{
+    const int e = blockIdx.y;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31;
+    const bool valid = p < HW;
+    const size_t g = (size_t)e * HW + (valid ? p : 0);
+    const int cell = valid ? __ldg(idx + g) : -1;
+    const bool s = valid && (samp ? __ldg(samp + g) != 0 : true);
+    const int prev = __shfl_up_sync(0xffffffffu, cell, 1);
+    const bool head = valid && (lane == 0 || prev != cell);
+    const unsigned heads = __ballot_sync(0xffffffffu, head);
+    const unsigned samps = __ballot_sync(0xffffffffu, s);
+    const unsigned valids = __ballot_sync(0xffffffffu, valid);
+    if (head) {
+        const unsigned above = heads & ~((2u << lane) - 1u);               // heads strictly after this lane
+        const unsigned end = above ? (unsigned)(__ffs(above) - 1) : 32u;   // run = [lane, end)
+        const unsigned run = ((end >= 32u) ? 0xffffffffu : ((1u << end) - 1u)) & ~((1u << lane) - 1u) & valids;
+        const unsigned n = __popc(samps & run);
+        uint32_t *dst = frame_cnt + (size_t)e * n_cells + cell;
+        if (n) atomicAdd(dst, n);
+        else atomicOr(dst, 0x80000000u);
+    }
+}
+
+__global__ void __launch_bounds__(256) finalize_counts_kernel(const int32_t *__restrict__ idx, int HW, int64_t n_cells,
+                                                              uint32_t *__restrict__ frame_cnt, float *__restrict__ counts,
+                                                              uint8_t *__restrict__ touched)
+{
+    const int e = blockIdx.y;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31;
+    const bool valid = p < HW;
+    const int cell = valid ? __ldg(idx + (size_t)e * HW + p) : -1;
+    const int prev = __shfl_up_sync(0xffffffffu, cell, 1);
+    if (valid && (lane == 0 || prev != cell)) {
+        const size_t c = (size_t)e * n_cells + cell;
+        const uint32_t old = atomicExch(frame_cnt + c, 0u);   // exactly one run head per cell sees old != 0
+        if (old) {
+            counts[c] += 1.0f;                               // custom_rcnn.py:699-701,743
+            if (touched && (old & 0x7fffffffu)) touched[c] = 1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// raster-order every-stride-th-observed-pixel selection (custom_rcnn.py:905-914): one CTA per episode,
+// chunked block scan with a running carry.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) sample_mask_kernel(const uint8_t *__restrict__ observed, int HW, int stride,
+                                                           uint8_t *__restrict__ samp, int32_t *__restrict__ n_sampled)
+{
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    const int e = blockIdx.x;
+    const uint8_t *obs = observed + (size_t)e * HW;
+    uint8_t *out = samp + (size_t)e * HW;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    int sampled_total = 0;
+    for (int base = 0; base < HW; base += 1024) {
+        const int p = base + threadIdx.x;
+        const bool o = p < HW && obs[p] != 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, o);
+        const int within = __popc(bal & ((1u << lane) - 1u));
+        if (lane == 0) s_warp[warp] = __popc(bal);
+        __syncthreads();
+        int pre = 0;
+        for (int w = 0; w < (int)warp; ++w) pre += s_warp[w];      // 32 broadcast reads; negligible
+        const int carry = s_carry;
+        const int rank = carry + pre + within;
+        const bool s = o && (rank % stride == 0);
+        if (p < HW) out[p] = s ? 1 : 0;
+        sampled_total += s ? 1 : 0;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + pre + __popc(bal);
+        __syncthreads();
+    }
+    if (n_sampled) {
+        // block reduction of sampled_total
+        for (int o = 16; o > 0; o >>= 1) sampled_total += __shfl_xor_sync(0xffffffffu, sampled_total, o);
+        if (lane == 0) s_warp[warp] = sampled_total;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < 32; ++w) t += s_warp[w];
+            n_sampled[e] = t;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// A6: per-pixel mean of the kept objects' feature vectors (custom_rcnn.py:884-901), same fp32 add order.
+// Thread = 4 consecutive pixels of one channel; K <= 128 object rows cached in shared memory per channel.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) box_to_image_kernel(const float *__restrict__ box_features, const uint8_t *__restrict__ masks,
+                                                           int K, int C, int HW, float *__restrict__ image_features,
+                                                           uint8_t *__restrict__ observed)
+{
+    extern __shared__ float s_feat[];          // (K, CH) channel slice of box_features
+    constexpr int CH = 16;                     // channels per CTA (blockIdx.y selects the slice)
+    const int c0 = blockIdx.y * CH;
+    for (int i = threadIdx.x; i < K * CH; i += blockDim.x) {
+        const int k = i / CH, c = i % CH;
+        s_feat[i] = (c0 + c < C) ? box_features[(size_t)k * C + c0 + c] : 0.f;
+    }
+    __syncthreads();
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW) return;
+    float acc[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) acc[c] = 0.f;
+    int n = 0;
+    for (int k = 0; k < K; ++k) {
+        if (__ldg(masks + (size_t)k * HW + p)) {
+            ++n;
+#pragma unroll
+            for (int c = 0; c < CH; ++c) acc[c] = __fadd_rn(acc[c], s_feat[k * CH + c]);
+        }
+    }
+    const float fn = (float)n;
+#pragma unroll
+    for (int c = 0; c < CH; ++c)
+        if (c0 + c < C) image_features[(size_t)(c0 + c) * HW + p] = n ? __fdiv_rn(acc[c], fn) : 0.f;
+    if (blockIdx.y == 0 && observed) observed[p] = n ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// main pass, shared pieces
+// ------------------------------------------------------------------------------------------------------
+
+// Element (channel c, pixel p) of a 128B-swizzled tile whose rows are 32 floats (TMA SWIZZLE_128B: the
+// 16-byte chunk index is XOR-ed with (row % 8)).
+__device__ __forceinline__ int swz(int c, int p) { return c * TILE_PX + ((((p >> 2) ^ (c & 7)) << 2) | (p & 3)); }
+
+// Flush the run sums of one tile: item (r, g) = run r, channels 4g..4g+3.  tile[swz(c, r)] holds run r of channel c.
+template <int C>
+__device__ __forceinline__ void flush_runs(const float *tile, const int *s_cells, unsigned heads, unsigned samps, int pvalid,
+                                           const uint32_t *__restrict__ frame_cnt_e, float *__restrict__ sums_e, int tid)
+{
+    constexpr int G = C / 4;
+    const int nruns = __popc(heads);
+    for (int item = tid; item < nruns * G; item += C) {
+        const int r = item / G, g = item - r * G;
+        const int p0 = __fns(heads, 0, r + 1);                          // first pixel of run r
+        const unsigned above = heads & ~((2u << p0) - 1u);
+        const int p1 = above ? (__ffs(above) - 1) : pvalid;
+        const unsigned run = ((p1 >= 32) ? 0xffffffffu : ((1u << p1) - 1u)) & ~((1u << p0) - 1u);
+        if (!(samps & run)) continue;                                   // no sampled pixel in this run
+        const int cell = s_cells[p0];
+        const float n = (float)(__ldg(frame_cnt_e + cell) & 0x7fffffffu);
+        const int c = 4 * g;
+        const float a = tile[swz(c, r)], b = tile[swz(c + 1, r)], d = tile[swz(c + 2, r)], f = tile[swz(c + 3, r)];
+        red_add_v4(sums_e + (size_t)cell * C + c, __fdiv_rn(a, n), __fdiv_rn(b, n), __fdiv_rn(d, n), __fdiv_rn(f, n));
+    }
+}
+
+// Consumer thread c: accumulate runs over the tile's pixels (tile row c, swizzled), write run sums in place.
+__device__ __forceinline__ void accumulate_runs(float *tile, int c, unsigned heads, unsigned samps)
+{
+    float acc = 0.f;
+    int r = 0;
+    const float4 *row = reinterpret_cast<const float4 *>(tile + c * TILE_PX);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 v = row[j ^ (c & 7)];
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int p = 4 * j + k;
+            if (p > 0 && ((heads >> p) & 1u)) {        // CTA-uniform
+                tile[swz(c, r)] = acc;                // slot r <= p - 1: its chunk was read already
+                ++r;
+                acc = 0.f;
+            }
+            if ((samps >> p) & 1u) acc = __fadd_rn(acc, vv[k]);
+        }
+    }
+    tile[swz(c, r)] = acc;
+}
+
+__device__ __forceinline__ void tile_masks(const int *s_cells, const uint8_t *s_samp, bool has_samp, int pvalid, unsigned lane,
+                                           unsigned &heads, unsigned &samps)
+{
+    const bool valid = (int)lane < pvalid;
+    const int cell = valid ? s_cells[lane] : -1;
+    const int prev = __shfl_up_sync(0xffffffffu, cell, 1);
+    heads = __ballot_sync(0xffffffffu, valid && (lane == 0 || prev != cell));
+    samps = __ballot_sync(0xffffffffu, valid && (has_samp ? s_samp[lane] != 0 : true));
+}
+
+// ------------------------------------------------------------------------------------------------------
+// main pass, CHW, LDG-staged
+// ------------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(C) write_mean_chw_ldg_kernel(const float *__restrict__ feat, const int32_t *__restrict__ idx,
+                                                               const uint8_t *__restrict__ samp, const uint32_t *__restrict__ frame_cnt,
+                                                               int HW, int64_t n_cells, int tiles_per_ep, int n_tiles,
+                                                               float *__restrict__ sums)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    float *tile = reinterpret_cast<float *>(smem_raw);              // C x 32, swizzled like the TMA path
+    int *s_cells = reinterpret_cast<int *>(tile + C * TILE_PX);
+    uint8_t *s_samp = reinterpret_cast<uint8_t *>(s_cells + TILE_PX);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = C / 32;
+
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int e = t / tiles_per_ep, p0 = (t - e * tiles_per_ep) * TILE_PX;
+        const int pvalid = min(TILE_PX, HW - p0);
+        const float *feat_e = feat + (size_t)e * C * HW;
+        // coalesced 128 B row segments: warp w loads channels w, w+NW, ...
+#pragma unroll 4
+        for (int c = warp; c < C; c += NW)
+            tile[swz(c, lane)] = lane < pvalid ? __ldg(feat_e + (size_t)c * HW + p0 + lane) : 0.f;
+        if (tid < TILE_PX) {
+            s_cells[tid] = tid < pvalid ? __ldg(idx + (size_t)e * HW + p0 + tid) : -1;
+            s_samp[tid] = (samp && tid < pvalid) ? __ldg(samp + (size_t)e * HW + p0 + tid) : 1;
+        }
+        __syncthreads();
+        unsigned heads, samps;
+        tile_masks(s_cells, s_samp, samp != nullptr, pvalid, lane, heads, samps);
+        accumulate_runs(tile, tid, heads, samps);
+        __syncthreads();
+        flush_runs<C>(tile, s_cells, heads, samps, pvalid, frame_cnt + (size_t)e * n_cells, sums + (size_t)e * n_cells * C, tid);
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// main pass, CHW, TMA-staged persistent kernel
+// ------------------------------------------------------------------------------------------------------
+template <int C>
+struct TmaCfg {
+    static constexpr int kTileBytes = C * TILE_PX * 4;
+    static constexpr int kStageBytes = kTileBytes + 1024;                 // + cells (128 B) + samp (32 B), keeps 1 KB alignment
+    static constexpr int kStages = (C <= 128) ? 8 : (C == 256 ? 6 : 3);
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kBoxC = C < 256 ? C : 256;                       // TMA box dims are limited to 256
+};
+
+template <int C>
+__global__ void __launch_bounds__(C + 32) write_mean_chw_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t *__restrict__ idx,
+                                                                    const uint8_t *__restrict__ samp, const uint32_t *__restrict__ frame_cnt,
+                                                                    int HW, int64_t n_cells, int tiles_per_ep, int n_tiles,
+                                                                    float *__restrict__ sums)
+{
+    using Cfg = TmaCfg<C>;
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    uint64_t *full = reinterpret_cast<uint64_t *>(base + Cfg::kStages * Cfg::kStageBytes);
+    uint64_t *empty = full + Cfg::kStages;
+
+    const int tid = threadIdx.x;
+    const bool has_samp = samp != nullptr;
+    if (tid == 0) {
+        for (int s = 0; s < Cfg::kStages; ++s) {
+            mbar_init(full + s, 1);          // producer's arrive.expect_tx
+            mbar_init(empty + s, C / 32);    // one arrive per consumer warp
+        }
+        mbar_fence_init();
+        fence_proxy_async();
+    }
+    __syncthreads();
+
+    if (tid >= C) {
+        // ===== producer warp: one elected lane issues all copies =====
+        if (tid == C) {
+            const uint32_t tx = Cfg::kTileBytes + TILE_PX * 4 + (has_samp ? TILE_PX : 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                mbar_wait(empty + stage, phase ^ 1);
+                const int e = t / tiles_per_ep, p0 = (t - e * tiles_per_ep) * TILE_PX;
+                unsigned char *st = base + stage * Cfg::kStageBytes;
+                mbar_expect_tx(full + stage, tx);
+#pragma unroll
+                for (int c0 = 0; c0 < C; c0 += Cfg::kBoxC)
+                    tma_load_3d(st + c0 * TILE_PX * 4, &tmap, p0, c0, e, full + stage);
+                bulk_load_1d(st + Cfg::kTileBytes, idx + (size_t)e * HW + p0, TILE_PX * 4, full + stage);
+                if (has_samp) bulk_load_1d(st + Cfg::kTileBytes + TILE_PX * 4, samp + (size_t)e * HW + p0, TILE_PX, full + stage);
+                if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+            }
+        }
+        return;
+    }
+
+    // ===== consumers: thread c owns channel c =====
+    const unsigned lane = tid & 31;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        mbar_wait(full + stage, phase);
+        const int e = t / tiles_per_ep;
+        unsigned char *st = base + stage * Cfg::kStageBytes;
+        float *tile = reinterpret_cast<float *>(st);
+        const int *s_cells = reinterpret_cast<const int *>(st + Cfg::kTileBytes);
+        const uint8_t *s_samp = st + Cfg::kTileBytes + TILE_PX * 4;
+        unsigned heads, samps;
+        tile_masks(s_cells, s_samp, has_samp, TILE_PX, lane, heads, samps);
+        accumulate_runs(tile, tid, heads, samps);
+        named_bar_sync(1, C);
+        flush_runs<C>(tile, s_cells, heads, samps, TILE_PX, frame_cnt + (size_t)e * n_cells, sums + (size_t)e * n_cells * C, tid);
+        fence_proxy_async();                 // generic-proxy accesses to the stage precede the next TMA write
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + stage);
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// main pass, HWC: warp per strip of 32 pixels, lanes own float4 channel groups
+// ------------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(256) write_mean_hwc_kernel(const float *__restrict__ feat, const int32_t *__restrict__ idx,
+                                                             const uint8_t *__restrict__ samp, const uint32_t *__restrict__ frame_cnt,
+                                                             int HW, int64_t n_cells, int strips_per_ep, int n_strips,
+                                                             float *__restrict__ sums)
+{
+    constexpr int V = C / 128;                 // float4 per lane per pixel
+    const unsigned lane = threadIdx.x & 31;
+    const int warps_total = gridDim.x * (blockDim.x >> 5);
+    for (int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); s < n_strips; s += warps_total) {
+        const int e = s / strips_per_ep, p0 = (s - e * strips_per_ep) * TILE_PX;
+        const int pvalid = min(TILE_PX, HW - p0);
+        const size_t pix0 = (size_t)e * HW + p0;
+        const int my_cell = (int)lane < pvalid ? __ldg(idx + pix0 + lane) : -1;
+        const bool my_s = (int)lane < pvalid && (samp ? __ldg(samp + pix0 + lane) != 0 : true);
+        const unsigned samps = __ballot_sync(0xffffffffu, my_s);
+        const uint32_t *cnt_e = frame_cnt + (size_t)e * n_cells;
+        float *sums_e = sums + (size_t)e * n_cells * C;
+        float4 acc[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        int cur = -1;
+        bool any = false;
+        auto flush = [&]() {
+            if (cur >= 0 && any) {
+                const float n = (float)(__ldg(cnt_e + cur) & 0x7fffffffu);
+#pragma unroll
+                for (int v = 0; v < V; ++v)
+                    red_add_v4(sums_e + (size_t)cur * C + v * 128 + 4 * lane, __fdiv_rn(acc[v].x, n), __fdiv_rn(acc[v].y, n),
+                               __fdiv_rn(acc[v].z, n), __fdiv_rn(acc[v].w, n));
+            }
+        };
+#pragma unroll 4
+        for (int p = 0; p < pvalid; ++p) {
+            const int cell = __shfl_sync(0xffffffffu, my_cell, p);
+            if (cell != cur) {
+                flush();
+                cur = cell;
+                any = false;
+#pragma unroll
+                for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if ((samps >> p) & 1u) {
+                any = true;
+                const float *row = feat + (pix0 + p) * C;
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    const float4 f = ldg_stream_f4(row + v * 128 + 4 * lane);
+                    acc[v].x = __fadd_rn(acc[v].x, f.x); acc[v].y = __fadd_rn(acc[v].y, f.y);
+                    acc[v].z = __fadd_rn(acc[v].z, f.z); acc[v].w = __fadd_rn(acc[v].w, f.w);
+                }
+            }
+        }
+        flush();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn()
+{
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+template <int C>
+int launch_tma(const float *feat, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt, int E, int HW,
+               int64_t n_cells, float *sums, cudaStream_t st)
+{
+    using Cfg = TmaCfg<C>;
+    PFN_encodeTiled enc = get_encode_fn();
+    EOD_REQUIRE(enc, EOD_ERR_LAUNCH, "eod_write_mean: cuTensorMapEncodeTiled entry point unavailable");
+    CUtensorMap tmap;
+    const cuuint64_t gdim[3] = {(cuuint64_t)HW, (cuuint64_t)C, (cuuint64_t)E};
+    const cuuint64_t gstr[2] = {(cuuint64_t)HW * 4, (cuuint64_t)HW * C * 4};
+    const cuuint32_t box[3] = {TILE_PX, (cuuint32_t)Cfg::kBoxC, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(feat), gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    EOD_REQUIRE(r == CUDA_SUCCESS, EOD_ERR_LAUNCH, "eod_write_mean: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(write_mean_chw_tma_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        attr_set = true;
+    }
+    const int tiles_per_ep = HW / TILE_PX, n_tiles = tiles_per_ep * E;
+    const int grid = n_tiles < eod_num_sms() ? n_tiles : eod_num_sms();
+    write_mean_chw_tma_kernel<C><<<grid, C + 32, Cfg::kSmemBytes, st>>>(tmap, idx, samp, frame_cnt, HW, n_cells, tiles_per_ep, n_tiles, sums);
+    return eod_check_launch("eod_write_mean[tma]");
+}
+
+template <int C>
+int launch_ldg(const float *feat, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt, int E, int HW,
+               int64_t n_cells, float *sums, cudaStream_t st)
+{
+    const int smem = C * TILE_PX * 4 + TILE_PX * 4 + TILE_PX;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(write_mean_chw_ldg_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_set = true;
+    }
+    const int tiles_per_ep = (HW + TILE_PX - 1) / TILE_PX, n_tiles = tiles_per_ep * E;
+    const int per_sm = (C >= 512) ? 3 : (C == 256 ? 6 : 8);
+    const int grid = min(n_tiles, eod_num_sms() * per_sm);
+    write_mean_chw_ldg_kernel<C><<<grid, C, smem, st>>>(feat, idx, samp, frame_cnt, HW, n_cells, tiles_per_ep, n_tiles, sums);
+    return eod_check_launch("eod_write_mean[ldg]");
+}
+
+template <int C>
+int launch_hwc(const float *feat, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt, int E, int HW,
+               int64_t n_cells, float *sums, cudaStream_t st)
+{
+    const int strips_per_ep = (HW + TILE_PX - 1) / TILE_PX, n_strips = strips_per_ep * E;
+    const int blocks = min((n_strips + 7) / 8, eod_num_sms() * 8);
+    write_mean_hwc_kernel<C><<<blocks, 256, 0, st>>>(feat, idx, samp, frame_cnt, HW, n_cells, strips_per_ep, n_strips, sums);
+    return eod_check_launch("eod_write_mean[hwc]");
+}
+
+template <int C>
+int dispatch(const float *feat, int layout, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt, int E, int HW,
+             int64_t n_cells, float *sums, int variant, cudaStream_t st)
+{
+    if (layout == EOD_LAYOUT_HWC) return launch_hwc<C>(feat, idx, samp, frame_cnt, E, HW, n_cells, sums, st);
+    const bool tma_ok = (HW % TILE_PX == 0) && (!samp || (reinterpret_cast<uintptr_t>(samp) % 16 == 0));
+    if (variant == EOD_WRITE_TMA) EOD_REQUIRE(tma_ok, EOD_ERR_UNSUPPORTED, "eod_write_mean: TMA variant needs HW %% 32 == 0");
+    if (variant == EOD_WRITE_LDG || !tma_ok) return launch_ldg<C>(feat, idx, samp, frame_cnt, E, HW, n_cells, sums, st);
+    return launch_tma<C>(feat, idx, samp, frame_cnt, E, HW, n_cells, sums, st);
+}
+
+}  // namespace
+
+extern "C" int eod_sample_mask(const uint8_t *observed, int n_episodes, int HW, int stride, uint8_t *samp, int32_t *n_sampled,
+                               eod_stream_t stream)
+{
+    EOD_REQUIRE(observed && samp, EOD_ERR_BADARG, "eod_sample_mask: null pointer");
+    EOD_REQUIRE(n_episodes > 0 && HW > 0 && stride > 0, EOD_ERR_BADARG, "eod_sample_mask: bad sizes");
+    sample_mask_kernel<<<n_episodes, 1024, 0, (cudaStream_t)stream>>>(observed, HW, stride, samp, n_sampled);
+    return eod_check_launch("eod_sample_mask");
+}
+
+extern "C" int eod_frame_count(const int32_t *idx, const uint8_t *samp, int n_episodes, int HW, int64_t n_cells,
+                               uint32_t *frame_cnt, eod_stream_t stream)
+{
+    EOD_REQUIRE(idx && frame_cnt, EOD_ERR_BADARG, "eod_frame_count: null pointer");
+    EOD_REQUIRE(n_episodes > 0 && n_episodes <= 65535 && HW > 0 && n_cells > 0, EOD_ERR_BADARG, "eod_frame_count: bad sizes");
+    dim3 grid((HW + 255) / 256, n_episodes);
+    frame_count_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(idx, samp, HW, n_cells, frame_cnt);
+    return eod_check_launch("eod_frame_count");
+}
+
+extern "C" int eod_finalize_counts(const int32_t *idx, int n_episodes, int HW, int64_t n_cells, uint32_t *frame_cnt,
+                                   float *counts, uint8_t *touched, eod_stream_t stream)
+{
+    EOD_REQUIRE(idx && frame_cnt && counts, EOD_ERR_BADARG, "eod_finalize_counts: null pointer");
+    EOD_REQUIRE(n_episodes > 0 && n_episodes <= 65535 && HW > 0 && n_cells > 0, EOD_ERR_BADARG, "eod_finalize_counts: bad sizes");
+    dim3 grid((HW + 255) / 256, n_episodes);
+    finalize_counts_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(idx, HW, n_cells, frame_cnt, counts, touched);
+    return eod_check_launch("eod_finalize_counts");
+}
+
+extern "C" int eod_write_mean(const float *feat, int layout, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt,
+                              int n_episodes, int C, int HW, int64_t n_cells, float *sums, int variant, eod_stream_t stream)
+{
+    EOD_REQUIRE(feat && idx && frame_cnt && sums, EOD_ERR_BADARG, "eod_write_mean: null pointer");
+    EOD_REQUIRE(n_episodes > 0 && HW > 0 && n_cells > 0, EOD_ERR_BADARG, "eod_write_mean: bad sizes");
+    EOD_REQUIRE(layout == EOD_LAYOUT_CHW || layout == EOD_LAYOUT_HWC, EOD_ERR_BADARG, "eod_write_mean: bad layout");
+    EOD_REQUIRE(variant >= EOD_WRITE_AUTO && variant <= EOD_WRITE_TMA, EOD_ERR_BADARG, "eod_write_mean: bad variant");
+    EOD_REQUIRE(eod_aligned16(feat) && eod_aligned16(sums) && eod_aligned16(idx), EOD_ERR_ALIGN, "eod_write_mean: pointers must be 16-byte aligned");
+    EOD_REQUIRE(layout == EOD_LAYOUT_HWC || HW % 4 == 0, EOD_ERR_ALIGN, "eod_write_mean: CHW rows must be 16-byte aligned (HW %% 4 == 0)");
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (C) {
+    case 128: return dispatch<128>(feat, layout, idx, samp, frame_cnt, n_episodes, HW, n_cells, sums, variant, st);
+    case 256: return dispatch<256>(feat, layout, idx, samp, frame_cnt, n_episodes, HW, n_cells, sums, variant, st);
+    case 512: return dispatch<512>(feat, layout, idx, samp, frame_cnt, n_episodes, HW, n_cells, sums, variant, st);
+    default:
+        eod_set_error("eod_write_mean: C=%d not compiled in (128, 256, 512)", C);
+        return EOD_ERR_UNSUPPORTED;
+    }
+}
+
+extern "C" int eod_box_to_image_features(const float *box_features, const uint8_t *masks, int K, int C, int HW,
+                                         float *image_features, uint8_t *observed, eod_stream_t stream)
+{
+    EOD_REQUIRE(box_features && masks && image_features, EOD_ERR_BADARG, "eod_box_to_image_features: null pointer");
+    EOD_REQUIRE(K > 0 && K <= 256 && C > 0 && HW > 0, EOD_ERR_BADARG, "eod_box_to_image_features: bad sizes (K must be 1..256)");
+    dim3 grid((HW + 255) / 256, (C + 15) / 16);
+    box_to_image_kernel<<<grid, 256, (size_t)K * 16 * sizeof(float), (cudaStream_t)stream>>>(box_features, masks, K, C, HW, image_features, observed);
+    return eod_check_launch("eod_box_to_image_features");
+}

@@ -1,0 +1,105 @@
+"""Memory read + projection + weighted fusion behind the reference's backbone call surface.
+
+Mirrors the memory block of ``CustomRecurrentFPN`` (detic/modeling/backbone/timm.py:54-213):
+  * parameters ``map_merge_projection{1,2,3}`` = Conv2d(512, 256, 1, bias=True) (timm.py:78-86) - same
+    state-dict names, so reference checkpoints load and the 'map_merge' LR/un-freeze rules keep matching;
+  * ``forward(x, map_memory, proj_indices, observations, sequence_name=None) -> (features dict, map_memory[0])``
+    (timm.py:91,213);
+  * MODEL.MEMORY_TYPE image_only | implicit_memory, MODEL.MAP_FEAT_FUSION sum | mem_only | image_only,
+    MODEL.MAP_FEATURE_WEIGHT (timm.py:142,177-186).
+
+The gather -> avg-pool 4 -> (avg-pool 2 -> half) x3 chain runs as ONE kernel (eod_read_pool); the 1x1
+projection is a library GEMM (torch conv2d on the channels-last levels) and the ``* weight`` / ``+ res``
+epilogue is eod_fuse.  The dense backbone itself is out of scope and supplied by the caller.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from ._lib import FUSE_IMAGE_ONLY, FUSE_MEM_ONLY, FUSE_SUM
+
+_FUSE_MODES = {"sum": FUSE_SUM, "mem_only": FUSE_MEM_ONLY, "image_only": FUSE_IMAGE_ONLY}
+
+
+class MemoryFusion(nn.Module):
+    def __init__(self, memory_type: str = "implicit_memory", fusion: str = "sum", map_feature_weight: float = 500.0,
+                 memory_feature_weight: float = 100.0, merge_type: str = "", mem_feat_dim: int = 512,
+                 ego_feat_dim: int = 256):
+        super().__init__()
+        self.memory_type, self.feat_fusion, self.merge_type = memory_type, fusion, merge_type
+        self.map_feature_weight, self.memory_feature_weight = map_feature_weight, memory_feature_weight
+        self.memory_dim = mem_feat_dim
+        if memory_type == "implicit_memory":
+            self.map_merge_projection1 = nn.Conv2d(mem_feat_dim, ego_feat_dim, kernel_size=1, bias=True)
+            self.map_merge_projection2 = nn.Conv2d(mem_feat_dim, ego_feat_dim, kernel_size=1, bias=True)
+            self.map_merge_projection3 = nn.Conv2d(mem_feat_dim, ego_feat_dim, kernel_size=1, bias=True)
+
+    @property
+    def merge_map_projections(self) -> List[nn.Conv2d]:
+        return [self.map_merge_projection1, self.map_merge_projection2, self.map_merge_projection3]
+
+    def read(self, map_memory: Sequence[torch.Tensor], proj_indices: Sequence[torch.Tensor],
+             observations: Optional[Sequence[Optional[torch.Tensor]]] = None) -> List[torch.Tensor]:
+        """timm.py:144-168 -> three (B, C, h_l, w_l) fp16 tensors.  map_memory[i]: (cells, C) fp16 normalised table
+        (reference API) or fp32 sums with observations[i] (normalisation fused into the kernel)."""
+        per_image = []
+        for i, mem in enumerate(map_memory):
+            counts = None
+            if mem.dtype == torch.float32 and observations is not None and observations[i] is not None:
+                counts = observations[i].to(torch.float32).unsqueeze(0).contiguous()
+            idx = proj_indices[i]
+            if idx.dim() == 3 and idx.shape[-1] == 1:
+                idx = idx.squeeze(2)
+            per_image.append(ops.read_pool(mem.unsqueeze(0).contiguous(), counts, idx.unsqueeze(0).contiguous()))
+        if len(per_image) == 1:
+            return per_image[0]
+        return [torch.cat([lv[k] for lv in per_image], dim=0) for k in range(3)]
+
+    def forward(self, results: Sequence[torch.Tensor], map_memory, proj_indices, observations=None) -> List[torch.Tensor]:
+        """results = [p3, p4, p5] -> fused [p3, p4, p5] (timm.py:142-192)."""
+        if self.memory_type != "implicit_memory":
+            return list(results)
+        if self.feat_fusion not in _FUSE_MODES:
+            raise UnboundLocalError("new_res")        # the reference leaves new_res unbound here (timm.py:181-189)
+        levels = self.read(map_memory, proj_indices, observations)
+        out = []
+        for lvl, res, conv in zip(levels, results, self.merge_map_projections):
+            if self.feat_fusion == "image_only":
+                out.append(res)
+                continue
+            # timm.py:174: 1x1 conv in fp32 (eval, no autocast) == per-pixel GEMM on the channels-last level
+            x = lvl.permute(0, 2, 3, 1).to(torch.float32)                             # (B, h, w, C) contiguous
+            mem = torch.matmul(x, conv.weight.view(conv.weight.shape[0], -1).t()) + conv.bias
+            mem = mem.permute(0, 3, 1, 2).contiguous()                               # NCHW like res
+            res32 = res.to(torch.float32).contiguous()
+            fused = ops.fuse(res32, mem, float(self.map_feature_weight), _FUSE_MODES[self.feat_fusion])
+            out.append(fused.to(res.dtype))
+        return out
+
+
+class CustomRecurrentFPN(nn.Module):
+    """Backbone wrapper with the reference's forward signature (timm.py:91-213).  ``fpn_body(x)`` is the
+    caller's stock bottom-up + FPN returning ([p3, p4, p5], aux) ; ``top_block(p5)`` returns [p6, p7]."""
+
+    def __init__(self, fpn_body: Callable, top_block: Optional[Callable], fusion: MemoryFusion,
+                 out_features=("p3", "p4", "p5", "p6", "p7")):
+        super().__init__()
+        self.fpn_body, self.top_block, self.fusion = fpn_body, top_block, fusion
+        self._out_features = list(out_features)
+        # reference state-dict names live directly on the backbone (timm.py:78-86)
+        if fusion.memory_type == "implicit_memory":
+            self.map_merge_projection1 = fusion.map_merge_projection1
+            self.map_merge_projection2 = fusion.map_merge_projection2
+            self.map_merge_projection3 = fusion.map_merge_projection3
+
+    def forward(self, x, map_memory, proj_indices, observations, sequence_name=None):
+        results = self.fpn_body(x)
+        results = self.fusion(results, map_memory, proj_indices, observations)
+        if self.top_block is not None:
+            results = list(results) + list(self.top_block(results[-1]))
+        return {f: r for f, r in zip(self._out_features, results)}, map_memory[0]

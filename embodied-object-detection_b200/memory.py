@@ -1,0 +1,255 @@
+"""Spatial feature memory: grid state + write/read on the B200 kernels.
+
+Two host-side objects sit above the C ABI:
+
+``EpisodeBatch``
+    E independent episodes advanced in lock step (BASELINE config 2 "batched x64"): one launch per stage covers
+    all E grids.  This is the throughput path the bench measures:
+        project (depth, pose -> cell indices) -> read (pooled fp16 levels) -> write (features -> grid).
+
+``SpatialFeatureMemory``
+    Single-episode mirror of the memory methods of ``CustomRCNNRecurrent``
+    (detic/modeling/meta_arch/custom_rcnn.py:470-477, 681-936, 1019-1042) with the reference's method names,
+    argument meaning and state attributes (``implicit_memory``, ``observations``, ``semmap_features``,
+    ``observation_count``), so the meta-architecture can delegate to it.
+
+HBM layout per episode: ``sums`` (cells, C) fp32 row = cell ``z*map_w + x``; ``counts`` (cells) fp32;
+``frame_cnt`` (cells) int32 scratch, all-zero between frames.  State never leaves the device.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+from ._lib import LAYOUT_CHW, LAYOUT_HWC, ORDER_ZX, WRITE_AUTO, EodError
+
+
+class EpisodeBatch:
+    def __init__(self, n_episodes: int, map_w: int, map_h: int, channels: int, height: int = 480, width: int = 640,
+                 device: torch.device = torch.device("cuda"), layout: int = LAYOUT_CHW, variant: int = WRITE_AUTO):
+        if torch.device(device).type != "cuda":
+            raise EodError("EpisodeBatch needs a CUDA device (no CPU fallback)")
+        self.E, self.map_w, self.map_h, self.C, self.H, self.W = n_episodes, map_w, map_h, channels, height, width
+        self.n_cells = map_w * map_h
+        self.device, self.layout, self.variant = torch.device(device), layout, variant
+        z = dict(device=self.device)
+        self.sums = torch.zeros((self.E, self.n_cells, self.C), dtype=torch.float32, **z)
+        self.counts = torch.zeros((self.E, self.n_cells), dtype=torch.float32, **z)
+        self.frame_cnt = torch.zeros((self.E, self.n_cells), dtype=torch.int32, **z)
+        self.idx = torch.zeros((self.E, height, width), dtype=torch.int32, **z)
+        self.levels = [torch.empty((self.E, height >> s, width >> s, self.C), dtype=torch.float16, **z) for s in (3, 4, 5)]
+        self._proj_out = {"idx": self.idx}
+        self.stage_events = None      # dict(stage -> [(start, end) CUDA events]) when profiling is on
+
+    def profile(self, on: bool = True) -> None:
+        """Record a CUDA-event pair around every stage launch (same stream, no synchronisation added)."""
+        self.stage_events = {"project": [], "read": [], "count": [], "write": [], "finalize": []} if on else None
+
+    def _timed(self, stage: str, fn, *args, **kw):
+        if self.stage_events is None:
+            return fn(*args, **kw)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = fn(*args, **kw)
+        b.record()
+        self.stage_events[stage].append((a, b))
+        return out
+
+    def stage_ms(self) -> dict:
+        """Mean launch duration per stage in ms (call after a synchronize)."""
+        return {k: (sum(a.elapsed_time(b) for a, b in v) / len(v) if v else 0.0) for k, v in (self.stage_events or {}).items()}
+
+    def reset(self) -> None:
+        """memory_reset (custom_rcnn.py:470-477) for every episode of the batch."""
+        self.sums.zero_()
+        self.counts.zero_()
+        self.frame_cnt.zero_()
+
+    def project(self, depth: torch.Tensor, pose: torch.Tensor, shifts: torch.Tensor, intr: Sequence[float], cell: float,
+                order: int = ORDER_ZX) -> torch.Tensor:
+        """depth (E,H,W) f32, pose (E,12), shifts (E,6) -> self.idx (E,H,W) int32 (A2-A5)."""
+        self._timed("project", ops.backproject_quantize, depth, pose, shifts, intr, cell, self.map_w, self.map_h, order,
+                    out=self._proj_out)
+        return self.idx
+
+    def set_indices(self, idx: torch.Tensor) -> None:
+        """Use precomputed proj_indices (E,H,W) int32, as the reference does from memory_data/*.h5."""
+        self.idx.copy_(idx)
+
+    def read(self) -> List[torch.Tensor]:
+        """A10-A12 fused: [L0 (E,C,H/8,W/8), L1, L2] fp16 (channels_last memory)."""
+        return self._timed("read", ops.read_pool, self.sums, self.counts, self.idx, out=self.levels)
+
+    def write(self, feat: torch.Tensor, samp: Optional[torch.Tensor] = None) -> None:
+        """A7 + A8 for one frame of every episode: feat (E,C,H,W) [CHW] or (E,H,W,C) [HWC] fp32;
+        samp (E,H,W) u8 selects the contributing pixels (None = all)."""
+        self._timed("count", ops.frame_count, self.idx, samp, self.frame_cnt)
+        self._timed("write", ops.write_mean, feat, self.idx, samp, self.frame_cnt, self.sums, self.layout, self.variant)
+        self._timed("finalize", ops.finalize_counts, self.idx, self.frame_cnt, self.counts)
+
+    def step(self, depth, pose, shifts, intr, cell, feat, samp=None) -> List[torch.Tensor]:
+        """One frame of the hot path for all E episodes, in the reference's order: the read of frame t sees
+        the state written by frame t-1 (custom_rcnn.py:489-515)."""
+        self.project(depth, pose, shifts, intr, cell)
+        levels = self.read()
+        self.write(feat, samp)
+        return levels
+
+
+class SpatialFeatureMemory:
+    """Reference-facing, one episode in flight (like one ``CustomRCNNRecurrent`` instance).
+
+    semmap_gt_info / replica_map_info: the dicts of SMNet/semmap_GT_info.json / replica_map_info.json used by the map
+    size lookup of custom_rcnn.py:704-729; downsample = 10 (:364).
+    """
+
+    def __init__(self, mem_feat_dim: int = 512, device: torch.device = torch.device("cuda"), test_type: str = "default",
+                 semmap_gt_info: Optional[dict] = None, replica_map_info: Optional[dict] = None, downsample: int = 10,
+                 sample_stride: int = 8, height: int = 480, width: int = 640):
+        if torch.device(device).type != "cuda":
+            raise EodError("SpatialFeatureMemory needs a CUDA device (no CPU fallback)")
+        self.C, self.device, self.test_type = mem_feat_dim, torch.device(device), test_type
+        self.semmap_gt_info, self.replica_map_info = semmap_gt_info or {}, replica_map_info or {}
+        self.downsample, self.sample_stride, self.H, self.W = downsample, sample_stride, height, width
+        self.implicit_memory: Optional[torch.Tensor] = None     # (cells, C) f32 sums        (custom_rcnn.py:476,759)
+        self.observations: Optional[torch.Tensor] = None        # (cells,)  f32 counts      (:477,760)
+        self._frame_cnt: Optional[torch.Tensor] = None
+        self._touched: Optional[torch.Tensor] = None
+
+    # ---- state ---------------------------------------------------------------------------------------
+    def reset(self, n_cells: int) -> None:
+        """frame['memory_reset'] (custom_rcnn.py:470-477); the state is created on the device."""
+        self.implicit_memory = torch.zeros((n_cells, self.C), dtype=torch.float32, device=self.device)
+        self.observations = torch.zeros((n_cells,), dtype=torch.float32, device=self.device)
+        self._frame_cnt = torch.zeros((1, n_cells), dtype=torch.int32, device=self.device)
+        self._touched = torch.zeros((1, n_cells), dtype=torch.uint8, device=self.device)
+
+    def map_dims(self, sequence_name: str) -> Tuple[int, int]:
+        """(map_w, map_h) as custom_rcnn.py:704-729 resolves them (MP3D table, Replica table, else 200x200)."""
+        try:
+            map_w, _, map_h = self.semmap_gt_info[sequence_name[0:13]]["dim"]
+            return math.ceil(map_w / self.downsample), math.ceil(map_h / self.downsample)
+        except KeyError:
+            try:
+                parts = sequence_name.split("_")
+                if len(parts) == 5:
+                    env = "_".join((parts[0] + "_" + parts[1] + "_" + parts[2], parts[3]))
+                elif len(parts) == 4:
+                    env = "_".join((parts[0] + "_" + parts[1], parts[2]))
+                else:
+                    env = parts[0] + "_" + parts[1]
+                map_w, _, map_h = self.replica_map_info[env]["dim"]
+                return map_w, map_h
+            except Exception:
+                return 200, 200
+
+    @property
+    def semmap_features(self) -> Optional[torch.Tensor]:
+        """(1, C, map_h, map_w) view of the sums (custom_rcnn.py:731-742) when the map dims are known."""
+        return None if self.implicit_memory is None or not hasattr(self, "_dims") else \
+            self.implicit_memory.reshape(self._dims[1], self._dims[0], self.C).permute(2, 0, 1).unsqueeze(0)
+
+    @property
+    def observation_count(self) -> Optional[torch.Tensor]:
+        return None if self.observations is None or not hasattr(self, "_dims") else \
+            self.observations.reshape(1, self._dims[1], self._dims[0])
+
+    # ---- read ----------------------------------------------------------------------------------------
+    def create_implicit_memory(self, frame: Dict) -> Tuple[torch.Tensor, torch.Tensor]:
+        """custom_rcnn.py:762-775,823: (memory / observations where observations > 1, proj_indices)."""
+        mem = torch.as_tensor(frame["memory"]).to(self.device, torch.float32).contiguous()
+        obs = torch.as_tensor(frame["observations"]).to(self.device, torch.float32).contiguous()
+        return ops.normalize_memory(mem, obs), frame["proj_indices"]
+
+    def preprocess_spatial_memory(self, batched_inputs: Sequence[Dict]):
+        """custom_rcnn.py:1019-1042: lists of (memory f16, proj_indices int64, observations)."""
+        memory, projection, observations = [], [], []
+        for x in batched_inputs:
+            m = torch.as_tensor(x["memory"]).to(self.device)
+            p = torch.as_tensor(x["proj_indices"]).to(self.device)
+            if p.dim() == 3:
+                p = p.squeeze(2)
+            o = x.get("observations")
+            if o is not None and not torch.is_tensor(o):
+                o = torch.as_tensor(o).to(self.device).to(torch.half)
+            memory.append(m.to(torch.half))
+            projection.append(p.to(torch.long))
+            observations.append(o)
+        return memory, projection, observations
+
+    def read_levels(self, proj_indices: torch.Tensor, memory: Optional[torch.Tensor] = None,
+                    observations: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
+        """Fused A10-A12 for this episode: the three pooled fp16 levels (1,C,h,w) from the live state (or from
+        an explicit memory table: fp32 sums + observations, or an already normalised fp16 table)."""
+        table = self.implicit_memory if memory is None else memory
+        counts = self.observations if memory is None else observations
+        if table.dtype == torch.float16:
+            counts = None
+        idx = proj_indices.to(self.device)
+        if idx.dim() == 3 and idx.shape[-1] == 1:
+            idx = idx.squeeze(2)
+        if idx.dtype not in (torch.int32, torch.int64):
+            idx = idx.to(torch.int64)
+        return ops.read_pool(table.unsqueeze(0).contiguous(), None if counts is None else counts.unsqueeze(0).contiguous(),
+                             idx.unsqueeze(0).contiguous())
+
+    # ---- write ---------------------------------------------------------------------------------------
+    def box_to_image_features(self, box_features: torch.Tensor, masks: torch.Tensor):
+        """custom_rcnn.py:884-901 (bit-exact)."""
+        return ops.box_to_image_features(box_features.to(self.device, torch.float32).contiguous(),
+                                         masks.to(self.device).contiguous())
+
+    def _idx32(self, proj_indices: torch.Tensor) -> torch.Tensor:
+        p = proj_indices.to(self.device)
+        if p.dim() == 3 and p.shape[-1] == 1:
+            p = p.squeeze(2)
+        return p.to(torch.int32).reshape(1, -1).contiguous()
+
+    def project_image_features(self, image_features: torch.Tensor, observed_pixels: torch.Tensor,
+                               proj_indices: Sequence[torch.Tensor], memory: Sequence[torch.Tensor]):
+        """custom_rcnn.py:903-936: (mean (M,C) f32 in ascending cell order, observed_mem (cells,) bool)."""
+        n_cells = memory[0].shape[0]
+        C = image_features.shape[1]
+        idx = self._idx32(proj_indices[0])
+        samp = ops.sample_mask(observed_pixels.to(self.device).reshape(1, -1).view(torch.uint8).contiguous(), self.sample_stride)
+        scratch = torch.zeros((1, n_cells, C), dtype=torch.float32, device=self.device)
+        cnt = torch.zeros((1, n_cells), dtype=torch.int32, device=self.device)
+        touched = torch.zeros((1, n_cells), dtype=torch.uint8, device=self.device)
+        dummy_counts = torch.zeros((1, n_cells), dtype=torch.float32, device=self.device)
+        feat = image_features.to(self.device, torch.float32).reshape(1, C, -1).contiguous()
+        ops.frame_count(idx, samp, cnt)
+        ops.write_mean(feat, idx, samp, cnt, scratch, LAYOUT_CHW)
+        ops.finalize_counts(idx, cnt, dummy_counts, touched)
+        observed_mem = touched[0].view(torch.bool)
+        return scratch[0][observed_mem], observed_mem
+
+    def update_implicit_memory(self, inference_results, proj_indices: torch.Tensor, memory: torch.Tensor, frame: Dict,
+                               visualise: bool = False) -> None:
+        """custom_rcnn.py:681-760.  ``inference_results`` is what ``inference_with_proposals`` returns
+        (:882): None (no kept detection -> no write at all, :686) or (boxes, box_features (K,C), masks
+        (K,H,W) bool, pred_instances).  Sums and visibility counts are accumulated in place on the device."""
+        if inference_results is None:
+            return
+        _, box_features, masks, _ = inference_results
+        if self.implicit_memory is None or self.implicit_memory.shape[0] != memory.shape[0]:
+            self.reset(memory.shape[0])
+        self._dims = self.map_dims(frame.get("sequence_name", ""))
+        image_features, observed = self.box_to_image_features(box_features, masks)
+        self.write_image_features(image_features, observed, proj_indices)
+
+    def write_image_features(self, image_features: torch.Tensor, observed_pixels: Optional[torch.Tensor],
+                             proj_indices: torch.Tensor, layout: int = LAYOUT_CHW) -> None:
+        """A7 + A8 on the live state: per-cell mean of every ``sample_stride``-th observed pixel, sums +=,
+        counts += 1 for all visible cells."""
+        idx = self._idx32(proj_indices)
+        samp = None
+        if observed_pixels is not None:
+            samp = ops.sample_mask(observed_pixels.to(self.device).reshape(1, -1).view(torch.uint8).contiguous(), self.sample_stride)
+        C = self.C
+        feat = image_features.to(self.device, torch.float32).reshape(1, -1).contiguous()
+        ops.frame_count(idx, samp, self._frame_cnt)
+        ops.write_mean(feat, idx, samp, self._frame_cnt, self.implicit_memory.unsqueeze(0), layout)
+        ops.finalize_counts(idx, self._frame_cnt, self.observations.unsqueeze(0))

@@ -1,0 +1,203 @@
+"""Torch-tensor front end of the C ABI: validates shapes/dtypes/devices, passes raw device pointers and the
+current CUDA stream to libeod_memory.so.  torch is used for device memory and streams only; every op
+here runs a hand-written kernel (no torch compute, no CPU fallback: CPU tensors raise).
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import (FUSE_IMAGE_ONLY, FUSE_MEM_ONLY, FUSE_SUM, LAYOUT_CHW, LAYOUT_HWC, ORDER_XZ, ORDER_ZX, WRITE_AUTO,
+                   WRITE_LDG, WRITE_TMA, EodError, check)
+
+# kernels launched through this module since import (bench.py reports it as gpu_launches)
+launch_count = 0
+
+_LAUNCHES = {"eod_backproject_quantize": 1, "eod_sample_mask": 1, "eod_frame_count": 1, "eod_write_mean": 1,
+             "eod_finalize_counts": 1, "eod_box_to_image_features": 1, "eod_write_max": 2, "eod_read_pool": 1,
+             "eod_fuse": 1, "eod_normalize_memory": 1}
+
+
+def _call(name: str, *args) -> None:
+    global launch_count
+    check(getattr(_lib.lib(), name)(*args), name)
+    launch_count += _LAUNCHES[name]
+
+
+def _dev(t: torch.Tensor, dtype: torch.dtype, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor")
+    if not t.is_cuda:
+        raise EodError(f"{name}: tensor is on {t.device}; the spatial memory runs on CUDA only (no CPU fallback)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: tensor must be contiguous")
+    return t
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def backproject_quantize(depth: torch.Tensor, pose: torch.Tensor, shifts: torch.Tensor, intr: Sequence[float], cell: float,
+                         map_w: int, map_h: int, order: int = ORDER_ZX, z_clip: float = 0.5, *, want_idx: bool = True,
+                         want_q2: bool = False, want_outlier: bool = False, want_height: bool = False,
+                         want_world: bool = False, out: Optional[dict] = None) -> dict:
+    """depth (E,H,W) f32, pose (E,12) f32, shifts (E,6) f32 -> dict(idx, q2, outlier, height, world)."""
+    _dev(depth, torch.float32, "depth"), _dev(pose, torch.float32, "pose"), _dev(shifts, torch.float32, "shifts")
+    E, H, W = depth.shape
+    if pose.shape != (E, 12) or shifts.shape != (E, 6):
+        raise ValueError("pose must be (E,12) and shifts (E,6)")
+    out = {} if out is None else out
+    dev = depth.device
+
+    def buf(key, want, shape, dtype):
+        if not want:
+            return None
+        if key not in out:
+            out[key] = torch.empty(shape, dtype=dtype, device=dev)
+        return _dev(out[key], dtype, key)
+
+    idx = buf("idx", want_idx, (E, H, W), torch.int32)
+    q2 = buf("q2", want_q2, (E, H, W, 2), torch.int32)
+    outlier = buf("outlier", want_outlier, (E, H, W), torch.uint8)
+    height = buf("height", want_height, (E, H, W), torch.float32)
+    world = buf("world", want_world, (E, H, W, 3), torch.float32)
+    fx, fy, cx, cy = (float(v) for v in intr)
+    _call("eod_backproject_quantize", depth.data_ptr(), pose.data_ptr(), shifts.data_ptr(), E, H, W, fx, fy, cx, cy,
+          float(cell), int(map_w), int(map_h), int(order), float(z_clip), _ptr(idx), _ptr(q2), _ptr(outlier),
+          _ptr(height), _ptr(world), _stream())
+    return out
+
+
+def sample_mask(observed: torch.Tensor, stride: int, samp: Optional[torch.Tensor] = None,
+                n_sampled: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """observed (E,HW) u8 -> samp (E,HW) u8: every stride-th observed pixel in raster order."""
+    _dev(observed, torch.uint8, "observed")
+    E, HW = observed.shape
+    samp = torch.empty_like(observed) if samp is None else _dev(samp, torch.uint8, "samp")
+    _call("eod_sample_mask", observed.data_ptr(), E, HW, int(stride), samp.data_ptr(), _ptr(n_sampled), _stream())
+    return samp
+
+
+def frame_count(idx: torch.Tensor, samp: Optional[torch.Tensor], frame_cnt: torch.Tensor) -> None:
+    """idx (E,HW) i32, samp (E,HW) u8 | None, frame_cnt (E,cells) i32 scratch (zero on entry)."""
+    _dev(idx, torch.int32, "idx"), _dev(frame_cnt, torch.int32, "frame_cnt")
+    E, HW = idx.shape[0], idx[0].numel()
+    if samp is not None:
+        _dev(samp, torch.uint8, "samp")
+    _call("eod_frame_count", idx.data_ptr(), _ptr(samp), E, HW, frame_cnt.shape[1], frame_cnt.data_ptr(), _stream())
+
+
+def write_mean(feat: torch.Tensor, idx: torch.Tensor, samp: Optional[torch.Tensor], frame_cnt: torch.Tensor,
+               sums: torch.Tensor, layout: int = LAYOUT_CHW, variant: int = WRITE_AUTO) -> None:
+    """feat (E,C,HW) [CHW] or (E,HW,C) [HWC] f32; sums (E,cells,C) f32 accumulated in place."""
+    _dev(feat, torch.float32, "feat"), _dev(idx, torch.int32, "idx"), _dev(sums, torch.float32, "sums")
+    _dev(frame_cnt, torch.int32, "frame_cnt")
+    E, n_cells, C = sums.shape
+    HW = idx[0].numel()
+    if feat.numel() != E * C * HW:
+        raise ValueError(f"feat has {feat.numel()} elements, expected E*C*HW = {E * C * HW}")
+    if samp is not None:
+        _dev(samp, torch.uint8, "samp")
+    _call("eod_write_mean", feat.data_ptr(), int(layout), idx.data_ptr(), _ptr(samp), frame_cnt.data_ptr(), E, C, HW,
+          n_cells, sums.data_ptr(), int(variant), _stream())
+
+
+def finalize_counts(idx: torch.Tensor, frame_cnt: torch.Tensor, counts: torch.Tensor,
+                    touched: Optional[torch.Tensor] = None) -> None:
+    _dev(idx, torch.int32, "idx"), _dev(frame_cnt, torch.int32, "frame_cnt"), _dev(counts, torch.float32, "counts")
+    if touched is not None:
+        _dev(touched, torch.uint8, "touched")
+    E, HW = idx.shape[0], idx[0].numel()
+    _call("eod_finalize_counts", idx.data_ptr(), E, HW, counts.shape[1], frame_cnt.data_ptr(), counts.data_ptr(),
+          _ptr(touched), _stream())
+
+
+def box_to_image_features(box_features: torch.Tensor, masks: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """box_features (K,C) f32, masks (K,H,W) bool/u8 -> image_features (1,C,H,W) f32, observed (H,W) bool."""
+    _dev(box_features, torch.float32, "box_features")
+    if masks.dtype == torch.bool:
+        masks = masks.view(torch.uint8)
+    _dev(masks, torch.uint8, "masks")
+    K, C = box_features.shape
+    H, W = masks.shape[1:]
+    img = torch.empty((1, C, H, W), dtype=torch.float32, device=masks.device)
+    obs = torch.empty((H, W), dtype=torch.uint8, device=masks.device)
+    _call("eod_box_to_image_features", box_features.data_ptr(), masks.data_ptr(), K, C, H * W, img.data_ptr(),
+          obs.data_ptr(), _stream())
+    return img, obs.view(torch.bool)
+
+
+def write_max(height: torch.Tensor, idx: torch.Tensor, outlier: Optional[torch.Tensor], feat: Optional[torch.Tensor],
+              height_map: torch.Tensor, key64: torch.Tensor, arg_pix: torch.Tensor, observed: Optional[torch.Tensor],
+              state: Optional[torch.Tensor], layout: int = LAYOUT_HWC, pix_stride: int = 1) -> None:
+    """height/idx/outlier (E,H,W); feat (E,H,W,C) [HWC] or (E,C,H,W) [CHW]; height_map (E,cells) f32;
+    key64 (E,cells) i64 scratch; arg_pix (E,cells) i32; observed (E,cells) u8; state (E,cells,C) f32."""
+    _dev(height, torch.float32, "height"), _dev(idx, torch.int32, "idx"), _dev(height_map, torch.float32, "height_map")
+    _dev(key64, torch.int64, "key64"), _dev(arg_pix, torch.int32, "arg_pix")
+    E, H, W = height.shape
+    C = 0
+    if feat is not None:
+        _dev(feat, torch.float32, "feat"), _dev(state, torch.float32, "state")
+        C = state.shape[2]
+    if outlier is not None:
+        if outlier.dtype == torch.bool:
+            outlier = outlier.view(torch.uint8)
+        _dev(outlier, torch.uint8, "outlier")
+    if observed is not None:
+        _dev(observed, torch.uint8, "observed")
+    _call("eod_write_max", height.data_ptr(), idx.data_ptr(), _ptr(outlier), _ptr(feat), int(layout), E, C, H, W,
+          int(pix_stride), height_map.shape[1], height_map.data_ptr(), key64.data_ptr(), arg_pix.data_ptr(),
+          _ptr(observed), _ptr(state), _stream())
+
+
+def read_pool(table: torch.Tensor, counts: Optional[torch.Tensor], idx: torch.Tensor, out: Optional[Sequence[torch.Tensor]] = None):
+    """table (E,cells,C) f32 sums (+ counts (E,cells) f32) or f16 normalised table; idx (E,H,W) i32/i64.
+    Returns [L0, L1, L2] as logical (E,C,h,w) f16 tensors in channels_last memory format."""
+    if table.dtype not in (torch.float32, torch.float16):
+        raise TypeError("table must be float32 (sums) or float16 (normalised memory)")
+    _dev(table, table.dtype, "table")
+    if idx.dtype not in (torch.int32, torch.int64):
+        raise TypeError("idx must be int32 or int64")
+    _dev(idx, idx.dtype, "idx")
+    E, n_cells, C = table.shape
+    _, H, W = idx.shape
+    if counts is not None:
+        _dev(counts, torch.float32, "counts")
+    if out is None:
+        out = [torch.empty((E, H >> s, W >> s, C), dtype=torch.float16, device=table.device) for s in (3, 4, 5)]
+    for o in out:
+        _dev(o, torch.float16, "level")
+    _call("eod_read_pool", table.data_ptr(), int(table.dtype == torch.float16), _ptr(counts), idx.data_ptr(),
+          int(idx.dtype == torch.int64), E, C, H, W, n_cells, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+          _stream())
+    return [o.permute(0, 3, 1, 2) for o in out]
+
+
+def fuse(res: Optional[torch.Tensor], mem: Optional[torch.Tensor], weight: float, mode: int,
+         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    ref = res if res is not None else mem
+    if res is not None:
+        _dev(res, torch.float32, "res")
+    if mem is not None:
+        _dev(mem, torch.float32, "mem")
+    out = torch.empty_like(ref) if out is None else _dev(out, torch.float32, "out")
+    _call("eod_fuse", _ptr(res), _ptr(mem), float(weight), int(mode), ref.numel(), out.data_ptr(), _stream())
+    return out
+
+
+def normalize_memory(sums: torch.Tensor, counts: torch.Tensor, half: bool = False) -> torch.Tensor:
+    """create_implicit_memory as a table: sums (..., cells, C) f32, counts (..., cells) f32 -> same shape, f32|f16."""
+    _dev(sums, torch.float32, "sums"), _dev(counts, torch.float32, "counts")
+    C = sums.shape[-1]
+    out = torch.empty(sums.shape, dtype=torch.float16 if half else torch.float32, device=sums.device)
+    _call("eod_normalize_memory", sums.data_ptr(), counts.data_ptr(), sums.numel() // C, C, out.data_ptr(), int(half), _stream())
+    return out

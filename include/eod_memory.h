@@ -1,0 +1,147 @@
+/*
+ * eod_memory.h - C ABI of the B200-native spatial feature memory (libeod_memory.so).
+ *
+ * This is the drop-in boundary for ONE path of nhcha6/embodied-object-detection: back-project ->
+ * memory write -> memory read -> fusion.  The reference has no FFI for this path today: it is a chain
+ * of torch ops inside two Python classes.  Each entry point below names the reference lines it
+ * replaces (paths relative to <reference>/Detic); INTEGRATION.md shows the ctypes stub a maintainer
+ * adds on the reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (torch allocates); the library allocates no
+ *     persistent memory and keeps no global state apart from a thread-local error string;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); calls are asynchronous and
+ *     thread-safe for distinct streams;
+ *   - return value: EOD_OK or a negative EOD_ERR_*; eod_last_error() describes the last failure of the
+ *     calling thread;
+ *   - leading dimension E = number of independent episodes processed by one launch ("batch x64");
+ *     tensors of different episodes are E-contiguous: element (e, i) lives at base + e*stride + i;
+ *   - grid state of one episode: sums (cells, C) fp32 row = cell, counts (cells) fp32 (integer valued),
+ *     frame_cnt (cells) u32 scratch that is all-zero between frames;
+ *   - cell indices are int32 (cells < 2^31); int64 indices of the reference API are accepted where
+ *     stated (idx_is_i64).
+ */
+#ifndef EOD_MEMORY_H
+#define EOD_MEMORY_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EOD_OK 0
+#define EOD_ERR_BADARG (-1)      /* null pointer / non-positive size / unsupported enum            */
+#define EOD_ERR_ALIGN (-2)       /* pointer or row stride not 16-byte aligned                       */
+#define EOD_ERR_LAUNCH (-3)      /* CUDA launch / driver error (message in eod_last_error)          */
+#define EOD_ERR_UNSUPPORTED (-4) /* shape not compiled in (C must be one of 128, 256, 512)          */
+
+#define EOD_ORDER_ZX 0 /* flat = q_z * map_w + q_x   SMNet/build_memory_data.py:143 */
+#define EOD_ORDER_XZ 1 /* flat = q_x * map_h + q_z   robot_demo.py:533               */
+
+#define EOD_LAYOUT_CHW 0 /* features (E, C, H*W): the reference's image_features, custom_rcnn.py:886 */
+#define EOD_LAYOUT_HWC 1 /* features (E, H*W, C): channels-last                                         */
+
+#define EOD_FUSE_SUM 0        /* res + w*mem   timm.py:181-182 */
+#define EOD_FUSE_MEM_ONLY 1   /* w*mem         timm.py:183-184 */
+#define EOD_FUSE_IMAGE_ONLY 2 /* res           timm.py:185-186 */
+
+#define EOD_WRITE_AUTO 0 /* TMA-staged kernel when the shape allows it, else LDG-staged */
+#define EOD_WRITE_LDG 1  /* force the LDG-staged kernel                                  */
+#define EOD_WRITE_TMA 2  /* force the TMA-staged kernel (error if shape unsupported)     */
+
+typedef void *eod_stream_t;
+
+int eod_version(void);
+const char *eod_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------------
+ * (1) Geometry.  Replaces SMNet/projector/core.py:107-175,220 (pixel_to_world_mapping),
+ * core.py:227-271 (discretize_point_cloud), projector.py:88-101, SMNet/build_memory_data.py:135-143,
+ * robot_demo.py:526-533.
+ *   depth  (E,H,W) f32 metres (0 = no depth)      pose (E,12) rows 0..2 of the 4x4 camera-to-world T
+ *   shifts (E,6): world_shift_origin xyz, map_world_shift xyz
+ *   intrinsics fx,fy,cx,cy are the fp32 values of core.py:68-77 (host computes them; the kernel does not)
+ * Outputs, each nullable: idx (E,H,W) clipped flat cell index; q2 (E,H,W,2) unclipped (x,z);
+ * outlier (E,H,W) u8; height (E,H,W) world y; world (E,H,W,3) xyz after world_shift_origin only.
+ * Bit-exact with torch-CPU execution of the cited lines (FMA-chain bmm, IEEE divide, round-half-even).
+ */
+int eod_backproject_quantize(const float *depth, const float *pose, const float *shifts, int n_episodes, int H,
+                             int W, float fx, float fy, float cx, float cy, float cell, int map_w, int map_h,
+                             int order, float z_clip, int32_t *idx, int32_t *q2, uint8_t *outlier, float *height,
+                             float *world, eod_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * (2) Write, mean mode.
+ */
+
+/* Raster-order "every stride-th observed pixel" selection, custom_rcnn.py:905-914.
+ * observed (E,HW) u8 -> samp (E,HW) u8 (1 = pixel is sampled).  n_sampled (E) i32 nullable. */
+int eod_sample_mask(const uint8_t *observed, int n_episodes, int HW, int stride, uint8_t *samp, int32_t *n_sampled,
+                    eod_stream_t stream);
+
+/* Per-frame pre-pass: frame_cnt[cell] += #sampled pixels of the cell; bit 31 marks cells that are
+ * visible but have no sampled pixel (torch.unique(proj_indices), custom_rcnn.py:699).  samp nullable
+ * (= every pixel sampled).  frame_cnt must be zero on entry. */
+int eod_frame_count(const int32_t *idx, const uint8_t *samp, int n_episodes, int HW, int64_t n_cells,
+                    uint32_t *frame_cnt, eod_stream_t stream);
+
+/* Main pass: sums[cell] += (sum of the sampled pixels' feature vectors) / n_cell, i.e. the per-cell mean
+ * of custom_rcnn.py:917-934 accumulated as in :696-697,742.  Warp/CTA-aggregated fp32 atomics:
+ * run-to-run results agree to ~1e-7 of scale, not bitwise. */
+int eod_write_mean(const float *feat, int layout, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt,
+                   int n_episodes, int C, int HW, int64_t n_cells, float *sums, int variant, eod_stream_t stream);
+
+/* Post-pass: counts[cell] += 1 for every visible cell (custom_rcnn.py:699-701,743) and frame_cnt := 0.
+ * touched (E,cells) u8 nullable: |= 1 where the cell received samples this frame (observed_mem, :922). */
+int eod_finalize_counts(const int32_t *idx, int n_episodes, int HW, int64_t n_cells, uint32_t *frame_cnt,
+                        float *counts, uint8_t *touched, eod_stream_t stream);
+
+/* Per-pixel mean of the kept objects' features, custom_rcnn.py:884-901 (objects added in index order,
+ * then / count): box_features (K,C) f32, masks (K,HW) u8 -> image_features (C,HW) f32 (zeros where
+ * unobserved), observed (HW) u8.  Bit-exact (same fp32 add order). */
+int eod_box_to_image_features(const float *box_features, const uint8_t *masks, int K, int C, int HW,
+                              float *image_features, uint8_t *observed, eod_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * (2b) Write, SMNet height-max mode (bytecode-only SMNet.encode, SURVEY 8a row A7').
+ * Per frame: for inlier pixels (outlier == 0) on the [::pix_stride, ::pix_stride] lattice,
+ * height_map[cell] = max(height_map[cell], height + 1000) with the canonical tie rule (highest raster
+ * index wins; an equal later value replaces).  arg_pix (E,cells) i32: winning raster pixel index or -1;
+ * observed (E,cells) u8 |= raised; state (E,cells,C) f32: raised cells := the winner's feature vector
+ * ('replace' update).  key64 (E,cells) u64 scratch, all-zero between frames.  feat nullable (then state
+ * is not touched). */
+int eod_write_max(const float *height, const int32_t *idx, const uint8_t *outlier, const float *feat, int layout,
+                  int n_episodes, int C, int H, int W, int pix_stride, int64_t n_cells, float *height_map,
+                  uint64_t *key64, int32_t *arg_pix, uint8_t *observed, float *state, eod_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * (3) Read.  Replaces create_implicit_memory (custom_rcnn.py:764-774), the fp16 cast (:1036) and
+ * timm.py:147-168 (gather to the image plane, avg-pool 4, then per level avg-pool 2 -> half) in ONE
+ * kernel; the (480,640,C) image-plane tensors are never materialised.
+ *   table: mem_is_f16 == 0: sums (E,cells,C) f32 with counts (E,cells) f32 (nullable = no normalise);
+ *          mem_is_f16 == 1: already normalised fp16 table (E,cells,C) (reference API: map_memory list)
+ *   idx (E,H,W) int32 or int64.  H, W multiples of 32.
+ *   L0 (E,H/8,W/8,C), L1 (E,H/16,W/16,C), L2 (E,H/32,W/32,C) fp16, channels-last.
+ * Bit-exact with torch-CPU (sequential row-major window sums, fp16 rounding between levels).
+ */
+int eod_read_pool(const void *table, int mem_is_f16, const float *counts, const void *idx, int idx_is_i64,
+                  int n_episodes, int C, int H, int W, int64_t n_cells, void *L0, void *L1, void *L2,
+                  eod_stream_t stream);
+
+
+/* Stand-alone create_implicit_memory (custom_rcnn.py:764-774, and the half cast of :1036 when out_is_f16):
+ * out[row] = sums[row] / counts[row] where counts[row] > 1 else sums[row].  n_rows = E*cells.  Only for
+ * callers that need the normalised table itself; eod_read_pool fuses this step. */
+int eod_normalize_memory(const float *sums, const float *counts, int64_t n_rows, int C, void *out, int out_is_f16,
+                         eod_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * (4) Fusion epilogue, timm.py:177-189: out = res + weight*mem | weight*mem | res (two roundings, no
+ * FMA contraction, as torch computes it).  n elements, fp32. */
+int eod_fuse(const float *res, const float *mem, float weight, int mode, int64_t n, float *out, eod_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EOD_MEMORY_H */

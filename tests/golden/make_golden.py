@@ -1,0 +1,198 @@
+"""Generate the golden fixtures under tests/golden/ by EXECUTING THE REFERENCE'S OWN SOURCE on the CPU.
+
+Needs /root/reference (dev container only; the GPU box never runs this).  Nothing from the reference is copied
+into the repo: its code is imported (projector package) or its cited line ranges are read from disk and
+exec'd in a scratch namespace at generation time.
+
+  geometry_*.npz   SMNet/projector (imported as is): Projector.forward(return_heights=True), PointCloud.forward,
+                   then the quantise lines SMNet/build_memory_data.py:135-143 exec'd verbatim
+  write_*.npz      methods box_to_image_features / project_image_features / create_implicit_memory of
+                   detic/modeling/meta_arch/custom_rcnn.py extracted with ast and exec'd (torch.cuda.* constructors
+                   and .cuda() patched to CPU), plus lines 696-701 of update_implicit_memory
+  read_*.npz       lines 142-192 of detic/modeling/backbone/timm.py exec'd verbatim
+
+Run:  python tests/golden/make_golden.py
+"""
+import ast
+import importlib
+import math
+import os
+import sys
+import textwrap
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+REF = "/root/reference/Detic"
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(REF, "SMNet"))
+
+eod_episodes = importlib.import_module("embodied-object-detection_b200.episodes")
+
+
+def patch_cpu():
+    torch.cuda.FloatTensor = torch.FloatTensor
+    torch.cuda.BoolTensor = torch.BoolTensor
+    torch.Tensor.cuda = lambda self, *a, **k: self
+
+
+def ref_methods():
+    """FunctionDefs of CustomRCNNRecurrent compiled stand-alone."""
+    path = os.path.join(REF, "detic/modeling/meta_arch/custom_rcnn.py")
+    src = open(path).read()
+    tree = ast.parse(src)
+    cls = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "CustomRCNNRecurrent"][0]
+    want = {"box_to_image_features", "project_image_features", "create_implicit_memory"}
+    ns = {"torch": torch, "np": np, "math": math, "autocast": torch.cuda.amp.autocast}
+    for fn in cls.body:
+        if isinstance(fn, ast.FunctionDef) and fn.name in want:
+            mod = ast.Module(body=[fn], type_ignores=[])
+            exec(compile(mod, path, "exec"), ns)
+    return ns, src.splitlines()
+
+
+def exec_lines(lines, lo, hi, ns):
+    """exec reference source lines lo..hi (1-based, inclusive), dedented."""
+    exec(textwrap.dedent("\n".join(lines[lo - 1:hi])), ns)
+    return ns
+
+
+def gen_geometry():
+    from projector.core import _transform3D
+    from projector.point_cloud import PointCloud
+    from projector.projector import Projector
+    vfov = math.radians(67.5)
+    bm_lines = open(os.path.join(REF, "SMNet/build_memory_data.py")).read().splitlines()
+    for name, (H, W, n_frames, seed, mw, mh, cell, room) in {
+        "geometry_small": (96, 128, 6, 7, 500, 500, 0.02 * 10, (12.0, 9.0)),
+        "geometry_full": (480, 640, 2, 1234, 500, 500, 0.02 * 10, (12.0, 9.0)),
+        "geometry_fine": (96, 128, 4, 11, 1000, 1000, 0.02, (24.0, 18.0)),     # out-of-map pixels: clip + mask
+    }.items():
+        ep = eod_episodes.make_episode(seed, n_frames, H, W, mw, mh, cell, room)
+        xyzhe = torch.from_numpy(ep.xyzhe)
+        T = _transform3D(xyzhe)
+        shift = torch.from_numpy(ep.map_world_shift)
+        depth = torch.from_numpy(ep.depth)
+        # Projector (create_coco_mp3d.py:94-102,157-159): world_shift_origin = map_world_shift
+        pr = Projector(vfov, 1, H, W, mh, mw, cell, shift, 0.5, device=torch.device("cpu"))
+        q2, outl, hts = [], [], []
+        for t in range(n_frames):
+            a, b, c = pr.forward(depth[t][None, None], T[t:t + 1], return_heights=True)
+            q2.append(a[0].numpy().astype(np.int32)); outl.append(b[0].numpy()); hts.append(c[0].numpy())
+        # PointCloud (build_data.py:98-103,209) then build_memory_data.py:135-143 verbatim
+        pc = PointCloud(vfov, 1, H, W, torch.zeros(3), 0.5, device=torch.device("cpu"))
+        world = torch.cat([pc.forward(depth[t][None, None], T[t:t + 1])[0] for t in range(n_frames)])
+        ns = {"torch": torch, "np": np, "projection_indices": world.clone(), "map_world_shift": shift.clone(),
+              "resolution": 0.02, "res_downsample": 10 if cell > 0.02 else 1, "map_height": mh, "map_width": mw}
+        exec_lines(bm_lines, 135, 144, ns)
+        flat = ns["pixels_in_map"][..., 0].astype(np.int32)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), depth=ep.depth, xyzhe=ep.xyzhe, T=T.numpy(),
+                            map_world_shift=ep.map_world_shift, cell=np.float32(ns["resolution"] * ns["res_downsample"]),
+                            map_w=mw, map_h=mh, vfov=vfov, q2=np.stack(q2), outlier=np.stack(outl), height=np.stack(hts),
+                            world=world.numpy(), flat=flat)
+        print(name, "unique cells/frame", [len(np.unique(f)) for f in flat], "outliers", np.stack(outl).mean())
+
+
+def gen_write():
+    patch_cpu()
+    ns, lines = ref_methods()
+    rng = np.random.default_rng(5)
+    H, W, C = 480, 640, 512                      # hard-coded in the reference (custom_rcnn.py:886-887)
+    mw, mh = 60, 45                              # small grid: the literal one-hot is (P', cells) bool
+    ep = eod_episodes.make_episode(21, 3, H, W, mw, mh, 0.02 * 10, (12.0, 9.0))
+    from projector.core import _transform3D
+    import oracle
+    T = _transform3D(torch.from_numpy(ep.xyzhe)).numpy()
+    intr = (320.0, 359.1853942871094, 320.0, 240.0)
+    sums = torch.zeros(mw * mh, C)
+    counts = torch.zeros(mw * mh)
+    out = {}
+    for t in range(3):
+        idx = oracle.backproject_quantize(ep.depth[t], T[t], intr, np.zeros(3, np.float32), ep.map_world_shift,
+                                          np.float32(0.2), mw, mh, 0, 0.5, want=("idx",))["idx"]
+        bf, masks = eod_episodes.make_detections(rng, H, W, C, (3, 6))
+        proj = torch.from_numpy(idx).long()
+        image_features, observed = ns["box_to_image_features"](None, torch.from_numpy(bf), torch.from_numpy(masks))
+        mean, observed_mem = ns["project_image_features"](None, image_features, observed, [proj], [sums])
+        # update_implicit_memory lines 696-701 verbatim, then the += of 742-743 on the flat views
+        u = {"torch": torch, "memory": sums, "observed_mem": observed_mem, "proj_features": mean, "proj_indices": proj}
+        exec_lines(lines, 696, 701, u)
+        sums = sums + u["semmap_update"]
+        counts = counts + u["observed_update"][:, 0]
+        norm, _ = ns["create_implicit_memory"](None, {"memory": sums, "observations": counts, "proj_indices": proj})
+        out.update({f"idx{t}": idx, f"box_features{t}": bf, f"masks{t}": np.packbits(masks, axis=None),
+                    f"K{t}": masks.shape[0], f"observed{t}": np.packbits(observed.numpy(), axis=None),
+                    f"img_sample{t}": image_features[0, :, ::16, ::16].numpy(),        # subsample: 629 MB otherwise
+                    f"img_checksum{t}": image_features.double().sum(dim=(0, 2, 3)).numpy(),
+                    f"mean{t}": mean.numpy(), f"observed_mem{t}": observed_mem.numpy(),
+                    f"sums{t}": sums.numpy().copy(), f"counts{t}": counts.numpy().copy(), f"norm{t}": norm.numpy()})
+        print("write frame", t, "K", masks.shape[0], "P", int(observed.sum()), "M", int(observed_mem.sum()),
+              "V", len(np.unique(idx)))
+    np.savez_compressed(os.path.join(HERE, "write_mean.npz"), map_w=mw, map_h=mh, **out)
+
+
+def gen_read():
+    patch_cpu()
+    lines = open(os.path.join(REF, "detic/modeling/backbone/timm.py")).read().splitlines()
+    torch.manual_seed(3)
+    H, W, C, CO = 480, 640, 128, 64               # channel counts are free in timm.py:142-192; kept small for size
+    mw, mh = 60, 45
+    ep = eod_episodes.make_episode(33, 2, H, W, mw, mh, 0.02 * 10, (12.0, 9.0))
+    from projector.core import _transform3D
+    import oracle
+    T = _transform3D(torch.from_numpy(ep.xyzhe)).numpy()
+    intr = (320.0, 359.1853942871094, 320.0, 240.0)
+    sums = torch.randn(mw * mh, C) * 30
+    counts = torch.randint(0, 6, (mw * mh,)).float()
+    sums[counts == 0] = 0
+    convs = [torch.nn.Conv2d(C, CO, 1, bias=True) for _ in range(3)]
+    out = {"sums": sums.numpy(), "counts": counts.numpy(), "map_w": mw, "map_h": mh}
+    for k, c in enumerate(convs):
+        out[f"w{k}"], out[f"b{k}"] = c.weight.detach().numpy(), c.bias.detach().numpy()
+    for t in range(2):
+        idx = oracle.backproject_quantize(ep.depth[t], T[t], intr, np.zeros(3, np.float32), ep.map_world_shift,
+                                          np.float32(0.2), mw, mh, 0, 0.5, want=("idx",))["idx"]
+        proj = torch.from_numpy(idx).long()
+        mem = sums.clone()
+        sel = counts > 1
+        mem[sel] = mem[sel] / counts.unsqueeze(1)[sel]
+        results = [torch.randn(1, CO, H >> s, W >> s).half().float() for s in (3, 4, 5)]
+        for fusion in (("sum", "mem_only", "image_only") if t == 0 else ("sum",)):
+            captured = {}
+
+            class _Conv:
+                def __init__(self, conv, k):
+                    self.conv, self.k = conv, k
+
+                def __call__(self, x):
+                    captured[self.k] = x.detach().clone()         # the pooled fp16-valued level fed to the conv
+                    return self.conv(x)
+
+            self_ns = type("S", (), {})()
+            self_ns.memory_type, self_ns.feat_fusion, self_ns.map_feature_weight = "implicit_memory", fusion, 5
+            self_ns.merge_map_projections = [_Conv(c, k) for k, c in enumerate(convs)]
+            ns = {"torch": torch, "F": F, "self": self_ns, "map_memory": [mem.to(torch.half)], "proj_indices": [proj],
+                  "observations": [counts.to(torch.half)], "results": [r.clone() for r in results]}
+            with torch.no_grad():
+                exec_lines(lines, 142, 192, ns)
+            for k in range(3):
+                out[f"fused_{fusion}_{t}_{k}"] = ns["results"][k].numpy()
+            if fusion == "sum":
+                for k in range(3):
+                    out[f"level{t}_{k}"] = captured[k].to(torch.half).numpy()
+                    out[f"res{t}_{k}"] = results[k].half().numpy()
+        out[f"idx{t}"] = idx
+    np.savez_compressed(os.path.join(HERE, "read_fuse.npz"), **out)
+    print("read: levels", [out[f"level0_{k}"].shape for k in range(3)])
+
+
+if __name__ == "__main__":
+    gen_geometry()
+    gen_write()
+    gen_read()
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

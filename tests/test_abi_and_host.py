@@ -1,0 +1,150 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/eod_memory.h declares, the product
+never touches the oracle, CPU tensors are refused (no fallback), host logic (config keys, map dims, sharding)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "embodied-object-detection_b200")
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "eod_memory.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(eod_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(eod):
+    eod.build.build()
+    handle = ctypes.CDLL(eod.build.SO_PATH)
+    declared = _declared_symbols()
+    assert len(declared) >= 12
+    for name in declared:
+        assert hasattr(handle, name), f"{name} declared in include/eod_memory.h but not exported"
+    # the ctypes table binds exactly the declared set
+    assert sorted(eod._lib.SIGNATURES) == declared
+    assert eod._lib.lib().eod_version() == 100
+
+
+def test_library_is_sm100a_only(eod):
+    out = subprocess.run(["cuobjdump", "--list-elf", eod.build.SO_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_product_never_imports_oracle():
+    bad = []
+    for dirpath, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M) or "oracle/" in src:
+                    bad.append(f)
+    assert not bad, bad
+
+
+def test_cpu_tensors_are_refused(eod):
+    with pytest.raises(eod.EodError):
+        eod.ops.fuse(torch.zeros(8), torch.zeros(8), 5.0, eod._lib.FUSE_SUM)
+    with pytest.raises(eod.EodError):
+        eod.EpisodeBatch(1, 10, 10, 128, device="cpu")
+    with pytest.raises(eod.EodError):
+        eod.SpatialFeatureMemory(device="cpu")
+
+
+def test_badarg_codes_without_gpu(eod):
+    lib = eod._lib.lib()
+    assert lib.eod_fuse(None, None, 1.0, 0, 0, None, None) == -1
+    assert b"eod_fuse" in lib.eod_last_error()
+    assert lib.eod_read_pool(None, 0, None, None, 0, 1, 256, 480, 640, 10, None, None, None, None) == -1
+    assert lib.eod_backproject_quantize(None, None, None, 1, 480, 640, 1.0, 1.0, 0.0, 0.0, 0.2, 10, 10, 0, 0.5,
+                                        None, None, None, None, None, None) == -1
+
+
+def test_config_keys_and_defaults(eod):
+    cfg = eod.config.add_detic_memory_config()
+    m = cfg.MODEL
+    assert (m.MEMORY_TYPE, m.MAP_FEAT_FUSION, m.MAP_FEATURE_WEIGHT, m.MEMORY_FEATURE_WEIGHT) == ("", "", 500, 100)
+    assert (m.MEMORY_CLS_SCORE_THRESH, m.MEMORY_OBS_SCORE_THRESH, m.TEST_TYPE) == (0.3, 0.4, "default")
+    eod.config.merge_from_list(cfg, ["MODEL.MEMORY_TYPE", "implicit_memory", "MODEL.MAP_FEAT_FUSION", "sum",
+                                     "MODEL.MAP_FEATURE_WEIGHT", "5"])
+    fusion = eod.config.build_memory_fusion(cfg)
+    assert fusion.map_feature_weight == 5.0 and fusion.feat_fusion == "sum"
+    names = sorted(k for k, _ in fusion.state_dict().items())
+    assert names == [f"map_merge_projection{i}.{p}" for i in (1, 2, 3) for p in ("bias", "weight")]
+    assert fusion.state_dict()["map_merge_projection1.weight"].shape == (256, 512, 1, 1)
+    cfg.MODEL.MAP_FEAT_FUSION = "ave"
+    with pytest.raises(ValueError):
+        eod.config.build_memory_fusion(cfg)
+    cfg.MODEL.MEMORY_TYPE = "image_only"
+    f2 = eod.config.build_memory_fusion(cfg)
+    assert len(f2.state_dict()) == 0
+    res = [torch.zeros(1, 256, 4, 4)]
+    assert f2(res, None, None, None)[0] is res[0]        # image_only: FPN results untouched (timm.py:194-196)
+
+
+def test_map_dims_lookup(eod):
+    info = {"17DRP5sb8fy_0": {"dim": [1094, 1, 569]}}
+    rep = {"apartment_0": {"dim": [120, 1, 80]}}
+    mem = eod.SpatialFeatureMemory.__new__(eod.SpatialFeatureMemory)
+    mem.semmap_gt_info, mem.replica_map_info, mem.downsample = info, rep, 10
+    assert mem.map_dims("17DRP5sb8fy_0_12") == (110, 57)            # ceil(dim / 10), custom_rcnn.py:705-707
+    assert mem.map_dims("apartment_0_3") == (120, 80)               # replica table, :710-725
+    assert mem.map_dims("robot") == (200, 200)                      # default, :727-729
+
+
+def test_sharding_partitions(eod):
+    sh = eod.sharding
+    for world in (1, 2, 4, 8):
+        parts = [sh.shard_episodes(512, r, world) for r in range(world)]
+        assert sorted(sum(parts, [])) == list(range(512))
+        assert max(map(len, parts)) - min(map(len, parts)) <= 1
+    names = [f"scene{i % 5:08d}_{i // 5}" for i in range(40)]
+    parts = [sh.shard_scenes(names, r, 2) for r in range(2)]
+    assert sorted(sum(parts, [])) == list(range(40))
+    for p in parts:
+        assert len({names[i][:13] for i in p} & {names[i][:13] for i in parts[1 - parts.index(p)]}) == 0
+
+
+def test_episode_generator_is_deterministic_and_mp3d_shaped(eod):
+    a = eod.episodes.make_episode(1234, n_frames=2, H=96, W=128)
+    b = eod.episodes.make_episode(1234, n_frames=2, H=96, W=128)
+    assert np.array_equal(a.depth, b.depth) and np.array_equal(a.xyzhe, b.xyzhe)
+    assert a.depth.dtype == np.float32 and a.depth.max() <= 10.0 and (a.depth == 0).mean() > 0.005
+    assert np.allclose(a.xyzhe[:, 1], 1.25) and np.allclose(a.xyzhe[:, 4], np.pi)
+    step = np.linalg.norm(np.diff(a.xyzhe[:, [0, 2]], axis=0), axis=1)
+    assert ((np.abs(step - 0.1) < 1e-4) | (step < 1e-6)).all()
+
+
+def _gloo_worker(rank, world, port, q):
+    import importlib
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    eod = importlib.import_module("embodied-object-detection_b200")
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    r, _, w = eod.sharding.init_from_env(backend="gloo")
+    mine = eod.sharding.shard_episodes(11, r, w)
+    tot = eod.sharding.gather_counters({"frames": 20.0 * len(mine), "checksum": float(sum(mine))}, torch.device("cpu"))
+    mx = eod.sharding.max_over_ranks(float(rank + 1), torch.device("cpu"))
+    q.put((rank, tot, mx))
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_counters():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = [q.get(timeout=120) for _ in procs]
+    [p.join(60) for p in procs]
+    for _, tot, mx in res:
+        assert tot == {"checksum": float(sum(range(11))), "frames": 220.0}
+        assert mx == 2.0

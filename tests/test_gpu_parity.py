@@ -1,0 +1,390 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`).  Every CUDA result goes through the C ABI
+(embodied-object-detection_b200.ops -> libeod_memory.so) and is compared with
+  * the committed golden fixtures (outputs of the reference's own source, tests/golden/make_golden.py), and
+  * the CPU oracle (oracle/) on seeded inputs,
+bit-exact for indices / masks / counts / argmax / fp16 read outputs, and within 1e-5 of the feature scale for
+accumulated fp32 sums (tolerance stated by BASELINE.json north_star).
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import reference_ops as R
+
+pytestmark = pytest.mark.gpu
+
+SUM_TOL = 1e-5          # max|a-b| <= SUM_TOL * max|ref|   
+
+
+def _unpack(bits, shape):
+    return np.unpackbits(bits)[: int(np.prod(shape))].reshape(shape).astype(bool)
+
+
+def _t(a, dev, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    return t if dtype is None else t.to(dtype)
+
+
+# --------------------------------------------------------------------------------------------------------
+# geometry (A1-A5)
+# --------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["geometry_small", "geometry_full", "geometry_fine"])
+def test_backproject_matches_reference_golden(eod, cuda, golden, name):
+    g = golden(name)
+    T, H, W = g["depth"].shape
+    intr = eod.compute_intrinsics(W, H, float(g["vfov"]))
+    depth = _t(g["depth"], cuda)
+    pose = _t(g["T"][:, :3, :].reshape(T, 12), cuda)
+    zero = np.zeros(3, np.float32)
+    cell, mw, mh = float(g["cell"]), int(g["map_w"]), int(g["map_h"])
+    # Projector flow (create_coco_mp3d.py): one shift
+    sh = _t(np.tile(np.concatenate([g["map_world_shift"], zero]), (T, 1)), cuda)
+    r = eod.ops.backproject_quantize(depth, pose, sh, intr, cell, mw, mh, want_q2=True, want_outlier=True, want_height=True)
+    assert np.array_equal(r["q2"].cpu().numpy(), g["q2"])
+    assert np.array_equal(r["outlier"].cpu().numpy().astype(bool), g["outlier"])
+    assert np.array_equal(r["height"].cpu().numpy(), g["height"])
+    # PointCloud + build_memory_data flow: shift applied second, clip to the border
+    sh = _t(np.tile(np.concatenate([zero, g["map_world_shift"]]), (T, 1)), cuda)
+    r = eod.ops.backproject_quantize(depth, pose, sh, intr, cell, mw, mh, want_world=True)
+    assert np.array_equal(r["world"].cpu().numpy(), g["world"])
+    assert np.array_equal(r["idx"].cpu().numpy(), g["flat"])
+
+
+def test_backproject_randomised_vs_oracle(eod, cuda):
+    rng = np.random.default_rng(42)
+    H, W, E = 60, 100, 5                                           # ragged: not multiples of the block size
+    vfov = math.radians(67.5)
+    intr = eod.compute_intrinsics(W, H, vfov)
+    depth = rng.uniform(0.0, 10.0, (E, H, W)).astype(np.float32)
+    depth[rng.uniform(size=depth.shape) < 0.05] = 0.0
+    xyzhe = np.stack([rng.uniform(-5, 5, E), np.full(E, 1.25), rng.uniform(-5, 5, E), rng.uniform(0, 2 * np.pi, E),
+                      np.pi + rng.uniform(-0.2, 0.2, E)], 1).astype(np.float32)
+    T = eod.transform3d(torch.from_numpy(xyzhe))
+    assert torch.equal(T, R.transform3d(torch.from_numpy(xyzhe)))
+    shifts = np.concatenate([rng.uniform(-1, 1, (E, 3)), rng.uniform(-8, -2, (E, 3))], 1).astype(np.float32)
+    for order in (0, 1):
+        for cell, mw, mh in ((0.2, 37, 53), (0.02, 300, 200)):          # small maps: many out-of-map pixels on all sides
+            r = eod.ops.backproject_quantize(_t(depth, cuda), T[:, :3].reshape(E, 12).to(cuda), _t(shifts, cuda), intr, cell, mw, mh,
+                                             order, 0.5, want_q2=True, want_outlier=True, want_height=True, want_world=True)
+            for e in range(E):
+                o = oracle.backproject_quantize(depth[e], T[e].numpy(), intr, shifts[e, :3], shifts[e, 3:], cell, mw, mh, order, 0.5)
+                for k in ("idx", "q2", "outlier", "height", "world"):
+                    assert np.array_equal(r[k][e].cpu().numpy(), o[k]), (k, order, cell, e)
+            assert r["outlier"].float().mean().item() > 0.1 and (r["q2"] < 0).any().item()
+
+
+def test_projector_class_mirrors_reference_api(eod, cuda, golden):
+    g = golden("geometry_small")
+    T, H, W = g["depth"].shape
+    pr = eod.Projector(float(g["vfov"]), 1, H, W, int(g["map_h"]), int(g["map_w"]), float(g["cell"]), g["map_world_shift"], 0.5, device=cuda)
+    idx2d, outl, hts = pr.forward(torch.from_numpy(g["depth"][:, None]), torch.from_numpy(g["T"]), return_heights=True)
+    assert idx2d.dtype == torch.int64 and outl.dtype == torch.bool
+    assert np.array_equal(idx2d.cpu().numpy(), g["q2"]) and np.array_equal(outl.cpu().numpy(), g["outlier"])
+    assert np.array_equal(hts.cpu().numpy(), g["height"])
+    pc = eod.Projector(float(g["vfov"]), 1, H, W, int(g["map_h"]), int(g["map_w"]), float(g["cell"]), np.zeros(3), 0.5, device=cuda)
+    world, nodepth = pc.point_cloud(torch.from_numpy(g["depth"][:, None]), torch.from_numpy(g["T"]))
+    assert np.array_equal(world.cpu().numpy(), g["world"]) and np.array_equal(nodepth.cpu().numpy(), g["depth"] == 0)
+    flat = pc.flat_indices(torch.from_numpy(g["depth"][:, None]), torch.from_numpy(g["T"]), g["map_world_shift"])
+    assert flat.shape == (T, H, W, 1) and np.array_equal(flat[..., 0].cpu().numpy(), g["flat"])
+
+
+# --------------------------------------------------------------------------------------------------------
+# read (A10-A12) and fusion (A13)
+# --------------------------------------------------------------------------------------------------------
+def test_read_pool_matches_reference_golden(eod, cuda, golden):
+    g = golden("read_fuse")
+    sums, counts = _t(g["sums"], cuda), _t(g["counts"], cuda)
+    mem16 = R.create_implicit_memory(torch.from_numpy(g["sums"]), torch.from_numpy(g["counts"])).to(torch.half)
+    for t in range(2):
+        idx = _t(g[f"idx{t}"], cuda)
+        variants = {
+            "fused f32+counts, i32": eod.ops.read_pool(sums[None], counts[None], idx[None]),
+            "f16 table, i64": eod.ops.read_pool(mem16.to(cuda)[None].contiguous(), None, idx.long()[None].contiguous()),
+            "f16 table, i32": eod.ops.read_pool(mem16.to(cuda)[None].contiguous(), None, idx[None]),
+        }
+        for name, levels in variants.items():
+            for k in range(3):
+                got = levels[k].contiguous().cpu().numpy().view(np.uint16)           # logical (1,C,h,w)
+                assert got.shape == g[f"level{t}_{k}"].shape
+                assert np.array_equal(got, g[f"level{t}_{k}"].view(np.uint16)), (name, t, k)
+    norm = eod.ops.normalize_memory(sums, counts)
+    assert np.array_equal(norm.cpu().numpy(), R.create_implicit_memory(torch.from_numpy(g["sums"]), torch.from_numpy(g["counts"])).numpy())
+    assert np.array_equal(eod.ops.normalize_memory(sums, counts, half=True).cpu().numpy().view(np.uint16), mem16.numpy().view(np.uint16))
+
+
+@pytest.mark.parametrize("C,E,H,W", [(128, 3, 64, 96), (256, 2, 96, 64), (512, 2, 32, 64)])
+def test_read_pool_randomised_vs_oracle(eod, cuda, C, E, H, W):
+    rng = np.random.default_rng(C)
+    cells = 150
+    sums = (rng.standard_normal((E, cells, C)) * rng.choice([1e-3, 1.0, 300.0], (E, cells, 1))).astype(np.float32)
+    sums[:, :5] = -0.0                                                         # signed zeros survive the chain
+    sums[:, 5:8] = 7e4                                                         # > fp16 max: rounds to inf like torch
+    counts = rng.integers(0, 7, (E, cells)).astype(np.float32)
+    # piecewise-constant index plane with ragged patches, like a real projection
+    idx = (rng.integers(0, cells, (E, H // 4 + 1, W // 8 + 1)).repeat(4, 1).repeat(8, 2)[:, :H, :W]).astype(np.int32)
+    idx[:, ::7, ::5] = rng.integers(0, cells, idx[:, ::7, ::5].shape)
+    levels = eod.ops.read_pool(_t(sums, cuda), _t(counts, cuda), _t(idx, cuda))
+    for e in range(E):
+        ref = R.read_frame(torch.from_numpy(sums[e]), torch.from_numpy(counts[e]), torch.from_numpy(idx[e]))
+        for k in range(3):
+            a = levels[k][e].contiguous().cpu().numpy().view(np.uint16)
+            b = ref[k][0].numpy().view(np.uint16)
+            assert np.array_equal(a, b), (e, k, np.mean(a != b))
+
+
+def test_fuse_bit_exact(eod, cuda):
+    rng = np.random.default_rng(1)
+    for n in (1, 3, 4, 1000, 256 * 60 * 80 + 3):
+        res = rng.standard_normal(n).astype(np.float32)
+        mem = (rng.standard_normal(n) * 10).astype(np.float32)
+        for w in (5.0, 500.0, 0.3):
+            exp = {0: torch.from_numpy(mem) * w + torch.from_numpy(res), 1: torch.from_numpy(mem) * w, 2: torch.from_numpy(res)}
+            for mode in (0, 1, 2):
+                out = eod.ops.fuse(_t(res, cuda), _t(mem, cuda), w, mode)
+                assert np.array_equal(out.cpu().numpy(), exp[mode].numpy()), (n, w, mode)
+
+
+def test_memory_fusion_module_matches_reference_golden(eod, cuda, golden):
+    g = golden("read_fuse")
+    C, CO = g["sums"].shape[1], g["w0"].shape[0]
+    mem16 = R.create_implicit_memory(torch.from_numpy(g["sums"]), torch.from_numpy(g["counts"])).to(torch.half)
+    for fusion in ("sum", "mem_only", "image_only"):
+        mod = eod.MemoryFusion("implicit_memory", fusion, 5, mem_feat_dim=C, ego_feat_dim=CO).to(cuda)
+        sd = {f"map_merge_projection{k + 1}.{p}": torch.from_numpy(g[f"{q}{k}"]) for k in range(3) for p, q in (("weight", "w"), ("bias", "b"))}
+        mod.load_state_dict(sd)
+        res = [_t(g[f"res0_{k}"], cuda, torch.float32) for k in range(3)]
+        idx = _t(g["idx0"], cuda).long()
+        with torch.no_grad():
+            out_ref_api = mod(res, [mem16.to(cuda)], [idx], [None])                          # reference call surface
+            out_fused = mod(res, [_t(g["sums"], cuda)], [idx], [_t(g["counts"], cuda)])      # fp32 sums + counts
+        for out in (out_ref_api, out_fused):
+            for k in range(3):
+                ref = g[f"fused_{fusion}_0_{k}"]
+                assert out[k].shape == ref.shape
+                assert np.abs(out[k].cpu().numpy() - ref).max() <= SUM_TOL * np.abs(ref).max(), (fusion, k)
+    bad = eod.MemoryFusion("implicit_memory", "ave", 5, mem_feat_dim=C, ego_feat_dim=CO).to(cuda)
+    with pytest.raises(UnboundLocalError):
+        bad([_t(g[f"res0_{k}"], cuda, torch.float32) for k in range(3)], [mem16.to(cuda)], [_t(g["idx0"], cuda).long()], [None])
+
+
+# --------------------------------------------------------------------------------------------------------
+# write, mean mode (A6-A8)
+# --------------------------------------------------------------------------------------------------------
+def test_sample_mask_and_box_features_bit_exact(eod, cuda):
+    rng = np.random.default_rng(3)
+    H, W, C = 48, 80, 64
+    for stride in (1, 3, 8):
+        obs = rng.uniform(size=(3, H * W)) < rng.uniform(0.0, 0.9)
+        obs[2] = False                                                     # empty: nothing observed
+        n = torch.zeros(3, dtype=torch.int32, device=cuda)
+        samp = eod.ops.sample_mask(_t(obs.view(np.uint8), cuda), stride, n_sampled=n)
+        for e in range(3):
+            ref = R.sample_mask(torch.from_numpy(obs[e]), stride).numpy()
+            assert np.array_equal(samp[e].cpu().numpy().astype(bool), ref)
+            assert int(n[e]) == int(ref.sum())
+    bf, masks = eod.episodes.make_detections(rng, H, W, C, (7, 9))
+    img, observed = eod.ops.box_to_image_features(_t(bf, cuda), _t(masks, cuda))
+    ref_img, ref_obs = R.box_to_image_features(torch.from_numpy(bf), torch.from_numpy(masks))
+    assert np.array_equal(observed.cpu().numpy(), ref_obs.numpy())
+    assert np.array_equal(img.cpu().numpy(), ref_img.numpy())              # same fp32 add order -> bit-exact
+
+
+def _write_case(eod, cuda, C, E, H, W, cells, layout, variant, with_samp, seed):
+    rng = np.random.default_rng(seed)
+    HW = H * W
+    feat = rng.standard_normal((E, C, H, W)).astype(np.float32) * 3
+    idx = (rng.integers(0, cells, (E, H // 2 + 1, W // 16 + 1)).repeat(2, 1).repeat(16, 2)[:, :H, :W]).astype(np.int32)
+    idx[:, ::5, ::3] = rng.integers(0, cells, idx[:, ::5, ::3].shape)
+    samp = (rng.uniform(size=(E, H, W)) < 0.3).astype(np.uint8) if with_samp else None
+    if with_samp:
+        samp[0, : H // 2] = 0                                              # whole tiles without a sampled pixel
+    sums0 = rng.standard_normal((E, cells, C)).astype(np.float32)
+    counts0 = rng.integers(0, 4, (E, cells)).astype(np.float32)
+    d_sums, d_counts = _t(sums0, cuda), _t(counts0, cuda)
+    d_cnt = torch.zeros((E, cells), dtype=torch.int32, device=cuda)
+    d_touched = torch.zeros((E, cells), dtype=torch.uint8, device=cuda)
+    d_idx = _t(idx, cuda)
+    d_samp = None if samp is None else _t(samp, cuda)
+    f_dev = _t(feat if layout == 0 else feat.transpose(0, 2, 3, 1), cuda)
+    eod.ops.frame_count(d_idx, d_samp, d_cnt)
+    eod.ops.write_mean(f_dev, d_idx, d_samp, d_cnt, d_sums, layout, variant)
+    eod.ops.finalize_counts(d_idx, d_cnt, d_counts, d_touched)
+    torch.cuda.synchronize()
+    assert int(d_cnt.abs().sum()) == 0                                     # scratch returned to zero
+    for e in range(E):
+        s, n = oracle.cell_sums_seq(feat[e], idx[e], None if samp is None else samp[e], cells)
+        mean = np.where(n[:, None] > 0, s / np.maximum(n, 1)[:, None].astype(np.float32), 0).astype(np.float32)
+        ref = sums0[e] + mean
+        got = d_sums[e].cpu().numpy()
+        assert np.abs(got - ref).max() <= SUM_TOL * np.abs(ref).max(), (e, np.abs(got - ref).max())
+        untouched = n == 0
+        assert np.array_equal(got[untouched], sums0[e][untouched])         # cells without samples are not written at all
+        vis = np.zeros(cells, np.float32)
+        vis[np.unique(idx[e])] = 1
+        assert np.array_equal(d_counts[e].cpu().numpy(), counts0[e] + vis)
+        assert np.array_equal(d_touched[e].cpu().numpy().astype(bool), n > 0)
+
+
+@pytest.mark.parametrize("C", [128, 256, 512])
+@pytest.mark.parametrize("variant", [1, 2])            # EOD_WRITE_LDG, EOD_WRITE_TMA
+@pytest.mark.parametrize("with_samp", [False, True])
+def test_write_mean_chw_vs_oracle(eod, cuda, C, variant, with_samp):
+    _write_case(eod, cuda, C, 3, 64, 96, 200, 0, variant, with_samp, seed=C + variant)
+
+
+def test_write_mean_chw_ragged_tail_ldg(eod, cuda):
+    _write_case(eod, cuda, 256, 2, 30, 52, 90, 0, 0, True, seed=9)        # HW % 32 != 0 -> AUTO picks the LDG kernel
+
+
+@pytest.mark.parametrize("C", [128, 256, 512])
+def test_write_mean_hwc_vs_oracle(eod, cuda, C):
+    _write_case(eod, cuda, C, 2, 30, 52, 90, 1, 0, True, seed=C)
+    _write_case(eod, cuda, C, 2, 64, 96, 200, 1, 0, False, seed=C + 1)
+
+
+def test_write_path_matches_reference_golden(eod, cuda, golden):
+    """Reference call surface (box_to_image_features / project_image_features / update_implicit_memory) against the
+    outputs of the reference's own source over a 3-frame sequence."""
+    g = golden("write_mean")
+    n_cells = int(g["map_w"]) * int(g["map_h"])
+    mem = eod.SpatialFeatureMemory(512, cuda)
+    mem.reset(n_cells)
+    for t in range(3):
+        K = int(g[f"K{t}"])
+        masks = _t(_unpack(g[f"masks{t}"], (K, 480, 640)), cuda)
+        bf = _t(g[f"box_features{t}"], cuda)
+        proj = _t(g[f"idx{t}"], cuda).long()
+        img, observed = mem.box_to_image_features(bf, masks)
+        assert np.array_equal(observed.cpu().numpy(), _unpack(g[f"observed{t}"], (480, 640)))
+        assert np.array_equal(img[0, :, ::16, ::16].cpu().numpy(), g[f"img_sample{t}"])
+        assert np.allclose(img.double().sum(dim=(0, 2, 3)).cpu().numpy(), g[f"img_checksum{t}"], rtol=1e-9)
+        mean, observed_mem = mem.project_image_features(img, observed, [proj], [mem.implicit_memory])
+        assert np.array_equal(observed_mem.cpu().numpy(), g[f"observed_mem{t}"])              # touched-cell set: exact
+        assert np.abs(mean.cpu().numpy() - g[f"mean{t}"]).max() <= SUM_TOL * np.abs(g[f"mean{t}"]).max()
+        mem.update_implicit_memory((None, bf, masks, None), proj, mem.implicit_memory, {"sequence_name": "synthetic"})
+        assert np.abs(mem.implicit_memory.cpu().numpy() - g[f"sums{t}"]).max() <= SUM_TOL * np.abs(g[f"sums{t}"]).max()
+        assert np.array_equal(mem.observations.cpu().numpy(), g[f"counts{t}"])                # visibility counts: exact
+        norm, _ = mem.create_implicit_memory({"memory": torch.from_numpy(g[f"sums{t}"]), "observations": torch.from_numpy(g[f"counts{t}"]), "proj_indices": proj})
+        assert np.array_equal(norm.cpu().numpy(), g[f"norm{t}"])
+    before = mem.implicit_memory.clone()
+    mem.update_implicit_memory(None, proj, mem.implicit_memory, {})                           # no detection -> no write (:686)
+    assert torch.equal(before, mem.implicit_memory)
+
+
+# --------------------------------------------------------------------------------------------------------
+# write, height-max mode (A7')
+# --------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("layout,stride", [(1, 1), (0, 1), (1, 4)])
+def test_write_max_vs_oracle(eod, cuda, layout, stride):
+    rng = np.random.default_rng(17 + stride)
+    H, W, C, mw, mh, T = 48, 64, 64, 23, 19, 4
+    cells = mw * mh
+    state = torch.zeros(cells, C)
+    observed = torch.zeros(cells, dtype=torch.bool)
+    hmap = torch.zeros(cells)
+    d_state = torch.zeros((1, cells, C), device=cuda)
+    d_obs = torch.zeros((1, cells), dtype=torch.uint8, device=cuda)
+    d_hmap = torch.zeros((1, cells), device=cuda)
+    d_key = torch.zeros((1, cells), dtype=torch.int64, device=cuda)
+    d_arg = torch.zeros((1, cells), dtype=torch.int32, device=cuda)
+    for t in range(T):
+        w2m = np.stack([rng.integers(0, mw, (H // 4, W // 4)).repeat(4, 0).repeat(4, 1), rng.integers(0, mh, (H // 4, W // 4)).repeat(4, 0).repeat(4, 1)], -1)
+        inl = rng.uniform(size=(H, W)) < 0.7
+        heights = (np.round(rng.uniform(-1.5, 1.0, (H, W)) * 4) / 4).astype(np.float32)        # quantised -> many exact ties
+        if t == 2:
+            heights[:] = heights.min() - 5                                                       # nothing raised except new cells
+        feat = rng.standard_normal((H, W, C)).astype(np.float32)
+        state, observed, hmap, arg, m = R.smnet_heightmax_frame(state, observed, hmap, torch.from_numpy(feat), torch.from_numpy(w2m),
+                                                                torch.from_numpy(inl), torch.from_numpy(heights), mw, stride)
+        flat = (w2m[..., 1] * mw + w2m[..., 0]).astype(np.int32)
+        f_dev = _t(feat if layout == 1 else feat.transpose(2, 0, 1), cuda)[None].contiguous()
+        eod.ops.write_max(_t(heights, cuda)[None], _t(flat, cuda)[None], _t((~inl).view(np.uint8), cuda)[None], f_dev, d_hmap, d_key, d_arg,
+                          d_obs, d_state, layout, stride)
+        torch.cuda.synchronize()
+        # oracle arg indexes the compacted inlier lattice; convert to raster pixel indices of the full frame
+        lat = np.zeros((H, W), bool)
+        lat[::stride, ::stride] = True
+        pix_of_rank = np.nonzero((inl & lat).reshape(-1))[0]
+        arg_pix = np.where(arg.numpy() >= 0, pix_of_rank[np.maximum(arg.numpy(), 0)], -1)
+        assert np.array_equal(d_arg[0].cpu().numpy(), arg_pix), t                              # argmax: exact
+        assert np.array_equal(d_hmap[0].cpu().numpy(), hmap.numpy())
+        assert np.array_equal(d_obs[0].cpu().numpy().astype(bool), observed.numpy())
+        assert np.array_equal(d_state[0].cpu().numpy(), state.numpy())                         # winners' features: exact copies
+        assert int(d_key.abs().sum()) == 0
+
+
+# --------------------------------------------------------------------------------------------------------
+# full-size, size-independent properties (BASELINE sizes: 480x640, C=256, 500x500 grid)
+# --------------------------------------------------------------------------------------------------------
+def test_full_size_properties(eod, cuda):
+    E, C, H, W, mw, mh = 2, 256, 480, 640, 500, 500
+    eps = [eod.episodes.make_episode(1234 + e, n_frames=3) for e in range(E)]
+    intr = eod.compute_intrinsics(W, H, math.radians(67.5))
+    batch = eod.EpisodeBatch(E, mw, mh, C, H, W, cuda)
+    shifts = _t(np.stack([np.concatenate([np.zeros(3, np.float32), ep.map_world_shift]) for ep in eps]), cuda)
+    gen = torch.Generator(device=cuda).manual_seed(0)
+    total_vis = torch.zeros(E, device=cuda)
+    for t in range(3):
+        depth = _t(np.stack([ep.depth[t] for ep in eps]), cuda)
+        T = eod.transform3d(torch.from_numpy(np.stack([ep.xyzhe[t] for ep in eps])))
+        pose = T[:, :3].reshape(E, 12).to(cuda)
+        feat = torch.randn((E, C, H, W), device=cuda, generator=gen)
+        before = batch.sums.clone()
+        levels = batch.step(depth, pose, shifts, intr, 0.2, feat)
+        torch.cuda.synchronize()
+        for e in range(E):                                              # indices: bit-exact vs the oracle at full size
+            o = oracle.backproject_quantize(eps[e].depth[t], T[e].numpy(), intr, np.zeros(3, np.float32), eps[e].map_world_shift, 0.2, mw, mh, 0, 0.5, want=("idx",))
+            assert np.array_equal(batch.idx[e].cpu().numpy(), o["idx"])
+        # conservation: sum_c n_c * (delta sums)_c == sum over pixels of the features (per channel)
+        delta = batch.sums - before
+        for e in range(E):
+            cells, n = torch.unique(batch.idx[e].long(), return_counts=True)
+            lhs = (delta[e][cells].double() * n[:, None].double()).sum(0)
+            rhs = feat[e].double().sum(dim=(1, 2))
+            assert (lhs - rhs).abs().max().item() <= 1e-5 * feat[e].abs().sum(dim=(1, 2)).max().item()
+            total_vis[e] += cells.numel()
+            assert int(batch.counts[e].sum().item()) == int(total_vis[e].item())          # counts: +1 per visible cell per frame
+            touched = torch.zeros(mw * mh, dtype=torch.bool, device=cuda)
+            touched[cells] = True
+            assert (delta[e][~touched] == 0).all().item()
+        assert int(batch.frame_cnt.abs().sum()) == 0
+    # read after 3 frames vs the C oracle on the downloaded state (bit-exact fp16)
+    idx_np = batch.idx.cpu().numpy()
+    levels = batch.read()
+    torch.cuda.synchronize()
+    for e in range(E):
+        table16 = R.create_implicit_memory(batch.sums[e].cpu(), batch.counts[e].cpu()).half().numpy()
+        L = oracle.read_pool_f16(table16, idx_np[e])
+        for k in range(3):
+            assert np.array_equal(levels[k][e].contiguous().cpu().numpy().view(np.uint16), L[k].view(np.uint16)), (e, k)
+    # idempotence: a constant table reads back as that constant at every level
+    batch.sums[:] = torch.randn(C, device=cuda).half().float()
+    batch.counts.fill_(1.0)
+    levels = batch.read()
+    for lv in levels:
+        assert (lv == batch.sums[0, 0].half().view(1, C, 1, 1)).all().item()
+
+
+def test_tma_and_ldg_variants_agree_full_size(eod, cuda):
+    E, C, H, W, cells = 1, 256, 480, 640, 250000
+    ep = eod.episodes.make_episode(77, n_frames=1)
+    intr = eod.compute_intrinsics(W, H, math.radians(67.5))
+    T = eod.transform3d(torch.from_numpy(ep.xyzhe[:1]))
+    sh = _t(np.concatenate([np.zeros(3, np.float32), ep.map_world_shift])[None], cuda)
+    idx = eod.ops.backproject_quantize(_t(ep.depth[:1], cuda), T[:, :3].reshape(1, 12).to(cuda), sh, intr, 0.2, 500, 500)["idx"]
+    feat = torch.randn((E, C, H, W), device=cuda)
+    outs = []
+    for variant in (1, 2):
+        sums = torch.zeros((E, cells, C), device=cuda)
+        cnt = torch.zeros((E, cells), dtype=torch.int32, device=cuda)
+        eod.ops.frame_count(idx, None, cnt)
+        eod.ops.write_mean(feat, idx, None, cnt, sums, 0, variant)
+        outs.append(sums)
+    scale = outs[0].abs().max().item()
+    assert (outs[0] - outs[1]).abs().max().item() <= 1e-6 * scale
+    s, n = oracle.cell_sums_seq(feat[0].cpu().numpy(), idx[0].cpu().numpy(), None, cells)
+    ref = np.where(n[:, None] > 0, s / np.maximum(n, 1)[:, None].astype(np.float32), 0)
+    assert np.abs(outs[1][0].cpu().numpy() - ref).max() <= SUM_TOL * np.abs(ref).max()

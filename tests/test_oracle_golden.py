@@ -1,0 +1,126 @@
+"""The oracle (oracle/geometry.c + oracle/reference_ops.py) against fixtures produced by running the reference's own
+source (tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import reference_ops as R
+
+INTR_480 = (320.0, 359.1853942871094, 320.0, 240.0)
+
+
+@pytest.mark.parametrize("name", ["geometry_small", "geometry_full", "geometry_fine"])
+def test_geometry_c_oracle_matches_reference(golden, name):
+    g = golden(name)
+    T, H, W = g["depth"].shape
+    intr = R.intrinsics(W, H, float(g["vfov"]))
+    if (H, W) == (480, 640):
+        assert intr == INTR_480
+    zero = np.zeros(3, np.float32)
+    for t in range(T):
+        # Projector flow: single shift = map_world_shift
+        o = oracle.backproject_quantize(g["depth"][t], g["T"][t], intr, g["map_world_shift"], zero, float(g["cell"]),
+                                        int(g["map_w"]), int(g["map_h"]), 0, 0.5)
+        assert np.array_equal(o["q2"], g["q2"][t])
+        assert np.array_equal(o["outlier"].astype(bool), g["outlier"][t])
+        assert np.array_equal(o["height"], g["height"][t])
+        # PointCloud + build_memory_data flow: shift0 = 0, shift1 = map_world_shift, clip
+        o = oracle.backproject_quantize(g["depth"][t], g["T"][t], intr, zero, g["map_world_shift"], float(g["cell"]),
+                                        int(g["map_w"]), int(g["map_h"]), 0, 0.5)
+        assert np.array_equal(o["world"], g["world"][t])
+        assert np.array_equal(o["idx"], g["flat"][t])
+
+
+def test_geometry_torch_restatement_matches_reference(golden):
+    g = golden("geometry_fine")
+    depth, T = torch.from_numpy(g["depth"]), torch.from_numpy(g["T"])
+    shift = torch.from_numpy(g["map_world_shift"])
+    assert torch.equal(R.transform3d(torch.from_numpy(g["xyzhe"])), T)
+    q2, outl, hts = R.projector_forward(depth[:, None], T, float(g["vfov"]), int(g["map_h"]), int(g["map_w"]),
+                                        float(g["cell"]), shift, 0.5)
+    assert np.array_equal(q2.numpy().astype(np.int32), g["q2"])
+    assert np.array_equal(outl.numpy(), g["outlier"])
+    assert np.array_equal(hts.numpy(), g["height"])
+    flat = R.quantize_flat_index(torch.from_numpy(g["world"]), shift, float(g["cell"]), int(g["map_w"]), int(g["map_h"]))
+    assert np.array_equal(flat[..., 0].numpy(), g["flat"])
+    # some pixels must exercise the clip and the outlier mask
+    assert g["outlier"].mean() > 0.05 and ((g["q2"] < 0) | (g["q2"] >= int(g["map_w"]))).any()
+
+
+def _unpack(bits, shape):
+    return np.unpackbits(bits)[: int(np.prod(shape))].reshape(shape).astype(bool)
+
+
+def test_write_restatement_matches_reference(golden):
+    g = golden("write_mean")
+    n_cells = int(g["map_w"]) * int(g["map_h"])
+    sums, counts = torch.zeros(n_cells, 512), torch.zeros(n_cells)
+    for t in range(3):
+        K = int(g[f"K{t}"])
+        masks = torch.from_numpy(_unpack(g[f"masks{t}"], (K, 480, 640)))
+        bf = torch.from_numpy(g[f"box_features{t}"])
+        proj = torch.from_numpy(g[f"idx{t}"]).long()
+        img, observed = R.box_to_image_features(bf, masks)
+        assert np.array_equal(observed.numpy(), _unpack(g[f"observed{t}"], (480, 640)))
+        assert np.array_equal(img[0, :, ::16, ::16].numpy(), g[f"img_sample{t}"])          # bit-exact (same add order)
+        mean_d, om_d = R.project_image_features_dense(img, observed, proj, n_cells)
+        mean_s, om_s = R.project_image_features_sparse(img, observed, proj, n_cells)
+        assert np.array_equal(om_d.numpy(), g[f"observed_mem{t}"]) and np.array_equal(om_s.numpy(), g[f"observed_mem{t}"])
+        scale = np.abs(g[f"mean{t}"]).max()
+        assert np.abs(mean_d.numpy() - g[f"mean{t}"]).max() <= 1e-6 * scale
+        assert np.abs(mean_s.numpy() - g[f"mean{t}"]).max() <= 1e-5 * scale
+        sums, counts = R.accumulate(sums, counts, mean_d, om_d, proj)
+        assert np.abs(sums.numpy() - g[f"sums{t}"]).max() <= 1e-5 * np.abs(g[f"sums{t}"]).max()
+        assert np.array_equal(counts.numpy(), g[f"counts{t}"])
+        norm = R.create_implicit_memory(torch.from_numpy(g[f"sums{t}"]), torch.from_numpy(g[f"counts{t}"]))
+        assert np.array_equal(norm.numpy(), g[f"norm{t}"])
+        # the sampling mask helper selects exactly the pixels the reference's [::8] keeps
+        samp = R.sample_mask(observed, 8)
+        assert int(samp.sum()) == (int(observed.sum()) + 7) // 8
+        assert np.array_equal(np.unique(proj[samp].numpy()), np.nonzero(g[f"observed_mem{t}"])[0])
+
+
+def test_read_restatement_matches_reference(golden):
+    g = golden("read_fuse")
+    sums, counts = torch.from_numpy(g["sums"]), torch.from_numpy(g["counts"])
+    mem16 = R.create_implicit_memory(sums, counts).to(torch.half)
+    ws = [torch.from_numpy(g[f"w{k}"]) for k in range(3)]
+    bs = [torch.from_numpy(g[f"b{k}"]) for k in range(3)]
+    for t in range(2):
+        proj = torch.from_numpy(g[f"idx{t}"]).long()
+        levels = R.read_pool(mem16, proj)
+        for k in range(3):
+            assert np.array_equal(levels[k].numpy().view(np.uint16), g[f"level{t}_{k}"].view(np.uint16))
+        res = [torch.from_numpy(g[f"res{t}_{k}"]).float() for k in range(3)]
+        for fusion in (("sum", "mem_only", "image_only") if t == 0 else ("sum",)):
+            fused = R.project_and_fuse(levels, res, ws, bs, 5, fusion)
+            for k in range(3):
+                assert np.array_equal(fused[k].numpy(), g[f"fused_{fusion}_{t}_{k}"])
+        # plain-C pooling chain == torch chain, bit for bit
+        L = oracle.read_pool_f16(mem16.numpy(), g[f"idx{t}"])
+        for k in range(3):
+            assert np.array_equal(L[k].view(np.uint16), levels[k][0].numpy().view(np.uint16))
+
+
+def test_sequential_cell_sums_c_vs_numpy():
+    rng = np.random.default_rng(0)
+    C, H, W, cells = 8, 16, 32, 40
+    feat = rng.standard_normal((C, H, W)).astype(np.float32)
+    idx = rng.integers(0, cells, (H, W)).astype(np.int32)
+    samp = (rng.uniform(size=(H, W)) < 0.5).astype(np.uint8)
+    s, n = oracle.cell_sums_seq(feat, idx, samp, cells)
+    ref = np.zeros((cells, C), np.float32)
+    sel = samp.reshape(-1).astype(bool)
+    np.add.at(ref, idx.reshape(-1)[sel], feat.reshape(C, -1).T[sel])       # unbuffered, raster order
+    assert np.array_equal(s, ref)
+    assert np.array_equal(n, np.bincount(idx.reshape(-1)[sel], minlength=cells))
+
+
+def test_scatter_max_canonical_rule():
+    src = torch.tensor([1.0, 5.0, 5.0, 2.0, 7.0, 3.0])
+    index = torch.tensor([0, 0, 0, 1, 2, 2])
+    out = torch.tensor([0.0, 2.0, 9.0, 4.0])
+    o, arg = R.scatter_max_canonical(src, index, out)
+    assert o.tolist() == [5.0, 2.0, 9.0, 4.0]
+    assert arg.tolist() == [2, 3, -1, -1]         # tie -> highest index; equal to old -> replaced; lower -> -1
