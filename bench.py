@@ -219,7 +219,7 @@ def main_gpu(args, rank, local_rank, world):
     shifts = torch.from_numpy(np.concatenate([np.zeros_like(shift_h), shift_h], 1)).to(dev)   # (E, 6)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     slabs = [torch.randn((E, C, H, W), device=dev, generator=gen) for _ in range(2)]          # 2 x 20.1 GB
-    batch = eod.EpisodeBatch(E, MAP_W, MAP_H, C, H, W, dev)
+    batch = eod.EpisodeBatch(E, MAP_W, MAP_H, C, H, W, dev, variant=args.write_variant)
 
     def one_step():
         batch.reset()
@@ -231,13 +231,13 @@ def main_gpu(args, rank, local_rank, world):
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()                                                  # samples cover warm-up + timed steps (all under load)
     for _ in range(args.warmup):
         one_step()
     barrier()
     launches0 = eod.ops.launch_count
     batch.profile(True)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
@@ -262,7 +262,7 @@ def main_gpu(args, rank, local_rank, world):
     path_gbs = frame_bytes(vis_per_frame) * (value / world) / 1e9
 
     # ---- e2e through the plugin API with host buffers (rank-local, then max over ranks) ----
-    e2e = run_e2e(eod, batch, dev, depth_h, pose.cpu(), shifts, intr, args, world, sharding, slabs)
+    e2e = None if args.no_e2e else run_e2e(eod, batch, dev, depth_h, pose.cpu(), shifts, intr, args, world, sharding, slabs)
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -359,6 +359,8 @@ def main():
     ap.add_argument("--e2e-frames", type=int, default=4)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--write-variant", type=int, default=0, help="diagnostics: 0 auto, 1 LDG, 2 TMA, 3 TMA dry (no result)")
+    ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     rank, local_rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     if args.impl == "reference":

@@ -15,7 +15,7 @@ EOD_OK = 0
 ORDER_ZX, ORDER_XZ = 0, 1
 LAYOUT_CHW, LAYOUT_HWC = 0, 1
 FUSE_SUM, FUSE_MEM_ONLY, FUSE_IMAGE_ONLY = 0, 1, 2
-WRITE_AUTO, WRITE_LDG, WRITE_TMA = 0, 1, 2
+WRITE_AUTO, WRITE_LDG, WRITE_TMA, WRITE_TMA_DRY = 0, 1, 2, 3
 
 # name -> argtypes (restype is int unless listed in _RESTYPES); mirrors include/eod_memory.h one to one
 _P = c_void_p
@@ -27,7 +27,7 @@ SIGNATURES = {
     "eod_sample_mask": [_P, c_int, c_int, c_int, _P, _P, _P],
     "eod_frame_count": [_P, _P, c_int, c_int, c_int64, _P, _P],
     "eod_write_mean": [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int64, _P, c_int, _P],
-    "eod_finalize_counts": [_P, c_int, c_int, c_int64, _P, _P, _P, _P],
+    "eod_finalize_counts": [_P, c_int, c_int, c_int64, _P, _P, _P, _P, _P, c_int, _P],
     "eod_box_to_image_features": [_P, _P, c_int, c_int, c_int, _P, _P, _P],
     "eod_write_max": [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int64, _P, _P, _P, _P, _P, _P],
     "eod_read_pool": [_P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int64, _P, _P, _P, _P],

@@ -26,25 +26,42 @@ __device__ __forceinline__ float4 round_to_half(float4 v)
     return v;
 }
 
-__device__ __forceinline__ float4 fetch_row(const float *table, const float *counts, size_t cell, int C, int g)
+// Split row fetch: the global loads of a batch of pixels are issued first (load_raw, load_n), their
+// consumers (finish: normalise + fp16 rounding) run afterwards, so one memory latency is exposed per batch
+// instead of one per cell change.
+struct RawF32 { float4 v; float n; };
+struct RawF16 { uint2 v; };
+
+__device__ __forceinline__ RawF32 load_raw(const float *table, const float *counts, size_t cell, int C, int g)
 {
-    float4 v = __ldg(reinterpret_cast<const float4 *>(table + cell * C) + g);
-    if (counts) {
-        const float n = __ldg(counts + cell);
-        if (n > 1.0f) {          // custom_rcnn.py:774 (cells seen once or never are left as-is)
-            v.x = __fdiv_rn(v.x, n); v.y = __fdiv_rn(v.y, n); v.z = __fdiv_rn(v.z, n); v.w = __fdiv_rn(v.w, n);
-        }
+    RawF32 r;
+    r.v = __ldg(reinterpret_cast<const float4 *>(table + cell * C) + g);
+    r.n = counts ? __ldg(counts + cell) : 0.f;
+    return r;
+}
+__device__ __forceinline__ RawF16 load_raw(const __half *table, const float *, size_t cell, int C, int g)
+{
+    RawF16 r;
+    r.v = __ldg(reinterpret_cast<const uint2 *>(table + cell * C) + g);
+    return r;
+}
+__device__ __forceinline__ float4 finish(const RawF32 &r)
+{
+    float4 v = r.v;
+    if (r.n > 1.0f) {            // custom_rcnn.py:774 (cells seen once or never are left as-is)
+        v.x = __fdiv_rn(v.x, r.n); v.y = __fdiv_rn(v.y, r.n); v.z = __fdiv_rn(v.z, r.n); v.w = __fdiv_rn(v.w, r.n);
     }
     return round_to_half(v);     // custom_rcnn.py:1036
 }
-
-__device__ __forceinline__ float4 fetch_row(const __half *table, const float *, size_t cell, int C, int g)
+__device__ __forceinline__ float4 finish(const RawF16 &r)
 {
-    const uint2 raw = __ldg(reinterpret_cast<const uint2 *>(table + cell * C) + g);
-    const __half2 a = *reinterpret_cast<const __half2 *>(&raw.x), b = *reinterpret_cast<const __half2 *>(&raw.y);
+    const __half2 a = *reinterpret_cast<const __half2 *>(&r.v.x), b = *reinterpret_cast<const __half2 *>(&r.v.y);
     const float2 fa = __half22float2(a), fb = __half22float2(b);
     return make_float4(fa.x, fa.y, fb.x, fb.y);
 }
+template <typename T> struct RawOf;
+template <> struct RawOf<float> { using type = RawF32; };
+template <> struct RawOf<__half> { using type = RawF16; };
 
 __device__ __forceinline__ void store_half4(__half *dst, float4 v)
 {
@@ -89,22 +106,25 @@ __global__ void __launch_bounds__(C) read_pool_kernel(const TableT *__restrict__
     for (int l0 = 0; l0 < 4; ++l0) {                       // L0 pixels of the quadrant, row-major
         const int l0y = l0 >> 1, l0x = l0 & 1;
         float4 s2 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
+#pragma unroll 1
         for (int win = 0; win < 4; ++win) {                // 4x4 windows of the avg_pool2d(4) (timm.py:152)
             const int row0 = qy * 16 + l0y * 8 + (win >> 1) * 4, col0 = qx * 16 + l0x * 8 + (win & 1) * 4;
             float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int4 cells = *reinterpret_cast<const int4 *>(&s_idx[(row0 + r) * 32 + col0]);
-                const int cc[4] = {cells.x, cells.y, cells.z, cells.w};
+            for (int half = 0; half < 2; ++half) {         // two rows (8 pixels) per batch of loads
+                const int4 ca = *reinterpret_cast<const int4 *>(&s_idx[(row0 + 2 * half) * 32 + col0]);
+                const int4 cb = *reinterpret_cast<const int4 *>(&s_idx[(row0 + 2 * half + 1) * 32 + col0]);
+                const int cc[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+                typename RawOf<TableT>::type raw[8];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (cc[k] != cur_cell) {               // warp-uniform branch
-                        cur_cell = cc[k];
-                        cur = fetch_row(table_e, counts_e, (size_t)cur_cell, C, g);
-                    }
+                for (int k = 0; k < 8; ++k)                 // warp-uniform predicates; all loads in flight together
+                    if (cc[k] != (k == 0 ? cur_cell : cc[k - 1])) raw[k] = load_raw(table_e, counts_e, (size_t)cc[k], C, g);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (cc[k] != (k == 0 ? cur_cell : cc[k - 1])) cur = finish(raw[k]);
                     s4 = add4(s4, cur);
                 }
+                cur_cell = cc[7];
             }
             s2 = add4(s2, scale4(s4, 0.0625f));            // / 16 (exact)
         }

@@ -56,7 +56,8 @@ __global__ void __launch_bounds__(256) frame_count_kernel(const int32_t *__restr
 
 __global__ void __launch_bounds__(256) finalize_counts_kernel(const int32_t *__restrict__ idx, int HW, int64_t n_cells,
                                                               uint32_t *__restrict__ frame_cnt, float *__restrict__ counts,
-                                                              uint8_t *__restrict__ touched)
+                                                              uint8_t *__restrict__ touched, const float *__restrict__ sums,
+                                                              __half *__restrict__ norm16, int C)
 {
     const int e = blockIdx.y;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -64,12 +65,38 @@ __global__ void __launch_bounds__(256) finalize_counts_kernel(const int32_t *__r
     const bool valid = p < HW;
     const int cell = valid ? __ldg(idx + (size_t)e * HW + p) : -1;
     const int prev = __shfl_up_sync(0xffffffffu, cell, 1);
+    bool win = false;
+    float n_new = 0.f;
     if (valid && (lane == 0 || prev != cell)) {
         const size_t c = (size_t)e * n_cells + cell;
         const uint32_t old = atomicExch(frame_cnt + c, 0u);   // exactly one run head per cell sees old != 0
         if (old) {
-            counts[c] += 1.0f;                               // custom_rcnn.py:699-701,743
+            n_new = counts[c] + 1.0f;                        // custom_rcnn.py:699-701,743
+            counts[c] = n_new;
             if (touched && (old & 0x7fffffffu)) touched[c] = 1;
+            win = true;
+        }
+    }
+    if (!norm16) return;
+    // Refresh the normalised fp16 row (custom_rcnn.py:764-774 + :1036) of every visible cell: its count just
+    // changed, so its normalised value did.  The warp serves its winners cooperatively (lanes over channels).
+    unsigned todo = __ballot_sync(0xffffffffu, win);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int wc = __shfl_sync(0xffffffffu, cell, src);
+        const float wn = __shfl_sync(0xffffffffu, n_new, src);
+        const size_t row = ((size_t)e * n_cells + wc) * C;
+        const float4 *src_row = reinterpret_cast<const float4 *>(sums + row);
+        uint2 *dst_row = reinterpret_cast<uint2 *>(norm16 + row);
+        for (int k = lane; k < C / 4; k += 32) {
+            float4 v = src_row[k];
+            if (wn > 1.0f) { v.x = __fdiv_rn(v.x, wn); v.y = __fdiv_rn(v.y, wn); v.z = __fdiv_rn(v.z, wn); v.w = __fdiv_rn(v.w, wn); }
+            __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+            uint2 raw;
+            raw.x = *reinterpret_cast<uint32_t *>(&a);
+            raw.y = *reinterpret_cast<uint32_t *>(&b);
+            dst_row[k] = raw;
         }
     }
 }
@@ -261,26 +288,63 @@ __global__ void __launch_bounds__(C) write_mean_chw_ldg_kernel(const float *__re
 
 // ------------------------------------------------------------------------------------------------------
 // main pass, CHW, TMA-staged persistent kernel
+//
+// One CTA per SM: 1 producer warp + kGroups consumer groups of C threads.  Tile i of the CTA goes to ring
+// stage i % kStages and to consumer group i % kGroups, so while one group is in its flush (global
+// atomics) another is already accumulating the next tile.  Per tile and group:
+//   wait full[stage] -> every warp derives the run-head / sample masks from the staged cell ids ->
+//   warp 0 starts the loads of the per-cell sample counts (needed only at flush time) ->
+//   thread c accumulates its channel over the runs, run sums written in place -> group barrier ->
+//   flush items (run, 4 channels): red.global.add.v4.f32(sums[cell] + 4g, partial / n_cell) -> release stage.
 // ------------------------------------------------------------------------------------------------------
-template <int C>
-struct TmaCfg {
-    static constexpr int kTileBytes = C * TILE_PX * 4;
-    static constexpr int kStageBytes = kTileBytes + 1024;                 // + cells (128 B) + samp (32 B), keeps 1 KB alignment
-    static constexpr int kStages = (C <= 128) ? 8 : (C == 256 ? 6 : 3);
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-    static constexpr int kBoxC = C < 256 ? C : 256;                       // TMA box dims are limited to 256
-};
 
 template <int C>
-__global__ void __launch_bounds__(C + 32) write_mean_chw_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t *__restrict__ idx,
-                                                                    const uint8_t *__restrict__ samp, const uint32_t *__restrict__ frame_cnt,
-                                                                    int HW, int64_t n_cells, int tiles_per_ep, int n_tiles,
-                                                                    float *__restrict__ sums)
+struct TmaCfg {
+    static constexpr int kGroups = (C >= 512) ? 1 : (512 / C);            // consumer groups per CTA
+    static constexpr int kRunBuf = (C >= 512) ? 4 : 8;                    // runs per tile staged in the conflict-free run buffer (more -> in place)
+    static constexpr int kThreads = 32 + kGroups * C;
+    static constexpr int kTileBytes = C * TILE_PX * 4;
+    // aux area per stage: cells (128 B) | samp (32 B)
+    static constexpr int kAuxCells = 0, kAuxSamp = 128;
+    static constexpr int kStageBytes = kTileBytes + 1024;                 // keeps every tile 1 KB aligned (SWIZZLE_128B)
+    // per group, double buffered: run sums [kRunBuf][C] f32 | run_cell[32] i32 | run_n[32] f32
+    static constexpr int kRunBytes = kRunBuf * C * 4 + 256;
+    static constexpr int kRunTotal = kGroups * 2 * kRunBytes;
+    static constexpr int kStages = (C <= 128) ? 10 : (C == 256 ? 5 : 3);
+    static constexpr int kSmemBytes = kStages * kStageBytes + kRunTotal + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kBoxC = C < 256 ? C : 256;                       // TMA box dims are limited to 256
+    static_assert(kSmemBytes <= 232448, "exceeds 227 KB of shared memory");
+};
+
+__device__ __forceinline__ uint64_t make_evict_first_policy()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
+__device__ __forceinline__ void tma_load_3d_hint(void *dst, const void *tmap, int x, int y, int z, uint64_t *bar, uint64_t pol)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(
+            smem_u32(dst)),
+        "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)), "l"(pol)
+        : "memory");
+}
+
+// kDry: consumers only wait and release (no accumulation, no atomics) - measures the pure streaming
+// ceiling of this tile shape; selected with variant EOD_WRITE_TMA_DRY (bring-up / profiling only).
+template <int C, bool kDry>
+__global__ void __launch_bounds__(TmaCfg<C>::kThreads, 1)
+write_mean_chw_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t *__restrict__ idx, const uint8_t *__restrict__ samp,
+                          const uint32_t *__restrict__ frame_cnt, int HW, int64_t n_cells, int tiles_per_ep, int n_tiles,
+                          float *__restrict__ sums)
 {
     using Cfg = TmaCfg<C>;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-    uint64_t *full = reinterpret_cast<uint64_t *>(base + Cfg::kStages * Cfg::kStageBytes);
+    unsigned char *run_base = base + Cfg::kStages * Cfg::kStageBytes;
+    uint64_t *full = reinterpret_cast<uint64_t *>(run_base + Cfg::kRunTotal);
     uint64_t *empty = full + Cfg::kStages;
 
     const int tid = threadIdx.x;
@@ -288,55 +352,144 @@ __global__ void __launch_bounds__(C + 32) write_mean_chw_tma_kernel(const __grid
     if (tid == 0) {
         for (int s = 0; s < Cfg::kStages; ++s) {
             mbar_init(full + s, 1);          // producer's arrive.expect_tx
-            mbar_init(empty + s, C / 32);    // one arrive per consumer warp
+            mbar_init(empty + s, C / 32);    // one arrive per warp of the consuming group
         }
         mbar_fence_init();
         fence_proxy_async();
     }
     __syncthreads();
+    const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles blockIdx.x, +gridDim.x, ...
 
-    if (tid >= C) {
+    if (tid >= Cfg::kGroups * C) {
         // ===== producer warp: one elected lane issues all copies =====
-        if (tid == C) {
+        if (tid == Cfg::kGroups * C) {
+            const uint64_t pol = make_evict_first_policy();     // the feature stream is read exactly once
             const uint32_t tx = Cfg::kTileBytes + TILE_PX * 4 + (has_samp ? TILE_PX : 0);
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            for (int i = 0; i < my_tiles; ++i) {
+                const int t = blockIdx.x + i * gridDim.x;
                 mbar_wait(empty + stage, phase ^ 1);
                 const int e = t / tiles_per_ep, p0 = (t - e * tiles_per_ep) * TILE_PX;
                 unsigned char *st = base + stage * Cfg::kStageBytes;
                 mbar_expect_tx(full + stage, tx);
 #pragma unroll
                 for (int c0 = 0; c0 < C; c0 += Cfg::kBoxC)
-                    tma_load_3d(st + c0 * TILE_PX * 4, &tmap, p0, c0, e, full + stage);
-                bulk_load_1d(st + Cfg::kTileBytes, idx + (size_t)e * HW + p0, TILE_PX * 4, full + stage);
-                if (has_samp) bulk_load_1d(st + Cfg::kTileBytes + TILE_PX * 4, samp + (size_t)e * HW + p0, TILE_PX, full + stage);
+                    tma_load_3d_hint(st + c0 * TILE_PX * 4, &tmap, p0, c0, e, full + stage, pol);
+                bulk_load_1d(st + Cfg::kTileBytes + Cfg::kAuxCells, idx + (size_t)e * HW + p0, TILE_PX * 4, full + stage);
+                if (has_samp) bulk_load_1d(st + Cfg::kTileBytes + Cfg::kAuxSamp, samp + (size_t)e * HW + p0, TILE_PX, full + stage);
                 if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
             }
         }
         return;
     }
 
-    // ===== consumers: thread c owns channel c =====
+    // ===== consumers: group g, thread c owns channel c =====
+    const int g = tid / C, c = tid - g * C;
     const unsigned lane = tid & 31;
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        mbar_wait(full + stage, phase);
+    const bool warp0 = (c >> 5) == 0;
+    for (int i = g; i < my_tiles; i += Cfg::kGroups) {
+        const int stage = i % Cfg::kStages;
+        const uint32_t phase = (uint32_t)(i / Cfg::kStages) & 1u;
+        const int t = blockIdx.x + i * gridDim.x;
         const int e = t / tiles_per_ep;
         unsigned char *st = base + stage * Cfg::kStageBytes;
+        constexpr int kRunBuf = Cfg::kRunBuf;
         float *tile = reinterpret_cast<float *>(st);
-        const int *s_cells = reinterpret_cast<const int *>(st + Cfg::kTileBytes);
-        const uint8_t *s_samp = st + Cfg::kTileBytes + TILE_PX * 4;
-        unsigned heads, samps;
-        tile_masks(s_cells, s_samp, has_samp, TILE_PX, lane, heads, samps);
-        accumulate_runs(tile, tid, heads, samps);
-        named_bar_sync(1, C);
-        flush_runs<C>(tile, s_cells, heads, samps, TILE_PX, frame_cnt + (size_t)e * n_cells, sums + (size_t)e * n_cells * C, tid);
-        fence_proxy_async();                 // generic-proxy accesses to the stage precede the next TMA write
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty + stage);
-        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        const int *s_cells = reinterpret_cast<const int *>(st + Cfg::kTileBytes + Cfg::kAuxCells);
+        const uint8_t *s_samp = st + Cfg::kTileBytes + Cfg::kAuxSamp;
+        unsigned char *rb = run_base + (g * 2 + ((i / Cfg::kGroups) & 1)) * Cfg::kRunBytes;   // double buffered per group
+        float *runbuf = reinterpret_cast<float *>(rb);
+        int *s_run_cell = reinterpret_cast<int *>(rb + kRunBuf * C * 4);
+        float *s_run_n = reinterpret_cast<float *>(rb + kRunBuf * C * 4 + 128);
+
+        mbar_wait(full + stage, phase);
+        if (kDry) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + stage);
+            continue;
+        }
+
+        // run structure of the tile (identical in every warp; cheap, avoids a broadcast through smem)
+        const int cell = s_cells[lane];
+        const int prev = __shfl_up_sync(0xffffffffu, cell, 1);
+        const bool head = lane == 0 || prev != cell;
+        const unsigned heads = __ballot_sync(0xffffffffu, head);
+        const unsigned samps = has_samp ? __ballot_sync(0xffffffffu, s_samp[lane] != 0) : 0xffffffffu;
+        const int nruns = __popc(heads);
+
+        // warp 0: per-run cell id and per-cell sample count; the global load is issued now, consumed after the
+        // accumulation, so its latency hides behind the shared-memory pass.
+        uint32_t cnt_raw = 0;
+        int my_run = 0;
+        bool run_has_samples = false;
+        if (warp0 && head) {
+            my_run = __popc(heads & ((1u << lane) - 1u));
+            const unsigned above = heads & ~((2u << lane) - 1u);
+            const int p1 = above ? (__ffs(above) - 1) : TILE_PX;
+            const unsigned run = ((p1 >= 32) ? 0xffffffffu : ((1u << p1) - 1u)) & ~((1u << lane) - 1u);
+            run_has_samples = (samps & run) != 0;
+            if (run_has_samples) cnt_raw = __ldg(frame_cnt + (size_t)e * n_cells + cell);
+        }
+
+        // accumulate: all 32 pixels of channel c into registers first, then the run pass.  Run sums go to the
+        // group's run buffer (row = run, conflict-free); runs beyond kRunBuf are parked in place in the tile.
+        {
+            const float4 *row = reinterpret_cast<const float4 *>(tile + c * TILE_PX);
+            float4 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = row[j ^ (c & 7)];
+            float acc = 0.f;
+            int r = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float vv[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int p = 4 * j + k;
+                    if (p > 0 && ((heads >> p) & 1u)) {        // CTA-uniform
+                        if (r < kRunBuf) runbuf[r * C + c] = acc;
+                        else tile[swz(c, r)] = acc;
+                        ++r;
+                        acc = 0.f;
+                    }
+                    if ((samps >> p) & 1u) acc = __fadd_rn(acc, vv[k]);
+                }
+            }
+            if (r < kRunBuf) runbuf[r * C + c] = acc;
+            else tile[swz(c, r)] = acc;
+        }
+        const bool early = nruns <= kRunBuf;                    // the stage is no longer needed: release it now
+        if (early) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + stage);
+        }
+        if (warp0 && head) {
+            s_run_cell[my_run] = cell;
+            s_run_n[my_run] = run_has_samples ? (float)(cnt_raw & 0x7fffffffu) : 0.f;
+        }
+        named_bar_sync(1 + g, C);
+
+        // flush: item = (run r, channels 4q..4q+3)
+        {
+            constexpr int Q = C / 4;
+            float *sums_e = sums + (size_t)e * n_cells * C;
+            for (int item = c; item < nruns * Q; item += C) {
+                const int r = item / Q, q = item - r * Q;
+                const float n = s_run_n[r];
+                if (n == 0.f) continue;                         // run without a sampled pixel
+                const int ch = 4 * q;
+                float4 a;
+                if (r < kRunBuf) a = *reinterpret_cast<const float4 *>(runbuf + r * C + ch);
+                else a = make_float4(tile[swz(ch, r)], tile[swz(ch + 1, r)], tile[swz(ch + 2, r)], tile[swz(ch + 3, r)]);
+                red_add_v4(sums_e + (size_t)s_run_cell[r] * C + ch, __fdiv_rn(a.x, n), __fdiv_rn(a.y, n), __fdiv_rn(a.z, n), __fdiv_rn(a.w, n));
+            }
+        }
+        if (!early) {
+            fence_proxy_async();             // generic-proxy writes to the stage precede the next TMA write
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + stage);
+        }
     }
 }
 
@@ -419,7 +572,7 @@ PFN_encodeTiled get_encode_fn()
     return fn;
 }
 
-template <int C>
+template <int C, bool kDry>
 int launch_tma(const float *feat, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt, int E, int HW,
                int64_t n_cells, float *sums, cudaStream_t st)
 {
@@ -437,12 +590,12 @@ int launch_tma(const float *feat, const int32_t *idx, const uint8_t *samp, const
     EOD_REQUIRE(r == CUDA_SUCCESS, EOD_ERR_LAUNCH, "eod_write_mean: cuTensorMapEncodeTiled failed (%d)", (int)r);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(write_mean_chw_tma_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        cudaFuncSetAttribute(write_mean_chw_tma_kernel<C, kDry>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         attr_set = true;
     }
     const int tiles_per_ep = HW / TILE_PX, n_tiles = tiles_per_ep * E;
     const int grid = n_tiles < eod_num_sms() ? n_tiles : eod_num_sms();
-    write_mean_chw_tma_kernel<C><<<grid, C + 32, Cfg::kSmemBytes, st>>>(tmap, idx, samp, frame_cnt, HW, n_cells, tiles_per_ep, n_tiles, sums);
+    write_mean_chw_tma_kernel<C, kDry><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmap, idx, samp, frame_cnt, HW, n_cells, tiles_per_ep, n_tiles, sums);
     return eod_check_launch("eod_write_mean[tma]");
 }
 
@@ -479,9 +632,10 @@ int dispatch(const float *feat, int layout, const int32_t *idx, const uint8_t *s
 {
     if (layout == EOD_LAYOUT_HWC) return launch_hwc<C>(feat, idx, samp, frame_cnt, E, HW, n_cells, sums, st);
     const bool tma_ok = (HW % TILE_PX == 0) && (!samp || (reinterpret_cast<uintptr_t>(samp) % 16 == 0));
-    if (variant == EOD_WRITE_TMA) EOD_REQUIRE(tma_ok, EOD_ERR_UNSUPPORTED, "eod_write_mean: TMA variant needs HW %% 32 == 0");
+    if (variant == EOD_WRITE_TMA || variant == EOD_WRITE_TMA_DRY) EOD_REQUIRE(tma_ok, EOD_ERR_UNSUPPORTED, "eod_write_mean: TMA variant needs HW %% 32 == 0");
+    if (variant == EOD_WRITE_TMA_DRY) return launch_tma<C, true>(feat, idx, samp, frame_cnt, E, HW, n_cells, sums, st);
     if (variant == EOD_WRITE_LDG || !tma_ok) return launch_ldg<C>(feat, idx, samp, frame_cnt, E, HW, n_cells, sums, st);
-    return launch_tma<C>(feat, idx, samp, frame_cnt, E, HW, n_cells, sums, st);
+    return launch_tma<C, false>(feat, idx, samp, frame_cnt, E, HW, n_cells, sums, st);
 }
 
 }  // namespace
@@ -506,12 +660,15 @@ extern "C" int eod_frame_count(const int32_t *idx, const uint8_t *samp, int n_ep
 }
 
 extern "C" int eod_finalize_counts(const int32_t *idx, int n_episodes, int HW, int64_t n_cells, uint32_t *frame_cnt,
-                                   float *counts, uint8_t *touched, eod_stream_t stream)
+                                   float *counts, uint8_t *touched, const float *sums, void *norm16, int C,
+                                   eod_stream_t stream)
 {
+    EOD_REQUIRE(!norm16 || (sums && C > 0 && C % 4 == 0 && eod_aligned16(sums) && eod_aligned16(norm16)), EOD_ERR_BADARG,
+                "eod_finalize_counts: norm16 needs sums, C %% 4 == 0 and 16-byte aligned pointers");
     EOD_REQUIRE(idx && frame_cnt && counts, EOD_ERR_BADARG, "eod_finalize_counts: null pointer");
     EOD_REQUIRE(n_episodes > 0 && n_episodes <= 65535 && HW > 0 && n_cells > 0, EOD_ERR_BADARG, "eod_finalize_counts: bad sizes");
     dim3 grid((HW + 255) / 256, n_episodes);
-    finalize_counts_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(idx, HW, n_cells, frame_cnt, counts, touched);
+    finalize_counts_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(idx, HW, n_cells, frame_cnt, counts, touched, sums, (__half *)norm16, C);
     return eod_check_launch("eod_finalize_counts");
 }
 
@@ -521,7 +678,7 @@ extern "C" int eod_write_mean(const float *feat, int layout, const int32_t *idx,
     EOD_REQUIRE(feat && idx && frame_cnt && sums, EOD_ERR_BADARG, "eod_write_mean: null pointer");
     EOD_REQUIRE(n_episodes > 0 && HW > 0 && n_cells > 0, EOD_ERR_BADARG, "eod_write_mean: bad sizes");
     EOD_REQUIRE(layout == EOD_LAYOUT_CHW || layout == EOD_LAYOUT_HWC, EOD_ERR_BADARG, "eod_write_mean: bad layout");
-    EOD_REQUIRE(variant >= EOD_WRITE_AUTO && variant <= EOD_WRITE_TMA, EOD_ERR_BADARG, "eod_write_mean: bad variant");
+    EOD_REQUIRE(variant >= EOD_WRITE_AUTO && variant <= EOD_WRITE_TMA_DRY, EOD_ERR_BADARG, "eod_write_mean: bad variant");
     EOD_REQUIRE(eod_aligned16(feat) && eod_aligned16(sums) && eod_aligned16(idx), EOD_ERR_ALIGN, "eod_write_mean: pointers must be 16-byte aligned");
     EOD_REQUIRE(layout == EOD_LAYOUT_HWC || HW % 4 == 0, EOD_ERR_ALIGN, "eod_write_mean: CHW rows must be 16-byte aligned (HW %% 4 == 0)");
     cudaStream_t st = (cudaStream_t)stream;

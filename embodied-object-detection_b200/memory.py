@@ -14,7 +14,8 @@ Two host-side objects sit above the C ABI:
     ``observation_count``), so the meta-architecture can delegate to it.
 
 HBM layout per episode: ``sums`` (cells, C) fp32 row = cell ``z*map_w + x``; ``counts`` (cells) fp32;
-``frame_cnt`` (cells) int32 scratch, all-zero between frames.  State never leaves the device.
+``frame_cnt`` (cells) int32 scratch, all-zero between frames; ``norm16`` (cells, C) fp16 = the normalised table the
+read gathers from, refreshed per frame for the visible cells only.  State never leaves the device.
 """
 from __future__ import annotations
 
@@ -39,6 +40,9 @@ class EpisodeBatch:
         self.sums = torch.zeros((self.E, self.n_cells, self.C), dtype=torch.float32, **z)
         self.counts = torch.zeros((self.E, self.n_cells), dtype=torch.float32, **z)
         self.frame_cnt = torch.zeros((self.E, self.n_cells), dtype=torch.int32, **z)
+        # always-current normalised fp16 copy of the grid (what create_implicit_memory + .half() would return); only
+        # the rows of the cells visible in a frame change, and the write's post-pass refreshes exactly those
+        self.norm16 = torch.zeros((self.E, self.n_cells, self.C), dtype=torch.float16, **z)
         self.idx = torch.zeros((self.E, height, width), dtype=torch.int32, **z)
         self.levels = [torch.empty((self.E, height >> s, width >> s, self.C), dtype=torch.float16, **z) for s in (3, 4, 5)]
         self._proj_out = {"idx": self.idx}
@@ -67,6 +71,7 @@ class EpisodeBatch:
         self.sums.zero_()
         self.counts.zero_()
         self.frame_cnt.zero_()
+        self.norm16.zero_()
 
     def project(self, depth: torch.Tensor, pose: torch.Tensor, shifts: torch.Tensor, intr: Sequence[float], cell: float,
                 order: int = ORDER_ZX) -> torch.Tensor:
@@ -81,14 +86,14 @@ class EpisodeBatch:
 
     def read(self) -> List[torch.Tensor]:
         """A10-A12 fused: [L0 (E,C,H/8,W/8), L1, L2] fp16 (channels_last memory)."""
-        return self._timed("read", ops.read_pool, self.sums, self.counts, self.idx, out=self.levels)
+        return self._timed("read", ops.read_pool, self.norm16, None, self.idx, out=self.levels)
 
     def write(self, feat: torch.Tensor, samp: Optional[torch.Tensor] = None) -> None:
         """A7 + A8 for one frame of every episode: feat (E,C,H,W) [CHW] or (E,H,W,C) [HWC] fp32;
         samp (E,H,W) u8 selects the contributing pixels (None = all)."""
         self._timed("count", ops.frame_count, self.idx, samp, self.frame_cnt)
         self._timed("write", ops.write_mean, feat, self.idx, samp, self.frame_cnt, self.sums, self.layout, self.variant)
-        self._timed("finalize", ops.finalize_counts, self.idx, self.frame_cnt, self.counts)
+        self._timed("finalize", ops.finalize_counts, self.idx, self.frame_cnt, self.counts, None, self.sums, self.norm16)
 
     def step(self, depth, pose, shifts, intr, cell, feat, samp=None) -> List[torch.Tensor]:
         """One frame of the hot path for all E episodes, in the reference's order: the read of frame t sees

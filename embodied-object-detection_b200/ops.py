@@ -112,13 +112,20 @@ def write_mean(feat: torch.Tensor, idx: torch.Tensor, samp: Optional[torch.Tenso
 
 
 def finalize_counts(idx: torch.Tensor, frame_cnt: torch.Tensor, counts: torch.Tensor,
-                    touched: Optional[torch.Tensor] = None) -> None:
+                    touched: Optional[torch.Tensor] = None, sums: Optional[torch.Tensor] = None,
+                    norm16: Optional[torch.Tensor] = None) -> None:
+    """counts += 1 per visible cell, frame_cnt := 0; optionally refresh the normalised fp16 rows (norm16 (E,cells,C))
+    of the visible cells from sums."""
     _dev(idx, torch.int32, "idx"), _dev(frame_cnt, torch.int32, "frame_cnt"), _dev(counts, torch.float32, "counts")
     if touched is not None:
         _dev(touched, torch.uint8, "touched")
+    C = 0
+    if norm16 is not None:
+        _dev(norm16, torch.float16, "norm16"), _dev(sums, torch.float32, "sums")
+        C = sums.shape[-1]
     E, HW = idx.shape[0], idx[0].numel()
     _call("eod_finalize_counts", idx.data_ptr(), E, HW, counts.shape[1], frame_cnt.data_ptr(), counts.data_ptr(),
-          _ptr(touched), _stream())
+          _ptr(touched), _ptr(sums) if norm16 is not None else None, _ptr(norm16), C, _stream())
 
 
 def box_to_image_features(box_features: torch.Tensor, masks: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -49,6 +49,7 @@ extern "C" {
 #define EOD_WRITE_AUTO 0 /* TMA-staged kernel when the shape allows it, else LDG-staged */
 #define EOD_WRITE_LDG 1  /* force the LDG-staged kernel                                  */
 #define EOD_WRITE_TMA 2  /* force the TMA-staged kernel (error if shape unsupported)     */
+#define EOD_WRITE_TMA_DRY 3 /* profiling only: stream the tiles, no accumulation (no result) */
 
 typedef void *eod_stream_t;
 
@@ -93,9 +94,13 @@ int eod_write_mean(const float *feat, int layout, const int32_t *idx, const uint
                    int n_episodes, int C, int HW, int64_t n_cells, float *sums, int variant, eod_stream_t stream);
 
 /* Post-pass: counts[cell] += 1 for every visible cell (custom_rcnn.py:699-701,743) and frame_cnt := 0.
- * touched (E,cells) u8 nullable: |= 1 where the cell received samples this frame (observed_mem, :922). */
+ * touched (E,cells) u8 nullable: |= 1 where the cell received samples this frame (observed_mem, :922).
+ * norm16 (E,cells,C) f16 nullable: when given (with sums, C), the normalised fp16 row of every visible cell
+ * is refreshed, norm16[cell] = half(sums[cell] / counts[cell] if counts[cell] > 1 else sums[cell])
+ * (custom_rcnn.py:764-774,1036), so eod_read_pool can gather from an always-current fp16 table. */
 int eod_finalize_counts(const int32_t *idx, int n_episodes, int HW, int64_t n_cells, uint32_t *frame_cnt,
-                        float *counts, uint8_t *touched, eod_stream_t stream);
+                        float *counts, uint8_t *touched, const float *sums, void *norm16, int C,
+                        eod_stream_t stream);
 
 /* Per-pixel mean of the kept objects' features, custom_rcnn.py:884-901 (objects added in index order,
  * then / count): box_features (K,C) f32, masks (K,HW) u8 -> image_features (C,HW) f32 (zeros where

@@ -211,9 +211,17 @@ def _write_case(eod, cuda, C, E, H, W, cells, layout, variant, with_samp, seed):
     f_dev = _t(feat if layout == 0 else feat.transpose(0, 2, 3, 1), cuda)
     eod.ops.frame_count(d_idx, d_samp, d_cnt)
     eod.ops.write_mean(f_dev, d_idx, d_samp, d_cnt, d_sums, layout, variant)
-    eod.ops.finalize_counts(d_idx, d_cnt, d_counts, d_touched)
+    d_norm = torch.zeros((E, cells, C), dtype=torch.float16, device=cuda)
+    eod.ops.finalize_counts(d_idx, d_cnt, d_counts, d_touched, d_sums, d_norm)
     torch.cuda.synchronize()
     assert int(d_cnt.abs().sum()) == 0                                     # scratch returned to zero
+    for e in range(E):                                                     # refreshed fp16 rows: exactly the visible cells
+        vis = np.unique(idx[e])
+        ref16 = R.create_implicit_memory(d_sums[e].cpu(), d_counts[e].cpu()).half().numpy()
+        got16 = d_norm[e].cpu().numpy()
+        assert np.array_equal(got16[vis].view(np.uint16), ref16[vis].view(np.uint16))
+        hidden = np.setdiff1d(np.arange(cells), vis)
+        assert not got16[hidden].any()
     for e in range(E):
         s, n = oracle.cell_sums_seq(feat[e], idx[e], None if samp is None else samp[e], cells)
         mean = np.where(n[:, None] > 0, s / np.maximum(n, 1)[:, None].astype(np.float32), 0).astype(np.float32)
@@ -229,7 +237,7 @@ def _write_case(eod, cuda, C, E, H, W, cells, layout, variant, with_samp, seed):
 
 
 @pytest.mark.parametrize("C", [128, 256, 512])
-@pytest.mark.parametrize("variant", [1, 2])            # EOD_WRITE_LDG, EOD_WRITE_TMA
+@pytest.mark.parametrize("variant", [1, 2], ids=["ldg", "tma"])            # EOD_WRITE_LDG, EOD_WRITE_TMA
 @pytest.mark.parametrize("with_samp", [False, True])
 def test_write_mean_chw_vs_oracle(eod, cuda, C, variant, with_samp):
     _write_case(eod, cuda, C, 3, 64, 96, 200, 0, variant, with_samp, seed=C + variant)
@@ -360,12 +368,14 @@ def test_full_size_properties(eod, cuda):
         L = oracle.read_pool_f16(table16, idx_np[e])
         for k in range(3):
             assert np.array_equal(levels[k][e].contiguous().cpu().numpy().view(np.uint16), L[k].view(np.uint16)), (e, k)
+        # the incrementally maintained fp16 table equals a full re-normalisation of the grid
+        assert np.array_equal(batch.norm16[e].cpu().numpy().view(np.uint16), table16.view(np.uint16))
     # idempotence: a constant table reads back as that constant at every level
-    batch.sums[:] = torch.randn(C, device=cuda).half().float()
-    batch.counts.fill_(1.0)
+    const = torch.randn(C, device=cuda).half()
+    batch.norm16[:] = const
     levels = batch.read()
     for lv in levels:
-        assert (lv == batch.sums[0, 0].half().view(1, C, 1, 1)).all().item()
+        assert (lv == const.view(1, C, 1, 1)).all().item()
 
 
 def test_tma_and_ldg_variants_agree_full_size(eod, cuda):
