@@ -101,6 +101,18 @@ __global__ void __launch_bounds__(256) finalize_counts_kernel(const int32_t *__r
     }
 }
 
+// pix_n[p] = number of sampled pixels of p's cell in this frame (as fp32): lets the main pass take the divisor
+// of a run from the staged tile instead of a dependent global load per run.
+__global__ void __launch_bounds__(256) expand_counts_kernel(const int32_t *__restrict__ idx, const uint32_t *__restrict__ frame_cnt,
+                                                            int HW, int64_t n_cells, float *__restrict__ pix_n)
+{
+    const int e = blockIdx.y;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW) return;
+    const size_t g = (size_t)e * HW + p;
+    pix_n[g] = (float)(__ldg(frame_cnt + (size_t)e * n_cells + __ldg(idx + g)) & 0x7fffffffu);
+}
+
 // ------------------------------------------------------------------------------------------------------
 // raster-order every-stride-th-observed-pixel selection (custom_rcnn.py:905-914): one CTA per episode,
 // chunked block scan with a running carry.
@@ -301,19 +313,22 @@ __global__ void __launch_bounds__(C) write_mean_chw_ldg_kernel(const float *__re
 template <int C>
 struct TmaCfg {
     static constexpr int kGroups = (C >= 512) ? 1 : (512 / C);            // consumer groups per CTA
-    static constexpr int kRunBuf = (C >= 512) ? 4 : 8;                    // runs per tile staged in the conflict-free run buffer (more -> in place)
+    static constexpr int kRunBuf = (C >= 256) ? 4 : 8;                    // runs per tile staged in the conflict-free run buffer (more -> in place)
     static constexpr int kThreads = 32 + kGroups * C;
     static constexpr int kTileBytes = C * TILE_PX * 4;
-    // aux area per stage: cells (128 B) | samp (32 B)
-    static constexpr int kAuxCells = 0, kAuxSamp = 128;
+    // aux area per stage: cells (128 B) | samp (32 B) | pad | per-pixel divisors (128 B)
+    static constexpr int kAuxCells = 0, kAuxSamp = 128, kAuxPixN = 256;
     static constexpr int kStageBytes = kTileBytes + 1024;                 // keeps every tile 1 KB aligned (SWIZZLE_128B)
     // per group, double buffered: run sums [kRunBuf][C] f32 | run_cell[32] i32 | run_n[32] f32
     static constexpr int kRunBytes = kRunBuf * C * 4 + 256;
     static constexpr int kRunTotal = kGroups * 2 * kRunBytes;
-    static constexpr int kStages = (C <= 128) ? 10 : (C == 256 ? 5 : 3);
+    static constexpr int kStages = (C <= 128) ? 8 : (C == 256 ? 6 : 3);
     static constexpr int kSmemBytes = kStages * kStageBytes + kRunTotal + 1024 /*align slack*/ + 256 /*barriers*/;
     static constexpr int kBoxC = C < 256 ? C : 256;                       // TMA box dims are limited to 256
     static_assert(kSmemBytes <= 232448, "exceeds 227 KB of shared memory");
+    // A stage must always be consumed by the same group: the parity wait on full[stage] is only valid if the
+    // waiter observes EVERY phase of that barrier (a group that skips a phase would see a stale parity).
+    static_assert(kStages % kGroups == 0, "kStages must be a multiple of kGroups");
 };
 
 __device__ __forceinline__ uint64_t make_evict_first_policy()
@@ -337,8 +352,8 @@ __device__ __forceinline__ void tma_load_3d_hint(void *dst, const void *tmap, in
 template <int C, bool kDry>
 __global__ void __launch_bounds__(TmaCfg<C>::kThreads, 1)
 write_mean_chw_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t *__restrict__ idx, const uint8_t *__restrict__ samp,
-                          const uint32_t *__restrict__ frame_cnt, int HW, int64_t n_cells, int tiles_per_ep, int n_tiles,
-                          float *__restrict__ sums)
+                          const uint32_t *__restrict__ frame_cnt, const float *__restrict__ pix_n, int HW, int64_t n_cells,
+                          int tiles_per_ep, int n_tiles, float *__restrict__ sums)
 {
     using Cfg = TmaCfg<C>;
     extern __shared__ unsigned char smem_dyn[];
@@ -349,6 +364,7 @@ write_mean_chw_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int32_
 
     const int tid = threadIdx.x;
     const bool has_samp = samp != nullptr;
+    const bool has_pixn = pix_n != nullptr;
     if (tid == 0) {
         for (int s = 0; s < Cfg::kStages; ++s) {
             mbar_init(full + s, 1);          // producer's arrive.expect_tx
@@ -364,7 +380,7 @@ write_mean_chw_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int32_
         // ===== producer warp: one elected lane issues all copies =====
         if (tid == Cfg::kGroups * C) {
             const uint64_t pol = make_evict_first_policy();     // the feature stream is read exactly once
-            const uint32_t tx = Cfg::kTileBytes + TILE_PX * 4 + (has_samp ? TILE_PX : 0);
+            const uint32_t tx = Cfg::kTileBytes + TILE_PX * 4 + (has_samp ? TILE_PX : 0) + (has_pixn ? TILE_PX * 4 : 0);
             int stage = 0;
             uint32_t phase = 0;
             for (int i = 0; i < my_tiles; ++i) {
@@ -378,6 +394,7 @@ write_mean_chw_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int32_
                     tma_load_3d_hint(st + c0 * TILE_PX * 4, &tmap, p0, c0, e, full + stage, pol);
                 bulk_load_1d(st + Cfg::kTileBytes + Cfg::kAuxCells, idx + (size_t)e * HW + p0, TILE_PX * 4, full + stage);
                 if (has_samp) bulk_load_1d(st + Cfg::kTileBytes + Cfg::kAuxSamp, samp + (size_t)e * HW + p0, TILE_PX, full + stage);
+                if (has_pixn) bulk_load_1d(st + Cfg::kTileBytes + Cfg::kAuxPixN, pix_n + (size_t)e * HW + p0, TILE_PX * 4, full + stage);
                 if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
             }
         }
@@ -418,9 +435,10 @@ write_mean_chw_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int32_
         const unsigned samps = has_samp ? __ballot_sync(0xffffffffu, s_samp[lane] != 0) : 0xffffffffu;
         const int nruns = __popc(heads);
 
-        // warp 0: per-run cell id and per-cell sample count; the global load is issued now, consumed after the
-        // accumulation, so its latency hides behind the shared-memory pass.
+        // warp 0: per-run cell id and divisor (the cell's sample count).  With pix_n the divisor arrived with the
+        // tile; otherwise it is a global load issued now and consumed after the accumulation.
         uint32_t cnt_raw = 0;
+        float n_run = 0.f;
         int my_run = 0;
         bool run_has_samples = false;
         if (warp0 && head) {
@@ -429,7 +447,10 @@ write_mean_chw_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int32_
             const int p1 = above ? (__ffs(above) - 1) : TILE_PX;
             const unsigned run = ((p1 >= 32) ? 0xffffffffu : ((1u << p1) - 1u)) & ~((1u << lane) - 1u);
             run_has_samples = (samps & run) != 0;
-            if (run_has_samples) cnt_raw = __ldg(frame_cnt + (size_t)e * n_cells + cell);
+            if (run_has_samples) {
+                if (has_pixn) n_run = reinterpret_cast<const float *>(st + Cfg::kTileBytes + Cfg::kAuxPixN)[lane];
+                else cnt_raw = __ldg(frame_cnt + (size_t)e * n_cells + cell);
+            }
         }
 
         // accumulate: all 32 pixels of channel c into registers first, then the run pass.  Run sums go to the
@@ -466,7 +487,7 @@ write_mean_chw_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int32_
         }
         if (warp0 && head) {
             s_run_cell[my_run] = cell;
-            s_run_n[my_run] = run_has_samples ? (float)(cnt_raw & 0x7fffffffu) : 0.f;
+            s_run_n[my_run] = !run_has_samples ? 0.f : (has_pixn ? n_run : (float)(cnt_raw & 0x7fffffffu));
         }
         named_bar_sync(1 + g, C);
 
@@ -573,7 +594,7 @@ PFN_encodeTiled get_encode_fn()
 }
 
 template <int C, bool kDry>
-int launch_tma(const float *feat, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt, int E, int HW,
+int launch_tma(const float *feat, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt, float *pix_n, int E, int HW,
                int64_t n_cells, float *sums, cudaStream_t st)
 {
     using Cfg = TmaCfg<C>;
@@ -593,9 +614,15 @@ int launch_tma(const float *feat, const int32_t *idx, const uint8_t *samp, const
         cudaFuncSetAttribute(write_mean_chw_tma_kernel<C, kDry>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         attr_set = true;
     }
+    if (pix_n) {
+        dim3 g2((HW + 255) / 256, E);
+        expand_counts_kernel<<<g2, 256, 0, st>>>(idx, frame_cnt, HW, n_cells, pix_n);
+        const int rc = eod_check_launch("eod_write_mean[expand]");
+        if (rc) return rc;
+    }
     const int tiles_per_ep = HW / TILE_PX, n_tiles = tiles_per_ep * E;
     const int grid = n_tiles < eod_num_sms() ? n_tiles : eod_num_sms();
-    write_mean_chw_tma_kernel<C, kDry><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmap, idx, samp, frame_cnt, HW, n_cells, tiles_per_ep, n_tiles, sums);
+    write_mean_chw_tma_kernel<C, kDry><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmap, idx, samp, frame_cnt, pix_n, HW, n_cells, tiles_per_ep, n_tiles, sums);
     return eod_check_launch("eod_write_mean[tma]");
 }
 
@@ -627,15 +654,15 @@ int launch_hwc(const float *feat, const int32_t *idx, const uint8_t *samp, const
 }
 
 template <int C>
-int dispatch(const float *feat, int layout, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt, int E, int HW,
+int dispatch(const float *feat, int layout, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt, float *pix_n, int E, int HW,
              int64_t n_cells, float *sums, int variant, cudaStream_t st)
 {
     if (layout == EOD_LAYOUT_HWC) return launch_hwc<C>(feat, idx, samp, frame_cnt, E, HW, n_cells, sums, st);
     const bool tma_ok = (HW % TILE_PX == 0) && (!samp || (reinterpret_cast<uintptr_t>(samp) % 16 == 0));
     if (variant == EOD_WRITE_TMA || variant == EOD_WRITE_TMA_DRY) EOD_REQUIRE(tma_ok, EOD_ERR_UNSUPPORTED, "eod_write_mean: TMA variant needs HW %% 32 == 0");
-    if (variant == EOD_WRITE_TMA_DRY) return launch_tma<C, true>(feat, idx, samp, frame_cnt, E, HW, n_cells, sums, st);
+    if (variant == EOD_WRITE_TMA_DRY) return launch_tma<C, true>(feat, idx, samp, frame_cnt, pix_n, E, HW, n_cells, sums, st);
     if (variant == EOD_WRITE_LDG || !tma_ok) return launch_ldg<C>(feat, idx, samp, frame_cnt, E, HW, n_cells, sums, st);
-    return launch_tma<C, false>(feat, idx, samp, frame_cnt, E, HW, n_cells, sums, st);
+    return launch_tma<C, false>(feat, idx, samp, frame_cnt, pix_n, E, HW, n_cells, sums, st);
 }
 
 }  // namespace
@@ -673,8 +700,10 @@ extern "C" int eod_finalize_counts(const int32_t *idx, int n_episodes, int HW, i
 }
 
 extern "C" int eod_write_mean(const float *feat, int layout, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt,
-                              int n_episodes, int C, int HW, int64_t n_cells, float *sums, int variant, eod_stream_t stream)
+                              int n_episodes, int C, int HW, int64_t n_cells, float *sums, int variant, float *pix_n_ws,
+                              eod_stream_t stream)
 {
+    EOD_REQUIRE(!pix_n_ws || eod_aligned16(pix_n_ws), EOD_ERR_ALIGN, "eod_write_mean: pix_n_ws must be 16-byte aligned");
     EOD_REQUIRE(feat && idx && frame_cnt && sums, EOD_ERR_BADARG, "eod_write_mean: null pointer");
     EOD_REQUIRE(n_episodes > 0 && HW > 0 && n_cells > 0, EOD_ERR_BADARG, "eod_write_mean: bad sizes");
     EOD_REQUIRE(layout == EOD_LAYOUT_CHW || layout == EOD_LAYOUT_HWC, EOD_ERR_BADARG, "eod_write_mean: bad layout");
@@ -683,9 +712,9 @@ extern "C" int eod_write_mean(const float *feat, int layout, const int32_t *idx,
     EOD_REQUIRE(layout == EOD_LAYOUT_HWC || HW % 4 == 0, EOD_ERR_ALIGN, "eod_write_mean: CHW rows must be 16-byte aligned (HW %% 4 == 0)");
     cudaStream_t st = (cudaStream_t)stream;
     switch (C) {
-    case 128: return dispatch<128>(feat, layout, idx, samp, frame_cnt, n_episodes, HW, n_cells, sums, variant, st);
-    case 256: return dispatch<256>(feat, layout, idx, samp, frame_cnt, n_episodes, HW, n_cells, sums, variant, st);
-    case 512: return dispatch<512>(feat, layout, idx, samp, frame_cnt, n_episodes, HW, n_cells, sums, variant, st);
+    case 128: return dispatch<128>(feat, layout, idx, samp, frame_cnt, pix_n_ws, n_episodes, HW, n_cells, sums, variant, st);
+    case 256: return dispatch<256>(feat, layout, idx, samp, frame_cnt, pix_n_ws, n_episodes, HW, n_cells, sums, variant, st);
+    case 512: return dispatch<512>(feat, layout, idx, samp, frame_cnt, pix_n_ws, n_episodes, HW, n_cells, sums, variant, st);
     default:
         eod_set_error("eod_write_mean: C=%d not compiled in (128, 256, 512)", C);
         return EOD_ERR_UNSUPPORTED;

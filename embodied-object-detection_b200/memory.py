@@ -44,6 +44,7 @@ class EpisodeBatch:
         # the rows of the cells visible in a frame change, and the write's post-pass refreshes exactly those
         self.norm16 = torch.zeros((self.E, self.n_cells, self.C), dtype=torch.float16, **z)
         self.idx = torch.zeros((self.E, height, width), dtype=torch.int32, **z)
+        self.pix_n = torch.zeros((self.E, height, width), dtype=torch.float32, **z)     # per-pixel divisors (write workspace)
         self.levels = [torch.empty((self.E, height >> s, width >> s, self.C), dtype=torch.float16, **z) for s in (3, 4, 5)]
         self._proj_out = {"idx": self.idx}
         self.stage_events = None      # dict(stage -> [(start, end) CUDA events]) when profiling is on
@@ -92,7 +93,8 @@ class EpisodeBatch:
         """A7 + A8 for one frame of every episode: feat (E,C,H,W) [CHW] or (E,H,W,C) [HWC] fp32;
         samp (E,H,W) u8 selects the contributing pixels (None = all)."""
         self._timed("count", ops.frame_count, self.idx, samp, self.frame_cnt)
-        self._timed("write", ops.write_mean, feat, self.idx, samp, self.frame_cnt, self.sums, self.layout, self.variant)
+        self._timed("write", ops.write_mean, feat, self.idx, samp, self.frame_cnt, self.sums, self.layout, self.variant,
+                    self.pix_n)
         self._timed("finalize", ops.finalize_counts, self.idx, self.frame_cnt, self.counts, None, self.sums, self.norm16)
 
     def step(self, depth, pose, shifts, intr, cell, feat, samp=None) -> List[torch.Tensor]:

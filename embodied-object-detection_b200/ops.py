@@ -97,7 +97,8 @@ def frame_count(idx: torch.Tensor, samp: Optional[torch.Tensor], frame_cnt: torc
 
 
 def write_mean(feat: torch.Tensor, idx: torch.Tensor, samp: Optional[torch.Tensor], frame_cnt: torch.Tensor,
-               sums: torch.Tensor, layout: int = LAYOUT_CHW, variant: int = WRITE_AUTO) -> None:
+               sums: torch.Tensor, layout: int = LAYOUT_CHW, variant: int = WRITE_AUTO,
+               pix_n_ws: Optional[torch.Tensor] = None) -> None:
     """feat (E,C,HW) [CHW] or (E,HW,C) [HWC] f32; sums (E,cells,C) f32 accumulated in place."""
     _dev(feat, torch.float32, "feat"), _dev(idx, torch.int32, "idx"), _dev(sums, torch.float32, "sums")
     _dev(frame_cnt, torch.int32, "frame_cnt")
@@ -107,8 +108,15 @@ def write_mean(feat: torch.Tensor, idx: torch.Tensor, samp: Optional[torch.Tenso
         raise ValueError(f"feat has {feat.numel()} elements, expected E*C*HW = {E * C * HW}")
     if samp is not None:
         _dev(samp, torch.uint8, "samp")
+    if pix_n_ws is not None:
+        _dev(pix_n_ws, torch.float32, "pix_n_ws")
+        if pix_n_ws.numel() < E * HW:
+            raise ValueError("pix_n_ws must hold E*HW floats")
     _call("eod_write_mean", feat.data_ptr(), int(layout), idx.data_ptr(), _ptr(samp), frame_cnt.data_ptr(), E, C, HW,
-          n_cells, sums.data_ptr(), int(variant), _stream())
+          n_cells, sums.data_ptr(), int(variant), _ptr(pix_n_ws), _stream())
+    global launch_count
+    if pix_n_ws is not None and layout == LAYOUT_CHW and HW % 32 == 0 and variant != WRITE_LDG:
+        launch_count += 1                       # the expand pre-kernel
 
 
 def finalize_counts(idx: torch.Tensor, frame_cnt: torch.Tensor, counts: torch.Tensor,

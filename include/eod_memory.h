@@ -89,9 +89,13 @@ int eod_frame_count(const int32_t *idx, const uint8_t *samp, int n_episodes, int
 
 /* Main pass: sums[cell] += (sum of the sampled pixels' feature vectors) / n_cell, i.e. the per-cell mean
  * of custom_rcnn.py:917-934 accumulated as in :696-697,742.  Warp/CTA-aggregated fp32 atomics:
- * run-to-run results agree to ~1e-7 of scale, not bitwise. */
+ * run-to-run results agree to ~1e-7 of scale, not bitwise.
+ * pix_n_ws: optional caller workspace (E,HW) f32.  When given, a pre-kernel expands the per-cell sample
+ * counts to per-pixel divisors that travel with the feature tiles (no dependent global load in the main
+ * kernel); results are identical either way. */
 int eod_write_mean(const float *feat, int layout, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt,
-                   int n_episodes, int C, int HW, int64_t n_cells, float *sums, int variant, eod_stream_t stream);
+                   int n_episodes, int C, int HW, int64_t n_cells, float *sums, int variant, float *pix_n_ws,
+                   eod_stream_t stream);
 
 /* Post-pass: counts[cell] += 1 for every visible cell (custom_rcnn.py:699-701,743) and frame_cnt := 0.
  * touched (E,cells) u8 nullable: |= 1 where the cell received samples this frame (observed_mem, :922).
