@@ -32,6 +32,11 @@ __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float 
                  : "memory");
 }
 
+__device__ __forceinline__ void red_add_f32(float *addr, float a)
+{
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
+}
+
 __device__ __forceinline__ float4 ldg_stream_f4(const float *p)
 {
     float4 r;

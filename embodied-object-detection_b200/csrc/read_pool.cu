@@ -76,12 +76,13 @@ __device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(
 __device__ __forceinline__ float4 scale4(float4 a, float s) { return make_float4(__fmul_rn(a.x, s), __fmul_rn(a.y, s), __fmul_rn(a.z, s), __fmul_rn(a.w, s)); }
 
 template <int C, typename TableT, typename IdxT>
-__global__ void __launch_bounds__(C) read_pool_kernel(const TableT *__restrict__ table, const float *__restrict__ counts,
+__global__ void __launch_bounds__(C, 1024 / C) read_pool_kernel(const TableT *__restrict__ table, const float *__restrict__ counts,
                                                       const IdxT *__restrict__ idx, int H, int W, int64_t n_cells,
                                                       __half *__restrict__ L0, __half *__restrict__ L1, __half *__restrict__ L2)
 {
     constexpr int G = C / 4;                 // channel groups == threads per quadrant
     __shared__ int s_idx[32 * 32];
+    __shared__ int s_wcell[64];              // per 4x4 window (8x8 of them): the cell id if all 16 pixels agree, else -1
     __shared__ float4 s_l1[4][G];
 
     const int e = blockIdx.z, by = blockIdx.y, bx = blockIdx.x;
@@ -92,6 +93,18 @@ __global__ void __launch_bounds__(C) read_pool_kernel(const TableT *__restrict__
     for (int i = threadIdx.x; i < 1024; i += C) {
         const int r = i >> 5, c = i & 31;
         s_idx[i] = load_cell(idx_e + (size_t)(by * 32 + r) * W + bx * 32 + c);
+    }
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        const int wy = threadIdx.x >> 3, wx = threadIdx.x & 7;
+        const int4 r0 = *reinterpret_cast<const int4 *>(&s_idx[(wy * 4 + 0) * 32 + wx * 4]);
+        const int4 r1 = *reinterpret_cast<const int4 *>(&s_idx[(wy * 4 + 1) * 32 + wx * 4]);
+        const int4 r2 = *reinterpret_cast<const int4 *>(&s_idx[(wy * 4 + 2) * 32 + wx * 4]);
+        const int4 r3 = *reinterpret_cast<const int4 *>(&s_idx[(wy * 4 + 3) * 32 + wx * 4]);
+        const int c0 = r0.x;
+        const bool u = (r0.y == c0) & (r0.z == c0) & (r0.w == c0) & (r1.x == c0) & (r1.y == c0) & (r1.z == c0) & (r1.w == c0) &
+                       (r2.x == c0) & (r2.y == c0) & (r2.z == c0) & (r2.w == c0) & (r3.x == c0) & (r3.y == c0) & (r3.z == c0) & (r3.w == c0);
+        s_wcell[threadIdx.x] = u ? c0 : -1;
     }
     __syncthreads();
 
@@ -105,30 +118,50 @@ __global__ void __launch_bounds__(C) read_pool_kernel(const TableT *__restrict__
 #pragma unroll 1
     for (int l0 = 0; l0 < 4; ++l0) {                       // L0 pixels of the quadrant, row-major
         const int l0y = l0 >> 1, l0x = l0 & 1;
-        float4 s2 = make_float4(0.f, 0.f, 0.f, 0.f);
+        // The four 4x4 windows of this L0 pixel.  A window whose 16 pixels hit ONE cell needs no additions: the
+        // gathered value x is an fp16 number, so the sequential fp32 sum x+x+...+x is exact at every step
+        // (k*x, k <= 16, has at most 15 significant bits) and avg_pool2d(4) returns x itself.
+        const int wbase = (qy * 4 + l0y * 2) * 8 + qx * 4 + l0x * 2;
+        const int w00 = s_wcell[wbase];
+        float4 v0;
+        if (w00 >= 0 && w00 == s_wcell[wbase + 1] && w00 == s_wcell[wbase + 8] && w00 == s_wcell[wbase + 9]) {
+            // whole 8x8 block in one cell: pool(4), pool(2) and the fp16 rounding all return the gathered value
+            if (w00 != cur_cell) cur = finish(load_raw(table_e, counts_e, (size_t)w00, C, g));
+            cur_cell = w00;
+            v0 = cur;
+        } else {
+            float4 s2 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
-        for (int win = 0; win < 4; ++win) {                // 4x4 windows of the avg_pool2d(4) (timm.py:152)
-            const int row0 = qy * 16 + l0y * 8 + (win >> 1) * 4, col0 = qx * 16 + l0x * 8 + (win & 1) * 4;
-            float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {         // two rows (8 pixels) per batch of loads
-                const int4 ca = *reinterpret_cast<const int4 *>(&s_idx[(row0 + 2 * half) * 32 + col0]);
-                const int4 cb = *reinterpret_cast<const int4 *>(&s_idx[(row0 + 2 * half + 1) * 32 + col0]);
-                const int cc[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
-                typename RawOf<TableT>::type raw[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k)                 // warp-uniform predicates; all loads in flight together
-                    if (cc[k] != (k == 0 ? cur_cell : cc[k - 1])) raw[k] = load_raw(table_e, counts_e, (size_t)cc[k], C, g);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    if (cc[k] != (k == 0 ? cur_cell : cc[k - 1])) cur = finish(raw[k]);
-                    s4 = add4(s4, cur);
+            for (int win = 0; win < 4; ++win) {            // 4x4 windows of the avg_pool2d(4) (timm.py:152)
+                const int wc = s_wcell[wbase + (win >> 1) * 8 + (win & 1)];
+                if (wc >= 0) {
+                    if (wc != cur_cell) cur = finish(load_raw(table_e, counts_e, (size_t)wc, C, g));
+                    cur_cell = wc;
+                    s2 = add4(s2, cur);
+                    continue;
                 }
-                cur_cell = cc[7];
+                const int row0 = qy * 16 + l0y * 8 + (win >> 1) * 4, col0 = qx * 16 + l0x * 8 + (win & 1) * 4;
+                float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {     // two rows (8 pixels) per batch of loads
+                    const int4 ca = *reinterpret_cast<const int4 *>(&s_idx[(row0 + 2 * half) * 32 + col0]);
+                    const int4 cb = *reinterpret_cast<const int4 *>(&s_idx[(row0 + 2 * half + 1) * 32 + col0]);
+                    const int cc[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+                    typename RawOf<TableT>::type raw[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)             // warp-uniform predicates; all loads in flight together
+                        if (cc[k] != (k == 0 ? cur_cell : cc[k - 1])) raw[k] = load_raw(table_e, counts_e, (size_t)cc[k], C, g);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        if (cc[k] != (k == 0 ? cur_cell : cc[k - 1])) cur = finish(raw[k]);
+                        s4 = add4(s4, cur);
+                    }
+                    cur_cell = cc[7];
+                }
+                s2 = add4(s2, scale4(s4, 0.0625f));        // / 16 (exact)
             }
-            s2 = add4(s2, scale4(s4, 0.0625f));            // / 16 (exact)
+            v0 = round_to_half(scale4(s2, 0.25f));         // avg_pool2d(2) -> half (timm.py:168, level 0)
         }
-        const float4 v0 = round_to_half(scale4(s2, 0.25f)); // avg_pool2d(2) -> half (timm.py:168, level 0)
         const int y0 = by * 4 + qy * 2 + l0y, x0 = bx * 4 + qx * 2 + l0x;
         store_half4(L0 + (((size_t)e * h0 + y0) * w0 + x0) * C + 4 * g, v0);
         l1acc = add4(l1acc, v0);

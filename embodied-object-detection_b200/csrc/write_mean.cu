@@ -9,15 +9,16 @@
 //   * CHW features (the reference's (1,C,480,640) layout): a persistent CTA per SM walks 32-pixel tiles;
 //     a producer warp issues ONE 3-D TMA box load (32 px x C channels, 128B-swizzled) + a 128 B bulk copy
 //     of the tile's cell indices per stage into a 3..6-deep mbarrier ring; consumer thread c owns channel
-//     c, reads its 32 pixels with conflict-free LDS.128, and accumulates runs of equal cell id in a
-//     register (neighbouring pixels fall into the same map cell); per run the C-vector is staged in shared
-//     memory (in place, same swizzle) and flushed with 128-bit red.global.add.v4.f32 - one L2 atomic
-//     transaction per four channels per run instead of one per pixel.
+//     c, reads its pixels with conflict-free LDS.128, and accumulates each run of equal cell id in a
+//     register (neighbouring pixels fall into the same map cell); a run leaves the SM as one
+//     red.global.add.f32 per channel (a warp covers 128 contiguous bytes of the cell row) - one L2
+//     reduction per run instead of one per pixel.
 //   * an LDG-staged variant of the same algorithm (padded smem tile) handles shapes the TMA path does
 //     not (HW % 32 != 0) and is the bring-up comparator (variant = EOD_WRITE_LDG).
 //   * HWC features: a warp walks a strip of pixels, lanes own float4 channel groups, runs accumulate in
 //     registers and flush straight from registers.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "eod_common.cuh"
 
@@ -101,8 +102,8 @@ __global__ void __launch_bounds__(256) finalize_counts_kernel(const int32_t *__r
     }
 }
 
-// pix_n[p] = number of sampled pixels of p's cell in this frame (as fp32): lets the main pass take the divisor
-// of a run from the staged tile instead of a dependent global load per run.
+// pix_n[p] = 1 / (number of sampled pixels of p's cell in this frame), correctly rounded: lets the main pass take
+// the scale of a run from the staged tile instead of a dependent global load (and a division) per run.
 __global__ void __launch_bounds__(256) expand_counts_kernel(const int32_t *__restrict__ idx, const uint32_t *__restrict__ frame_cnt,
                                                             int HW, int64_t n_cells, float *__restrict__ pix_n)
 {
@@ -110,7 +111,8 @@ __global__ void __launch_bounds__(256) expand_counts_kernel(const int32_t *__res
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= HW) return;
     const size_t g = (size_t)e * HW + p;
-    pix_n[g] = (float)(__ldg(frame_cnt + (size_t)e * n_cells + __ldg(idx + g)) & 0x7fffffffu);
+    const uint32_t n = __ldg(frame_cnt + (size_t)e * n_cells + __ldg(idx + g)) & 0x7fffffffu;
+    pix_n[g] = n ? __frcp_rn((float)n) : 0.f;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -301,34 +303,29 @@ __global__ void __launch_bounds__(C) write_mean_chw_ldg_kernel(const float *__re
 // ------------------------------------------------------------------------------------------------------
 // main pass, CHW, TMA-staged persistent kernel
 //
-// One CTA per SM: 1 producer warp + kGroups consumer groups of C threads.  Tile i of the CTA goes to ring
-// stage i % kStages and to consumer group i % kGroups, so while one group is in its flush (global
-// atomics) another is already accumulating the next tile.  Per tile and group:
-//   wait full[stage] -> every warp derives the run-head / sample masks from the staged cell ids ->
-//   warp 0 starts the loads of the per-cell sample counts (needed only at flush time) ->
-//   thread c accumulates its channel over the runs, run sums written in place -> group barrier ->
-//   flush items (run, 4 channels): red.global.add.v4.f32(sums[cell] + 4g, partial / n_cell) -> release stage.
+// One CTA per SM: kStages consumer warps + 1 producer warp.  The unit of work is (32-pixel tile, block of 128
+// channels) = one 16 KB TMA box; unit u of the CTA lands in ring stage u % kStages and is consumed by warp
+// u % kStages, i.e. every consumer warp OWNS one stage: no CTA- or group-level barrier anywhere, the only
+// synchronisation is the full/empty mbarrier pair of the stage.  Per unit the warp
+//   waits full[stage] -> derives the run-head / sample masks from the staged cell ids (ballot) ->
+//   per run (consecutive pixels of one map cell): lane l sums channels l, l+32, l+64, l+96 over the run's
+//   pixels straight from the swizzled tile (4 independent LDS.128 + FADD chains), scales by the staged
+//   1/n_cell and issues 4 x red.global.add.f32 (each a warp-wide 128-byte segment of the cell row) ->
+//   __syncwarp, one arrive on empty[stage].
 // ------------------------------------------------------------------------------------------------------
 
 template <int C>
 struct TmaCfg {
-    static constexpr int kGroups = (C >= 512) ? 1 : (512 / C);            // consumer groups per CTA
-    static constexpr int kRunBuf = (C >= 256) ? 4 : 8;                    // runs per tile staged in the conflict-free run buffer (more -> in place)
-    static constexpr int kThreads = 32 + kGroups * C;
-    static constexpr int kTileBytes = C * TILE_PX * 4;
-    // aux area per stage: cells (128 B) | samp (32 B) | pad | per-pixel divisors (128 B)
-    static constexpr int kAuxCells = 0, kAuxSamp = 128, kAuxPixN = 256;
-    static constexpr int kStageBytes = kTileBytes + 1024;                 // keeps every tile 1 KB aligned (SWIZZLE_128B)
-    // per group, double buffered: run sums [kRunBuf][C] f32 | run_cell[32] i32 | run_n[32] f32
-    static constexpr int kRunBytes = kRunBuf * C * 4 + 256;
-    static constexpr int kRunTotal = kGroups * 2 * kRunBytes;
-    static constexpr int kStages = (C <= 128) ? 8 : (C == 256 ? 6 : 3);
-    static constexpr int kSmemBytes = kStages * kStageBytes + kRunTotal + 1024 /*align slack*/ + 256 /*barriers*/;
-    static constexpr int kBoxC = C < 256 ? C : 256;                       // TMA box dims are limited to 256
+    static constexpr int kChanBlk = 128;                                  // channels per unit (TMA box height)
+    static constexpr int kBlocks = C / kChanBlk;                          // units per tile
+    static constexpr int kStages = 12;                                    // ring depth == consumer warps
+    static constexpr int kThreads = 32 * (kStages + 1);
+    static constexpr int kUnitBytes = kChanBlk * TILE_PX * 4;             // 16 KB, keeps every stage 1 KB aligned (SWIZZLE_128B)
+    // aux area per stage: cells (128 B) | samp (32 B) | pad | per-pixel 1/n (128 B)
+    static constexpr int kAuxCells = 0, kAuxSamp = 128, kAuxPixN = 256, kAuxBytes = 512;
+    static constexpr int kSmemBytes = kStages * (kUnitBytes + kAuxBytes) + 1024 /*align slack*/ + 256 /*barriers*/;
+    static_assert(C % kChanBlk == 0, "C must be a multiple of 128");
     static_assert(kSmemBytes <= 232448, "exceeds 227 KB of shared memory");
-    // A stage must always be consumed by the same group: the parity wait on full[stage] is only valid if the
-    // waiter observes EVERY phase of that barrier (a group that skips a phase would see a stale parity).
-    static_assert(kStages % kGroups == 0, "kStages must be a multiple of kGroups");
 };
 
 __device__ __forceinline__ uint64_t make_evict_first_policy()
@@ -338,18 +335,56 @@ __device__ __forceinline__ uint64_t make_evict_first_policy()
     return pol;
 }
 
-__device__ __forceinline__ void tma_load_3d_hint(void *dst, const void *tmap, int x, int y, int z, uint64_t *bar, uint64_t pol)
+__device__ __forceinline__ void tma_load_3d_hint(uint32_t dst, const void *tmap, int x, int y, int z, uint32_t bar, uint64_t pol)
 {
     asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(
-            smem_u32(dst)),
-        "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)), "l"(pol)
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(dst),
+        "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(bar), "l"(pol)
         : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d_s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP_S:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_S;\n\t"
+        "bra WAIT_LOOP_S;\n\t"
+        "DONE_S:\n\t"
+        "}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds8(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
 }
 
 // kDry: consumers only wait and release (no accumulation, no atomics) - measures the pure streaming
 // ceiling of this tile shape; selected with variant EOD_WRITE_TMA_DRY (bring-up / profiling only).
-template <int C, bool kDry>
+// kPixN: the per-pixel reciprocal divisors 1/n_cell arrive with the tile (pix_n workspace); otherwise the
+// divisor of a run is a dependent global load from frame_cnt.
+template <int C, bool kDry, bool kPixN>
 __global__ void __launch_bounds__(TmaCfg<C>::kThreads, 1)
 write_mean_chw_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t *__restrict__ idx, const uint8_t *__restrict__ samp,
                           const uint32_t *__restrict__ frame_cnt, const float *__restrict__ pix_n, int HW, int64_t n_cells,
@@ -357,160 +392,117 @@ write_mean_chw_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int32_
 {
     using Cfg = TmaCfg<C>;
     extern __shared__ unsigned char smem_dyn[];
-    unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-    unsigned char *run_base = base + Cfg::kStages * Cfg::kStageBytes;
-    uint64_t *full = reinterpret_cast<uint64_t *>(run_base + Cfg::kRunTotal);
-    uint64_t *empty = full + Cfg::kStages;
+    const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;          // shared-window address of stage 0
+    const uint32_t aux0 = base + Cfg::kStages * Cfg::kUnitBytes;
+    const uint32_t full0 = aux0 + Cfg::kStages * Cfg::kAuxBytes, empty0 = full0 + 8 * Cfg::kStages;
 
     const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const unsigned lane = tid & 31;
     const bool has_samp = samp != nullptr;
-    const bool has_pixn = pix_n != nullptr;
     if (tid == 0) {
         for (int s = 0; s < Cfg::kStages; ++s) {
-            mbar_init(full + s, 1);          // producer's arrive.expect_tx
-            mbar_init(empty + s, C / 32);    // one arrive per warp of the consuming group
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full0 + 8 * s), "r"(1));    // producer's arrive.expect_tx
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty0 + 8 * s), "r"(1));   // the owning warp's arrive
         }
         mbar_fence_init();
         fence_proxy_async();
     }
     __syncthreads();
-    const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles blockIdx.x, +gridDim.x, ...
 
-    if (tid >= Cfg::kGroups * C) {
+    // Tiles are handed out in PAIRS of raster neighbours (pair q -> CTA q % gridDim.x): the two 128-byte row
+    // segments of a pair form one 256-byte L2 line fill, so the second tile's TMA load hits what the first one
+    // brought in instead of a second DRAM fetch by some other CTA at some other time.
+    const int G = (int)gridDim.x, b = (int)blockIdx.x;
+    const bool paired = (n_tiles & 1) == 0;
+    const int n_slots = paired ? (n_tiles >> 1) : n_tiles;
+    const int my_slots = (n_slots - b + G - 1) / G;
+    const int my_units = (paired ? 2 * my_slots : my_slots) * Cfg::kBlocks;
+    auto tile_of = [&](int i) { return paired ? 2 * (b + (i >> 1) * G) + (i & 1) : b + i * G; };
+
+    if (warp == Cfg::kStages) {
         // ===== producer warp: one elected lane issues all copies =====
-        if (tid == Cfg::kGroups * C) {
+        if (lane == 0) {
             const uint64_t pol = make_evict_first_policy();     // the feature stream is read exactly once
-            const uint32_t tx = Cfg::kTileBytes + TILE_PX * 4 + (has_samp ? TILE_PX : 0) + (has_pixn ? TILE_PX * 4 : 0);
+            const uint32_t tx = Cfg::kUnitBytes + TILE_PX * 4 + (has_samp ? TILE_PX : 0) + (kPixN ? TILE_PX * 4 : 0);
             int stage = 0;
             uint32_t phase = 0;
-            for (int i = 0; i < my_tiles; ++i) {
-                const int t = blockIdx.x + i * gridDim.x;
-                mbar_wait(empty + stage, phase ^ 1);
+            for (int u = 0; u < my_units; ++u) {
+                const int i = u / Cfg::kBlocks, cb = u - i * Cfg::kBlocks;
+                const int t = tile_of(i);
                 const int e = t / tiles_per_ep, p0 = (t - e * tiles_per_ep) * TILE_PX;
-                unsigned char *st = base + stage * Cfg::kStageBytes;
-                mbar_expect_tx(full + stage, tx);
-#pragma unroll
-                for (int c0 = 0; c0 < C; c0 += Cfg::kBoxC)
-                    tma_load_3d_hint(st + c0 * TILE_PX * 4, &tmap, p0, c0, e, full + stage, pol);
-                bulk_load_1d(st + Cfg::kTileBytes + Cfg::kAuxCells, idx + (size_t)e * HW + p0, TILE_PX * 4, full + stage);
-                if (has_samp) bulk_load_1d(st + Cfg::kTileBytes + Cfg::kAuxSamp, samp + (size_t)e * HW + p0, TILE_PX, full + stage);
-                if (has_pixn) bulk_load_1d(st + Cfg::kTileBytes + Cfg::kAuxPixN, pix_n + (size_t)e * HW + p0, TILE_PX * 4, full + stage);
+                const uint32_t fullb = full0 + 8 * stage, aux = aux0 + stage * Cfg::kAuxBytes;
+                mbar_wait_s(empty0 + 8 * stage, phase ^ 1);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fullb), "r"(tx) : "memory");
+                tma_load_3d_hint(base + stage * Cfg::kUnitBytes, &tmap, p0, cb * Cfg::kChanBlk, e, fullb, pol);
+                bulk_load_1d_s(aux + Cfg::kAuxCells, idx + (size_t)e * HW + p0, TILE_PX * 4, fullb);
+                if (has_samp) bulk_load_1d_s(aux + Cfg::kAuxSamp, samp + (size_t)e * HW + p0, TILE_PX, fullb);
+                if (kPixN) bulk_load_1d_s(aux + Cfg::kAuxPixN, pix_n + (size_t)e * HW + p0, TILE_PX * 4, fullb);
                 if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
             }
         }
         return;
     }
 
-    // ===== consumers: group g, thread c owns channel c =====
-    const int g = tid / C, c = tid - g * C;
-    const unsigned lane = tid & 31;
-    const bool warp0 = (c >> 5) == 0;
-    for (int i = g; i < my_tiles; i += Cfg::kGroups) {
-        const int stage = i % Cfg::kStages;
-        const uint32_t phase = (uint32_t)(i / Cfg::kStages) & 1u;
-        const int t = blockIdx.x + i * gridDim.x;
-        const int e = t / tiles_per_ep;
-        unsigned char *st = base + stage * Cfg::kStageBytes;
-        constexpr int kRunBuf = Cfg::kRunBuf;
-        float *tile = reinterpret_cast<float *>(st);
-        const int *s_cells = reinterpret_cast<const int *>(st + Cfg::kTileBytes + Cfg::kAuxCells);
-        const uint8_t *s_samp = st + Cfg::kTileBytes + Cfg::kAuxSamp;
-        unsigned char *rb = run_base + (g * 2 + ((i / Cfg::kGroups) & 1)) * Cfg::kRunBytes;   // double buffered per group
-        float *runbuf = reinterpret_cast<float *>(rb);
-        int *s_run_cell = reinterpret_cast<int *>(rb + kRunBuf * C * 4);
-        float *s_run_n = reinterpret_cast<float *>(rb + kRunBuf * C * 4 + 128);
+    // ===== consumer warp `warp`: owns ring stage `warp`, lane l owns channels l, l+32, l+64, l+96 of the block =====
+    const uint32_t tile = base + warp * Cfg::kUnitBytes + lane * (TILE_PX * 4);   // row `lane` of the box
+    const uint32_t aux = aux0 + warp * Cfg::kAuxBytes;
+    const uint32_t fullb = full0 + 8 * warp, emptyb = empty0 + 8 * warp;
+    const uint32_t sw = lane & 7;                                                  // rows l + 32k share the swizzle phase
+    uint32_t phase = 0;
+    for (int u = warp; u < my_units; u += Cfg::kStages, phase ^= 1) {
+        mbar_wait_s(fullb, phase);
+        if (!kDry) {
+            const int i = u / Cfg::kBlocks, cb = u - i * Cfg::kBlocks;
+            const int e = tile_of(i) / tiles_per_ep;
+            // run structure of the tile: lane p looks at pixel p
+            const int cell = (int)lds32(aux + Cfg::kAuxCells + 4 * lane);
+            const int prev = __shfl_up_sync(0xffffffffu, cell, 1);
+            unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || prev != cell);
+            const unsigned samps = has_samp ? __ballot_sync(0xffffffffu, lds8(aux + Cfg::kAuxSamp + lane) != 0) : 0xffffffffu;
+            const float my_inv = kPixN ? __uint_as_float(lds32(aux + Cfg::kAuxPixN + 4 * lane)) : 0.f;
+            float *dst = sums + ((size_t)e * n_cells) * C + cb * Cfg::kChanBlk + lane;
+            const uint32_t *cnt_e = frame_cnt + (size_t)e * n_cells;
 
-        mbar_wait(full + stage, phase);
-        if (kDry) {
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty + stage);
-            continue;
-        }
-
-        // run structure of the tile (identical in every warp; cheap, avoids a broadcast through smem)
-        const int cell = s_cells[lane];
-        const int prev = __shfl_up_sync(0xffffffffu, cell, 1);
-        const bool head = lane == 0 || prev != cell;
-        const unsigned heads = __ballot_sync(0xffffffffu, head);
-        const unsigned samps = has_samp ? __ballot_sync(0xffffffffu, s_samp[lane] != 0) : 0xffffffffu;
-        const int nruns = __popc(heads);
-
-        // warp 0: per-run cell id and divisor (the cell's sample count).  With pix_n the divisor arrived with the
-        // tile; otherwise it is a global load issued now and consumed after the accumulation.
-        uint32_t cnt_raw = 0;
-        float n_run = 0.f;
-        int my_run = 0;
-        bool run_has_samples = false;
-        if (warp0 && head) {
-            my_run = __popc(heads & ((1u << lane) - 1u));
-            const unsigned above = heads & ~((2u << lane) - 1u);
-            const int p1 = above ? (__ffs(above) - 1) : TILE_PX;
-            const unsigned run = ((p1 >= 32) ? 0xffffffffu : ((1u << p1) - 1u)) & ~((1u << lane) - 1u);
-            run_has_samples = (samps & run) != 0;
-            if (run_has_samples) {
-                if (has_pixn) n_run = reinterpret_cast<const float *>(st + Cfg::kTileBytes + Cfg::kAuxPixN)[lane];
-                else cnt_raw = __ldg(frame_cnt + (size_t)e * n_cells + cell);
-            }
-        }
-
-        // accumulate: all 32 pixels of channel c into registers first, then the run pass.  Run sums go to the
-        // group's run buffer (row = run, conflict-free); runs beyond kRunBuf are parked in place in the tile.
-        {
-            const float4 *row = reinterpret_cast<const float4 *>(tile + c * TILE_PX);
-            float4 v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = row[j ^ (c & 7)];
-            float acc = 0.f;
-            int r = 0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float vv[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int p = 4 * j + k;
-                    if (p > 0 && ((heads >> p) & 1u)) {        // CTA-uniform
-                        if (r < kRunBuf) runbuf[r * C + c] = acc;
-                        else tile[swz(c, r)] = acc;
-                        ++r;
-                        acc = 0.f;
+            while (heads) {
+                const int p0 = __ffs(heads) - 1;
+                heads &= heads - 1;
+                const int p1 = heads ? (__ffs(heads) - 1) : TILE_PX;
+                const unsigned m = samps & (0xffffffffu >> (32 - p1)) & (0xffffffffu << p0);
+                if (m == 0) continue;                                  // no sampled pixel in this run
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                const int j1 = (p1 - 1) >> 2;
+#pragma unroll 1
+                for (int j = p0 >> 2; j <= j1; ++j) {
+                    const unsigned mj = (m >> (4 * j)) & 15u;
+                    if (mj == 0) continue;
+                    const uint32_t a = tile + (((uint32_t)j ^ sw) << 4);
+                    const float4 v0 = lds128(a), v1 = lds128(a + 32 * TILE_PX * 4), v2 = lds128(a + 64 * TILE_PX * 4),
+                                 v3 = lds128(a + 96 * TILE_PX * 4);
+                    if (mj == 15u) {                                   // whole chunk inside the run, all sampled
+                        a0 = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(a0, v0.x), v0.y), v0.z), v0.w);
+                        a1 = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(a1, v1.x), v1.y), v1.z), v1.w);
+                        a2 = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(a2, v2.x), v2.y), v2.z), v2.w);
+                        a3 = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(a3, v3.x), v3.y), v3.z), v3.w);
+                    } else {                                           // run edge / sparsely sampled chunk (warp-uniform predicates)
+                        if (mj & 1u) { a0 = __fadd_rn(a0, v0.x); a1 = __fadd_rn(a1, v1.x); a2 = __fadd_rn(a2, v2.x); a3 = __fadd_rn(a3, v3.x); }
+                        if (mj & 2u) { a0 = __fadd_rn(a0, v0.y); a1 = __fadd_rn(a1, v1.y); a2 = __fadd_rn(a2, v2.y); a3 = __fadd_rn(a3, v3.y); }
+                        if (mj & 4u) { a0 = __fadd_rn(a0, v0.z); a1 = __fadd_rn(a1, v1.z); a2 = __fadd_rn(a2, v2.z); a3 = __fadd_rn(a3, v3.z); }
+                        if (mj & 8u) { a0 = __fadd_rn(a0, v0.w); a1 = __fadd_rn(a1, v1.w); a2 = __fadd_rn(a2, v2.w); a3 = __fadd_rn(a3, v3.w); }
                     }
-                    if ((samps >> p) & 1u) acc = __fadd_rn(acc, vv[k]);
                 }
-            }
-            if (r < kRunBuf) runbuf[r * C + c] = acc;
-            else tile[swz(c, r)] = acc;
-        }
-        const bool early = nruns <= kRunBuf;                    // the stage is no longer needed: release it now
-        if (early) {
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty + stage);
-        }
-        if (warp0 && head) {
-            s_run_cell[my_run] = cell;
-            s_run_n[my_run] = !run_has_samples ? 0.f : (has_pixn ? n_run : (float)(cnt_raw & 0x7fffffffu));
-        }
-        named_bar_sync(1 + g, C);
-
-        // flush: item = (run r, channels 4q..4q+3)
-        {
-            constexpr int Q = C / 4;
-            float *sums_e = sums + (size_t)e * n_cells * C;
-            for (int item = c; item < nruns * Q; item += C) {
-                const int r = item / Q, q = item - r * Q;
-                const float n = s_run_n[r];
-                if (n == 0.f) continue;                         // run without a sampled pixel
-                const int ch = 4 * q;
-                float4 a;
-                if (r < kRunBuf) a = *reinterpret_cast<const float4 *>(runbuf + r * C + ch);
-                else a = make_float4(tile[swz(ch, r)], tile[swz(ch + 1, r)], tile[swz(ch + 2, r)], tile[swz(ch + 3, r)]);
-                red_add_v4(sums_e + (size_t)s_run_cell[r] * C + ch, __fdiv_rn(a.x, n), __fdiv_rn(a.y, n), __fdiv_rn(a.z, n), __fdiv_rn(a.w, n));
+                const int rc = __shfl_sync(0xffffffffu, cell, p0);
+                float inv = __shfl_sync(0xffffffffu, my_inv, p0);
+                if (!kPixN) inv = __frcp_rn((float)(__ldg(cnt_e + rc) & 0x7fffffffu));
+                float *d = dst + (size_t)rc * C;
+                red_add_f32(d, __fmul_rn(a0, inv));
+                red_add_f32(d + 32, __fmul_rn(a1, inv));
+                red_add_f32(d + 64, __fmul_rn(a2, inv));
+                red_add_f32(d + 96, __fmul_rn(a3, inv));
             }
         }
-        if (!early) {
-            fence_proxy_async();             // generic-proxy writes to the stage precede the next TMA write
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty + stage);
-        }
+        __syncwarp();                                                  // every lane's tile reads are done: release the stage
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(emptyb) : "memory");
     }
 }
 
@@ -593,6 +585,23 @@ PFN_encodeTiled get_encode_fn()
     return fn;
 }
 
+template <int C, bool kDry, bool kPixN>
+int launch_tma_kernel(const CUtensorMap &tmap, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt, const float *pix_n,
+                      int E, int HW, int64_t n_cells, float *sums, cudaStream_t st)
+{
+    using Cfg = TmaCfg<C>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(write_mean_chw_tma_kernel<C, kDry, kPixN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        attr_set = true;
+    }
+    const int tiles_per_ep = HW / TILE_PX, n_tiles = tiles_per_ep * E;
+    const int n_slots = (n_tiles & 1) ? n_tiles : n_tiles / 2;
+    const int grid = n_slots < eod_num_sms() ? n_slots : eod_num_sms();
+    write_mean_chw_tma_kernel<C, kDry, kPixN><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmap, idx, samp, frame_cnt, pix_n, HW, n_cells, tiles_per_ep, n_tiles, sums);
+    return eod_check_launch("eod_write_mean[tma]");
+}
+
 template <int C, bool kDry>
 int launch_tma(const float *feat, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt, float *pix_n, int E, int HW,
                int64_t n_cells, float *sums, cudaStream_t st)
@@ -603,27 +612,22 @@ int launch_tma(const float *feat, const int32_t *idx, const uint8_t *samp, const
     CUtensorMap tmap;
     const cuuint64_t gdim[3] = {(cuuint64_t)HW, (cuuint64_t)C, (cuuint64_t)E};
     const cuuint64_t gstr[2] = {(cuuint64_t)HW * 4, (cuuint64_t)HW * C * 4};
-    const cuuint32_t box[3] = {TILE_PX, (cuuint32_t)Cfg::kBoxC, 1};
+    const cuuint32_t box[3] = {TILE_PX, (cuuint32_t)Cfg::kChanBlk, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
+    static const int promo_env = [] { const char *v = getenv("EOD_TMA_L2_PROMOTION"); return v ? atoi(v) : 256; }();   // tuning knob: 0 | 128 | 256
+    const CUtensorMapL2promotion promo = promo_env == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                         : (promo_env == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
     const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(feat), gdim, gstr, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     EOD_REQUIRE(r == CUDA_SUCCESS, EOD_ERR_LAUNCH, "eod_write_mean: cuTensorMapEncodeTiled failed (%d)", (int)r);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(write_mean_chw_tma_kernel<C, kDry>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-        attr_set = true;
-    }
     if (pix_n) {
         dim3 g2((HW + 255) / 256, E);
         expand_counts_kernel<<<g2, 256, 0, st>>>(idx, frame_cnt, HW, n_cells, pix_n);
         const int rc = eod_check_launch("eod_write_mean[expand]");
         if (rc) return rc;
+        return launch_tma_kernel<C, kDry, true>(tmap, idx, samp, frame_cnt, pix_n, E, HW, n_cells, sums, st);
     }
-    const int tiles_per_ep = HW / TILE_PX, n_tiles = tiles_per_ep * E;
-    const int grid = n_tiles < eod_num_sms() ? n_tiles : eod_num_sms();
-    write_mean_chw_tma_kernel<C, kDry><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmap, idx, samp, frame_cnt, pix_n, HW, n_cells, tiles_per_ep, n_tiles, sums);
-    return eod_check_launch("eod_write_mean[tma]");
+    return launch_tma_kernel<C, kDry, false>(tmap, idx, samp, frame_cnt, nullptr, E, HW, n_cells, sums, st);
 }
 
 template <int C>
