@@ -102,6 +102,48 @@ __global__ void __launch_bounds__(256) finalize_counts_kernel(const int32_t *__r
     }
 }
 
+// Same post-pass driven by the CELL plane instead of the pixel plane: a warp scans 32 consecutive cells of
+// frame_cnt (coalesced, no atomics - every cell has exactly one owner), bumps the counts of the non-zero ones and
+// refreshes their fp16 rows.  Cheaper than the pixel-driven pass whenever the grid is not much larger than the
+// image (E*cells*4 bytes streamed instead of E*HW*4 plus one atomic per run of pixels).
+__global__ void __launch_bounds__(256) finalize_cells_kernel(int64_t n_rows, int64_t n_cells, uint32_t *__restrict__ frame_cnt,
+                                                             float *__restrict__ counts, uint8_t *__restrict__ touched,
+                                                             const float *__restrict__ sums, __half *__restrict__ norm16, int C)
+{
+    const unsigned lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t base = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; base < n_rows; base += warps * 32) {
+        const int64_t row = base + lane;
+        const uint32_t v = row < n_rows ? frame_cnt[row] : 0u;
+        float n_new = 0.f;
+        if (v) {
+            frame_cnt[row] = 0u;
+            n_new = counts[row] + 1.0f;                          // custom_rcnn.py:699-701,743
+            counts[row] = n_new;
+            if (touched && (v & 0x7fffffffu)) touched[row] = 1;
+        }
+        if (!norm16) continue;
+        unsigned todo = __ballot_sync(0xffffffffu, v != 0u);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const float wn = __shfl_sync(0xffffffffu, n_new, src);
+            const size_t r = (size_t)(base + src) * C;
+            const float4 *src_row = reinterpret_cast<const float4 *>(sums + r);
+            uint2 *dst_row = reinterpret_cast<uint2 *>(norm16 + r);
+            for (int k = lane; k < C / 4; k += 32) {
+                float4 x = src_row[k];
+                if (wn > 1.0f) { x.x = __fdiv_rn(x.x, wn); x.y = __fdiv_rn(x.y, wn); x.z = __fdiv_rn(x.z, wn); x.w = __fdiv_rn(x.w, wn); }
+                __half2 a = __floats2half2_rn(x.x, x.y), b = __floats2half2_rn(x.z, x.w);
+                uint2 raw;
+                raw.x = *reinterpret_cast<uint32_t *>(&a);
+                raw.y = *reinterpret_cast<uint32_t *>(&b);
+                dst_row[k] = raw;
+            }
+        }
+    }
+}
+
 // pix_n[p] = 1 / (number of sampled pixels of p's cell in this frame), correctly rounded: lets the main pass take
 // the scale of a run from the staged tile instead of a dependent global load (and a division) per run.
 __global__ void __launch_bounds__(256) expand_counts_kernel(const int32_t *__restrict__ idx, const uint32_t *__restrict__ frame_cnt,
@@ -388,7 +430,7 @@ template <int C, bool kDry, bool kPixN>
 __global__ void __launch_bounds__(TmaCfg<C>::kThreads, 1)
 write_mean_chw_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t *__restrict__ idx, const uint8_t *__restrict__ samp,
                           const uint32_t *__restrict__ frame_cnt, const float *__restrict__ pix_n, int HW, int64_t n_cells,
-                          int tiles_per_ep, int n_tiles, float *__restrict__ sums)
+                          int tiles_per_ep, int n_tiles, int group, float *__restrict__ sums)
 {
     using Cfg = TmaCfg<C>;
     extern __shared__ unsigned char smem_dyn[];
@@ -410,15 +452,20 @@ write_mean_chw_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int32_
     }
     __syncthreads();
 
-    // Tiles are handed out in PAIRS of raster neighbours (pair q -> CTA q % gridDim.x): the two 128-byte row
-    // segments of a pair form one 256-byte L2 line fill, so the second tile's TMA load hits what the first one
-    // brought in instead of a second DRAM fetch by some other CTA at some other time.
+    // Tiles are handed out in GROUPS of `group` raster neighbours (group q -> CTA q % gridDim.x) and a group's units
+    // are issued channel-block-major: the 128-byte row segments of neighbouring tiles are requested back to back, so
+    // they share one 256-byte L2 line fill (no second DRAM fetch by some other CTA at some other time) and fall into
+    // the same open DRAM page.
     const int G = (int)gridDim.x, b = (int)blockIdx.x;
-    const bool paired = (n_tiles & 1) == 0;
-    const int n_slots = paired ? (n_tiles >> 1) : n_tiles;
-    const int my_slots = (n_slots - b + G - 1) / G;
-    const int my_units = (paired ? 2 * my_slots : my_slots) * Cfg::kBlocks;
-    auto tile_of = [&](int i) { return paired ? 2 * (b + (i >> 1) * G) + (i & 1) : b + i * G; };
+    const int n_groups = n_tiles / group;                        // host guarantees n_tiles % group == 0
+    const int my_groups = (n_groups - b + G - 1) / G;
+    const int units_per_group = group * Cfg::kBlocks;
+    const int my_units = my_groups * units_per_group;
+    auto unit_of = [&](int u, int &t, int &cb) {
+        const int q = u / units_per_group, k = u - q * units_per_group;
+        cb = k / group;
+        t = group * (b + q * G) + (k - cb * group);
+    };
 
     if (warp == Cfg::kStages) {
         // ===== producer warp: one elected lane issues all copies =====
@@ -428,8 +475,8 @@ write_mean_chw_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int32_
             int stage = 0;
             uint32_t phase = 0;
             for (int u = 0; u < my_units; ++u) {
-                const int i = u / Cfg::kBlocks, cb = u - i * Cfg::kBlocks;
-                const int t = tile_of(i);
+                int t, cb;
+                unit_of(u, t, cb);
                 const int e = t / tiles_per_ep, p0 = (t - e * tiles_per_ep) * TILE_PX;
                 const uint32_t fullb = full0 + 8 * stage, aux = aux0 + stage * Cfg::kAuxBytes;
                 mbar_wait_s(empty0 + 8 * stage, phase ^ 1);
@@ -453,8 +500,9 @@ write_mean_chw_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int32_
     for (int u = warp; u < my_units; u += Cfg::kStages, phase ^= 1) {
         mbar_wait_s(fullb, phase);
         if (!kDry) {
-            const int i = u / Cfg::kBlocks, cb = u - i * Cfg::kBlocks;
-            const int e = tile_of(i) / tiles_per_ep;
+            int t, cb;
+            unit_of(u, t, cb);
+            const int e = t / tiles_per_ep;
             // run structure of the tile: lane p looks at pixel p
             const int cell = (int)lds32(aux + Cfg::kAuxCells + 4 * lane);
             const int prev = __shfl_up_sync(0xffffffffu, cell, 1);
@@ -596,14 +644,17 @@ int launch_tma_kernel(const CUtensorMap &tmap, const int32_t *idx, const uint8_t
         attr_set = true;
     }
     const int tiles_per_ep = HW / TILE_PX, n_tiles = tiles_per_ep * E;
-    const int n_slots = (n_tiles & 1) ? n_tiles : n_tiles / 2;
-    const int grid = n_slots < eod_num_sms() ? n_slots : eod_num_sms();
-    write_mean_chw_tma_kernel<C, kDry, kPixN><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmap, idx, samp, frame_cnt, pix_n, HW, n_cells, tiles_per_ep, n_tiles, sums);
+    static const int group_env = [] { const char *v = getenv("EOD_TMA_TILE_GROUP"); return v ? atoi(v) : 2; }();   // tuning knob: 1 | 2 | 4 | 8
+    int group = (group_env == 1 || group_env == 2 || group_env == 4 || group_env == 8) ? group_env : 2;
+    while (group > 1 && n_tiles % group) group >>= 1;
+    const int n_groups = n_tiles / group;
+    const int grid = n_groups < eod_num_sms() ? n_groups : eod_num_sms();
+    write_mean_chw_tma_kernel<C, kDry, kPixN><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmap, idx, samp, frame_cnt, pix_n, HW, n_cells, tiles_per_ep, n_tiles, group, sums);
     return eod_check_launch("eod_write_mean[tma]");
 }
 
 template <int C, bool kDry>
-int launch_tma(const float *feat, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt, float *pix_n, int E, int HW,
+int launch_tma(const float *feat, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt, const float *pix_n, int E, int HW,
                int64_t n_cells, float *sums, cudaStream_t st)
 {
     using Cfg = TmaCfg<C>;
@@ -620,13 +671,7 @@ int launch_tma(const float *feat, const int32_t *idx, const uint8_t *samp, const
     const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(feat), gdim, gstr, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     EOD_REQUIRE(r == CUDA_SUCCESS, EOD_ERR_LAUNCH, "eod_write_mean: cuTensorMapEncodeTiled failed (%d)", (int)r);
-    if (pix_n) {
-        dim3 g2((HW + 255) / 256, E);
-        expand_counts_kernel<<<g2, 256, 0, st>>>(idx, frame_cnt, HW, n_cells, pix_n);
-        const int rc = eod_check_launch("eod_write_mean[expand]");
-        if (rc) return rc;
-        return launch_tma_kernel<C, kDry, true>(tmap, idx, samp, frame_cnt, pix_n, E, HW, n_cells, sums, st);
-    }
+    if (pix_n) return launch_tma_kernel<C, kDry, true>(tmap, idx, samp, frame_cnt, pix_n, E, HW, n_cells, sums, st);
     return launch_tma_kernel<C, kDry, false>(tmap, idx, samp, frame_cnt, nullptr, E, HW, n_cells, sums, st);
 }
 
@@ -658,7 +703,7 @@ int launch_hwc(const float *feat, const int32_t *idx, const uint8_t *samp, const
 }
 
 template <int C>
-int dispatch(const float *feat, int layout, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt, float *pix_n, int E, int HW,
+int dispatch(const float *feat, int layout, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt, const float *pix_n, int E, int HW,
              int64_t n_cells, float *sums, int variant, cudaStream_t st)
 {
     if (layout == EOD_LAYOUT_HWC) return launch_hwc<C>(feat, idx, samp, frame_cnt, E, HW, n_cells, sums, st);
@@ -698,16 +743,35 @@ extern "C" int eod_finalize_counts(const int32_t *idx, int n_episodes, int HW, i
                 "eod_finalize_counts: norm16 needs sums, C %% 4 == 0 and 16-byte aligned pointers");
     EOD_REQUIRE(idx && frame_cnt && counts, EOD_ERR_BADARG, "eod_finalize_counts: null pointer");
     EOD_REQUIRE(n_episodes > 0 && n_episodes <= 65535 && HW > 0 && n_cells > 0, EOD_ERR_BADARG, "eod_finalize_counts: bad sizes");
+    if (n_cells <= 4 * (int64_t)HW) {
+        // grid comparable to the image: stream the cell plane once, no atomics
+        const int64_t n_rows = (int64_t)n_episodes * n_cells;
+        int64_t blocks = (n_rows + 255) / 256;
+        const int64_t cap = (int64_t)eod_num_sms() * 16;
+        if (blocks > cap) blocks = cap;
+        finalize_cells_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(n_rows, n_cells, frame_cnt, counts, touched, sums, (__half *)norm16, C);
+        return eod_check_launch("eod_finalize_counts[cells]");
+    }
     dim3 grid((HW + 255) / 256, n_episodes);
     finalize_counts_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(idx, HW, n_cells, frame_cnt, counts, touched, sums, (__half *)norm16, C);
     return eod_check_launch("eod_finalize_counts");
 }
 
+extern "C" int eod_expand_counts(const int32_t *idx, const uint32_t *frame_cnt, int n_episodes, int HW, int64_t n_cells,
+                                 float *pix_inv_n, eod_stream_t stream)
+{
+    EOD_REQUIRE(idx && frame_cnt && pix_inv_n, EOD_ERR_BADARG, "eod_expand_counts: null pointer");
+    EOD_REQUIRE(n_episodes > 0 && n_episodes <= 65535 && HW > 0 && n_cells > 0, EOD_ERR_BADARG, "eod_expand_counts: bad sizes");
+    dim3 grid((HW + 255) / 256, n_episodes);
+    expand_counts_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(idx, frame_cnt, HW, n_cells, pix_inv_n);
+    return eod_check_launch("eod_expand_counts");
+}
+
 extern "C" int eod_write_mean(const float *feat, int layout, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt,
-                              int n_episodes, int C, int HW, int64_t n_cells, float *sums, int variant, float *pix_n_ws,
+                              int n_episodes, int C, int HW, int64_t n_cells, float *sums, int variant, const float *pix_inv_n,
                               eod_stream_t stream)
 {
-    EOD_REQUIRE(!pix_n_ws || eod_aligned16(pix_n_ws), EOD_ERR_ALIGN, "eod_write_mean: pix_n_ws must be 16-byte aligned");
+    EOD_REQUIRE(!pix_inv_n || eod_aligned16(pix_inv_n), EOD_ERR_ALIGN, "eod_write_mean: pix_inv_n must be 16-byte aligned");
     EOD_REQUIRE(feat && idx && frame_cnt && sums, EOD_ERR_BADARG, "eod_write_mean: null pointer");
     EOD_REQUIRE(n_episodes > 0 && HW > 0 && n_cells > 0, EOD_ERR_BADARG, "eod_write_mean: bad sizes");
     EOD_REQUIRE(layout == EOD_LAYOUT_CHW || layout == EOD_LAYOUT_HWC, EOD_ERR_BADARG, "eod_write_mean: bad layout");
@@ -716,9 +780,9 @@ extern "C" int eod_write_mean(const float *feat, int layout, const int32_t *idx,
     EOD_REQUIRE(layout == EOD_LAYOUT_HWC || HW % 4 == 0, EOD_ERR_ALIGN, "eod_write_mean: CHW rows must be 16-byte aligned (HW %% 4 == 0)");
     cudaStream_t st = (cudaStream_t)stream;
     switch (C) {
-    case 128: return dispatch<128>(feat, layout, idx, samp, frame_cnt, pix_n_ws, n_episodes, HW, n_cells, sums, variant, st);
-    case 256: return dispatch<256>(feat, layout, idx, samp, frame_cnt, pix_n_ws, n_episodes, HW, n_cells, sums, variant, st);
-    case 512: return dispatch<512>(feat, layout, idx, samp, frame_cnt, pix_n_ws, n_episodes, HW, n_cells, sums, variant, st);
+    case 128: return dispatch<128>(feat, layout, idx, samp, frame_cnt, pix_inv_n, n_episodes, HW, n_cells, sums, variant, st);
+    case 256: return dispatch<256>(feat, layout, idx, samp, frame_cnt, pix_inv_n, n_episodes, HW, n_cells, sums, variant, st);
+    case 512: return dispatch<512>(feat, layout, idx, samp, frame_cnt, pix_inv_n, n_episodes, HW, n_cells, sums, variant, st);
     default:
         eod_set_error("eod_write_mean: C=%d not compiled in (128, 256, 512)", C);
         return EOD_ERR_UNSUPPORTED;

@@ -29,29 +29,69 @@ from ._lib import LAYOUT_CHW, LAYOUT_HWC, ORDER_ZX, WRITE_AUTO, EodError
 
 
 class EpisodeBatch:
+    """E episodes in lock step.  ``step`` runs the frame on two internal streams so that independent stages overlap:
+
+        geometry stream : project -> count -> expand                    -> read  (needs finalize of frame t-1)
+        write stream    :                      write (needs expand)  -> finalize (needs read: it refreshes ``norm16``)
+
+    The read (an L1/L2 gather) runs next to the HBM-bound write instead of in front of it, and with
+    ``pipeline=True`` the geometry of frame t+1 runs under the write of frame t (index plane, per-frame counts and
+    reciprocal divisors are double buffered).  Results are identical in either mode: the read of frame t always
+    sees exactly the state finalised by frame t-1 (custom_rcnn.py:489-515).
+
+    ``pipeline=False`` (default): fully stream-ordered for the caller - on return the caller's stream has been made
+    to wait for everything ``step`` enqueued.
+    ``pipeline=True``: the caller promises that depth / pose / shifts / samp of a step are ready when ``step`` is
+    called and stay untouched until the next ``step`` (or ``join``) - they are consumed ahead of the caller's stream.
+    The returned levels are ordered on the caller's stream; grid state (``sums``, ``counts``, ``norm16``) must be read
+    after ``join()``.
+    """
+
     def __init__(self, n_episodes: int, map_w: int, map_h: int, channels: int, height: int = 480, width: int = 640,
-                 device: torch.device = torch.device("cuda"), layout: int = LAYOUT_CHW, variant: int = WRITE_AUTO):
+                 device: torch.device = torch.device("cuda"), layout: int = LAYOUT_CHW, variant: int = WRITE_AUTO,
+                 pipeline: bool = False):
         if torch.device(device).type != "cuda":
             raise EodError("EpisodeBatch needs a CUDA device (no CPU fallback)")
         self.E, self.map_w, self.map_h, self.C, self.H, self.W = n_episodes, map_w, map_h, channels, height, width
         self.n_cells = map_w * map_h
-        self.device, self.layout, self.variant = torch.device(device), layout, variant
+        self.device, self.layout, self.variant, self.pipeline = torch.device(device), layout, variant, pipeline
         z = dict(device=self.device)
         self.sums = torch.zeros((self.E, self.n_cells, self.C), dtype=torch.float32, **z)
         self.counts = torch.zeros((self.E, self.n_cells), dtype=torch.float32, **z)
-        self.frame_cnt = torch.zeros((self.E, self.n_cells), dtype=torch.int32, **z)
         # always-current normalised fp16 copy of the grid (what create_implicit_memory + .half() would return); only
         # the rows of the cells visible in a frame change, and the write's post-pass refreshes exactly those
         self.norm16 = torch.zeros((self.E, self.n_cells, self.C), dtype=torch.float16, **z)
-        self.idx = torch.zeros((self.E, height, width), dtype=torch.int32, **z)
-        self.pix_n = torch.zeros((self.E, height, width), dtype=torch.float32, **z)     # per-pixel divisors (write workspace)
+        # per-frame planes, double buffered (frame t uses buffer t & 1)
+        self._idx2 = [torch.zeros((self.E, height, width), dtype=torch.int32, **z) for _ in range(2)]
+        self._frame_cnt2 = [torch.zeros((self.E, self.n_cells), dtype=torch.int32, **z) for _ in range(2)]
+        self._pix_inv_n2 = [torch.zeros((self.E, height, width), dtype=torch.float32, **z) for _ in range(2)]
         self.levels = [torch.empty((self.E, height >> s, width >> s, self.C), dtype=torch.float16, **z) for s in (3, 4, 5)]
-        self._proj_out = {"idx": self.idx}
+        self._k = 0
+        self._t = 0
+        with torch.cuda.device(self.device):
+            self._geo = torch.cuda.Stream(priority=0)
+            self._wr = torch.cuda.Stream(priority=-1)      # the HBM-bound stage gets the SMs first
+        self._e_fin: Optional[torch.cuda.Event] = None
+        self._e_read: Optional[torch.cuda.Event] = None
+        self._sync_next = True
         self.stage_events = None      # dict(stage -> [(start, end) CUDA events]) when profiling is on
 
+    # current frame's planes
+    @property
+    def idx(self) -> torch.Tensor:
+        return self._idx2[self._k]
+
+    @property
+    def frame_cnt(self) -> torch.Tensor:
+        return self._frame_cnt2[self._k]
+
+    @property
+    def pix_inv_n(self) -> torch.Tensor:
+        return self._pix_inv_n2[self._k]
+
     def profile(self, on: bool = True) -> None:
-        """Record a CUDA-event pair around every stage launch (same stream, no synchronisation added)."""
-        self.stage_events = {"project": [], "read": [], "count": [], "write": [], "finalize": []} if on else None
+        """Record a CUDA-event pair around every stage launch (on the stream it is launched on, no synchronisation added)."""
+        self.stage_events = {"project": [], "read": [], "count": [], "expand": [], "write": [], "finalize": []} if on else None
 
     def _timed(self, stage: str, fn, *args, **kw):
         if self.stage_events is None:
@@ -67,18 +107,34 @@ class EpisodeBatch:
         """Mean launch duration per stage in ms (call after a synchronize)."""
         return {k: (sum(a.elapsed_time(b) for a, b in v) / len(v) if v else 0.0) for k, v in (self.stage_events or {}).items()}
 
-    def reset(self) -> None:
-        """memory_reset (custom_rcnn.py:470-477) for every episode of the batch."""
-        self.sums.zero_()
-        self.counts.zero_()
-        self.frame_cnt.zero_()
-        self.norm16.zero_()
+    def join(self) -> None:
+        """Make the caller's current stream wait for everything ``step`` has enqueued on the internal streams."""
+        s0 = torch.cuda.current_stream(self.device)
+        for ev in (self._e_read, self._e_fin):
+            if ev is not None:
+                s0.wait_event(ev)
 
+    def reset(self, full: bool = False) -> None:
+        """memory_reset (custom_rcnn.py:470-477) for every episode of the batch.  Only rows of cells seen since the
+        last reset can be non-zero, so by default just those are cleared (eod_reset_touched); ``full=True`` rewrites
+        the whole grid (use it if the state tensors were modified from outside)."""
+        self.join()
+        if full:
+            self.sums.zero_()
+            self.counts.zero_()
+            self.norm16.zero_()
+            for f in self._frame_cnt2:
+                f.zero_()
+        else:
+            ops.reset_touched(self.counts, self.sums, self.norm16)      # frame_cnt is all-zero between frames already
+        self._sync_next = True        # the next step must not run ahead of these fills
+
+    # ---- single stages on the caller's stream (serial use, tests) ------------------------------------------
     def project(self, depth: torch.Tensor, pose: torch.Tensor, shifts: torch.Tensor, intr: Sequence[float], cell: float,
                 order: int = ORDER_ZX) -> torch.Tensor:
         """depth (E,H,W) f32, pose (E,12), shifts (E,6) -> self.idx (E,H,W) int32 (A2-A5)."""
         self._timed("project", ops.backproject_quantize, depth, pose, shifts, intr, cell, self.map_w, self.map_h, order,
-                    out=self._proj_out)
+                    out={"idx": self.idx})
         return self.idx
 
     def set_indices(self, idx: torch.Tensor) -> None:
@@ -89,20 +145,63 @@ class EpisodeBatch:
         """A10-A12 fused: [L0 (E,C,H/8,W/8), L1, L2] fp16 (channels_last memory)."""
         return self._timed("read", ops.read_pool, self.norm16, None, self.idx, out=self.levels)
 
+    def _count(self, samp: Optional[torch.Tensor]) -> None:
+        self._timed("count", ops.frame_count, self.idx, samp, self.frame_cnt)
+        self._timed("expand", ops.expand_counts, self.idx, self.frame_cnt, self.pix_inv_n)
+
+    def _write(self, feat: torch.Tensor, samp: Optional[torch.Tensor]) -> None:
+        self._timed("write", ops.write_mean, feat, self.idx, samp, self.frame_cnt, self.sums, self.layout, self.variant,
+                    self.pix_inv_n)
+
+    def _finalize(self) -> None:
+        self._timed("finalize", ops.finalize_counts, self.idx, self.frame_cnt, self.counts, None, self.sums, self.norm16)
+
     def write(self, feat: torch.Tensor, samp: Optional[torch.Tensor] = None) -> None:
         """A7 + A8 for one frame of every episode: feat (E,C,H,W) [CHW] or (E,H,W,C) [HWC] fp32;
         samp (E,H,W) u8 selects the contributing pixels (None = all)."""
-        self._timed("count", ops.frame_count, self.idx, samp, self.frame_cnt)
-        self._timed("write", ops.write_mean, feat, self.idx, samp, self.frame_cnt, self.sums, self.layout, self.variant,
-                    self.pix_n)
-        self._timed("finalize", ops.finalize_counts, self.idx, self.frame_cnt, self.counts, None, self.sums, self.norm16)
+        self._count(samp)
+        self._write(feat, samp)
+        self._finalize()
 
-    def step(self, depth, pose, shifts, intr, cell, feat, samp=None) -> List[torch.Tensor]:
+    # ---- one frame, overlapped -------------------------------------------------------------------------------
+    def step(self, depth, pose, shifts, intr, cell, feat, samp=None, order: int = ORDER_ZX) -> List[torch.Tensor]:
         """One frame of the hot path for all E episodes, in the reference's order: the read of frame t sees
-        the state written by frame t-1 (custom_rcnn.py:489-515)."""
-        self.project(depth, pose, shifts, intr, cell)
-        levels = self.read()
-        self.write(feat, samp)
+        the state written by frame t-1 (custom_rcnn.py:489-515).  See the class docstring for the stream layout."""
+        s0 = torch.cuda.current_stream(self.device)
+        self._k = self._t & 1
+        self._t += 1
+        strict = (not self.pipeline) or self._sync_next
+        self._sync_next = False
+        e_in = torch.cuda.Event()
+        e_in.record(s0)
+        with torch.cuda.stream(self._geo):
+            if strict:
+                self._geo.wait_event(e_in)                 # inputs (and a preceding reset) are ordered on the caller's stream
+            self.project(depth, pose, shifts, intr, cell, order)
+            self._count(samp)
+            e_geo = torch.cuda.Event()
+            e_geo.record()
+            if not strict:
+                self._geo.wait_event(e_in)                 # the caller has consumed the previous frame's levels
+            if self._e_fin is not None:
+                self._geo.wait_event(self._e_fin)          # norm16 as finalised by frame t-1
+            levels = self.read()
+            e_read = torch.cuda.Event()
+            e_read.record()
+        with torch.cuda.stream(self._wr):
+            self._wr.wait_event(e_in)                      # feat is ordered on the caller's stream
+            self._wr.wait_event(e_geo)
+            self._write(feat, samp)
+            self._wr.wait_event(e_read)                    # finalize rewrites the norm16 rows the read gathers from
+            self._finalize()
+            e_fin = torch.cuda.Event()
+            e_fin.record()
+        self._e_read, self._e_fin = e_read, e_fin
+        s0.wait_event(e_read)
+        if self.pipeline:
+            feat.record_stream(self._wr)
+        else:
+            s0.wait_event(e_fin)
         return levels
 
 

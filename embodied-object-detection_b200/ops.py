@@ -15,9 +15,9 @@ from ._lib import (FUSE_IMAGE_ONLY, FUSE_MEM_ONLY, FUSE_SUM, LAYOUT_CHW, LAYOUT_
 # kernels launched through this module since import (bench.py reports it as gpu_launches)
 launch_count = 0
 
-_LAUNCHES = {"eod_backproject_quantize": 1, "eod_sample_mask": 1, "eod_frame_count": 1, "eod_write_mean": 1,
+_LAUNCHES = {"eod_backproject_quantize": 1, "eod_sample_mask": 1, "eod_frame_count": 1, "eod_expand_counts": 1, "eod_write_mean": 1,
              "eod_finalize_counts": 1, "eod_box_to_image_features": 1, "eod_write_max": 2, "eod_read_pool": 1,
-             "eod_fuse": 1, "eod_normalize_memory": 1}
+             "eod_fuse": 1, "eod_normalize_memory": 1, "eod_reset_touched": 1}
 
 
 def _call(name: str, *args) -> None:
@@ -96,10 +96,21 @@ def frame_count(idx: torch.Tensor, samp: Optional[torch.Tensor], frame_cnt: torc
     _call("eod_frame_count", idx.data_ptr(), _ptr(samp), E, HW, frame_cnt.shape[1], frame_cnt.data_ptr(), _stream())
 
 
+def expand_counts(idx: torch.Tensor, frame_cnt: torch.Tensor, pix_inv_n: torch.Tensor) -> torch.Tensor:
+    """pix_inv_n (E,HW) f32 := 1 / frame_cnt[idx] (after frame_count); feeds write_mean."""
+    _dev(idx, torch.int32, "idx"), _dev(frame_cnt, torch.int32, "frame_cnt"), _dev(pix_inv_n, torch.float32, "pix_inv_n")
+    E, HW = idx.shape[0], idx[0].numel()
+    if pix_inv_n.numel() < E * HW:
+        raise ValueError("pix_inv_n must hold E*HW floats")
+    _call("eod_expand_counts", idx.data_ptr(), frame_cnt.data_ptr(), E, HW, frame_cnt[0].numel(), pix_inv_n.data_ptr(), _stream())
+    return pix_inv_n
+
+
 def write_mean(feat: torch.Tensor, idx: torch.Tensor, samp: Optional[torch.Tensor], frame_cnt: torch.Tensor,
                sums: torch.Tensor, layout: int = LAYOUT_CHW, variant: int = WRITE_AUTO,
-               pix_n_ws: Optional[torch.Tensor] = None) -> None:
-    """feat (E,C,HW) [CHW] or (E,HW,C) [HWC] f32; sums (E,cells,C) f32 accumulated in place."""
+               pix_inv_n: Optional[torch.Tensor] = None) -> None:
+    """feat (E,C,HW) [CHW] or (E,HW,C) [HWC] f32; sums (E,cells,C) f32 accumulated in place.
+    pix_inv_n: output of expand_counts for this frame (optional, faster)."""
     _dev(feat, torch.float32, "feat"), _dev(idx, torch.int32, "idx"), _dev(sums, torch.float32, "sums")
     _dev(frame_cnt, torch.int32, "frame_cnt")
     E, n_cells, C = sums.shape
@@ -108,15 +119,21 @@ def write_mean(feat: torch.Tensor, idx: torch.Tensor, samp: Optional[torch.Tenso
         raise ValueError(f"feat has {feat.numel()} elements, expected E*C*HW = {E * C * HW}")
     if samp is not None:
         _dev(samp, torch.uint8, "samp")
-    if pix_n_ws is not None:
-        _dev(pix_n_ws, torch.float32, "pix_n_ws")
-        if pix_n_ws.numel() < E * HW:
-            raise ValueError("pix_n_ws must hold E*HW floats")
+    if pix_inv_n is not None:
+        _dev(pix_inv_n, torch.float32, "pix_inv_n")
+        if pix_inv_n.numel() < E * HW:
+            raise ValueError("pix_inv_n must hold E*HW floats")
     _call("eod_write_mean", feat.data_ptr(), int(layout), idx.data_ptr(), _ptr(samp), frame_cnt.data_ptr(), E, C, HW,
-          n_cells, sums.data_ptr(), int(variant), _ptr(pix_n_ws), _stream())
-    global launch_count
-    if pix_n_ws is not None and layout == LAYOUT_CHW and HW % 32 == 0 and variant != WRITE_LDG:
-        launch_count += 1                       # the expand pre-kernel
+          n_cells, sums.data_ptr(), int(variant), _ptr(pix_inv_n), _stream())
+
+
+def reset_touched(counts: torch.Tensor, sums: torch.Tensor, norm16: Optional[torch.Tensor] = None) -> None:
+    """memory_reset for library-maintained state: clears the rows of every cell with a non-zero count."""
+    _dev(counts, torch.float32, "counts"), _dev(sums, torch.float32, "sums")
+    if norm16 is not None:
+        _dev(norm16, torch.float16, "norm16")
+    C = sums.shape[-1]
+    _call("eod_reset_touched", counts.data_ptr(), sums.data_ptr(), _ptr(norm16), counts.numel(), C, _stream())
 
 
 def finalize_counts(idx: torch.Tensor, frame_cnt: torch.Tensor, counts: torch.Tensor,

@@ -87,14 +87,18 @@ int eod_sample_mask(const uint8_t *observed, int n_episodes, int HW, int stride,
 int eod_frame_count(const int32_t *idx, const uint8_t *samp, int n_episodes, int HW, int64_t n_cells,
                     uint32_t *frame_cnt, eod_stream_t stream);
 
+/* Optional companion of the pre-pass: pix_inv_n[p] = 1 / frame_cnt[idx[p]] (sample count of p's cell, IEEE
+ * reciprocal; 0 where the cell has no sample), (E,HW) f32.  Given to eod_write_mean, the scale of a run of
+ * pixels travels with the feature tile instead of being a dependent global load per run. */
+int eod_expand_counts(const int32_t *idx, const uint32_t *frame_cnt, int n_episodes, int HW, int64_t n_cells,
+                      float *pix_inv_n, eod_stream_t stream);
+
 /* Main pass: sums[cell] += (sum of the sampled pixels' feature vectors) / n_cell, i.e. the per-cell mean
- * of custom_rcnn.py:917-934 accumulated as in :696-697,742.  Warp/CTA-aggregated fp32 atomics:
- * run-to-run results agree to ~1e-7 of scale, not bitwise.
- * pix_n_ws: optional caller workspace (E,HW) f32.  When given, a pre-kernel expands the per-cell sample
- * counts to per-pixel divisors that travel with the feature tiles (no dependent global load in the main
- * kernel); results are identical either way. */
+ * of custom_rcnn.py:917-934 accumulated as in :696-697,742.  Warp-aggregated fp32 reductions
+ * (red.global.add.f32, one per run of equal cell id and channel): run-to-run results agree to ~1e-7 of
+ * scale, not bitwise.  pix_inv_n: nullable, output of eod_expand_counts for this frame. */
 int eod_write_mean(const float *feat, int layout, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt,
-                   int n_episodes, int C, int HW, int64_t n_cells, float *sums, int variant, float *pix_n_ws,
+                   int n_episodes, int C, int HW, int64_t n_cells, float *sums, int variant, const float *pix_inv_n,
                    eod_stream_t stream);
 
 /* Post-pass: counts[cell] += 1 for every visible cell (custom_rcnn.py:699-701,743) and frame_cnt := 0.
@@ -144,6 +148,11 @@ int eod_read_pool(const void *table, int mem_is_f16, const float *counts, const 
  * callers that need the normalised table itself; eod_read_pool fuses this step. */
 int eod_normalize_memory(const float *sums, const float *counts, int64_t n_rows, int C, void *out, int out_is_f16,
                          eod_stream_t stream);
+
+/* memory_reset (custom_rcnn.py:470-477) for state maintained by this library: clears counts, the sums row and
+ * (if given) the norm16 row of every cell whose count is non-zero - equivalent to zero-filling the grid because
+ * rows of never-visible cells are zero already.  n_rows = E*cells. */
+int eod_reset_touched(float *counts, float *sums, void *norm16, int64_t n_rows, int C, eod_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * (4) Fusion epilogue, timm.py:177-189: out = res + weight*mem | weight*mem | res (two roundings, no

@@ -192,7 +192,7 @@ def test_sample_mask_and_box_features_bit_exact(eod, cuda):
     assert np.array_equal(img.cpu().numpy(), ref_img.numpy())              # same fp32 add order -> bit-exact
 
 
-def _write_case(eod, cuda, C, E, H, W, cells, layout, variant, with_samp, seed):
+def _write_case(eod, cuda, C, E, H, W, cells, layout, variant, with_samp, seed, expand=False):
     rng = np.random.default_rng(seed)
     HW = H * W
     feat = rng.standard_normal((E, C, H, W)).astype(np.float32) * 3
@@ -210,7 +210,8 @@ def _write_case(eod, cuda, C, E, H, W, cells, layout, variant, with_samp, seed):
     d_samp = None if samp is None else _t(samp, cuda)
     f_dev = _t(feat if layout == 0 else feat.transpose(0, 2, 3, 1), cuda)
     eod.ops.frame_count(d_idx, d_samp, d_cnt)
-    eod.ops.write_mean(f_dev, d_idx, d_samp, d_cnt, d_sums, layout, variant)
+    pix = eod.ops.expand_counts(d_idx, d_cnt, torch.empty((E, H, W), device=cuda)) if expand else None
+    eod.ops.write_mean(f_dev, d_idx, d_samp, d_cnt, d_sums, layout, variant, pix)
     d_norm = torch.zeros((E, cells, C), dtype=torch.float16, device=cuda)
     eod.ops.finalize_counts(d_idx, d_cnt, d_counts, d_touched, d_sums, d_norm)
     torch.cuda.synchronize()
@@ -237,10 +238,17 @@ def _write_case(eod, cuda, C, E, H, W, cells, layout, variant, with_samp, seed):
 
 
 @pytest.mark.parametrize("C", [128, 256, 512])
-@pytest.mark.parametrize("variant", [1, 2], ids=["ldg", "tma"])            # EOD_WRITE_LDG, EOD_WRITE_TMA
+@pytest.mark.parametrize("variant,expand", [(1, False), (2, False), (2, True)], ids=["ldg", "tma", "tma+expand"])   # EOD_WRITE_LDG, EOD_WRITE_TMA
 @pytest.mark.parametrize("with_samp", [False, True])
-def test_write_mean_chw_vs_oracle(eod, cuda, C, variant, with_samp):
-    _write_case(eod, cuda, C, 3, 64, 96, 200, 0, variant, with_samp, seed=C + variant)
+def test_write_mean_chw_vs_oracle(eod, cuda, C, variant, expand, with_samp):
+    _write_case(eod, cuda, C, 3, 64, 96, 200, 0, variant, with_samp, seed=C + variant, expand=expand)
+
+
+def test_write_mean_large_grid_pixel_driven_finalize(eod, cuda):
+    """cells > 4*HW: eod_finalize_counts walks the pixel plane (atomicExch dedupe) instead of the cell plane;
+    E*tiles odd -> the TMA kernel falls back to ungrouped tiles."""
+    _write_case(eod, cuda, 128, 3, 32, 96, 13000, 0, 2, True, seed=5, expand=True)
+    _write_case(eod, cuda, 256, 1, 32, 32, 5000, 0, 2, False, seed=6, expand=True)
 
 
 def test_write_mean_chw_ragged_tail_ldg(eod, cuda):
@@ -358,7 +366,7 @@ def test_full_size_properties(eod, cuda):
             touched = torch.zeros(mw * mh, dtype=torch.bool, device=cuda)
             touched[cells] = True
             assert (delta[e][~touched] == 0).all().item()
-        assert int(batch.frame_cnt.abs().sum()) == 0
+        assert sum(int(f.abs().sum()) for f in batch._frame_cnt2) == 0
     # read after 3 frames vs the C oracle on the downloaded state (bit-exact fp16)
     idx_np = batch.idx.cpu().numpy()
     levels = batch.read()
@@ -376,6 +384,63 @@ def test_full_size_properties(eod, cuda):
     levels = batch.read()
     for lv in levels:
         assert (lv == const.view(1, C, 1, 1)).all().item()
+
+
+def test_pipelined_step_matches_stream_ordered_step(eod, cuda):
+    """pipeline=True (geometry of frame t+1 under the write of frame t, read next to the write) must give the
+    results of the stream-ordered mode: indices and counts bit-exact, sums to atomics-order noise, levels to fp16
+    rounding of that noise."""
+    E, C, H, W, mw, mh, T_ = 3, 128, 96, 128, 60, 45, 6
+    eps = [eod.episodes.make_episode(500 + e, T_, H, W, mw, mh, 0.2) for e in range(E)]
+    intr = eod.compute_intrinsics(W, H, math.radians(67.5))
+    shifts = _t(np.stack([np.concatenate([np.zeros(3, np.float32), ep.map_world_shift]) for ep in eps]), cuda)
+    depth = [_t(np.stack([ep.depth[t] for ep in eps]), cuda) for t in range(T_)]
+    pose = [eod.transform3d(torch.from_numpy(np.stack([ep.xyzhe[t] for ep in eps])))[:, :3].reshape(E, 12).to(cuda) for t in range(T_)]
+    gen = torch.Generator(device=cuda).manual_seed(3)
+    feat = [torch.randn((E, C, H, W), device=cuda, generator=gen) for _ in range(T_)]
+    torch.cuda.synchronize()
+    out = {}
+    for mode in (False, True):
+        batch = eod.EpisodeBatch(E, mw, mh, C, H, W, cuda, pipeline=mode)
+        lv, ix = [], []
+        for rep in range(2):                                   # second pass after a reset: reset must not race the pipeline
+            batch.reset()
+            lv, ix = [], []
+            for t in range(T_):
+                levels = batch.step(depth[t], pose[t], shifts, intr, 0.2, feat[t])
+                lv.append([l.clone() for l in levels])         # ordered on the caller's stream in both modes
+                ix.append(batch.idx.clone() if not mode else None)
+        batch.join()
+        torch.cuda.synchronize()
+        out[mode] = (batch.sums.clone(), batch.counts.clone(), lv, batch.idx.clone(), batch.norm16.clone())
+    (s0, c0, l0, i0, n0), (s1, c1, l1, i1, n1) = out[False], out[True]
+    assert torch.equal(c0, c1) and torch.equal(i0, i1)
+    assert (s0 - s1).abs().max().item() <= 1e-6 * s0.abs().max().item()
+    for t in range(T_):
+        for a, b in zip(l0[t], l1[t]):
+            assert torch.allclose(a.float(), b.float(), rtol=2e-3, atol=2e-3), t
+    assert torch.allclose(n0.float(), n1.float(), rtol=2e-3, atol=2e-3)
+
+
+def test_sparse_reset_clears_everything(eod, cuda):
+    """EpisodeBatch.reset() clears only the rows of cells seen since the last reset; the result must be the
+    all-zero state of custom_rcnn.py:470-477."""
+    E, C, H, W, mw, mh = 2, 128, 96, 128, 60, 45
+    eps = [eod.episodes.make_episode(900 + e, 3, H, W, mw, mh, 0.2) for e in range(E)]
+    intr = eod.compute_intrinsics(W, H, math.radians(67.5))
+    shifts = _t(np.stack([np.concatenate([np.zeros(3, np.float32), ep.map_world_shift]) for ep in eps]), cuda)
+    batch = eod.EpisodeBatch(E, mw, mh, C, H, W, cuda)
+    for t in range(3):
+        depth = _t(np.stack([ep.depth[t] for ep in eps]), cuda)
+        pose = eod.transform3d(torch.from_numpy(np.stack([ep.xyzhe[t] for ep in eps])))[:, :3].reshape(E, 12).to(cuda)
+        batch.step(depth, pose, shifts, intr, 0.2, torch.randn((E, C, H, W), device=cuda))
+    assert batch.counts.sum().item() > 0 and batch.sums.abs().sum().item() > 0 and batch.norm16.float().abs().sum().item() > 0
+    batch.reset()
+    torch.cuda.synchronize()
+    assert batch.counts.abs().sum().item() == 0
+    assert batch.sums.abs().sum().item() == 0
+    assert batch.norm16.float().abs().sum().item() == 0
+    assert sum(int(f.abs().sum()) for f in batch._frame_cnt2) == 0
 
 
 def test_tma_and_ldg_variants_agree_full_size(eod, cuda):
