@@ -118,6 +118,17 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_traffic(E: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one write-kernel launch, from the committed ncu pass
+    (profiles/write_kernel_traffic.json, written by profiles/summarize.py); None if it was taken at another batch size."""
+    p = os.path.join(ROOT, "profiles", "write_kernel_traffic.json")
+    try:
+        d = json.load(open(p))
+        return float(d["traffic_bytes_per_launch"]) if int(d["episodes_per_launch"]) == E else None
+    except Exception:
+        return None
+
+
 def write_launch_bytes(E: int, touched_per_launch: float) -> float:
     """Algorithmic bytes of ONE eod_write_mean launch over E episodes (DESIGN.md 'Roofline accounting'):
     features read once + index plane + touched grid rows read-modify-written + per-cell sample counts."""
@@ -273,7 +284,7 @@ def main_gpu(args, rank, local_rank, world):
         "e2e": e2e,
         "roofline": {"bound": "hbm", "kernel": "write_mean_chw_tma_kernel<256>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "frac_of_nominal_8TBs": (achieved / 8000.0) if achieved else None,
-                     "traffic": None, "peak_source": peak_src, "bytes_per_launch": wbytes, "launch_ms": stage_ms.get("write"),
+                     "traffic": measured_traffic(E), "peak_source": peak_src, "bytes_per_launch": wbytes, "launch_ms": stage_ms.get("write"),
                      "stage_ms": stage_ms, "visible_cells_per_frame": vis_per_frame,
                      "whole_path": {"bytes_per_frame": frame_bytes(vis_per_frame), "achieved_gbs_per_gpu": path_gbs,
                                     "frac": path_gbs / peak}},
