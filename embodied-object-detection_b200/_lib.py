@@ -25,11 +25,14 @@ SIGNATURES = {
     "eod_backproject_quantize": [_P, _P, _P, c_int, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_int,
                                  c_int, c_int, c_float, _P, _P, _P, _P, _P, _P],
     "eod_sample_mask": [_P, c_int, c_int, c_int, _P, _P, _P],
-    "eod_frame_count": [_P, _P, c_int, c_int, c_int64, _P, _P],
+    "eod_frame_count": [_P, _P, _P, c_int, c_int, c_int64, _P, _P, _P, _P, c_int, _P],
     "eod_expand_counts": [_P, _P, c_int, c_int, c_int64, _P, _P],
     "eod_write_mean": [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int64, _P, c_int, _P, _P],
     "eod_finalize_counts": [_P, c_int, c_int, c_int64, _P, _P, _P, _P, _P, c_int, _P],
     "eod_box_to_image_features": [_P, _P, c_int, c_int, c_int, _P, _P, _P],
+    "eod_masks_observed": [_P, _P, c_int, c_int, c_int, _P, _P],
+    "eod_write_objects": [_P, _P, _P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int64, c_int, _P, _P],
+    "eod_flush_slots": [_P, _P, _P, _P, c_int, c_int, c_int64, c_int, _P, _P, _P],
     "eod_write_max": [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int64, _P, _P, _P, _P, _P, _P],
     "eod_read_pool": [_P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int64, _P, _P, _P, _P],
     "eod_normalize_memory": [_P, _P, c_int64, c_int, _P, c_int, _P],

@@ -30,9 +30,12 @@ constexpr int TILE_PX = 32;
 // pre-pass / post-pass: one thread per pixel, warp-level run aggregation of the cell id
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) frame_count_kernel(const int32_t *__restrict__ idx, const uint8_t *__restrict__ samp,
-                                                          int HW, int64_t n_cells, uint32_t *__restrict__ frame_cnt)
+                                                          const int32_t *__restrict__ active, int HW, int64_t n_cells,
+                                                          uint32_t *__restrict__ frame_cnt, int32_t *__restrict__ slot_of_cell,
+                                                          int32_t *__restrict__ slot_cell, int32_t *__restrict__ n_slots, int S)
 {
     const int e = blockIdx.y;
+    if (active && __ldg(active + e) <= 0) return;      // episode without a kept detection: no write, no visibility (custom_rcnn.py:686)
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31;
     const bool valid = p < HW;
@@ -50,8 +53,16 @@ __global__ void __launch_bounds__(256) frame_count_kernel(const int32_t *__restr
         const unsigned run = ((end >= 32u) ? 0xffffffffu : ((1u << end) - 1u)) & ~((1u << lane) - 1u) & valids;
         const unsigned n = __popc(samps & run);
         uint32_t *dst = frame_cnt + (size_t)e * n_cells + cell;
-        if (n) atomicAdd(dst, n);
-        else atomicOr(dst, 0x80000000u);
+        if (n) {
+            const uint32_t old = atomicAdd(dst, n);
+            if (slot_of_cell && (old & 0x7fffffffu) == 0u) {               // first samples of this cell in this frame: claim a slot
+                const int sl = atomicAdd(n_slots + e, 1);
+                if (sl < S) {
+                    slot_of_cell[(size_t)e * n_cells + cell] = sl + 1;
+                    slot_cell[(size_t)e * S + sl] = cell;
+                }
+            }
+        } else atomicOr(dst, 0x80000000u);
     }
 }
 
@@ -725,13 +736,15 @@ extern "C" int eod_sample_mask(const uint8_t *observed, int n_episodes, int HW, 
     return eod_check_launch("eod_sample_mask");
 }
 
-extern "C" int eod_frame_count(const int32_t *idx, const uint8_t *samp, int n_episodes, int HW, int64_t n_cells,
-                               uint32_t *frame_cnt, eod_stream_t stream)
+extern "C" int eod_frame_count(const int32_t *idx, const uint8_t *samp, const int32_t *active, int n_episodes, int HW,
+                               int64_t n_cells, uint32_t *frame_cnt, int32_t *slot_of_cell, int32_t *slot_cell, int32_t *n_slots,
+                               int n_slots_max, eod_stream_t stream)
 {
     EOD_REQUIRE(idx && frame_cnt, EOD_ERR_BADARG, "eod_frame_count: null pointer");
     EOD_REQUIRE(n_episodes > 0 && n_episodes <= 65535 && HW > 0 && n_cells > 0, EOD_ERR_BADARG, "eod_frame_count: bad sizes");
     dim3 grid((HW + 255) / 256, n_episodes);
-    frame_count_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(idx, samp, HW, n_cells, frame_cnt);
+    EOD_REQUIRE(!slot_of_cell || (slot_cell && n_slots && n_slots_max > 0), EOD_ERR_BADARG, "eod_frame_count: slot_of_cell needs slot_cell, n_slots and n_slots_max");
+    frame_count_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(idx, samp, active, HW, n_cells, frame_cnt, slot_of_cell, slot_cell, n_slots, n_slots_max);
     return eod_check_launch("eod_frame_count");
 }
 

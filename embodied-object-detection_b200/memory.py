@@ -74,6 +74,7 @@ class EpisodeBatch:
         self._e_fin: Optional[torch.cuda.Event] = None
         self._e_read: Optional[torch.cuda.Event] = None
         self._sync_next = True
+        self._slots: Optional[ops.ObjectSlots] = None      # workspace of write_objects, created on first use
         self.stage_events = None      # dict(stage -> [(start, end) CUDA events]) when profiling is on
 
     # current frame's planes
@@ -163,6 +164,21 @@ class EpisodeBatch:
         self._write(feat, samp)
         self._finalize()
 
+    def write_objects(self, box_features: torch.Tensor, masks: torch.Tensor, n_obj: Optional[torch.Tensor] = None,
+                      sample_stride: int = 8) -> None:
+        """Object-feature regime (the reference's live path, custom_rcnn.py:681-743) for one frame of every episode,
+        fused: box_features (E,Kmax,C) f32 (= 50*normalize(feat), :848), masks (E,Kmax,H,W) bool, n_obj (E) i32 kept
+        detections per episode (None = Kmax).  Episodes with n_obj == 0 are skipped entirely, counts included (:686)."""
+        S = -(-self.H * self.W // sample_stride)
+        if self._slots is None or self._slots.S < S:
+            self._slots = ops.ObjectSlots(self.E, self.n_cells, self.C, S, self.device)
+        observed = ops.masks_observed(masks, n_obj)
+        samp = ops.sample_mask(observed, sample_stride)
+        ops.frame_count(self.idx, samp, self.frame_cnt, n_obj, self._slots)
+        ops.write_objects(box_features, masks, n_obj, self.idx, samp, self._slots)
+        ops.flush_slots(self.frame_cnt, self._slots, self.sums)
+        self._finalize()
+
     # ---- one frame, overlapped -------------------------------------------------------------------------------
     def step(self, depth, pose, shifts, intr, cell, feat, samp=None, order: int = ORDER_ZX) -> List[torch.Tensor]:
         """One frame of the hot path for all E episodes, in the reference's order: the read of frame t sees
@@ -214,9 +230,10 @@ class SpatialFeatureMemory:
 
     def __init__(self, mem_feat_dim: int = 512, device: torch.device = torch.device("cuda"), test_type: str = "default",
                  semmap_gt_info: Optional[dict] = None, replica_map_info: Optional[dict] = None, downsample: int = 10,
-                 sample_stride: int = 8, height: int = 480, width: int = 640):
+                 sample_stride: int = 8, height: int = 480, width: int = 640, fused_write: bool = True):
         if torch.device(device).type != "cuda":
             raise EodError("SpatialFeatureMemory needs a CUDA device (no CPU fallback)")
+        self.fused_write = fused_write      # False: materialise image_features like the reference (box_to_image_features)
         self.C, self.device, self.test_type = mem_feat_dim, torch.device(device), test_type
         self.semmap_gt_info, self.replica_map_info = semmap_gt_info or {}, replica_map_info or {}
         self.downsample, self.sample_stride, self.H, self.W = downsample, sample_stride, height, width
@@ -224,6 +241,7 @@ class SpatialFeatureMemory:
         self.observations: Optional[torch.Tensor] = None        # (cells,)  f32 counts      (:477,760)
         self._frame_cnt: Optional[torch.Tensor] = None
         self._touched: Optional[torch.Tensor] = None
+        self._slots: Optional[ops.ObjectSlots] = None
 
     # ---- state ---------------------------------------------------------------------------------------
     def reset(self, n_cells: int) -> None:
@@ -343,8 +361,29 @@ class SpatialFeatureMemory:
         if self.implicit_memory is None or self.implicit_memory.shape[0] != memory.shape[0]:
             self.reset(memory.shape[0])
         self._dims = self.map_dims(frame.get("sequence_name", ""))
-        image_features, observed = self.box_to_image_features(box_features, masks)
-        self.write_image_features(image_features, observed, proj_indices)
+        if self.fused_write:
+            self.write_object_features(box_features, masks, proj_indices)
+        else:
+            image_features, observed = self.box_to_image_features(box_features, masks)
+            self.write_image_features(image_features, observed, proj_indices)
+
+    def write_object_features(self, box_features: torch.Tensor, masks: torch.Tensor, proj_indices: torch.Tensor) -> None:
+        """A6 + A7 + A8 without the (1,C,H,W) image (custom_rcnn.py:690-701,738-743): the per-pixel object mean is
+        formed only for the every-``sample_stride``-th observed pixels, on the fly."""
+        idx = self._idx32(proj_indices)
+        bf = box_features.to(self.device, torch.float32).contiguous().unsqueeze(0)
+        m = masks.to(self.device).contiguous().unsqueeze(0)
+        HW = masks.shape[-2] * masks.shape[-1]
+        S = -(-HW // self.sample_stride)
+        n_cells = self.implicit_memory.shape[0]
+        if self._slots is None or self._slots.S < S or self._slots.n_cells != n_cells:
+            self._slots = ops.ObjectSlots(1, n_cells, self.C, S, self.device)
+        observed = ops.masks_observed(m)
+        samp = ops.sample_mask(observed, self.sample_stride)
+        ops.frame_count(idx, samp, self._frame_cnt, None, self._slots)
+        ops.write_objects(bf, m, None, idx.view(1, masks.shape[-2], masks.shape[-1]), samp, self._slots)
+        ops.flush_slots(self._frame_cnt, self._slots, self.implicit_memory.unsqueeze(0))
+        ops.finalize_counts(idx, self._frame_cnt, self.observations.unsqueeze(0))
 
     def write_image_features(self, image_features: torch.Tensor, observed_pixels: Optional[torch.Tensor],
                              proj_indices: torch.Tensor, layout: int = LAYOUT_CHW) -> None:

@@ -16,7 +16,7 @@ from ._lib import (FUSE_IMAGE_ONLY, FUSE_MEM_ONLY, FUSE_SUM, LAYOUT_CHW, LAYOUT_
 launch_count = 0
 
 _LAUNCHES = {"eod_backproject_quantize": 1, "eod_sample_mask": 1, "eod_frame_count": 1, "eod_expand_counts": 1, "eod_write_mean": 1,
-             "eod_finalize_counts": 1, "eod_box_to_image_features": 1, "eod_write_max": 2, "eod_read_pool": 1,
+             "eod_finalize_counts": 1, "eod_box_to_image_features": 1, "eod_masks_observed": 1, "eod_write_objects": 1, "eod_flush_slots": 2, "eod_write_max": 2, "eod_read_pool": 1,
              "eod_fuse": 1, "eod_normalize_memory": 1, "eod_reset_touched": 1}
 
 
@@ -87,13 +87,31 @@ def sample_mask(observed: torch.Tensor, stride: int, samp: Optional[torch.Tensor
     return samp
 
 
-def frame_count(idx: torch.Tensor, samp: Optional[torch.Tensor], frame_cnt: torch.Tensor) -> None:
-    """idx (E,HW) i32, samp (E,HW) u8 | None, frame_cnt (E,cells) i32 scratch (zero on entry)."""
+def frame_count(idx: torch.Tensor, samp: Optional[torch.Tensor], frame_cnt: torch.Tensor,
+                active: Optional[torch.Tensor] = None, slots: Optional["ObjectSlots"] = None) -> None:
+    """idx (E,HW) i32, samp (E,HW) u8 | None, frame_cnt (E,cells) i32 scratch (zero on entry);
+    active (E) i32 | None: episodes with active <= 0 are skipped (no kept detection -> no write, no visibility);
+    slots: when given, every cell that receives samples claims a compact slot (object-regime write)."""
     _dev(idx, torch.int32, "idx"), _dev(frame_cnt, torch.int32, "frame_cnt")
     E, HW = idx.shape[0], idx[0].numel()
     if samp is not None:
         _dev(samp, torch.uint8, "samp")
-    _call("eod_frame_count", idx.data_ptr(), _ptr(samp), E, HW, frame_cnt.shape[1], frame_cnt.data_ptr(), _stream())
+    if active is not None:
+        _dev(active, torch.int32, "active")
+    sl = (None, None, None, 0) if slots is None else (slots.slot_of_cell.data_ptr(), slots.slot_cell.data_ptr(), slots.n_slots.data_ptr(), slots.S)
+    _call("eod_frame_count", idx.data_ptr(), _ptr(samp), _ptr(active), E, HW, frame_cnt.shape[1], frame_cnt.data_ptr(), *sl, _stream())
+
+
+class ObjectSlots:
+    """Per-frame workspace of the fused object write: a compact slot per touched cell and one zeroed fp32 row per slot
+    (all of it is back to zero after flush_slots).  S = ceil(HW / sample_stride) slots always suffice."""
+
+    def __init__(self, n_episodes: int, n_cells: int, channels: int, n_slots_max: int, device: torch.device):
+        self.E, self.n_cells, self.C, self.S = n_episodes, n_cells, channels, int(n_slots_max)
+        self.slot_of_cell = torch.zeros((n_episodes, n_cells), dtype=torch.int32, device=device)
+        self.slot_cell = torch.zeros((n_episodes, self.S), dtype=torch.int32, device=device)
+        self.n_slots = torch.zeros((n_episodes,), dtype=torch.int32, device=device)
+        self.scratch = torch.zeros((n_episodes, self.S, channels), dtype=torch.float32, device=device)
 
 
 def expand_counts(idx: torch.Tensor, frame_cnt: torch.Tensor, pix_inv_n: torch.Tensor) -> torch.Tensor:
@@ -166,6 +184,48 @@ def box_to_image_features(box_features: torch.Tensor, masks: torch.Tensor) -> Tu
     _call("eod_box_to_image_features", box_features.data_ptr(), masks.data_ptr(), K, C, H * W, img.data_ptr(),
           obs.data_ptr(), _stream())
     return img, obs.view(torch.bool)
+
+
+def _masks_u8(masks: torch.Tensor) -> torch.Tensor:
+    if masks.dtype == torch.bool:
+        masks = masks.view(torch.uint8)
+    return _dev(masks, torch.uint8, "masks")
+
+
+def masks_observed(masks: torch.Tensor, n_obj: Optional[torch.Tensor] = None, observed: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """masks (E,Kmax,H,W) bool/u8, n_obj (E) i32 | None -> observed (E,H*W) u8 (1 where any object covers the pixel)."""
+    masks = _masks_u8(masks)
+    E, Kmax, H, W = masks.shape
+    if n_obj is not None:
+        _dev(n_obj, torch.int32, "n_obj")
+    observed = torch.empty((E, H * W), dtype=torch.uint8, device=masks.device) if observed is None else _dev(observed, torch.uint8, "observed")
+    _call("eod_masks_observed", masks.data_ptr(), _ptr(n_obj), E, Kmax, H * W, observed.data_ptr(), _stream())
+    return observed
+
+
+def write_objects(box_features: torch.Tensor, masks: torch.Tensor, n_obj: Optional[torch.Tensor], idx: torch.Tensor,
+                  samp: torch.Tensor, slots: ObjectSlots) -> None:
+    """Fused A6+A7 (first half): box_features (E,Kmax,C) f32, masks (E,Kmax,H,W), idx (E,H,W) i32, samp (E,HW) u8;
+    the per-pixel object means of the sampled pixels are reduced into slots.scratch."""
+    masks = _masks_u8(masks)
+    _dev(box_features, torch.float32, "box_features"), _dev(idx, torch.int32, "idx"), _dev(samp, torch.uint8, "samp")
+    E, Kmax, H, W = masks.shape
+    if box_features.shape != (E, Kmax, slots.C) or slots.E != E:
+        raise ValueError("box_features must be (E,Kmax,C) matching masks (E,Kmax,H,W) and the slot workspace")
+    if n_obj is not None:
+        _dev(n_obj, torch.int32, "n_obj")
+    _call("eod_write_objects", box_features.data_ptr(), masks.data_ptr(), _ptr(n_obj), Kmax, idx.data_ptr(), samp.data_ptr(),
+          slots.slot_of_cell.data_ptr(), E, slots.C, H * W, slots.n_cells, slots.S, slots.scratch.data_ptr(), _stream())
+
+
+def flush_slots(frame_cnt: torch.Tensor, slots: ObjectSlots, sums: torch.Tensor) -> None:
+    """sums[cell] += scratch[slot] / n_cell for every claimed slot; the workspace returns to zero."""
+    _dev(frame_cnt, torch.int32, "frame_cnt"), _dev(sums, torch.float32, "sums")
+    E, n_cells, C = sums.shape
+    if (E, n_cells, C) != (slots.E, slots.n_cells, slots.C):
+        raise ValueError("sums does not match the slot workspace")
+    _call("eod_flush_slots", frame_cnt.data_ptr(), slots.slot_of_cell.data_ptr(), slots.slot_cell.data_ptr(), slots.n_slots.data_ptr(),
+          E, C, n_cells, slots.S, slots.scratch.data_ptr(), sums.data_ptr(), _stream())
 
 
 def write_max(height: torch.Tensor, idx: torch.Tensor, outlier: Optional[torch.Tensor], feat: Optional[torch.Tensor],

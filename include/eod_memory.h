@@ -83,9 +83,15 @@ int eod_sample_mask(const uint8_t *observed, int n_episodes, int HW, int stride,
 
 /* Per-frame pre-pass: frame_cnt[cell] += #sampled pixels of the cell; bit 31 marks cells that are
  * visible but have no sampled pixel (torch.unique(proj_indices), custom_rcnn.py:699).  samp nullable
- * (= every pixel sampled).  frame_cnt must be zero on entry. */
-int eod_frame_count(const int32_t *idx, const uint8_t *samp, int n_episodes, int HW, int64_t n_cells,
-                    uint32_t *frame_cnt, eod_stream_t stream);
+ * (= every pixel sampled).  active (E) i32 nullable: episodes with active[e] <= 0 are skipped altogether
+ * (a frame without kept detections writes nothing, not even visibility: custom_rcnn.py:686,872-873).
+ * frame_cnt must be zero on entry.
+ * Slot table (all nullable together; used by eod_write_objects): the first sample of a cell claims the next
+ * free slot of its episode: slot_of_cell (E,cells) i32 := slot + 1, slot_cell (E,n_slots_max) i32 := cell,
+ * n_slots (E) i32 += 1.  slot_of_cell and n_slots must be zero on entry (eod_flush_slots leaves them so). */
+int eod_frame_count(const int32_t *idx, const uint8_t *samp, const int32_t *active, int n_episodes, int HW,
+                    int64_t n_cells, uint32_t *frame_cnt, int32_t *slot_of_cell, int32_t *slot_cell, int32_t *n_slots,
+                    int n_slots_max, eod_stream_t stream);
 
 /* Optional companion of the pre-pass: pix_inv_n[p] = 1 / frame_cnt[idx[p]] (sample count of p's cell, IEEE
  * reciprocal; 0 where the cell has no sample), (E,HW) f32.  Given to eod_write_mean, the scale of a run of
@@ -115,6 +121,27 @@ int eod_finalize_counts(const int32_t *idx, int n_episodes, int HW, int64_t n_ce
  * unobserved), observed (HW) u8.  Bit-exact (same fp32 add order). */
 int eod_box_to_image_features(const float *box_features, const uint8_t *masks, int K, int C, int HW,
                               float *image_features, uint8_t *observed, eod_stream_t stream);
+
+/* Fused object-regime write (custom_rcnn.py:884-936 without the (C,H,W) image): observed[p] = any_k masks[k][p].
+ * masks (E,Kmax,HW) u8, n_obj (E) i32 nullable (= Kmax objects everywhere) -> observed (E,HW) u8.  HW %% 4 == 0. */
+int eod_masks_observed(const uint8_t *masks, const int32_t *n_obj, int n_episodes, int Kmax, int HW, uint8_t *observed,
+                       eod_stream_t stream);
+
+/* For every sampled pixel (samp from eod_sample_mask(observed, 8); slots from eod_frame_count):
+ *   g = (sum over the objects covering the pixel, ascending index, of box_features[k]) / #objects   - bit-identical
+ *       to the value eod_box_to_image_features / custom_rcnn.py:890-899 stores for that pixel;
+ *   scratch[slot(cell)] += g.
+ * box_features (E,Kmax,C) f32, masks (E,Kmax,HW) u8, scratch (E,n_slots_max,C) f32 zero on entry;
+ * n_slots_max >= number of sampled pixels per episode (HW/stride rounded up is always enough). */
+int eod_write_objects(const float *box_features, const uint8_t *masks, const int32_t *n_obj, int Kmax, const int32_t *idx,
+                      const uint8_t *samp, const int32_t *slot_of_cell, int n_episodes, int C, int HW, int64_t n_cells,
+                      int n_slots_max, float *scratch, eod_stream_t stream);
+
+/* sums[cell] += scratch[slot] / n_cell for every claimed slot (the per-cell mean of custom_rcnn.py:931-934 added
+ * once, :696-697,742); scratch rows, slot_of_cell entries and n_slots return to zero.  Run before
+ * eod_finalize_counts (which clears frame_cnt). */
+int eod_flush_slots(const uint32_t *frame_cnt, int32_t *slot_of_cell, const int32_t *slot_cell, int32_t *n_slots, int n_episodes,
+                    int C, int64_t n_cells, int n_slots_max, float *scratch, float *sums, eod_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * (2b) Write, SMNet height-max mode (bytecode-only SMNet.encode, SURVEY 8a row A7').

@@ -261,12 +261,13 @@ def test_write_mean_hwc_vs_oracle(eod, cuda, C):
     _write_case(eod, cuda, C, 2, 64, 96, 200, 1, 0, False, seed=C + 1)
 
 
-def test_write_path_matches_reference_golden(eod, cuda, golden):
+@pytest.mark.parametrize("fused", [True, False], ids=["fused", "image-buffer"])
+def test_write_path_matches_reference_golden(eod, cuda, golden, fused):
     """Reference call surface (box_to_image_features / project_image_features / update_implicit_memory) against the
     outputs of the reference's own source over a 3-frame sequence."""
     g = golden("write_mean")
     n_cells = int(g["map_w"]) * int(g["map_h"])
-    mem = eod.SpatialFeatureMemory(512, cuda)
+    mem = eod.SpatialFeatureMemory(512, cuda, fused_write=fused)
     mem.reset(n_cells)
     for t in range(3):
         K = int(g[f"K{t}"])
@@ -288,6 +289,43 @@ def test_write_path_matches_reference_golden(eod, cuda, golden):
     before = mem.implicit_memory.clone()
     mem.update_implicit_memory(None, proj, mem.implicit_memory, {})                           # no detection -> no write (:686)
     assert torch.equal(before, mem.implicit_memory)
+
+
+def test_batched_fused_object_write_vs_oracle(eod, cuda):
+    """EpisodeBatch.write_objects (masks -> observed -> every 8th -> per-cell mean, no image buffer) against the
+    restated reference chain box_to_image_features -> project_image_features -> accumulate, per episode; an episode
+    without detections must not change at all (custom_rcnn.py:686)."""
+    E, C, H, W, mw, mh, Kmax = 4, 128, 96, 128, 40, 30, 11
+    cells = mw * mh
+    rng = np.random.default_rng(21)
+    batch = eod.EpisodeBatch(E, mw, mh, C, H, W, cuda)
+    sums = [torch.zeros(cells, C) for _ in range(E)]
+    counts = [torch.zeros(cells) for _ in range(E)]
+    for t in range(3):
+        idx = (rng.integers(0, cells, (E, H // 4 + 1, W // 8 + 1)).repeat(4, 1).repeat(8, 2)[:, :H, :W]).astype(np.int32)
+        n_obj = np.array([Kmax, 3, 0, 7], np.int32) if t != 1 else np.array([1, 0, 5, Kmax], np.int32)
+        bf = np.zeros((E, Kmax, C), np.float32)
+        masks = np.zeros((E, Kmax, H, W), bool)
+        for e in range(E):
+            if n_obj[e]:
+                f, m = eod.episodes.make_detections(rng, H, W, C, (int(n_obj[e]), int(n_obj[e])))
+                bf[e, : n_obj[e]], masks[e, : n_obj[e]] = f, m
+            # garbage beyond n_obj must be ignored
+            bf[e, n_obj[e]:] = 1e6
+            masks[e, n_obj[e]:] = True
+        batch.set_indices(_t(idx, cuda))
+        batch.write_objects(_t(bf, cuda), _t(masks, cuda), _t(n_obj, cuda))
+        torch.cuda.synchronize()
+        for e in range(E):
+            if n_obj[e]:
+                img, obs = R.box_to_image_features(torch.from_numpy(bf[e, : n_obj[e]]), torch.from_numpy(masks[e, : n_obj[e]]))
+                sums[e], counts[e] = R.write_mean_frame(sums[e], counts[e], img, obs, torch.from_numpy(idx[e]).long(), stride=8)
+            got = batch.sums[e].cpu().numpy()
+            ref = sums[e].numpy()
+            assert np.abs(got - ref).max() <= SUM_TOL * max(np.abs(ref).max(), 1e-30), (t, e)
+            assert np.array_equal(got == 0, ref == 0)                                     # touched-cell set: exact
+            assert np.array_equal(batch.counts[e].cpu().numpy(), counts[e].numpy()), (t, e)
+        assert sum(int(f.abs().sum()) for f in batch._frame_cnt2) == 0
 
 
 # --------------------------------------------------------------------------------------------------------
@@ -332,12 +370,59 @@ def test_write_max_vs_oracle(eod, cuda, layout, stride):
         assert int(d_key.abs().sum()) == 0
 
 
+def test_write_max_config3_full_size(eod, cuda):
+    """BASELINE configs[2]: SMNet-style height-max projection, 480x640, C=256, 0.02 m cells, 1000x1000 map.  Geometry
+    (unclipped cell coordinates, outlier mask, heights) comes from the back-projection kernel exactly as
+    create_coco_mp3d.py:157-165 obtains it from Projector.forward(..., return_heights=True); argmax, height map,
+    observed set and the winners' feature rows must equal the oracle bit for bit."""
+    H, W, C, mw, mh, T_ = 480, 640, 256, 1000, 1000, 3
+    cells = mw * mh
+    ep = eod.episodes.make_episode(4321, T_, H, W, mw, mh, 0.02, room_size=(24.0, 16.0))     # room larger than the 20 m map: out-of-map pixels
+    intr = eod.compute_intrinsics(W, H, math.radians(67.5))
+    Tm = eod.transform3d(torch.from_numpy(ep.xyzhe))
+    sh = _t(np.concatenate([ep.map_world_shift, np.zeros(3, np.float32)])[None], cuda)      # Projector subtracts map_world_shift as world_shift_origin
+    state = torch.zeros(cells, C)
+    observed = torch.zeros(cells, dtype=torch.bool)
+    hmap = torch.zeros(cells)
+    d_state = torch.zeros((1, cells, C), device=cuda)
+    d_obs = torch.zeros((1, cells), dtype=torch.uint8, device=cuda)
+    d_hmap = torch.zeros((1, cells), device=cuda)
+    d_key = torch.zeros((1, cells), dtype=torch.int64, device=cuda)
+    d_arg = torch.zeros((1, cells), dtype=torch.int32, device=cuda)
+    gen = torch.Generator(device=cuda).manual_seed(5)
+    n_raised = 0
+    for t in range(T_):
+        r = eod.ops.backproject_quantize(_t(ep.depth[t:t + 1], cuda), Tm[t:t + 1, :3].reshape(1, 12).to(cuda), sh, intr, 0.02, mw, mh,
+                                         want_q2=True, want_outlier=True, want_height=True)
+        o = oracle.backproject_quantize(ep.depth[t], Tm[t].numpy(), intr, ep.map_world_shift, np.zeros(3, np.float32), 0.02, mw, mh, 0, 0.5)
+        assert np.array_equal(r["q2"][0].cpu().numpy(), o["q2"]) and np.array_equal(r["outlier"][0].cpu().numpy(), o["outlier"])
+        assert np.array_equal(r["height"][0].cpu().numpy(), o["height"])
+        q2 = r["q2"][0]
+        flat = (q2[..., 1] * mw + q2[..., 0]).clamp(0, cells - 1).to(torch.int32)             # only inliers are used; they are in range
+        feat = torch.randn((1, H, W, C), device=cuda, generator=gen)
+        eod.ops.write_max(r["height"], flat[None].contiguous(), r["outlier"], feat, d_hmap, d_key, d_arg, d_obs, d_state, 1, 1)
+        torch.cuda.synchronize()
+        inl = ~torch.from_numpy(o["outlier"].astype(bool))
+        state, observed, hmap, arg, m = R.smnet_heightmax_frame(state, observed, hmap, feat[0].cpu(), torch.from_numpy(o["q2"]), inl,
+                                                                torch.from_numpy(o["height"]), mw, 1)
+        pix_of_rank = np.nonzero(inl.numpy().reshape(-1))[0]
+        arg_pix = np.where(arg.numpy() >= 0, pix_of_rank[np.maximum(arg.numpy(), 0)], -1)
+        assert np.array_equal(d_arg[0].cpu().numpy(), arg_pix), t
+        assert np.array_equal(d_hmap[0].cpu().numpy(), hmap.numpy())
+        assert np.array_equal(d_obs[0].cpu().numpy().astype(bool), observed.numpy())
+        assert torch.equal(d_state[0].cpu(), state)
+        assert int(d_key.abs().sum()) == 0
+        n_raised += int(m.sum())
+    assert n_raised > 1000 and 0 < float(inl.float().mean()) < 1                              # the case exercises inliers AND outliers
+
+
 # --------------------------------------------------------------------------------------------------------
 # full-size, size-independent properties (BASELINE sizes: 480x640, C=256, 500x500 grid)
 # --------------------------------------------------------------------------------------------------------
-def test_full_size_properties(eod, cuda):
-    E, C, H, W, mw, mh = 2, 256, 480, 640, 500, 500
-    eps = [eod.episodes.make_episode(1234 + e, n_frames=3) for e in range(E)]
+@pytest.mark.parametrize("C,mw,mh,cell", [(256, 500, 500, 0.2), (512, 1000, 1000, 0.02)], ids=["configs1-2", "configs5"])
+def test_full_size_properties(eod, cuda, C, mw, mh, cell):
+    E, H, W = 2, 480, 640
+    eps = [eod.episodes.make_episode(1234 + e, 3, H, W, mw, mh, cell) for e in range(E)]
     intr = eod.compute_intrinsics(W, H, math.radians(67.5))
     batch = eod.EpisodeBatch(E, mw, mh, C, H, W, cuda)
     shifts = _t(np.stack([np.concatenate([np.zeros(3, np.float32), ep.map_world_shift]) for ep in eps]), cuda)
@@ -349,10 +434,10 @@ def test_full_size_properties(eod, cuda):
         pose = T[:, :3].reshape(E, 12).to(cuda)
         feat = torch.randn((E, C, H, W), device=cuda, generator=gen)
         before = batch.sums.clone()
-        levels = batch.step(depth, pose, shifts, intr, 0.2, feat)
+        levels = batch.step(depth, pose, shifts, intr, cell, feat)
         torch.cuda.synchronize()
         for e in range(E):                                              # indices: bit-exact vs the oracle at full size
-            o = oracle.backproject_quantize(eps[e].depth[t], T[e].numpy(), intr, np.zeros(3, np.float32), eps[e].map_world_shift, 0.2, mw, mh, 0, 0.5, want=("idx",))
+            o = oracle.backproject_quantize(eps[e].depth[t], T[e].numpy(), intr, np.zeros(3, np.float32), eps[e].map_world_shift, cell, mw, mh, 0, 0.5, want=("idx",))
             assert np.array_equal(batch.idx[e].cpu().numpy(), o["idx"])
         # conservation: sum_c n_c * (delta sums)_c == sum over pixels of the features (per channel)
         delta = batch.sums - before
