@@ -15,7 +15,7 @@ EOD_OK = 0
 ORDER_ZX, ORDER_XZ = 0, 1
 LAYOUT_CHW, LAYOUT_HWC = 0, 1
 FUSE_SUM, FUSE_MEM_ONLY, FUSE_IMAGE_ONLY = 0, 1, 2
-WRITE_AUTO, WRITE_LDG, WRITE_TMA, WRITE_TMA_DRY = 0, 1, 2, 3
+WRITE_AUTO, WRITE_LDG, WRITE_TMA, WRITE_TMA_DRY, WRITE_DET = 0, 1, 2, 3, 4
 
 # name -> argtypes (restype is int unless listed in _RESTYPES); mirrors include/eod_memory.h one to one
 _P = c_void_p
@@ -28,6 +28,9 @@ SIGNATURES = {
     "eod_frame_count": [_P, _P, _P, c_int, c_int, c_int64, _P, _P, _P, _P, c_int, _P],
     "eod_expand_counts": [_P, _P, c_int, c_int, c_int64, _P, _P],
     "eod_write_mean": [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int64, _P, c_int, _P, _P],
+    "eod_write_mean_det_workspace_bytes": [c_int, c_int, c_int, c_int64, c_int],
+    "eod_write_mean_det_status_offset": [c_int, c_int64],
+    "eod_write_mean_det": [_P, _P, _P, _P, c_int, c_int, c_int, c_int64, _P, _P, c_int64, _P],
     "eod_finalize_counts": [_P, c_int, c_int, c_int64, _P, _P, _P, _P, _P, c_int, _P],
     "eod_box_to_image_features": [_P, _P, c_int, c_int, c_int, _P, _P, _P],
     "eod_masks_observed": [_P, _P, c_int, c_int, c_int, _P, _P],
@@ -39,7 +42,7 @@ SIGNATURES = {
     "eod_reset_touched": [_P, _P, _P, c_int64, c_int, _P],
     "eod_fuse": [_P, _P, c_float, c_int, c_int64, _P, _P],
 }
-_RESTYPES = {"eod_last_error": c_char_p}
+_RESTYPES = {"eod_last_error": c_char_p, "eod_write_mean_det_workspace_bytes": c_int64, "eod_write_mean_det_status_offset": c_int64}
 
 
 class EodError(RuntimeError):

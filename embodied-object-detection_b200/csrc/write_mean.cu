@@ -437,11 +437,22 @@ __device__ __forceinline__ uint32_t lds8(uint32_t addr)
 // ceiling of this tile shape; selected with variant EOD_WRITE_TMA_DRY (bring-up / profiling only).
 // kPixN: the per-pixel reciprocal divisors 1/n_cell arrive with the tile (pix_n workspace); otherwise the
 // divisor of a run is a dependent global load from frame_cnt.
-template <int C, bool kDry, bool kPixN>
+// kDet: deterministic variant - a run's (unscaled) channel sums are STORED to partials[tile_off[tile] + r] (raster run
+// order, no atomics) for the segmented reduce of det_reduce_kernel; runs beyond the workspace capacity fall back to
+// the reductions of the default variant and raise *status.
+struct DetArgs {
+    const int32_t *tile_off;     // (E, tiles) exclusive scan of the per-tile run counts, restarting per episode
+    float *partials;             // (E, cap, C)
+    int32_t *run_cell;           // (E, cap)
+    int32_t *status;             // set to 1 when a run did not fit
+    int cap;                     // runs per episode the workspace holds
+};
+
+template <int C, bool kDry, bool kPixN, bool kDet>
 __global__ void __launch_bounds__(TmaCfg<C>::kThreads, 1)
 write_mean_chw_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t *__restrict__ idx, const uint8_t *__restrict__ samp,
                           const uint32_t *__restrict__ frame_cnt, const float *__restrict__ pix_n, int HW, int64_t n_cells,
-                          int tiles_per_ep, int n_tiles, int group, float *__restrict__ sums)
+                          int tiles_per_ep, int n_tiles, int group, float *__restrict__ sums, const DetArgs det)
 {
     using Cfg = TmaCfg<C>;
     extern __shared__ unsigned char smem_dyn[];
@@ -509,10 +520,11 @@ write_mean_chw_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int32_
     const uint32_t sw = lane & 7;                                                  // rows l + 32k share the swizzle phase
     uint32_t phase = 0;
     for (int u = warp; u < my_units; u += Cfg::kStages, phase ^= 1) {
+        int t, cb;
+        unit_of(u, t, cb);
+        int run_pos = kDet ? __ldg(det.tile_off + t) : 0;          // issued before the wait: its latency hides behind the TMA load
         mbar_wait_s(fullb, phase);
         if (!kDry) {
-            int t, cb;
-            unit_of(u, t, cb);
             const int e = t / tiles_per_ep;
             // run structure of the tile: lane p looks at pixel p
             const int cell = (int)lds32(aux + Cfg::kAuxCells + 4 * lane);
@@ -551,6 +563,16 @@ write_mean_chw_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int32_
                     }
                 }
                 const int rc = __shfl_sync(0xffffffffu, cell, p0);
+                if (kDet) {
+                    const int pos = run_pos++;
+                    if (pos < det.cap) {
+                        float *d = det.partials + ((size_t)e * det.cap + pos) * C + cb * Cfg::kChanBlk + lane;
+                        d[0] = a0; d[32] = a1; d[64] = a2; d[96] = a3;
+                        if (cb == 0 && lane == 0) det.run_cell[(size_t)e * det.cap + pos] = rc;
+                        continue;
+                    }
+                    if (cb == 0 && lane == 0) *det.status = 1;     // workspace too small: correct, but not reproducible
+                }
                 float inv = __shfl_sync(0xffffffffu, my_inv, p0);
                 if (!kPixN) inv = __frcp_rn((float)(__ldg(cnt_e + rc) & 0x7fffffffu));
                 float *d = dst + (size_t)rc * C;
@@ -644,14 +666,14 @@ PFN_encodeTiled get_encode_fn()
     return fn;
 }
 
-template <int C, bool kDry, bool kPixN>
+template <int C, bool kDry, bool kPixN, bool kDet = false>
 int launch_tma_kernel(const CUtensorMap &tmap, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt, const float *pix_n,
-                      int E, int HW, int64_t n_cells, float *sums, cudaStream_t st)
+                      int E, int HW, int64_t n_cells, float *sums, cudaStream_t st, const DetArgs det = DetArgs{})
 {
     using Cfg = TmaCfg<C>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(write_mean_chw_tma_kernel<C, kDry, kPixN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        cudaFuncSetAttribute(write_mean_chw_tma_kernel<C, kDry, kPixN, kDet>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         attr_set = true;
     }
     const int tiles_per_ep = HW / TILE_PX, n_tiles = tiles_per_ep * E;
@@ -660,18 +682,16 @@ int launch_tma_kernel(const CUtensorMap &tmap, const int32_t *idx, const uint8_t
     while (group > 1 && n_tiles % group) group >>= 1;
     const int n_groups = n_tiles / group;
     const int grid = n_groups < eod_num_sms() ? n_groups : eod_num_sms();
-    write_mean_chw_tma_kernel<C, kDry, kPixN><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmap, idx, samp, frame_cnt, pix_n, HW, n_cells, tiles_per_ep, n_tiles, group, sums);
+    write_mean_chw_tma_kernel<C, kDry, kPixN, kDet><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmap, idx, samp, frame_cnt, pix_n, HW, n_cells, tiles_per_ep, n_tiles, group, sums, det);
     return eod_check_launch("eod_write_mean[tma]");
 }
 
-template <int C, bool kDry>
-int launch_tma(const float *feat, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt, const float *pix_n, int E, int HW,
-               int64_t n_cells, float *sums, cudaStream_t st)
+template <int C>
+int make_feature_tmap(const float *feat, int E, int HW, CUtensorMap *tmap)
 {
     using Cfg = TmaCfg<C>;
     PFN_encodeTiled enc = get_encode_fn();
     EOD_REQUIRE(enc, EOD_ERR_LAUNCH, "eod_write_mean: cuTensorMapEncodeTiled entry point unavailable");
-    CUtensorMap tmap;
     const cuuint64_t gdim[3] = {(cuuint64_t)HW, (cuuint64_t)C, (cuuint64_t)E};
     const cuuint64_t gstr[2] = {(cuuint64_t)HW * 4, (cuuint64_t)HW * C * 4};
     const cuuint32_t box[3] = {TILE_PX, (cuuint32_t)Cfg::kChanBlk, 1};
@@ -679,11 +699,362 @@ int launch_tma(const float *feat, const int32_t *idx, const uint8_t *samp, const
     static const int promo_env = [] { const char *v = getenv("EOD_TMA_L2_PROMOTION"); return v ? atoi(v) : 256; }();   // tuning knob: 0 | 128 | 256
     const CUtensorMapL2promotion promo = promo_env == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
                                          : (promo_env == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
-    const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(feat), gdim, gstr, box, estr,
+    const CUresult r = enc(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(feat), gdim, gstr, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     EOD_REQUIRE(r == CUDA_SUCCESS, EOD_ERR_LAUNCH, "eod_write_mean: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return EOD_OK;
+}
+
+template <int C, bool kDry>
+int launch_tma(const float *feat, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt, const float *pix_n, int E, int HW,
+               int64_t n_cells, float *sums, cudaStream_t st)
+{
+    CUtensorMap tmap;
+    const int rc = make_feature_tmap<C>(feat, E, HW, &tmap);
+    if (rc) return rc;
     if (pix_n) return launch_tma_kernel<C, kDry, true>(tmap, idx, samp, frame_cnt, pix_n, E, HW, n_cells, sums, st);
     return launch_tma_kernel<C, kDry, false>(tmap, idx, samp, frame_cnt, nullptr, E, HW, n_cells, sums, st);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// deterministic variant (EOD_WRITE_DET): raster-ordered run partials + per-cell segmented reduce in fixed order
+//
+//   det_tile_runs      runs (with samples) per 32-pixel tile                       -> tile_off (counts)
+//   det_scan_tiles     exclusive scan per episode                                 -> tile_off, n_runs
+//   det_cell_runs      runs per cell (only runs that fit the workspace); the first run of a cell appends the cell
+//                      to the episode's compact cell list                         -> cell_runs, cell_list, n_list
+//   det_scan_list      exclusive scan of the listed cells' run counts             -> list_off, cell_off[cell]
+//   main pass (kDet)   partials[tile_off[tile] + r] = run sums, run_cell[...] = cell            (no atomics)
+//   det_claim          run -> slot inside its cell's segment (claim order is arbitrary)         -> seg
+//   det_reduce         warp per listed cell: SORT the segment by run position (registers / shared-memory bitonic),
+//                      add the partials in that order, divide by n, add ONCE to sums[cell]
+//                      => bitwise reproducible, and the reference's own arithmetic shape
+// List order and slot order depend on scheduling; the result does not: every cell is reduced on its own, in raster order.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void det_tile_masks(const int32_t *idx, const uint8_t *samp, size_t g0, unsigned lane, int &cell, unsigned &heads,
+                                               unsigned &samps)
+{
+    cell = __ldg(idx + g0 + lane);
+    const int prev = __shfl_up_sync(0xffffffffu, cell, 1);
+    heads = __ballot_sync(0xffffffffu, lane == 0 || prev != cell);
+    samps = samp ? __ballot_sync(0xffffffffu, __ldg(samp + g0 + lane) != 0) : 0xffffffffu;
+}
+
+// does the run starting at head bit p0 contain a sampled pixel?
+__device__ __forceinline__ bool det_run_sampled(unsigned heads, unsigned samps, int p0)
+{
+    const unsigned above = heads & ~((2u << p0) - 1u);
+    const int p1 = above ? (__ffs(above) - 1) : 32;
+    const unsigned m = samps & (0xffffffffu >> (32 - p1)) & (0xffffffffu << p0);
+    return m != 0;
+}
+
+__global__ void __launch_bounds__(256) det_tile_runs_kernel(const int32_t *__restrict__ idx, const uint8_t *__restrict__ samp, int HW,
+                                                            int tiles_per_ep, int32_t *__restrict__ tile_off, int32_t *__restrict__ n_list)
+{
+    const int e = blockIdx.y, tile = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const unsigned lane = threadIdx.x & 31;
+    if (blockIdx.x == 0 && threadIdx.x == 0) n_list[e] = 0;        // consumed by the previous call's reduce, refilled by det_cell_runs
+    if (tile >= tiles_per_ep) return;
+    int cell;
+    unsigned heads, samps;
+    det_tile_masks(idx, samp, (size_t)e * HW + (size_t)tile * 32, lane, cell, heads, samps);
+    const bool mine = ((heads >> lane) & 1u) && det_run_sampled(heads, samps, lane);
+    const unsigned runs = __ballot_sync(0xffffffffu, mine);
+    if (lane == 0) tile_off[(size_t)e * tiles_per_ep + tile] = __popc(runs);
+}
+
+// one CTA per episode: in-place exclusive scan of n values (chunks of 1024 with a running carry); total -> *total_out
+__device__ void det_block_exclusive_scan(const int32_t *in, int32_t *out, int n, int32_t *total_out)
+{
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < n ? in[i] : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((int)lane >= o) x += y;
+        }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, w, o);
+                if ((int)lane >= o) w += y;
+            }
+            s_warp[lane] = w;                              // inclusive scan of the warp totals
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        const int excl = carry + (warp ? s_warp[warp - 1] : 0) + x - v;
+        if (i < n) out[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + s_warp[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total_out) *total_out = s_carry;
+}
+
+__global__ void __launch_bounds__(1024) det_scan_tiles_kernel(int32_t *__restrict__ tile_off, int tiles_per_ep, int32_t *__restrict__ n_runs)
+{
+    const int e = blockIdx.x;
+    det_block_exclusive_scan(tile_off + (size_t)e * tiles_per_ep, tile_off + (size_t)e * tiles_per_ep, tiles_per_ep, n_runs + e);
+}
+
+__global__ void __launch_bounds__(256) det_cell_runs_kernel(const int32_t *__restrict__ idx, const uint8_t *__restrict__ samp, int HW,
+                                                            int tiles_per_ep, int64_t n_cells, const int32_t *__restrict__ tile_off, int cap,
+                                                            int32_t *__restrict__ cell_runs, int32_t *__restrict__ cell_list,
+                                                            int32_t *__restrict__ n_list)
+{
+    const int e = blockIdx.y, tile = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const unsigned lane = threadIdx.x & 31;
+    if (tile >= tiles_per_ep) return;
+    int cell;
+    unsigned heads, samps;
+    det_tile_masks(idx, samp, (size_t)e * HW + (size_t)tile * 32, lane, cell, heads, samps);
+    const bool mine = ((heads >> lane) & 1u) && det_run_sampled(heads, samps, lane);
+    const unsigned runs = __ballot_sync(0xffffffffu, mine);
+    if (mine) {
+        const int pos = __ldg(tile_off + (size_t)e * tiles_per_ep + tile) + __popc(runs & ((1u << lane) - 1u));
+        if (pos < cap && atomicAdd(cell_runs + (size_t)e * n_cells + cell, 1) == 0)      // integer count: order-independent
+            cell_list[(size_t)e * cap + atomicAdd(n_list + e, 1)] = cell;                // #cells <= #runs <= cap
+    }
+}
+
+// one CTA per episode: list_off = exclusive scan of the listed cells' run counts; cell_off[cell] = its segment start
+__global__ void __launch_bounds__(1024) det_scan_list_kernel(const int32_t *__restrict__ cell_runs, const int32_t *__restrict__ cell_list,
+                                                             const int32_t *__restrict__ n_list, int cap, int64_t n_cells,
+                                                             int32_t *__restrict__ list_off, int32_t *__restrict__ cell_off)
+{
+    const int e = blockIdx.x;
+    const int n = __ldg(n_list + e);
+    const int32_t *list = cell_list + (size_t)e * cap;
+    int32_t *off = list_off + (size_t)e * cap;
+    for (int i = threadIdx.x; i < n; i += 1024) off[i] = cell_runs[(size_t)e * n_cells + list[i]];
+    __syncthreads();
+    det_block_exclusive_scan(off, off, n, nullptr);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += 1024) cell_off[(size_t)e * n_cells + list[i]] = off[i];
+}
+
+__global__ void __launch_bounds__(256) det_claim_kernel(const int32_t *__restrict__ run_cell, const int32_t *__restrict__ n_runs, int cap,
+                                                        int64_t n_cells, const int32_t *__restrict__ cell_off, int32_t *__restrict__ cell_runs,
+                                                        int32_t *__restrict__ seg)
+{
+    const int e = blockIdx.y, pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= min(__ldg(n_runs + e), cap)) return;
+    const int c = __ldg(run_cell + (size_t)e * cap + pos);
+    const int k = atomicSub(cell_runs + (size_t)e * n_cells + c, 1) - 1;           // leaves cell_runs all-zero again
+    seg[(size_t)e * cap + cell_off[(size_t)e * n_cells + c] + k] = pos;
+}
+
+// ascending bitonic sort of buf[0, n2) (n2 a power of two >= 32) by one warp
+__device__ __forceinline__ void bitonic_sort_warp(int *buf, int n2, unsigned lane)
+{
+    for (int size = 2; size <= n2; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int q = lane; q < (n2 >> 1); q += 32) {
+                const int lo = 2 * q - (q & (stride - 1)), hi = lo + stride;
+                const int a = buf[lo], b = buf[hi];
+                const bool asc = (lo & size) == 0;
+                if ((a > b) == asc) { buf[lo] = b; buf[hi] = a; }
+            }
+            __syncwarp();
+        }
+}
+
+constexpr int DET_SORT_MAX = 2048;       // segment length a warp sorts in shared memory; longer ones use selection
+constexpr int DET_WARPS = 4;
+
+// warp per listed cell
+template <int C>
+__global__ void __launch_bounds__(32 * DET_WARPS) det_reduce_kernel(const int32_t *__restrict__ cell_list, const int32_t *__restrict__ list_off,
+                                                                    const int32_t *__restrict__ n_list, const int32_t *__restrict__ n_runs, int cap,
+                                                                    int64_t n_cells, int32_t *__restrict__ seg, const float *__restrict__ partials,
+                                                                    const uint32_t *__restrict__ frame_cnt, float *__restrict__ sums)
+{
+    constexpr int J = C / 32;
+    __shared__ int s_sort[DET_WARPS][DET_SORT_MAX];
+    const int e = blockIdx.y;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = __ldg(n_list + e);
+    const int total = min(__ldg(n_runs + e), cap);
+    const float *part_e = partials + (size_t)e * cap * C + lane;
+    int *buf = s_sort[warp];
+    for (int i = blockIdx.x * DET_WARPS + warp; i < n; i += gridDim.x * DET_WARPS) {
+        const int cell = __ldg(cell_list + (size_t)e * cap + i);
+        const int s0 = __ldg(list_off + (size_t)e * cap + i);
+        const int s1 = (i + 1 < n) ? __ldg(list_off + (size_t)e * cap + i + 1) : total;
+        const int k = s1 - s0;
+        int32_t *sg = seg + (size_t)e * cap + s0;
+        float acc[J];
+#pragma unroll
+        for (int j = 0; j < J; ++j) acc[j] = 0.f;
+
+        auto add_row = [&](int pos) {
+            const float *row = part_e + (size_t)pos * C;
+#pragma unroll
+            for (int j = 0; j < J; ++j) acc[j] = __fadd_rn(acc[j], __ldg(row + 32 * j));
+        };
+        // rows of `count` sorted positions, U rows in flight, added strictly in order
+        auto sum_sorted = [&](const int *sorted, int count) {
+            constexpr int U = (J <= 8) ? 8 : 4;
+            int it = 0;
+            for (; it + U <= count; it += U) {
+                float r[U][J];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const float *row = part_e + (size_t)sorted[it + u] * C;
+#pragma unroll
+                    for (int j = 0; j < J; ++j) r[u][j] = __ldg(row + 32 * j);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int j = 0; j < J; ++j) acc[j] = __fadd_rn(acc[j], r[u][j]);
+            }
+            for (; it < count; ++it) add_row(sorted[it]);
+        };
+
+        if (k <= DET_SORT_MAX) {
+            int n2 = 32;
+            while (n2 < k) n2 <<= 1;
+            for (int q = lane; q < n2; q += 32) buf[q] = q < k ? sg[q] : 0x7fffffff;
+            __syncwarp();
+            bitonic_sort_warp(buf, n2, lane);
+            sum_sorted(buf, k);
+        } else if (k <= 64 * DET_SORT_MAX) {
+            // long segment (a cell that fills much of the frame): sort it chunk by chunk in shared memory, write the
+            // sorted chunks back in place, then merge them (lane l feeds chunks l and l + 32) 2048 positions at a time
+            const int m = (k + DET_SORT_MAX - 1) / DET_SORT_MAX;
+            for (int c = 0; c < m; ++c) {
+                int32_t *chunk = sg + c * DET_SORT_MAX;
+                const int len = min(DET_SORT_MAX, k - c * DET_SORT_MAX);
+                int n2 = 32;
+                while (n2 < len) n2 <<= 1;
+                for (int q = lane; q < n2; q += 32) buf[q] = q < len ? chunk[q] : 0x7fffffff;
+                __syncwarp();
+                bitonic_sort_warp(buf, n2, lane);
+                for (int q = lane; q < len; q += 32) chunk[q] = buf[q];
+                __syncwarp();
+            }
+            const int c0 = (int)lane, c1 = (int)lane + 32;
+            const int len0 = c0 < m ? min(DET_SORT_MAX, k - c0 * DET_SORT_MAX) : 0;
+            const int len1 = c1 < m ? min(DET_SORT_MAX, k - c1 * DET_SORT_MAX) : 0;
+            int ptr0 = 0, ptr1 = 0;
+            int head0 = len0 > 0 ? sg[c0 * DET_SORT_MAX] : 0x7fffffff;
+            int head1 = len1 > 0 ? sg[c1 * DET_SORT_MAX] : 0x7fffffff;
+            for (int done = 0; done < k; done += DET_SORT_MAX) {
+                const int cnt = min(DET_SORT_MAX, k - done);
+                for (int it = 0; it < cnt; ++it) {
+                    int best = min(head0, head1);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+                    if (head0 == best) { ++ptr0; head0 = ptr0 < len0 ? sg[c0 * DET_SORT_MAX + ptr0] : 0x7fffffff; }
+                    else if (head1 == best) { ++ptr1; head1 = ptr1 < len1 ? sg[c1 * DET_SORT_MAX + ptr1] : 0x7fffffff; }
+                    if (lane == 0) buf[it] = best;
+                }
+                __syncwarp();
+                sum_sorted(buf, cnt);
+                __syncwarp();
+            }
+        } else {
+            int last = -1;                                         // last resort: smallest position greater than the last one
+            for (int it = 0; it < k; ++it) {
+                int best = 0x7fffffff;
+                for (int q = lane; q < k; q += 32) {
+                    const int v = sg[q];
+                    if (v > last && v < best) best = v;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+                last = best;
+                add_row(best);
+            }
+        }
+        const float nn = (float)(__ldg(frame_cnt + (size_t)e * n_cells + cell) & 0x7fffffffu);
+        float *dst = sums + ((size_t)e * n_cells + cell) * C + lane;
+#pragma unroll
+        for (int j = 0; j < J; ++j) dst[32 * j] = __fadd_rn(dst[32 * j], __fdiv_rn(acc[j], nn));     // custom_rcnn.py:934, :742
+        __syncwarp();
+    }
+}
+
+struct DetWorkspace {
+    int32_t *tile_off, *n_runs, *n_list, *status, *cell_runs, *cell_off, *run_cell, *seg, *cell_list, *list_off;
+    float *partials;
+    int cap;
+};
+
+size_t det_align(size_t x) { return (x + 255) & ~size_t(255); }
+
+// Carves the caller's workspace.  cell_runs must be all-zero between frames (the library leaves it so; the caller
+// zero-fills the workspace once).  Returns the bytes needed for `cap` runs per episode.
+size_t det_carve(void *ws, int E, int C, int tiles_per_ep, int64_t n_cells, int cap, DetWorkspace *out)
+{
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o += det_align(bytes); return ws ? (char *)ws + at : (char *)nullptr; };
+    DetWorkspace w;
+    w.cell_runs = (int32_t *)take((size_t)E * n_cells * 4);
+    w.status = (int32_t *)take(256);
+    w.n_runs = (int32_t *)take((size_t)E * 4);
+    w.n_list = (int32_t *)take((size_t)E * 4);
+    w.tile_off = (int32_t *)take((size_t)E * tiles_per_ep * 4);
+    w.cell_off = (int32_t *)take((size_t)E * n_cells * 4);
+    w.run_cell = (int32_t *)take((size_t)E * cap * 4);
+    w.seg = (int32_t *)take((size_t)E * cap * 4);
+    w.cell_list = (int32_t *)take((size_t)E * cap * 4);
+    w.list_off = (int32_t *)take((size_t)E * cap * 4);
+    w.partials = (float *)take((size_t)E * cap * C * 4);
+    w.cap = cap;
+    if (out) *out = w;
+    return o;
+}
+
+template <int C>
+int launch_det(const float *feat, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt, int E, int HW, int64_t n_cells,
+               float *sums, void *ws, size_t ws_bytes, cudaStream_t st)
+{
+    EOD_REQUIRE(HW % TILE_PX == 0 && (!samp || (reinterpret_cast<uintptr_t>(samp) % 16 == 0)), EOD_ERR_UNSUPPORTED,
+                "eod_write_mean_det: needs HW %% 32 == 0 and a 16-byte aligned sample mask");
+    EOD_REQUIRE(n_cells < (int64_t)INT32_MAX, EOD_ERR_BADARG, "eod_write_mean_det: grid too large");
+    const int tiles_per_ep = HW / TILE_PX;
+    // capacity: whatever the workspace holds beyond the fixed planes (at most one run per pixel)
+    const size_t fixed = det_carve(nullptr, E, C, tiles_per_ep, n_cells, 0, nullptr);
+    EOD_REQUIRE(ws && eod_aligned16(ws) && ws_bytes > fixed + 4096, EOD_ERR_BADARG, "eod_write_mean_det: workspace missing or too small (see eod_write_mean_det_workspace_bytes)");
+    int64_t cap = (int64_t)((ws_bytes - fixed - 6 * 256) / ((size_t)E * (C * 4 + 16)));
+    if (cap > HW) cap = HW;
+    EOD_REQUIRE(cap >= 1, EOD_ERR_BADARG, "eod_write_mean_det: workspace too small");
+    DetWorkspace w;
+    while (det_carve(ws, E, C, tiles_per_ep, n_cells, (int)cap, &w) > ws_bytes) --cap;
+    CUtensorMap tmap;
+    int rc = make_feature_tmap<C>(feat, E, HW, &tmap);
+    if (rc) return rc;
+    dim3 gt((tiles_per_ep + 7) / 8, E);
+    det_tile_runs_kernel<<<gt, 256, 0, st>>>(idx, samp, HW, tiles_per_ep, w.tile_off, w.n_list);
+    det_scan_tiles_kernel<<<E, 1024, 0, st>>>(w.tile_off, tiles_per_ep, w.n_runs);
+    det_cell_runs_kernel<<<gt, 256, 0, st>>>(idx, samp, HW, tiles_per_ep, n_cells, w.tile_off, w.cap, w.cell_runs, w.cell_list, w.n_list);
+    det_scan_list_kernel<<<E, 1024, 0, st>>>(w.cell_runs, w.cell_list, w.n_list, w.cap, n_cells, w.list_off, w.cell_off);
+    if ((rc = eod_check_launch("eod_write_mean_det[prepass]"))) return rc;
+    DetArgs det{w.tile_off, w.partials, w.run_cell, w.status, w.cap};
+    rc = launch_tma_kernel<C, false, false, true>(tmap, idx, samp, frame_cnt, nullptr, E, HW, n_cells, sums, st, det);
+    if (rc) return rc;
+    dim3 gc((w.cap + 255) / 256, E);
+    det_claim_kernel<<<gc, 256, 0, st>>>(w.run_cell, w.n_runs, w.cap, n_cells, w.cell_off, w.cell_runs, w.seg);
+    // at most min(cells, cap) cells carry runs; warps beyond n_list[e] exit at once
+    const int64_t max_list = n_cells < (int64_t)w.cap ? n_cells : (int64_t)w.cap;
+    const int64_t want_blocks = (max_list + DET_WARPS - 1) / DET_WARPS;
+    dim3 gr((unsigned)(want_blocks < 128 ? want_blocks : 128), E);          // warps stride over the episode's cell list
+    det_reduce_kernel<C><<<gr, 32 * DET_WARPS, 0, st>>>(w.cell_list, w.list_off, w.n_list, w.n_runs, w.cap, n_cells, w.seg, w.partials, frame_cnt, sums);
+    return eod_check_launch("eod_write_mean_det[reduce]");
 }
 
 template <int C>
@@ -768,6 +1139,35 @@ extern "C" int eod_finalize_counts(const int32_t *idx, int n_episodes, int HW, i
     dim3 grid((HW + 255) / 256, n_episodes);
     finalize_counts_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(idx, HW, n_cells, frame_cnt, counts, touched, sums, (__half *)norm16, C);
     return eod_check_launch("eod_finalize_counts");
+}
+
+extern "C" int64_t eod_write_mean_det_workspace_bytes(int n_episodes, int C, int HW, int64_t n_cells, int runs_per_episode)
+{
+    if (n_episodes <= 0 || C <= 0 || HW <= 0 || n_cells <= 0) return -1;
+    const int cap = runs_per_episode > 0 ? (runs_per_episode < HW ? runs_per_episode : HW) : HW / 4;
+    return (int64_t)det_carve(nullptr, n_episodes, C, HW / TILE_PX, n_cells, cap, nullptr) + 4096;
+}
+
+extern "C" int64_t eod_write_mean_det_status_offset(int n_episodes, int64_t n_cells)
+{
+    return (int64_t)det_align((size_t)n_episodes * n_cells * 4);
+}
+
+extern "C" int eod_write_mean_det(const float *feat, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt, int n_episodes, int C,
+                                  int HW, int64_t n_cells, float *sums, void *workspace, int64_t workspace_bytes, eod_stream_t stream)
+{
+    EOD_REQUIRE(feat && idx && frame_cnt && sums, EOD_ERR_BADARG, "eod_write_mean_det: null pointer");
+    EOD_REQUIRE(n_episodes > 0 && n_episodes <= 65535 && HW > 0 && n_cells > 0 && workspace_bytes > 0, EOD_ERR_BADARG, "eod_write_mean_det: bad sizes");
+    EOD_REQUIRE(eod_aligned16(feat) && eod_aligned16(idx) && eod_aligned16(sums), EOD_ERR_ALIGN, "eod_write_mean_det: pointers must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (C) {
+    case 128: return launch_det<128>(feat, idx, samp, frame_cnt, n_episodes, HW, n_cells, sums, workspace, (size_t)workspace_bytes, st);
+    case 256: return launch_det<256>(feat, idx, samp, frame_cnt, n_episodes, HW, n_cells, sums, workspace, (size_t)workspace_bytes, st);
+    case 512: return launch_det<512>(feat, idx, samp, frame_cnt, n_episodes, HW, n_cells, sums, workspace, (size_t)workspace_bytes, st);
+    default:
+        eod_set_error("eod_write_mean_det: C=%d not compiled in (128, 256, 512)", C);
+        return EOD_ERR_UNSUPPORTED;
+    }
 }
 
 extern "C" int eod_expand_counts(const int32_t *idx, const uint32_t *frame_cnt, int n_episodes, int HW, int64_t n_cells,

@@ -25,7 +25,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import ops
-from ._lib import LAYOUT_CHW, LAYOUT_HWC, ORDER_ZX, WRITE_AUTO, EodError
+from ._lib import LAYOUT_CHW, LAYOUT_HWC, ORDER_ZX, WRITE_AUTO, WRITE_DET, EodError
 
 
 class EpisodeBatch:
@@ -75,6 +75,8 @@ class EpisodeBatch:
         self._e_read: Optional[torch.cuda.Event] = None
         self._sync_next = True
         self._slots: Optional[ops.ObjectSlots] = None      # workspace of write_objects, created on first use
+        self._det_ws: Optional[ops.DetWorkspace] = None    # workspace of the deterministic write (variant=WRITE_DET)
+        self.det_runs_per_episode = 0                      # 0: HW/4 runs per episode and frame
         self.stage_events = None      # dict(stage -> [(start, end) CUDA events]) when profiling is on
 
     # current frame's planes
@@ -148,9 +150,15 @@ class EpisodeBatch:
 
     def _count(self, samp: Optional[torch.Tensor]) -> None:
         self._timed("count", ops.frame_count, self.idx, samp, self.frame_cnt)
-        self._timed("expand", ops.expand_counts, self.idx, self.frame_cnt, self.pix_inv_n)
+        if self.variant != WRITE_DET:                      # the deterministic write divides once per cell, from frame_cnt
+            self._timed("expand", ops.expand_counts, self.idx, self.frame_cnt, self.pix_inv_n)
 
     def _write(self, feat: torch.Tensor, samp: Optional[torch.Tensor]) -> None:
+        if self.variant == WRITE_DET:
+            if self._det_ws is None:
+                self._det_ws = ops.DetWorkspace(self.E, self.C, self.H * self.W, self.n_cells, self.device, self.det_runs_per_episode)
+            self._timed("write", ops.write_mean_det, feat, self.idx, samp, self.frame_cnt, self.sums, self._det_ws)
+            return
         self._timed("write", ops.write_mean, feat, self.idx, samp, self.frame_cnt, self.sums, self.layout, self.variant,
                     self.pix_inv_n)
 

@@ -10,12 +10,12 @@ import torch
 
 from . import _lib
 from ._lib import (FUSE_IMAGE_ONLY, FUSE_MEM_ONLY, FUSE_SUM, LAYOUT_CHW, LAYOUT_HWC, ORDER_XZ, ORDER_ZX, WRITE_AUTO,
-                   WRITE_LDG, WRITE_TMA, EodError, check)
+                   WRITE_DET, WRITE_LDG, WRITE_TMA, EodError, check)
 
 # kernels launched through this module since import (bench.py reports it as gpu_launches)
 launch_count = 0
 
-_LAUNCHES = {"eod_backproject_quantize": 1, "eod_sample_mask": 1, "eod_frame_count": 1, "eod_expand_counts": 1, "eod_write_mean": 1,
+_LAUNCHES = {"eod_backproject_quantize": 1, "eod_sample_mask": 1, "eod_frame_count": 1, "eod_expand_counts": 1, "eod_write_mean": 1, "eod_write_mean_det": 7,
              "eod_finalize_counts": 1, "eod_box_to_image_features": 1, "eod_masks_observed": 1, "eod_write_objects": 1, "eod_flush_slots": 2, "eod_write_max": 2, "eod_read_pool": 1,
              "eod_fuse": 1, "eod_normalize_memory": 1, "eod_reset_touched": 1}
 
@@ -152,6 +152,37 @@ def reset_touched(counts: torch.Tensor, sums: torch.Tensor, norm16: Optional[tor
         _dev(norm16, torch.float16, "norm16")
     C = sums.shape[-1]
     _call("eod_reset_touched", counts.data_ptr(), sums.data_ptr(), _ptr(norm16), counts.numel(), C, _stream())
+
+
+class DetWorkspace:
+    """Caller-owned workspace of the deterministic write (eod_write_mean_det), zero-filled once."""
+
+    def __init__(self, n_episodes: int, channels: int, hw: int, n_cells: int, device: torch.device, runs_per_episode: int = 0):
+        lib = _lib.lib()
+        self.nbytes = int(lib.eod_write_mean_det_workspace_bytes(n_episodes, channels, hw, n_cells, int(runs_per_episode)))
+        if self.nbytes <= 0:
+            raise ValueError("bad sizes for the deterministic-write workspace")
+        self.buf = torch.zeros((self.nbytes,), dtype=torch.uint8, device=device)
+        self._status_off = int(lib.eod_write_mean_det_status_offset(n_episodes, n_cells))
+
+    def overflowed(self) -> bool:
+        """True if some run did not fit since the workspace was created (those runs used fp32 reductions)."""
+        return bool(self.buf[self._status_off:self._status_off + 4].view(torch.int32).item())
+
+
+def write_mean_det(feat: torch.Tensor, idx: torch.Tensor, samp: Optional[torch.Tensor], frame_cnt: torch.Tensor,
+                   sums: torch.Tensor, ws: DetWorkspace) -> None:
+    """Deterministic main pass (CHW features, HW % 32 == 0): same contract as write_mean, bitwise reproducible."""
+    _dev(feat, torch.float32, "feat"), _dev(idx, torch.int32, "idx"), _dev(sums, torch.float32, "sums")
+    _dev(frame_cnt, torch.int32, "frame_cnt")
+    E, n_cells, C = sums.shape
+    HW = idx[0].numel()
+    if feat.numel() != E * C * HW:
+        raise ValueError(f"feat has {feat.numel()} elements, expected E*C*HW = {E * C * HW}")
+    if samp is not None:
+        _dev(samp, torch.uint8, "samp")
+    _call("eod_write_mean_det", feat.data_ptr(), idx.data_ptr(), _ptr(samp), frame_cnt.data_ptr(), E, C, HW, n_cells,
+          sums.data_ptr(), ws.buf.data_ptr(), ws.nbytes, _stream())
 
 
 def finalize_counts(idx: torch.Tensor, frame_cnt: torch.Tensor, counts: torch.Tensor,

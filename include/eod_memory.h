@@ -50,6 +50,7 @@ extern "C" {
 #define EOD_WRITE_LDG 1  /* force the LDG-staged kernel                                  */
 #define EOD_WRITE_TMA 2  /* force the TMA-staged kernel (error if shape unsupported)     */
 #define EOD_WRITE_TMA_DRY 3 /* profiling only: stream the tiles, no accumulation (no result) */
+#define EOD_WRITE_DET 4  /* host-side selector of eod_write_mean_det (deterministic segmented reduce)   */
 
 typedef void *eod_stream_t;
 
@@ -106,6 +107,21 @@ int eod_expand_counts(const int32_t *idx, const uint32_t *frame_cnt, int n_episo
 int eod_write_mean(const float *feat, int layout, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt,
                    int n_episodes, int C, int HW, int64_t n_cells, float *sums, int variant, const float *pix_inv_n,
                    eod_stream_t stream);
+
+/* Deterministic variant of the main pass (CHW features, HW %% 32 == 0): run sums are stored in raster run order
+ * (no atomics), then every touched cell adds the partial sums of its runs in ascending run position, divides by
+ * n_cell and adds the mean ONCE to sums[cell] - bitwise reproducible run to run and independent of how episodes are
+ * batched, and the arithmetic shape of custom_rcnn.py:930-934,742 (sum, divide, add).
+ * workspace: caller-owned, 256-byte aligned, zero-filled ONCE before first use (the library leaves its persistent
+ * planes zero again after every call); eod_write_mean_det_workspace_bytes(E, C, HW, cells, runs_per_episode) sizes
+ * it for runs_per_episode runs of equal cell id per episode and frame (<= 0: HW/4).  Runs that do not fit fall back
+ * to the fp32 reductions of eod_write_mean (still correct) and set the int32 at byte offset
+ * eod_write_mean_det_status_offset(E, cells) of the workspace to 1. */
+int64_t eod_write_mean_det_workspace_bytes(int n_episodes, int C, int HW, int64_t n_cells, int runs_per_episode);
+int64_t eod_write_mean_det_status_offset(int n_episodes, int64_t n_cells);
+int eod_write_mean_det(const float *feat, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt, int n_episodes,
+                       int C, int HW, int64_t n_cells, float *sums, void *workspace, int64_t workspace_bytes,
+                       eod_stream_t stream);
 
 /* Post-pass: counts[cell] += 1 for every visible cell (custom_rcnn.py:699-701,743) and frame_cnt := 0.
  * touched (E,cells) u8 nullable: |= 1 where the cell received samples this frame (observed_mem, :922).

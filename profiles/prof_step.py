@@ -12,7 +12,7 @@ H, W, MW, MH = 480, 640, 500, 500
 dev = torch.device("cuda:0")
 eps = [eod.episodes.make_episode(1234 + e, T, H, W, MW, MH, 0.2) for e in range(E)]
 intr = eod.compute_intrinsics(W, H, math.radians(67.5))
-batch = eod.EpisodeBatch(E, MW, MH, C, H, W, dev)
+batch = eod.EpisodeBatch(E, MW, MH, C, H, W, dev, variant=int(os.environ.get('PROF_VARIANT', 0)))
 shifts = torch.from_numpy(np.stack([np.concatenate([np.zeros(3, np.float32), ep.map_world_shift]) for ep in eps])).to(dev)
 feat = [torch.randn((E, C, H, W), device=dev) for _ in range(2)]
 for t in range(T):

@@ -244,6 +244,110 @@ def test_write_mean_chw_vs_oracle(eod, cuda, C, variant, expand, with_samp):
     _write_case(eod, cuda, C, 3, 64, 96, 200, 0, variant, with_samp, seed=C + variant, expand=expand)
 
 
+@pytest.mark.parametrize("C", [128, 256, 512])
+@pytest.mark.parametrize("with_samp", [False, True])
+def test_write_mean_det_reproducible_and_correct(eod, cuda, C, with_samp):
+    """EOD_WRITE_DET: bitwise reproducible run to run and under a different batching of the same episodes; within the
+    fp32 tolerance of the oracle; cells without samples untouched; an undersized workspace degrades to the atomic path
+    (flagged) without losing correctness."""
+    rng = np.random.default_rng(40 + C)
+    E, H, W, cells = 3, 64, 96, 211
+    feat = rng.standard_normal((E, C, H, W)).astype(np.float32) * 3
+    idx = (rng.integers(0, cells, (E, H // 2 + 1, W // 16 + 1)).repeat(2, 1).repeat(16, 2)[:, :H, :W]).astype(np.int32)
+    idx[:, ::5, ::3] = rng.integers(0, cells, idx[:, ::5, ::3].shape)
+    idx[0, :8] = 7                                                         # one long segment: > 32 runs in a cell
+    samp = (rng.uniform(size=(E, H, W)) < 0.3).astype(np.uint8) if with_samp else None
+    sums0 = rng.standard_normal((E, cells, C)).astype(np.float32)
+
+    def run(order, runs_per_episode=0):
+        order = list(order)
+        d_idx = _t(idx[order], cuda)
+        d_samp = None if samp is None else _t(samp[order], cuda)
+        d_sums = _t(sums0[order], cuda)
+        d_cnt = torch.zeros((len(order), cells), dtype=torch.int32, device=cuda)
+        ws = eod.ops.DetWorkspace(len(order), C, H * W, cells, cuda, runs_per_episode)
+        eod.ops.frame_count(d_idx, d_samp, d_cnt)
+        eod.ops.write_mean_det(_t(feat[order], cuda), d_idx, d_samp, d_cnt, d_sums, ws)
+        out1 = d_sums.clone()                                              # second call: the workspace is reusable as left behind
+        d_sums.copy_(_t(sums0[order], cuda))
+        eod.ops.write_mean_det(_t(feat[order], cuda), d_idx, d_samp, d_cnt, d_sums, ws)
+        torch.cuda.synchronize()
+        if not runs_per_episode:
+            assert torch.equal(out1, d_sums)                               # run to run: bitwise (unless runs overflowed to atomics)
+        inv = np.argsort(order)
+        return d_sums.cpu().numpy()[inv], ws.overflowed()
+
+    a, ovf = run(range(E))
+    assert not ovf
+    b, _ = run([2, 0, 1])
+    assert np.array_equal(a, b)                                            # batching order: bitwise
+    c, _ = run([1])
+    assert np.array_equal(a[1:2], c)                                       # an episode alone: bitwise
+    small, ovf = run(range(E), runs_per_episode=5)
+    assert ovf
+    for e in range(E):
+        s_, n = oracle.cell_sums_seq(feat[e], idx[e], None if samp is None else samp[e], cells)
+        mean = np.where(n[:, None] > 0, s_ / np.maximum(n, 1)[:, None].astype(np.float32), 0).astype(np.float32)
+        ref = sums0[e] + mean
+        for got in (a[e], small[e]):
+            assert np.abs(got - ref).max() <= SUM_TOL * np.abs(ref).max()
+            assert np.array_equal(got[n == 0], sums0[e][n == 0])
+
+
+def test_write_mean_det_very_long_segment(eod, cuda):
+    """A cell with more runs than a warp sorts in shared memory at once (2048) takes the chunk-sort + merge path of
+    det_reduce."""
+    rng = np.random.default_rng(77)
+    E, C, H, W, cells = 1, 128, 64, 96, 50
+    feat = rng.standard_normal((E, C, H, W)).astype(np.float32)
+    idx = rng.integers(8, cells, (E, H, W)).astype(np.int32)
+    idx[0, :50, ::2] = 7                                                    # 50 rows x 48 isolated pixels = 2400 runs of cell 7
+    d_idx, d_feat = _t(idx, cuda), _t(feat, cuda)
+    d_cnt = torch.zeros((E, cells), dtype=torch.int32, device=cuda)
+    eod.ops.frame_count(d_idx, None, d_cnt)
+    ws = eod.ops.DetWorkspace(E, C, H * W, cells, cuda, H * W)
+    outs = []
+    for _ in range(2):
+        d_sums = torch.zeros((E, cells, C), device=cuda)
+        eod.ops.write_mean_det(d_feat, d_idx, None, d_cnt, d_sums, ws)
+        outs.append(d_sums)
+    torch.cuda.synchronize()
+    assert not ws.overflowed() and torch.equal(outs[0], outs[1])
+    s_, n = oracle.cell_sums_seq(feat[0], idx[0], None, cells)
+    ref = np.where(n[:, None] > 0, s_ / np.maximum(n, 1)[:, None].astype(np.float32), 0).astype(np.float32)
+    assert n[7] == 2400
+    assert np.abs(outs[0][0].cpu().numpy() - ref).max() <= SUM_TOL * np.abs(ref).max()
+
+
+def test_episode_batch_deterministic_variant(eod, cuda):
+    """EpisodeBatch(variant=WRITE_DET) end to end: two identical runs give identical bits (sums, norm16, levels)."""
+    E, C, H, W, mw, mh, T_ = 2, 128, 96, 128, 60, 45, 4
+    eps = [eod.episodes.make_episode(700 + e, T_, H, W, mw, mh, 0.2) for e in range(E)]
+    intr = eod.compute_intrinsics(W, H, math.radians(67.5))
+    shifts = _t(np.stack([np.concatenate([np.zeros(3, np.float32), ep.map_world_shift]) for ep in eps]), cuda)
+    gen = torch.Generator(device=cuda).manual_seed(11)
+    feat = [torch.randn((E, C, H, W), device=cuda, generator=gen) for _ in range(T_)]
+    outs = []
+    for rep in range(2):
+        batch = eod.EpisodeBatch(E, mw, mh, C, H, W, cuda, variant=4, pipeline=bool(rep))
+        batch.det_runs_per_episode = H * W                 # low resolution: a run is ~3 pixels, more than the default HW/4 runs
+        lv = []
+        for t in range(T_):
+            depth = _t(np.stack([ep.depth[t] for ep in eps]), cuda)
+            pose = eod.transform3d(torch.from_numpy(np.stack([ep.xyzhe[t] for ep in eps])))[:, :3].reshape(E, 12).to(cuda)
+            torch.cuda.synchronize()
+            lv.append([l.clone() for l in batch.step(depth, pose, shifts, intr, 0.2, feat[t])])
+        batch.join()
+        torch.cuda.synchronize()
+        assert not batch._det_ws.overflowed()
+        outs.append((batch.sums.clone(), batch.counts.clone(), batch.norm16.clone(), lv))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+    for t in range(T_):
+        for a, b in zip(outs[0][3][t], outs[1][3][t]):
+            assert torch.equal(a, b)
+    assert outs[0][0].abs().sum().item() > 0
+
+
 def test_write_mean_large_grid_pixel_driven_finalize(eod, cuda):
     """cells > 4*HW: eod_finalize_counts walks the pixel plane (atomicExch dedupe) instead of the cell plane;
     E*tiles odd -> the TMA kernel falls back to ungrouped tiles."""
