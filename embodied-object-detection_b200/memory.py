@@ -393,6 +393,37 @@ class SpatialFeatureMemory:
         ops.flush_slots(self._frame_cnt, self._slots, self.implicit_memory.unsqueeze(0))
         ops.finalize_counts(idx, self._frame_cnt, self.observations.unsqueeze(0))
 
+    def dense_backbone_write(self, p3: torch.Tensor, proj_indices: torch.Tensor, n_cells: int,
+                             weight: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None, step: int = 8):
+        """Dense backbone-feature write (SURVEY 8a row A7'', bytecode-only older CustomMapFPN.forward): p3 (1,C,h,w) ->
+        bilinear (H,W) align_corners=True -> [::step, ::step] -> optional 1x1 projection (map_merge_forward_projection,
+        library GEMM) -> per-cell mean with proj_indices[::step, ::step]; returns (memory (cells,C') f32 with the mean in the
+        observed cells and zeros elsewhere - the reference REPLACES the memory - and observed_mem (cells,) bool)."""
+        idx_full = proj_indices.to(self.device)
+        if idx_full.dim() == 3 and idx_full.shape[-1] == 1:
+            idx_full = idx_full.squeeze(2)
+        H, W = idx_full.shape
+        f = ops.bilinear_lattice(p3.to(self.device, torch.float32).contiguous(), (H, W), step)
+        layout = LAYOUT_CHW
+        C = f.shape[1]
+        if weight is not None:                             # 1x1 conv == per-sample GEMM (fp32 library matmul, no TF32), output HWC
+            w2 = weight.to(self.device, torch.float32).reshape(weight.shape[0], -1)
+            f = torch.matmul(f[0].reshape(C, -1).t().contiguous(), w2.t())
+            if bias is not None:
+                f = f + bias.to(self.device, torch.float32)
+            f, C, layout = f.unsqueeze(0).contiguous(), w2.shape[0], LAYOUT_HWC
+        else:
+            f = f.reshape(1, C, -1).contiguous()
+        idx = idx_full[::step, ::step].to(torch.int32).reshape(1, -1).contiguous()
+        table = torch.zeros((1, n_cells, C), dtype=torch.float32, device=self.device)
+        cnt = torch.zeros((1, n_cells), dtype=torch.int32, device=self.device)
+        touched = torch.zeros((1, n_cells), dtype=torch.uint8, device=self.device)
+        dummy = torch.zeros((1, n_cells), dtype=torch.float32, device=self.device)
+        ops.frame_count(idx, None, cnt)
+        ops.write_mean(f, idx, None, cnt, table, layout)
+        ops.finalize_counts(idx, cnt, dummy, touched)
+        return table[0], touched[0].view(torch.bool)
+
     def write_image_features(self, image_features: torch.Tensor, observed_pixels: Optional[torch.Tensor],
                              proj_indices: torch.Tensor, layout: int = LAYOUT_CHW) -> None:
         """A7 + A8 on the live state: per-cell mean of every ``sample_stride``-th observed pixel, sums +=,

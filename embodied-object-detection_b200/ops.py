@@ -16,7 +16,7 @@ from ._lib import (FUSE_IMAGE_ONLY, FUSE_MEM_ONLY, FUSE_SUM, LAYOUT_CHW, LAYOUT_
 launch_count = 0
 
 _LAUNCHES = {"eod_backproject_quantize": 1, "eod_sample_mask": 1, "eod_frame_count": 1, "eod_expand_counts": 1, "eod_write_mean": 1, "eod_write_mean_det": 7,
-             "eod_finalize_counts": 1, "eod_box_to_image_features": 1, "eod_masks_observed": 1, "eod_write_objects": 1, "eod_flush_slots": 2, "eod_write_max": 2, "eod_read_pool": 1,
+             "eod_finalize_counts": 1, "eod_box_to_image_features": 1, "eod_masks_observed": 1, "eod_bilinear_lattice": 1, "eod_write_objects": 1, "eod_flush_slots": 2, "eod_write_max": 2, "eod_read_pool": 1,
              "eod_fuse": 1, "eod_normalize_memory": 1, "eod_reset_touched": 1}
 
 
@@ -257,6 +257,16 @@ def flush_slots(frame_cnt: torch.Tensor, slots: ObjectSlots, sums: torch.Tensor)
         raise ValueError("sums does not match the slot workspace")
     _call("eod_flush_slots", frame_cnt.data_ptr(), slots.slot_of_cell.data_ptr(), slots.slot_cell.data_ptr(), slots.n_slots.data_ptr(),
           E, C, n_cells, slots.S, slots.scratch.data_ptr(), sums.data_ptr(), _stream())
+
+
+def bilinear_lattice(src: torch.Tensor, out_hw: Tuple[int, int], step: int) -> torch.Tensor:
+    """F.interpolate(src, out_hw, mode='bilinear', align_corners=True)[:, :, ::step, ::step] for src (E,C,h,w) f32."""
+    _dev(src, torch.float32, "src")
+    E, C, h, w = src.shape
+    H, W = int(out_hw[0]), int(out_hw[1])
+    out = torch.empty((E, C, -(-H // step), -(-W // step)), dtype=torch.float32, device=src.device)
+    _call("eod_bilinear_lattice", src.data_ptr(), E, C, h, w, H, W, int(step), out.data_ptr(), _stream())
+    return out
 
 
 def write_max(height: torch.Tensor, idx: torch.Tensor, outlier: Optional[torch.Tensor], feat: Optional[torch.Tensor],

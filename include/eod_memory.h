@@ -159,6 +159,14 @@ int eod_write_objects(const float *box_features, const uint8_t *masks, const int
 int eod_flush_slots(const uint32_t *frame_cnt, int32_t *slot_of_cell, const int32_t *slot_cell, int32_t *n_slots, int n_episodes,
                     int C, int64_t n_cells, int n_slots_max, float *scratch, float *sums, eod_stream_t stream);
 
+/* Front end of the dense backbone-feature write (SURVEY 8a row A7'', bytecode-only CustomMapFPN.forward):
+ * out = F.interpolate(src, (H_out, W_out), mode='bilinear', align_corners=True)[:, :, ::step, ::step] without building the
+ * upsampled tensor.  src (E,C,h,w) f32 -> out (E,C,ceil(H_out/step),ceil(W_out/step)) f32; bit-exact with ATen CPU.
+ * The samples then go through eod_frame_count / eod_write_mean with idx = proj_indices[::step, ::step] into a ZEROED
+ * table (the reference replaces the memory: memory[observed_mem] = per-cell mean). */
+int eod_bilinear_lattice(const float *src, int n_episodes, int C, int h, int w, int H_out, int W_out, int step, float *out,
+                         eod_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * (2b) Write, SMNet height-max mode (bytecode-only SMNet.encode, SURVEY 8a row A7').
  * Per frame: for inlier pixels (outlier == 0) on the [::pix_stride, ::pix_stride] lattice,

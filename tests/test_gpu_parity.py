@@ -432,6 +432,31 @@ def test_batched_fused_object_write_vs_oracle(eod, cuda):
         assert sum(int(f.abs().sum()) for f in batch._frame_cnt2) == 0
 
 
+def test_dense_backbone_write_vs_oracle(eod, cuda):
+    """A7'' (bytecode-only lineage): bilinear lattice samples bit-exact vs torch-CPU F.interpolate, per-cell means of the
+    projected samples within the fp32 tolerance, observed set exact, memory REPLACED (zeros elsewhere)."""
+    rng = np.random.default_rng(8)
+    C, h, w, H, W, mw, mh = 256, 60, 80, 480, 640, 120, 90
+    cells = mw * mh
+    p3 = torch.from_numpy(rng.standard_normal((1, C, h, w)).astype(np.float32))
+    proj = torch.from_numpy((rng.integers(0, cells, (H // 16 + 1, W // 16 + 1)).repeat(16, 0).repeat(16, 1)[:H, :W]).astype(np.int64))
+    lat = eod.ops.bilinear_lattice(p3.to(cuda), (H, W), 8)
+    ref_lat = torch.nn.functional.interpolate(p3, (H, W), mode="bilinear", align_corners=True)[:, :, ::8, ::8]
+    assert torch.equal(lat.cpu(), ref_lat)                                  # bit-exact lattice samples
+    odd = eod.ops.bilinear_lattice(p3[:, :8, :37, :53].contiguous().to(cuda), (101, 203), 3)
+    assert torch.equal(odd.cpu(), torch.nn.functional.interpolate(p3[:, :8, :37, :53], (101, 203), mode="bilinear", align_corners=True)[:, :, ::3, ::3])
+    weight = torch.from_numpy(rng.standard_normal((C, C, 1, 1)).astype(np.float32) / 16)
+    bias = torch.from_numpy(rng.standard_normal(C).astype(np.float32))
+    mem = eod.SpatialFeatureMemory(C, cuda)
+    for wgt, b in ((None, None), (weight, bias)):
+        got, obs = mem.dense_backbone_write(p3, proj, cells, wgt, b)
+        ref, ref_obs = R.dense_backbone_write(p3, proj, cells, wgt, b)
+        assert np.array_equal(obs.cpu().numpy(), ref_obs.numpy())
+        tol = SUM_TOL if wgt is None else 1e-4                              # library GEMM (TF32-free fp32) vs MKL: summation order
+        assert (got.cpu() - ref).abs().max().item() <= tol * ref.abs().max().item()
+        assert not got.cpu()[~ref_obs].any()
+
+
 # --------------------------------------------------------------------------------------------------------
 # write, height-max mode (A7')
 # --------------------------------------------------------------------------------------------------------
