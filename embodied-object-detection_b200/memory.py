@@ -238,11 +238,17 @@ class SpatialFeatureMemory:
 
     def __init__(self, mem_feat_dim: int = 512, device: torch.device = torch.device("cuda"), test_type: str = "default",
                  semmap_gt_info: Optional[dict] = None, replica_map_info: Optional[dict] = None, downsample: int = 10,
-                 sample_stride: int = 8, height: int = 480, width: int = 640, fused_write: bool = True):
+                 sample_stride: int = 8, height: int = 480, width: int = 640, fused_write: bool = True,
+                 zs_weight: Optional[torch.Tensor] = None, obs_score_thresh: float = 0.4, n_semmap_classes: int = 20):
         if torch.device(device).type != "cuda":
             raise EodError("SpatialFeatureMemory needs a CUDA device (no CPU fallback)")
-        self.fused_write = fused_write      # False: materialise image_features like the reference (box_to_image_features)
         self.C, self.device, self.test_type = mem_feat_dim, torch.device(device), test_type
+        self.fused_write = fused_write      # False: materialise image_features like the reference (box_to_image_features)
+        # explicit semantic map (custom_rcnn.py:747-756,938-978): maintained when the CLIP classifier table is given
+        self.zs_weight = None if zs_weight is None else zs_weight.to(self.device, torch.float32).contiguous()   # (C, K)
+        self.obs_score_thresh, self.n_semmap_classes = obs_score_thresh, n_semmap_classes       # MODEL.MEMORY_OBS_SCORE_THRESH
+        self._intensity: Optional[torch.Tensor] = None
+        self._cls: Optional[torch.Tensor] = None
         self.semmap_gt_info, self.replica_map_info = semmap_gt_info or {}, replica_map_info or {}
         self.downsample, self.sample_stride, self.H, self.W = downsample, sample_stride, height, width
         self.implicit_memory: Optional[torch.Tensor] = None     # (cells, C) f32 sums        (custom_rcnn.py:476,759)
@@ -258,6 +264,8 @@ class SpatialFeatureMemory:
         self.observations = torch.zeros((n_cells,), dtype=torch.float32, device=self.device)
         self._frame_cnt = torch.zeros((1, n_cells), dtype=torch.int32, device=self.device)
         self._touched = torch.zeros((1, n_cells), dtype=torch.uint8, device=self.device)
+        self._intensity = torch.zeros((1, n_cells), dtype=torch.float32, device=self.device)
+        self._cls = torch.zeros((1, n_cells), dtype=torch.int32, device=self.device)     # argmax of all-zero logits is class 0
 
     def map_dims(self, sequence_name: str) -> Tuple[int, int]:
         """(map_w, map_h) as custom_rcnn.py:704-729 resolves them (MP3D table, Replica table, else 200x200)."""
@@ -288,6 +296,19 @@ class SpatialFeatureMemory:
     def observation_count(self) -> Optional[torch.Tensor]:
         return None if self.observations is None or not hasattr(self, "_dims") else \
             self.observations.reshape(1, self._dims[1], self._dims[0])
+
+    @property
+    def semmap(self) -> Optional[torch.Tensor]:
+        """(cells,) int32 explicit semantic map as custom_rcnn.py:756 leaves it in ``self.semmap`` (class id, -1 below the
+        observation-intensity threshold); None without a classifier table.  Stays on the device."""
+        if self.zs_weight is None or self._intensity is None:
+            return None
+        return ops.semmap_decode(self._intensity, self._cls, self.obs_score_thresh)[0]
+
+    def _semmap_update(self) -> None:
+        if self.zs_weight is not None:
+            ops.semmap_update(self._frame_cnt, self.observations.unsqueeze(0), self.implicit_memory.unsqueeze(0), self.zs_weight,
+                              self.n_semmap_classes, self._intensity, self._cls)
 
     # ---- read ----------------------------------------------------------------------------------------
     def create_implicit_memory(self, frame: Dict) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -391,6 +412,7 @@ class SpatialFeatureMemory:
         ops.frame_count(idx, samp, self._frame_cnt, None, self._slots)
         ops.write_objects(bf, m, None, idx.view(1, masks.shape[-2], masks.shape[-1]), samp, self._slots)
         ops.flush_slots(self._frame_cnt, self._slots, self.implicit_memory.unsqueeze(0))
+        self._semmap_update()
         ops.finalize_counts(idx, self._frame_cnt, self.observations.unsqueeze(0))
 
     def dense_backbone_write(self, p3: torch.Tensor, proj_indices: torch.Tensor, n_cells: int,
@@ -436,4 +458,5 @@ class SpatialFeatureMemory:
         feat = image_features.to(self.device, torch.float32).reshape(1, -1).contiguous()
         ops.frame_count(idx, samp, self._frame_cnt)
         ops.write_mean(feat, idx, samp, self._frame_cnt, self.implicit_memory.unsqueeze(0), layout)
+        self._semmap_update()
         ops.finalize_counts(idx, self._frame_cnt, self.observations.unsqueeze(0))

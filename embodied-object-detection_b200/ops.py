@@ -17,7 +17,7 @@ launch_count = 0
 
 _LAUNCHES = {"eod_backproject_quantize": 1, "eod_sample_mask": 1, "eod_frame_count": 1, "eod_expand_counts": 1, "eod_write_mean": 1, "eod_write_mean_det": 7,
              "eod_finalize_counts": 1, "eod_box_to_image_features": 1, "eod_masks_observed": 1, "eod_bilinear_lattice": 1, "eod_write_objects": 1, "eod_flush_slots": 2, "eod_write_max": 2, "eod_read_pool": 1,
-             "eod_fuse": 1, "eod_normalize_memory": 1, "eod_reset_touched": 1}
+             "eod_fuse": 1, "eod_normalize_memory": 1, "eod_reset_touched": 1, "eod_semmap_update": 1, "eod_semmap_decode": 2}
 
 
 def _call(name: str, *args) -> None:
@@ -143,6 +143,29 @@ def write_mean(feat: torch.Tensor, idx: torch.Tensor, samp: Optional[torch.Tenso
             raise ValueError("pix_inv_n must hold E*HW floats")
     _call("eod_write_mean", feat.data_ptr(), int(layout), idx.data_ptr(), _ptr(samp), frame_cnt.data_ptr(), E, C, HW,
           n_cells, sums.data_ptr(), int(variant), _ptr(pix_inv_n), _stream())
+
+
+def semmap_update(frame_cnt: torch.Tensor, counts: torch.Tensor, sums: torch.Tensor, zs_weight: torch.Tensor, n_cls: int,
+                  intensity: torch.Tensor, cls: torch.Tensor) -> None:
+    """Refresh intensity / class of the cells visible in the current frame (call between the write and finalize_counts).
+    zs_weight (C, K>=n_cls) f32 as the reference holds it; intensity (E,cells) f32, cls (E,cells) i32."""
+    _dev(frame_cnt, torch.int32, "frame_cnt"), _dev(counts, torch.float32, "counts"), _dev(sums, torch.float32, "sums")
+    _dev(zs_weight, torch.float32, "zs_weight"), _dev(intensity, torch.float32, "intensity"), _dev(cls, torch.int32, "cls")
+    E, n_cells, C = sums.shape
+    if zs_weight.shape[0] != C or zs_weight.shape[1] < n_cls:
+        raise ValueError("zs_weight must be (C, K) with K >= n_cls")
+    _call("eod_semmap_update", frame_cnt.data_ptr(), counts.data_ptr(), sums.data_ptr(), zs_weight.data_ptr(), zs_weight.shape[1],
+          int(n_cls), E, C, n_cells, intensity.data_ptr(), cls.data_ptr(), _stream())
+
+
+def semmap_decode(intensity: torch.Tensor, cls: torch.Tensor, thresh: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(E,cells) int32 explicit map: class id, or -1 where the min-max normalised intensity is below thresh."""
+    _dev(intensity, torch.float32, "intensity"), _dev(cls, torch.int32, "cls")
+    E, n_cells = intensity.shape
+    out = torch.empty((E, n_cells), dtype=torch.int32, device=intensity.device) if out is None else _dev(out, torch.int32, "semmap")
+    ws = torch.empty((E, 2), dtype=torch.float32, device=intensity.device)
+    _call("eod_semmap_decode", intensity.data_ptr(), cls.data_ptr(), E, n_cells, float(thresh), ws.data_ptr(), out.data_ptr(), _stream())
+    return out
 
 
 def reset_touched(counts: torch.Tensor, sums: torch.Tensor, norm16: Optional[torch.Tensor] = None) -> None:

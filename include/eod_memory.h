@@ -200,6 +200,20 @@ int eod_read_pool(const void *table, int mem_is_f16, const float *counts, const 
 int eod_normalize_memory(const float *sums, const float *counts, int64_t n_rows, int C, void *out, int out_is_f16,
                          eod_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Explicit semantic map (custom_rcnn.py:747-756 and visualise_clip_image_features :938-978), maintained
+ * incrementally.  eod_semmap_update: for every cell visible in the current frame (frame_cnt != 0; call it after
+ * the write and BEFORE eod_finalize_counts) refresh intensity[cell] = mean_ch|sums| (/ n if n > 1, n = counts + 1)
+ * and cls[cell] = argmax_{k < n_cls} <sums[cell], zs_weight[:, k]> (zs_weight (C, ldz) f32 row-major, the
+ * reference's zs_weight; n_cls = 20 there, <= 32 here).  eod_semmap_decode: semmap[cell] = cls[cell], or -1 where
+ * (intensity - min) / (max - min) < thresh with the min / max taken over the episode's whole grid (:751,968).
+ * minmax_ws: (E,2) f32 scratch. */
+int eod_semmap_update(const uint32_t *frame_cnt, const float *counts, const float *sums, const float *zs_weight, int ldz,
+                      int n_cls, int n_episodes, int C, int64_t n_cells, float *intensity, int32_t *cls,
+                      eod_stream_t stream);
+int eod_semmap_decode(const float *intensity, const int32_t *cls, int n_episodes, int64_t n_cells, float thresh,
+                      float *minmax_ws, int32_t *semmap, eod_stream_t stream);
+
 /* memory_reset (custom_rcnn.py:470-477) for state maintained by this library: clears counts, the sums row and
  * (if given) the norm16 row of every cell whose count is non-zero - equivalent to zero-filling the grid because
  * rows of never-visible cells are zero already.  n_rows = E*cells. */

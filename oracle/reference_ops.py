@@ -193,6 +193,22 @@ def dense_backbone_write(p3: torch.Tensor, proj: torch.Tensor, n_cells: int, wei
     return mem, m
 
 
+def explicit_semmap(sums: torch.Tensor, counts: torch.Tensor, zs_weight: torch.Tensor, thresh: float, n_cls: int = 20):
+    """custom_rcnn.py:747-756 + visualise_clip_image_features (:938-978) on the flat views: returns
+    (semmap (cells,) int64 with -1 below the threshold, normalised intensity (cells,), logits (cells, n_cls))."""
+    inten = sums.abs().mean(dim=1)                                           # :747
+    sel = counts > 1
+    inten[sel] = inten[sel] / counts[sel]                                    # :748
+    inten = (inten - inten.min()) / (inten.max() - inten.min())              # :751
+    norm = 50.0 * F.normalize(sums, p=2, dim=1)                              # :949
+    scores = torch.mm(norm, zs_weight)[:, :n_cls]                            # :952
+    prob = scores.softmax(dim=1)                                             # :955
+    _, idx = torch.max(prob, dim=1)                                          # :958
+    idx = idx.clone()
+    idx[inten < thresh] = -1                                                 # :968 (mask replaces the scores, :964)
+    return idx, inten, scores
+
+
 # --------------------------------------------------------------------------------------------------
 # SMNet height-max write (A7', bytecode-only; torch_scatter 1.4.0 scatter_max canonical tie rule)
 # --------------------------------------------------------------------------------------------------

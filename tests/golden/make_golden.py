@@ -189,10 +189,50 @@ def gen_read():
     print("read: levels", [out[f"level0_{k}"].shape for k in range(3)])
 
 
+def gen_semmap():
+    """Explicit semantic map: custom_rcnn.py:747-751 exec'd verbatim on tensors shaped as :731-743 leave them (permuted
+    views), then the reference's own visualise_clip_image_features (:938-1017, cv2 headless, visualise=False)."""
+    import cv2
+    patch_cpu()
+    path = os.path.join(REF, "detic/modeling/meta_arch/custom_rcnn.py")
+    src = open(path).read()
+    lines = src.splitlines()
+    tree = ast.parse(src)
+    cls = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "CustomRCNNRecurrent"][0]
+    fn = [f for f in cls.body if isinstance(f, ast.FunctionDef) and f.name == "visualise_clip_image_features"][0]
+    ns = {"torch": torch, "np": np, "cv2": cv2, "palette": np.zeros((256, 3), np.uint8)}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
+    rng = np.random.default_rng(12)
+    mw, mh, C, K = 40, 30, 512, 21
+    cells = mw * mh
+    counts = rng.integers(0, 5, cells).astype(np.float32)
+    sums = (rng.standard_normal((cells, C)) * rng.uniform(0.2, 30, (cells, 1))).astype(np.float32)
+    sums[counts == 0] = 0
+    zs = rng.standard_normal((C, K)).astype(np.float32)
+    zs /= np.linalg.norm(zs, axis=0, keepdims=True)
+    self_ns = type("S", (), {})()
+    self_ns.semmap_features = torch.from_numpy(sums).reshape(mh, mw, C).permute(2, 0, 1).unsqueeze(0)      # :731-732
+    self_ns.observation_count = torch.from_numpy(counts).reshape(mh, mw, 1).permute(2, 0, 1)               # :734-735
+    u = {"torch": torch, "self": self_ns}
+    exec_lines(lines, 747, 751, u)
+    inten = u["observation_intensity"]
+    out = {"sums": sums, "counts": counts, "zs_weight": zs, "map_w": mw, "map_h": mh, "intensity": inten.reshape(-1).numpy()}
+    for thresh in (0.4, 0.1):
+        sem = ns["visualise_clip_image_features"](None, self_ns.semmap_features, torch.from_numpy(zs), "semmap", mask=inten,
+                                                  thresh=thresh, visualise=False)
+        out[f"semmap_{thresh}"] = np.asarray(sem).astype(np.int32)
+        print("semmap thresh", thresh, "classes kept", int((out[f'semmap_{thresh}'] >= 0).sum()), "of", cells)
+    np.savez_compressed(os.path.join(HERE, "semmap.npz"), **out)
+
+
 if __name__ == "__main__":
+    if "--only-semmap" in sys.argv:
+        gen_semmap()
+        sys.exit(0)
     gen_geometry()
     gen_write()
     gen_read()
+    gen_semmap()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

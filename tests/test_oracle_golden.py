@@ -124,3 +124,13 @@ def test_scatter_max_canonical_rule():
     o, arg = R.scatter_max_canonical(src, index, out)
     assert o.tolist() == [5.0, 2.0, 9.0, 4.0]
     assert arg.tolist() == [2, 3, -1, -1]         # tie -> highest index; equal to old -> replaced; lower -> -1
+
+
+def test_explicit_semmap_restatement_matches_reference(golden):
+    """custom_rcnn.py:747-751 + visualise_clip_image_features executed from the reference source (semmap.npz) vs the
+    oracle restatement: intensity plane and labels bit-exact."""
+    g = golden("semmap")
+    for th in (0.4, 0.1):
+        sem, inten, _ = R.explicit_semmap(torch.from_numpy(g["sums"]), torch.from_numpy(g["counts"]), torch.from_numpy(g["zs_weight"]), th)
+        assert np.array_equal(inten.numpy(), g["intensity"])
+        assert np.array_equal(sem.numpy(), g[f"semmap_{th}"])
