@@ -24,6 +24,7 @@ SIGNATURES = {
     "eod_last_error": [],
     "eod_backproject_quantize": [_P, _P, _P, c_int, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_int,
                                  c_int, c_int, c_float, _P, _P, _P, _P, _P, _P],
+    "eod_quantize_world": [_P, c_int64, c_float, c_float, c_float, c_int, c_int, c_int, _P, _P],
     "eod_sample_mask": [_P, c_int, c_int, c_int, _P, _P, _P],
     "eod_frame_count": [_P, _P, _P, c_int, c_int, c_int64, _P, _P, _P, _P, c_int, _P],
     "eod_expand_counts": [_P, _P, c_int, c_int, c_int64, _P, _P],

@@ -74,7 +74,35 @@ __global__ void __launch_bounds__(256) backproject_quantize_kernel(const Backpro
     }
 }
 
+// World xyz (as stored in sensor_data/*.h5 'projection_indices', SMNet/build_data.py:209-213,280) -> flat clipped cell
+// index: exactly SMNet/build_memory_data.py:135-143 (shift, IEEE divide, round-half-even, clip, z*map_w + x).
+__global__ void __launch_bounds__(256) quantize_world_kernel(const float *__restrict__ world, int64_t n, float sx, float sz, float cell,
+                                                             int map_w, int map_h, int order, int32_t *__restrict__ idx)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = __ldg(world + 3 * i), z = __ldg(world + 3 * i + 2);
+    const float qx = rintf(__fdiv_rn(__fsub_rn(x, sx), cell));
+    const float qz = rintf(__fdiv_rn(__fsub_rn(z, sz), cell));
+    const int ix = (int)fminf(fmaxf(qx, 0.0f), (float)(map_w - 1));
+    const int iz = (int)fminf(fmaxf(qz, 0.0f), (float)(map_h - 1));
+    idx[i] = order == EOD_ORDER_XZ ? ix * map_h + iz : iz * map_w + ix;
+}
+
 }  // namespace
+
+extern "C" int eod_quantize_world(const float *world, int64_t n_points, float shift_x, float shift_z, float cell, int map_w, int map_h,
+                                  int order, int32_t *idx, eod_stream_t stream)
+{
+    EOD_REQUIRE(world && idx, EOD_ERR_BADARG, "eod_quantize_world: null pointer");
+    EOD_REQUIRE(n_points > 0 && map_w > 0 && map_h > 0 && cell > 0.0f, EOD_ERR_BADARG, "eod_quantize_world: bad sizes");
+    EOD_REQUIRE(order == EOD_ORDER_ZX || order == EOD_ORDER_XZ, EOD_ERR_BADARG, "eod_quantize_world: bad order");
+    EOD_REQUIRE((int64_t)map_w * map_h < (int64_t)INT32_MAX, EOD_ERR_BADARG, "eod_quantize_world: map too large");
+    const int64_t blocks = (n_points + 255) / 256;
+    EOD_REQUIRE(blocks <= 0x7fffffff, EOD_ERR_BADARG, "eod_quantize_world: too many points for one launch");
+    quantize_world_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(world, n_points, shift_x, shift_z, cell, map_w, map_h, order, idx);
+    return eod_check_launch("eod_quantize_world");
+}
 
 extern "C" int eod_backproject_quantize(const float *depth, const float *pose, const float *shifts, int n_episodes,
                                         int H, int W, float fx, float fy, float cx, float cy, float cell, int map_w,

@@ -15,7 +15,7 @@ from ._lib import (FUSE_IMAGE_ONLY, FUSE_MEM_ONLY, FUSE_SUM, LAYOUT_CHW, LAYOUT_
 # kernels launched through this module since import (bench.py reports it as gpu_launches)
 launch_count = 0
 
-_LAUNCHES = {"eod_backproject_quantize": 1, "eod_sample_mask": 1, "eod_frame_count": 1, "eod_expand_counts": 1, "eod_write_mean": 1, "eod_write_mean_det": 7,
+_LAUNCHES = {"eod_backproject_quantize": 1, "eod_quantize_world": 1, "eod_sample_mask": 1, "eod_frame_count": 1, "eod_expand_counts": 1, "eod_write_mean": 1, "eod_write_mean_det": 7,
              "eod_finalize_counts": 1, "eod_box_to_image_features": 1, "eod_masks_observed": 1, "eod_bilinear_lattice": 1, "eod_write_objects": 1, "eod_flush_slots": 2, "eod_write_max": 2, "eod_read_pool": 1,
              "eod_fuse": 1, "eod_normalize_memory": 1, "eod_reset_touched": 1, "eod_semmap_update": 1, "eod_semmap_decode": 2}
 
@@ -74,6 +74,18 @@ def backproject_quantize(depth: torch.Tensor, pose: torch.Tensor, shifts: torch.
     _call("eod_backproject_quantize", depth.data_ptr(), pose.data_ptr(), shifts.data_ptr(), E, H, W, fx, fy, cx, cy,
           float(cell), int(map_w), int(map_h), int(order), float(z_clip), _ptr(idx), _ptr(q2), _ptr(outlier),
           _ptr(height), _ptr(world), _stream())
+    return out
+
+
+def quantize_world(world: torch.Tensor, map_world_shift: Sequence[float], cell: float, map_w: int, map_h: int,
+                   order: int = ORDER_ZX) -> torch.Tensor:
+    """world (..., 3) f32 (sensor_data 'projection_indices') -> (..., 1) int32 proj_indices (build_memory_data.py:135-144)."""
+    _dev(world, torch.float32, "world")
+    if world.shape[-1] != 3:
+        raise ValueError("world must be (..., 3)")
+    out = torch.empty(world.shape[:-1] + (1,), dtype=torch.int32, device=world.device)
+    _call("eod_quantize_world", world.data_ptr(), world.numel() // 3, float(map_world_shift[0]), float(map_world_shift[2]), float(cell),
+          int(map_w), int(map_h), int(order), out.data_ptr(), _stream())
     return out
 
 

@@ -73,6 +73,11 @@ int eod_backproject_quantize(const float *depth, const float *pose, const float 
                              int order, float z_clip, int32_t *idx, int32_t *q2, uint8_t *outlier, float *height,
                              float *world, eod_stream_t stream);
 
+/* Offline builder's quantise step on STORED world coordinates (sensor_data/*.h5 'projection_indices'):
+ * SMNet/build_memory_data.py:135-143.  world (n_points,3) f32 -> idx (n_points) i32, clipped, bit-exact. */
+int eod_quantize_world(const float *world, int64_t n_points, float shift_x, float shift_z, float cell, int map_w, int map_h,
+                       int order, int32_t *idx, eod_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * (2) Write, mean mode.
  */

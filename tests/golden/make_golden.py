@@ -225,7 +225,34 @@ def gen_semmap():
     np.savez_compressed(os.path.join(HERE, "semmap.npz"), **out)
 
 
+def gen_loader_order():
+    """Episode ordering / reset flags: SMNet/loader.py:97-117 and :289-293 exec'd verbatim on a synthetic file list."""
+    import json
+    lines = open(os.path.join(REF, "SMNet/loader.py")).read().splitlines()
+    rng = np.random.default_rng(4)
+    files = [f"{scene}_{lvl}_{i}.h5" for scene, lvl, n in (("17DRP5sb8fy", 0, 50), ("1LXtFkjw3qL", 1, 50), ("2azQ1b91cZZ", 0, 50)) for i in range(n)]
+    files = [files[i] for i in rng.permutation(len(files))]
+    out = {"files": files}
+    for test_type in ("default", "episodic", "longterm"):
+        self_ns = type("S", (), {})()
+        self_ns.files, self_ns.test_type = list(files), test_type
+        exec_lines(lines, 97, 117, {"self": self_ns})
+        out[f"order_{test_type}"] = self_ns.files
+        flags = []
+        for file in self_ns.files[:120]:
+            for i in (0, 1):
+                u = {"self": self_ns, "file": file, "i": i}
+                exec_lines(lines, 289, 293, u)
+                flags.append(bool(u["mem_reset"]))
+        out[f"reset_{test_type}"] = flags
+    json.dump(out, open(os.path.join(HERE, "loader_order.json"), "w"))
+    print("loader order: longterm length", len(out["order_longterm"]))
+
+
 if __name__ == "__main__":
+    if "--only-loader" in sys.argv:
+        gen_loader_order()
+        sys.exit(0)
     if "--only-semmap" in sys.argv:
         gen_semmap()
         sys.exit(0)
@@ -233,6 +260,7 @@ if __name__ == "__main__":
     gen_write()
     gen_read()
     gen_semmap()
+    gen_loader_order()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

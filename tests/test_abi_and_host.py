@@ -148,3 +148,53 @@ def test_gloo_world2_counters():
     for _, tot, mx in res:
         assert tot == {"checksum": float(sum(range(11))), "frames": 220.0}
         assert mx == 2.0
+
+
+def test_episode_order_and_reset_flags_match_reference(eod):
+    """formats.order_files / memory_reset_flag vs SMNet/loader.py:97-117,289-293 executed from the reference source
+    (tests/golden/loader_order.json)."""
+    import json
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "loader_order.json")))
+    F = eod.formats
+    for test_type in ("default", "episodic", "longterm"):
+        order = F.order_files(g["files"], test_type)
+        assert order == g[f"order_{test_type}"], test_type
+        flags = [F.memory_reset_flag(test_type, f, i) for f in order[:120] for i in (0, 1)]
+        assert flags == g[f"reset_{test_type}"], test_type
+
+
+def test_store_round_trip_and_episode_dataset(eod, tmp_path):
+    """npz container with the reference's dataset names: memory_data, saved memory (impicit_memory [sic]) and the
+    episode iteration contract of SMNetDetectionLoader."""
+    F = eod.formats
+    root = tmp_path / "mp3d_val"
+    cells, T, H, W = 60, 23, 8, 12
+    rng = np.random.default_rng(0)
+    for seq in ("sceneA_0_1", "sceneA_0_0", "sceneB_1_0"):
+        proj = rng.integers(0, cells, (T, H, W)).astype(np.int64)
+        F.write_memory_data(str(root / "memory_data" / (seq + ".h5")), proj, cells)
+        F.write_store(str(root / "sensor_data" / (seq + ".h5")), {"rgb": rng.integers(0, 255, (T, H, W, 3)).astype(np.uint8),
+                                                                   "depth": rng.uniform(0, 10, (T, H, W)).astype(np.float32)})
+    ds = F.EpisodeDataset(str(root), test_type="default")
+    assert [f.split(".")[0] for f in ds.files] == ["sceneA_0_0", "sceneA_0_1", "sceneB_1_0"]
+    ep = ds[0]
+    assert len(ep) == 20                                                    # max_sequence_length (loader.py:71)
+    assert ep[0]["memory_reset"] and not ep[1]["memory_reset"] and not ds[1][0]["memory_reset"] and ds[2][0]["memory_reset"]
+    assert ep[0]["proj_indices"].shape == (H, W, 1) and ep[0]["proj_indices"].dtype == np.int32
+    assert ep[0]["memory_features"].shape == (cells, 256) and ep[0]["observations"] is None
+    assert ep[3]["image"].shape == (H, W, 3) and ep[3]["depth"].shape == (H, W)
+    assert all(fr[0]["memory_reset"] for fr in F.EpisodeDataset(str(root), test_type="episodic"))
+    # saved memory round trip (custom_rcnn.py:527-530 -> loader.py:216-223)
+    sem = rng.integers(-1, 20, cells)
+    mem = rng.standard_normal((cells, 512)).astype(np.float32)
+    obs = rng.integers(0, 5, cells).astype(np.float32)
+    for seq in ("sceneA_0_0", "sceneA_0_1", "sceneB_1_0"):
+        F.save_memory(str(tmp_path / "memory" / (seq + ".h5")), sem, mem, obs)
+    d = F.open_store(str(tmp_path / "memory" / "sceneA_0_0.h5"))
+    assert set(d) == {"semmap", "impicit_memory", "observations"} and d["semmap"].dtype == np.int32
+    sem1, mem1, obs1 = F.load_memory(str(tmp_path / "memory" / "sceneA_0_0.h5"))
+    assert np.array_equal(sem1, sem + 1) and np.array_equal(mem1, mem) and np.array_equal(obs1, obs)
+    ds2 = F.EpisodeDataset(str(root), semmap_path=str(tmp_path / "memory"))
+    assert np.array_equal(ds2[1][5]["memory_features"], mem) and np.array_equal(ds2[1][5]["observations"], obs)
+    with pytest.raises(F.StoreError):
+        F.open_store(str(tmp_path / "nope.h5"))                             # no silent zero-memory fallback

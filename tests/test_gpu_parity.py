@@ -53,6 +53,15 @@ def test_backproject_matches_reference_golden(eod, cuda, golden, name):
     assert np.array_equal(r["idx"].cpu().numpy(), g["flat"])
 
 
+@pytest.mark.parametrize("name", ["geometry_small", "geometry_full", "geometry_fine"])
+def test_quantize_world_matches_reference_golden(eod, cuda, golden, name):
+    """Stored world coordinates -> proj_indices: SMNet/build_memory_data.py:135-143 executed from the reference source."""
+    g = golden(name)
+    got = eod.ops.quantize_world(_t(g["world"], cuda), g["map_world_shift"], float(g["cell"]), int(g["map_w"]), int(g["map_h"]))
+    assert got.shape == g["flat"].shape + (1,) and got.dtype == torch.int32
+    assert np.array_equal(got[..., 0].cpu().numpy(), g["flat"])
+
+
 def test_backproject_randomised_vs_oracle(eod, cuda):
     rng = np.random.default_rng(42)
     H, W, E = 60, 100, 5                                           # ragged: not multiples of the block size
