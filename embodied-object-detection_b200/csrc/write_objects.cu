@@ -21,9 +21,124 @@
 //
 // Work is ~P'(=observed/8) * K * C adds per frame (a few 10^8): the kernel is latency-, not bandwidth-bound;
 // what matters is that the 629 MB image and the K host round trips are gone.
+//
+// Mask pasting (8f rank 1, second half).  The reference turns the mask head's (K,28,28) probabilities into (K,480,640)
+// bools with detectron2's paste_masks_in_image (custom_rcnn.py:880): per object, pixel centres of the box's integer
+// neighbourhood are mapped into the 28x28 map, bilinearly sampled with F.grid_sample(align_corners=False, zero
+// padding) and thresholded at 0.5.  Here that test is a pure function of (object, pixel) - paste_covers() - with the
+// exact fp32 operation sequence of ATen's vectorised CPU sampler (canonical: torch CPU, AVX2/AVX-512 build:
+// ix = fma(gx + 1, S/2, -0.5); out = fma(se_v, se, fma(sw_v, sw, fma(ne_v, ne, nw_v * nw)))), so the (K,480,640)
+// masks need never exist: eod_paste_masks folds them straight into `observed`, and the pasted variant of the write
+// re-evaluates the test for the ~1/8 sampled pixels only.
 #include "eod_common.cuh"
 
 namespace {
+
+// One kept detection prepared for pasting (detectron2 _do_paste_mask with skip_empty=True, one chunk per mask).
+struct PasteObj {
+    float x0, y0, dx, dy;      // box corner and extents x1 - x0, y1 - y0 (fp32 subtraction as torch does it)
+    int rx0, ry0, rx1, ry1;    // integer region [rx0, rx1) x [ry0, ry1) outside of which the pasted mask is False
+};
+
+__device__ __forceinline__ PasteObj paste_prepare(const float *__restrict__ box, int H, int W)
+{
+    PasteObj o;
+    const float x0 = __ldg(box), y0 = __ldg(box + 1), x1 = __ldg(box + 2), y1 = __ldg(box + 3);
+    o.x0 = x0; o.y0 = y0;
+    o.dx = __fsub_rn(x1, x0); o.dy = __fsub_rn(y1, y0);
+    // clamp(floor(x0) - 1, min=0), clamp(ceil(x1) + 1, max=W); the extra clamps only keep the float->int conversion defined
+    o.rx0 = (int)fminf(fmaxf(__fsub_rn(floorf(x0), 1.f), 0.f), (float)W);
+    o.ry0 = (int)fminf(fmaxf(__fsub_rn(floorf(y0), 1.f), 0.f), (float)H);
+    o.rx1 = (int)fmaxf(fminf(__fadd_rn(ceilf(x1), 1.f), (float)W), 0.f);
+    o.ry1 = (int)fmaxf(fminf(__fadd_rn(ceilf(y1), 1.f), (float)H), 0.f);
+    return o;
+}
+
+// source coordinate of pixel centre c + 0.5 along one axis: ((c + 0.5 - b0) / extent * 2 - 1) un-normalised for an S-wide map
+__device__ __forceinline__ float paste_coord(int c, float b0, float extent, float half_S)
+{
+    const float g = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(__fadd_rn((float)c, 0.5f), b0), extent), 2.f), 1.f);
+    return __fmaf_rn(__fadd_rn(g, 1.f), half_S, -0.5f);
+}
+
+// pasted-mask value test for one (object, pixel); m = the object's (S,S) probabilities
+__device__ __forceinline__ bool paste_covers(const float *__restrict__ m, const PasteObj &o, int S, int px, int py, float thr)
+{
+    if (px < o.rx0 || px >= o.rx1 || py < o.ry0 || py >= o.ry1) return false;
+    const float half_S = (float)S * 0.5f, fS = (float)S;
+    const float ix = paste_coord(px, o.x0, o.dx, half_S), iy = paste_coord(py, o.y0, o.dy, half_S);
+    const float xw = floorf(ix), yn = floorf(iy);
+    const float xe = __fadd_rn(xw, 1.f), ys = __fadd_rn(yn, 1.f);
+    const float w = __fsub_rn(ix, xw), e = __fsub_rn(1.f, w), n = __fsub_rn(iy, yn), s = __fsub_rn(1.f, n);
+    const bool in_w = xw > -1.f && xw < fS, in_e = xe > -1.f && xe < fS, in_n = yn > -1.f && yn < fS, in_s = ys > -1.f && ys < fS;
+    if (!((in_w || in_e) && (in_n || in_s))) {
+        // every tap is padding: the sampler returns 0 * weights (NaN for non-finite coordinates): covered only if 0 >= thr
+        const float z = __fmul_rn(0.f, __fmul_rn(s, e));
+        return __fmaf_rn(0.f, __fmul_rn(n, w), __fmaf_rn(0.f, __fmul_rn(n, e), __fmaf_rn(0.f, __fmul_rn(s, w), z))) >= thr;
+    }
+    const int jx = in_w ? (int)xw : 0, jy = in_n ? (int)yn : 0;
+    const int kx = in_e ? (int)xe : 0, ky = in_s ? (int)ys : 0;
+    const float v_nw = (in_w && in_n) ? __ldg(m + jy * S + jx) : 0.f;
+    const float v_ne = (in_e && in_n) ? __ldg(m + jy * S + kx) : 0.f;
+    const float v_sw = (in_w && in_s) ? __ldg(m + ky * S + jx) : 0.f;
+    const float v_se = (in_e && in_s) ? __ldg(m + ky * S + kx) : 0.f;
+    float acc = __fmul_rn(v_nw, __fmul_rn(s, e));
+    acc = __fmaf_rn(v_ne, __fmul_rn(s, w), acc);
+    acc = __fmaf_rn(v_sw, __fmul_rn(n, e), acc);
+    acc = __fmaf_rn(v_se, __fmul_rn(n, w), acc);
+    return acc >= thr;
+}
+
+constexpr int kPasteChunk = 128;      // objects staged in shared memory at a time
+
+// thread per 4 consecutive pixels; masks (E,Kmax,HW) u8 and / or observed (E,HW) u8
+__global__ void __launch_bounds__(256) paste_masks_kernel(const float *__restrict__ probs, const float *__restrict__ boxes,
+                                                          const int32_t *__restrict__ n_obj, int Kmax, int S, int H, int W, float thr,
+                                                          uint8_t *__restrict__ masks, uint8_t *__restrict__ observed)
+{
+    __shared__ PasteObj s_obj[kPasteChunk];
+    const int e = blockIdx.y, HW = H * W;
+    const int p0 = (blockIdx.x * 256 + threadIdx.x) * 4;
+    const int K = n_obj ? max(0, min(__ldg(n_obj + e), Kmax)) : Kmax;
+    int px[4], py[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) { px[b] = (p0 + b) % W; py[b] = (p0 + b) / W; }
+    uint32_t any = 0;
+    for (int k0 = 0; k0 < Kmax; k0 += kPasteChunk) {
+        const int kn = min(kPasteChunk, Kmax - k0);
+        __syncthreads();
+        if ((int)threadIdx.x < kn && k0 + (int)threadIdx.x < K) s_obj[threadIdx.x] = paste_prepare(boxes + ((size_t)e * Kmax + k0 + threadIdx.x) * 4, H, W);
+        __syncthreads();
+        if (p0 >= HW) continue;
+        for (int j = 0; j < kn; ++j) {
+            const int k = k0 + j;
+            uint32_t bits = 0;
+            if (k < K) {
+                const PasteObj o = s_obj[j];
+                // whole quad outside the object's rows / columns: skip (the common case)
+                if (!(py[3] < o.ry0 || py[0] >= o.ry1 || (py[0] == py[3] && (px[3] < o.rx0 || px[0] >= o.rx1)))) {
+                    const float *m = probs + ((size_t)e * Kmax + k) * S * S;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                        if (p0 + b < HW && paste_covers(m, o, S, px[b], py[b], thr)) bits |= 1u << (8 * b);
+                }
+            }
+            any |= bits;
+            if (masks) {                                   // objects beyond n_obj[e] get all-False planes
+                uint8_t *dst = masks + ((size_t)e * Kmax + k) * HW + p0;
+                if (p0 + 3 < HW && (reinterpret_cast<uintptr_t>(dst) & 3u) == 0) *reinterpret_cast<uint32_t *>(dst) = bits;
+                else
+                    for (int b = 0; b < 4 && p0 + b < HW; ++b) dst[b] = (bits >> (8 * b)) & 1u;
+            }
+        }
+    }
+    if (observed && p0 < HW) {
+        uint8_t *dst = observed + (size_t)e * HW + p0;
+        if (p0 + 3 < HW && (reinterpret_cast<uintptr_t>(dst) & 3u) == 0) *reinterpret_cast<uint32_t *>(dst) = any;
+        else
+            for (int b = 0; b < 4 && p0 + b < HW; ++b) dst[b] = (any >> (8 * b)) & 1u;
+    }
+}
 
 // one thread per 4 pixels (uchar4 mask loads): observed = OR over the episode's objects
 __global__ void __launch_bounds__(256) masks_observed_kernel(const uint8_t *__restrict__ masks, const int32_t *__restrict__ n_obj, int Kmax,
@@ -44,9 +159,11 @@ __global__ void __launch_bounds__(256) masks_observed_kernel(const uint8_t *__re
 
 // CTA = 256 consecutive pixels of one episode; a warp takes the CTA's sampled pixels round-robin, lanes own
 // channels c = lane + 32*j.  The per-object adds happen in object-index order (custom_rcnn.py:890-895).
-template <int C>
+// kPasted: the cover test is paste_covers() on the (Kmax,S,S) probabilities + boxes instead of a byte of the (Kmax,HW) masks.
+template <int C, bool kPasted>
 __global__ void __launch_bounds__(256) write_objects_kernel(const float *__restrict__ box_features, const uint8_t *__restrict__ masks,
-                                                            const int32_t *__restrict__ n_obj, int Kmax, const int32_t *__restrict__ idx,
+                                                            const float *__restrict__ probs, const float *__restrict__ boxes, int Sm, int W,
+                                                            float thr, const int32_t *__restrict__ n_obj, int Kmax, const int32_t *__restrict__ idx,
                                                             const uint8_t *__restrict__ samp, const int32_t *__restrict__ slot_of_cell, int HW,
                                                             int64_t n_cells, int S, float *__restrict__ scratch)
 {
@@ -63,7 +180,7 @@ __global__ void __launch_bounds__(256) write_objects_kernel(const float *__restr
     if (n == 0) return;
     const int K = n_obj ? min(__ldg(n_obj + e), Kmax) : Kmax;
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint8_t *m = masks + (size_t)e * Kmax * HW;
+    const uint8_t *m = kPasted ? nullptr : masks + (size_t)e * Kmax * HW;
     const float *f = box_features + (size_t)e * Kmax * C;
     for (int i = warp; i < n; i += 8) {
         const int px = s_list[i];
@@ -71,9 +188,18 @@ __global__ void __launch_bounds__(256) write_objects_kernel(const float *__restr
 #pragma unroll
         for (int j = 0; j < J; ++j) acc[j] = 0.f;
         int cnt = 0;
-        for (int k0 = 0; k0 < K; k0 += 32) {                       // lanes fetch 32 objects' mask bytes at once
+        for (int k0 = 0; k0 < K; k0 += 32) {                       // lanes test 32 objects at once
             const int k = k0 + (int)lane;
-            const unsigned cover = __ballot_sync(0xffffffffu, k < K && __ldg(m + (size_t)k * HW + px) != 0);
+            bool mine = false;
+            if (k < K) {
+                if (kPasted) {
+                    const PasteObj o = paste_prepare(boxes + ((size_t)e * Kmax + k) * 4, HW / W, W);
+                    mine = paste_covers(probs + ((size_t)e * Kmax + k) * Sm * Sm, o, Sm, px % W, px / W, thr);
+                } else {
+                    mine = __ldg(m + (size_t)k * HW + px) != 0;
+                }
+            }
+            const unsigned cover = __ballot_sync(0xffffffffu, mine);
             unsigned todo = cover;
             while (todo) {                                         // ascending object index
                 const int kk = k0 + __ffs(todo) - 1;
@@ -140,6 +266,33 @@ extern "C" int eod_masks_observed(const uint8_t *masks, const int32_t *n_obj, in
     return eod_check_launch("eod_masks_observed");
 }
 
+static int launch_write_objects(const char *what, bool pasted, const float *box_features, const uint8_t *masks, const float *probs,
+                                const float *boxes, int S, int W, float thr, const int32_t *n_obj, int Kmax, const int32_t *idx,
+                                const uint8_t *samp, const int32_t *slot_of_cell, int n_episodes, int C, int HW, int64_t n_cells,
+                                int n_slots_max, float *scratch, cudaStream_t st)
+{
+    dim3 grid((HW + 255) / 256, n_episodes);
+#define EOD_WO(CC)                                                                                                                      \
+    case CC:                                                                                                                            \
+        if (pasted)                                                                                                                     \
+            write_objects_kernel<CC, true><<<grid, 256, 0, st>>>(box_features, masks, probs, boxes, S, W, thr, n_obj, Kmax, idx, samp,  \
+                                                                 slot_of_cell, HW, n_cells, n_slots_max, scratch);                     \
+        else                                                                                                                            \
+            write_objects_kernel<CC, false><<<grid, 256, 0, st>>>(box_features, masks, probs, boxes, S, W, thr, n_obj, Kmax, idx, samp, \
+                                                                  slot_of_cell, HW, n_cells, n_slots_max, scratch);                    \
+        break;
+    switch (C) {
+        EOD_WO(128)
+        EOD_WO(256)
+        EOD_WO(512)
+    default:
+        eod_set_error("%s: C=%d not compiled in (128, 256, 512)", what, C);
+        return EOD_ERR_UNSUPPORTED;
+    }
+#undef EOD_WO
+    return eod_check_launch(what);
+}
+
 extern "C" int eod_write_objects(const float *box_features, const uint8_t *masks, const int32_t *n_obj, int Kmax, const int32_t *idx,
                                  const uint8_t *samp, const int32_t *slot_of_cell, int n_episodes, int C, int HW, int64_t n_cells,
                                  int n_slots_max, float *scratch, eod_stream_t stream)
@@ -147,17 +300,35 @@ extern "C" int eod_write_objects(const float *box_features, const uint8_t *masks
     EOD_REQUIRE(box_features && masks && idx && samp && slot_of_cell && scratch, EOD_ERR_BADARG, "eod_write_objects: null pointer");
     EOD_REQUIRE(n_episodes > 0 && n_episodes <= 65535 && Kmax > 0 && HW > 0 && n_cells > 0 && n_slots_max > 0, EOD_ERR_BADARG,
                 "eod_write_objects: bad sizes");
-    dim3 grid((HW + 255) / 256, n_episodes);
-    cudaStream_t st = (cudaStream_t)stream;
-    switch (C) {
-    case 128: write_objects_kernel<128><<<grid, 256, 0, st>>>(box_features, masks, n_obj, Kmax, idx, samp, slot_of_cell, HW, n_cells, n_slots_max, scratch); break;
-    case 256: write_objects_kernel<256><<<grid, 256, 0, st>>>(box_features, masks, n_obj, Kmax, idx, samp, slot_of_cell, HW, n_cells, n_slots_max, scratch); break;
-    case 512: write_objects_kernel<512><<<grid, 256, 0, st>>>(box_features, masks, n_obj, Kmax, idx, samp, slot_of_cell, HW, n_cells, n_slots_max, scratch); break;
-    default:
-        eod_set_error("eod_write_objects: C=%d not compiled in (128, 256, 512)", C);
-        return EOD_ERR_UNSUPPORTED;
-    }
-    return eod_check_launch("eod_write_objects");
+    return launch_write_objects("eod_write_objects", false, box_features, masks, nullptr, nullptr, 0, 1, 0.f, n_obj, Kmax, idx, samp,
+                                slot_of_cell, n_episodes, C, HW, n_cells, n_slots_max, scratch, (cudaStream_t)stream);
+}
+
+extern "C" int eod_paste_masks(const float *mask_probs, const float *boxes, const int32_t *n_obj, int n_episodes, int Kmax, int S, int H,
+                               int W, float threshold, uint8_t *masks, uint8_t *observed, eod_stream_t stream)
+{
+    EOD_REQUIRE(mask_probs && boxes && (masks || observed), EOD_ERR_BADARG, "eod_paste_masks: null pointer");
+    EOD_REQUIRE(n_episodes > 0 && n_episodes <= 65535 && Kmax > 0 && S > 0 && S <= 4096 && H > 0 && W > 0 && (int64_t)H * W < (1ll << 31) - 1024,
+                EOD_ERR_BADARG, "eod_paste_masks: bad sizes");
+    EOD_REQUIRE(threshold >= 0.f, EOD_ERR_UNSUPPORTED, "eod_paste_masks: threshold < 0 (uint8 soft masks) is not supported");
+    dim3 grid((H * W + 1023) / 1024, n_episodes);
+    paste_masks_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mask_probs, boxes, n_obj, Kmax, S, H, W, threshold, masks, observed);
+    return eod_check_launch("eod_paste_masks");
+}
+
+extern "C" int eod_write_objects_pasted(const float *box_features, const float *mask_probs, const float *boxes, const int32_t *n_obj,
+                                        int Kmax, int S, int H, int W, float threshold, const int32_t *idx, const uint8_t *samp,
+                                        const int32_t *slot_of_cell, int n_episodes, int C, int64_t n_cells, int n_slots_max,
+                                        float *scratch, eod_stream_t stream)
+{
+    EOD_REQUIRE(box_features && mask_probs && boxes && idx && samp && slot_of_cell && scratch, EOD_ERR_BADARG,
+                "eod_write_objects_pasted: null pointer");
+    EOD_REQUIRE(n_episodes > 0 && n_episodes <= 65535 && Kmax > 0 && S > 0 && S <= 4096 && H > 0 && W > 0 && (int64_t)H * W < (1ll << 31) - 1024 &&
+                    n_cells > 0 && n_slots_max > 0,
+                EOD_ERR_BADARG, "eod_write_objects_pasted: bad sizes");
+    EOD_REQUIRE(threshold >= 0.f, EOD_ERR_UNSUPPORTED, "eod_write_objects_pasted: threshold < 0 is not supported");
+    return launch_write_objects("eod_write_objects_pasted", true, box_features, nullptr, mask_probs, boxes, S, W, threshold, n_obj, Kmax, idx,
+                                samp, slot_of_cell, n_episodes, C, H * W, n_cells, n_slots_max, scratch, (cudaStream_t)stream);
 }
 
 extern "C" int eod_flush_slots(const uint32_t *frame_cnt, int32_t *slot_of_cell, const int32_t *slot_cell, int32_t *n_slots, int n_episodes,

@@ -153,3 +153,32 @@ def make_detections(rng: np.random.Generator, H: int = 480, W: int = 640, C: int
         else:
             masks[k] = ((uu - cu) / hw) ** 2 + ((vv - cv) / hh) ** 2 <= 1.0
     return f, masks
+
+
+def make_mask_head_detections(rng: np.random.Generator, H: int = 480, W: int = 640, C: int = 512, k_range=(4, 16), S: int = 28,
+                              edge_cases: bool = False):
+    """Kept detections as the detector hands them over BEFORE pasting (custom_rcnn.py:876-880): box_features (K,C) =
+    50 * normalize(N(0,1)), mask_probs (K,S,S) f32 = sigmoid of a smooth blob logit (what mask_rcnn_inference leaves in
+    pred_masks), boxes (K,4) f32 XYXY in pixels with fractional corners.  edge_cases adds boxes that stick out of the
+    image, sub-pixel boxes and a saturated mask."""
+    K = int(rng.integers(k_range[0], k_range[1] + 1))
+    f = rng.standard_normal((K, C)).astype(np.float32)
+    f = (50.0 * f / np.linalg.norm(f, axis=1, keepdims=True)).astype(np.float32)
+    yy, xx = np.mgrid[0:S, 0:S].astype(np.float32)
+    probs = np.empty((K, S, S), np.float32)
+    boxes = np.empty((K, 4), np.float32)
+    for k in range(K):
+        cx, cy = rng.uniform(0.3 * S, 0.7 * S, 2)
+        rx, ry = rng.uniform(0.2 * S, 0.55 * S, 2)
+        logit = 6.0 * (1.0 - ((xx - cx) / rx) ** 2 - ((yy - cy) / ry) ** 2) + rng.standard_normal((S, S)) * 0.5
+        probs[k] = (1.0 / (1.0 + np.exp(-logit))).astype(np.float32)
+        bw, bh = rng.uniform(0.06 * W, 0.35 * W), rng.uniform(0.08 * H, 0.45 * H)
+        x0, y0 = rng.uniform(-0.1 * W, 0.9 * W) if edge_cases else rng.uniform(0, W - bw), \
+            rng.uniform(-0.1 * H, 0.9 * H) if edge_cases else rng.uniform(0, H - bh)
+        boxes[k] = (x0, y0, x0 + bw, y0 + bh)
+    if edge_cases and K >= 3:
+        boxes[0] = (W * 0.5 + 0.25, H * 0.5 + 0.25, W * 0.5 + 0.75, H * 0.5 + 0.6)      # thinner than a pixel
+        probs[1] = 1.0                                                                  # saturated: value == 0.5 on the box edge
+        boxes[1] = (np.floor(W * 0.25), np.floor(H * 0.25), np.floor(W * 0.25) + 28.0, np.floor(H * 0.25) + 56.0)
+        boxes[2] = (-30.5, -12.25, W + 17.0, H + 3.5)                                   # larger than the image
+    return f, probs, boxes

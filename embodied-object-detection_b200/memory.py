@@ -187,6 +187,22 @@ class EpisodeBatch:
         ops.flush_slots(self.frame_cnt, self._slots, self.sums)
         self._finalize()
 
+    def write_detections(self, box_features: torch.Tensor, mask_probs: torch.Tensor, boxes: torch.Tensor,
+                         n_obj: Optional[torch.Tensor] = None, sample_stride: int = 8, mask_thresh: float = 0.5) -> None:
+        """write_objects taking the detector's un-pasted output (custom_rcnn.py:876-880): mask_probs (E,Kmax,S,S) f32 (the
+        mask head's 28x28 probabilities), boxes (E,Kmax,4) f32 XYXY.  paste_masks_in_image is folded into the write: the
+        (K,480,640) masks are never built - one pass ORs the pasted test into ``observed``, the write re-evaluates it for
+        the sampled pixels only."""
+        S = -(-self.H * self.W // sample_stride)
+        if self._slots is None or self._slots.S < S:
+            self._slots = ops.ObjectSlots(self.E, self.n_cells, self.C, S, self.device)
+        _, observed = ops.paste_masks(mask_probs, boxes, (self.H, self.W), mask_thresh, n_obj, want_masks=False, want_observed=True)
+        samp = ops.sample_mask(observed, sample_stride)
+        ops.frame_count(self.idx, samp, self.frame_cnt, n_obj, self._slots)
+        ops.write_objects_pasted(box_features, mask_probs, boxes, n_obj, self.idx, samp, self._slots, mask_thresh)
+        ops.flush_slots(self.frame_cnt, self._slots, self.sums)
+        self._finalize()
+
     # ---- one frame, overlapped -------------------------------------------------------------------------------
     def step(self, depth, pose, shifts, intr, cell, feat, samp=None, order: int = ORDER_ZX) -> List[torch.Tensor]:
         """One frame of the hot path for all E episodes, in the reference's order: the read of frame t sees
@@ -383,18 +399,56 @@ class SpatialFeatureMemory:
                                visualise: bool = False) -> None:
         """custom_rcnn.py:681-760.  ``inference_results`` is what ``inference_with_proposals`` returns
         (:882): None (no kept detection -> no write at all, :686) or (boxes, box_features (K,C), masks
-        (K,H,W) bool, pred_instances).  Sums and visibility counts are accumulated in place on the device."""
+        (K,H,W) bool, pred_instances); floating-point masks (K,S,S) are taken as the mask head's probabilities BEFORE
+        paste_masks_in_image (:880) and pasted here with ``boxes`` (K,4).  Sums and visibility counts are accumulated in place on the device."""
         if inference_results is None:
             return
-        _, box_features, masks, _ = inference_results
+        boxes, box_features, masks, _ = inference_results
         if self.implicit_memory is None or self.implicit_memory.shape[0] != memory.shape[0]:
             self.reset(memory.shape[0])
         self._dims = self.map_dims(frame.get("sequence_name", ""))
+        if masks.is_floating_point():
+            # un-pasted mask-head output (K,S,S) with its boxes: paste_masks_in_image (:880) folded into the write
+            if self.fused_write:
+                self.write_detections(box_features, masks, boxes, proj_indices)
+                return
+            masks = self.paste_masks_in_image(masks, boxes, (self.H, self.W))
         if self.fused_write:
             self.write_object_features(box_features, masks, proj_indices)
         else:
             image_features, observed = self.box_to_image_features(box_features, masks)
             self.write_image_features(image_features, observed, proj_indices)
+
+    def paste_masks_in_image(self, masks: torch.Tensor, boxes: torch.Tensor, image_shape: Tuple[int, int],
+                             threshold: float = 0.5) -> torch.Tensor:
+        """detectron2's paste_masks_in_image as the reference calls it (custom_rcnn.py:880): masks (K,S,S) f32
+        probabilities, boxes (K,4) f32 XYXY -> (K,H,W) bool; bit-exact with torch-CPU."""
+        if masks.shape[0] == 0:
+            return torch.zeros((0,) + tuple(image_shape), dtype=torch.bool, device=self.device)
+        m, _ = ops.paste_masks(masks.to(self.device, torch.float32).contiguous().unsqueeze(0),
+                               boxes.to(self.device, torch.float32).contiguous().unsqueeze(0), image_shape, threshold)
+        return m[0]
+
+    def write_detections(self, box_features: torch.Tensor, mask_probs: torch.Tensor, boxes: torch.Tensor,
+                         proj_indices: torch.Tensor, mask_thresh: float = 0.5) -> None:
+        """custom_rcnn.py:876-880 + 690-701,738-743 in one go: the kept detections' (K,S,S) mask probabilities and boxes are
+        pasted on the fly (no (K,H,W) masks, no (1,C,H,W) image)."""
+        idx = self._idx32(proj_indices).view(1, self.H, self.W)
+        bf = box_features.to(self.device, torch.float32).contiguous().unsqueeze(0)
+        mp = mask_probs.to(self.device, torch.float32).contiguous().unsqueeze(0)
+        bx = boxes.to(self.device, torch.float32).contiguous().unsqueeze(0)
+        HW = self.H * self.W
+        S = -(-HW // self.sample_stride)
+        n_cells = self.implicit_memory.shape[0]
+        if self._slots is None or self._slots.S < S or self._slots.n_cells != n_cells:
+            self._slots = ops.ObjectSlots(1, n_cells, self.C, S, self.device)
+        _, observed = ops.paste_masks(mp, bx, (self.H, self.W), mask_thresh, want_masks=False, want_observed=True)
+        samp = ops.sample_mask(observed, self.sample_stride)
+        ops.frame_count(idx, samp, self._frame_cnt, None, self._slots)
+        ops.write_objects_pasted(bf, mp, bx, None, idx, samp, self._slots, mask_thresh)
+        ops.flush_slots(self._frame_cnt, self._slots, self.implicit_memory.unsqueeze(0))
+        self._semmap_update()
+        ops.finalize_counts(idx, self._frame_cnt, self.observations.unsqueeze(0))
 
     def write_object_features(self, box_features: torch.Tensor, masks: torch.Tensor, proj_indices: torch.Tensor) -> None:
         """A6 + A7 + A8 without the (1,C,H,W) image (custom_rcnn.py:690-701,738-743): the per-pixel object mean is

@@ -16,7 +16,7 @@ from ._lib import (FUSE_IMAGE_ONLY, FUSE_MEM_ONLY, FUSE_SUM, LAYOUT_CHW, LAYOUT_
 launch_count = 0
 
 _LAUNCHES = {"eod_backproject_quantize": 1, "eod_quantize_world": 1, "eod_sample_mask": 1, "eod_frame_count": 1, "eod_expand_counts": 1, "eod_write_mean": 1, "eod_write_mean_det": 7,
-             "eod_finalize_counts": 1, "eod_box_to_image_features": 1, "eod_masks_observed": 1, "eod_bilinear_lattice": 1, "eod_write_objects": 1, "eod_flush_slots": 2, "eod_write_max": 2, "eod_read_pool": 1,
+             "eod_finalize_counts": 1, "eod_box_to_image_features": 1, "eod_masks_observed": 1, "eod_paste_masks": 1, "eod_write_objects_pasted": 1, "eod_bilinear_lattice": 1, "eod_write_objects": 1, "eod_flush_slots": 2, "eod_write_max": 2, "eod_read_pool": 1,
              "eod_fuse": 1, "eod_normalize_memory": 1, "eod_reset_touched": 1, "eod_semmap_update": 1, "eod_semmap_decode": 2}
 
 
@@ -282,6 +282,49 @@ def write_objects(box_features: torch.Tensor, masks: torch.Tensor, n_obj: Option
         _dev(n_obj, torch.int32, "n_obj")
     _call("eod_write_objects", box_features.data_ptr(), masks.data_ptr(), _ptr(n_obj), Kmax, idx.data_ptr(), samp.data_ptr(),
           slots.slot_of_cell.data_ptr(), E, slots.C, H * W, slots.n_cells, slots.S, slots.scratch.data_ptr(), _stream())
+
+
+def _paste_args(mask_probs: torch.Tensor, boxes: torch.Tensor, n_obj: Optional[torch.Tensor]):
+    _dev(mask_probs, torch.float32, "mask_probs"), _dev(boxes, torch.float32, "boxes")
+    if mask_probs.dim() != 4 or mask_probs.shape[-1] != mask_probs.shape[-2]:
+        raise ValueError("mask_probs must be (E,Kmax,S,S): only square mask predictions are supported")
+    E, Kmax, S, _ = mask_probs.shape
+    if boxes.shape != (E, Kmax, 4):
+        raise ValueError("boxes must be (E,Kmax,4) XYXY matching mask_probs (E,Kmax,S,S)")
+    if n_obj is not None:
+        _dev(n_obj, torch.int32, "n_obj")
+    return E, Kmax, S
+
+
+def paste_masks(mask_probs: torch.Tensor, boxes: torch.Tensor, image_shape: Tuple[int, int], threshold: float = 0.5,
+                n_obj: Optional[torch.Tensor] = None, want_masks: bool = True, want_observed: bool = False):
+    """paste_masks_in_image (detectron2 mask_ops.py, custom_rcnn.py:880) for E episodes: mask_probs (E,Kmax,S,S) f32,
+    boxes (E,Kmax,4) f32 -> masks (E,Kmax,H,W) bool and / or observed (E,H*W) u8 (OR over the episode's objects)."""
+    E, Kmax, S = _paste_args(mask_probs, boxes, n_obj)
+    H, W = int(image_shape[0]), int(image_shape[1])
+    dev = mask_probs.device
+    masks = torch.empty((E, Kmax, H, W), dtype=torch.uint8, device=dev) if want_masks else None
+    observed = torch.empty((E, H * W), dtype=torch.uint8, device=dev) if want_observed else None
+    if Kmax == 0:
+        return (masks.view(torch.bool) if want_masks else None), (observed.zero_() if want_observed else None)
+    _call("eod_paste_masks", mask_probs.data_ptr(), boxes.data_ptr(), _ptr(n_obj), E, Kmax, S, H, W, float(threshold),
+          _ptr(masks), _ptr(observed), _stream())
+    return (masks.view(torch.bool) if want_masks else None), observed
+
+
+def write_objects_pasted(box_features: torch.Tensor, mask_probs: torch.Tensor, boxes: torch.Tensor, n_obj: Optional[torch.Tensor],
+                         idx: torch.Tensor, samp: torch.Tensor, slots: ObjectSlots, threshold: float = 0.5) -> None:
+    """write_objects with the pasted-mask test evaluated on the fly: mask_probs (E,Kmax,S,S), boxes (E,Kmax,4), idx (E,H,W)."""
+    E, Kmax, S = _paste_args(mask_probs, boxes, n_obj)
+    _dev(box_features, torch.float32, "box_features"), _dev(idx, torch.int32, "idx"), _dev(samp, torch.uint8, "samp")
+    if idx.dim() != 3:
+        raise ValueError("idx must be (E,H,W)")
+    _, H, W = idx.shape
+    if box_features.shape != (E, Kmax, slots.C) or slots.E != E:
+        raise ValueError("box_features must be (E,Kmax,C) matching mask_probs and the slot workspace")
+    _call("eod_write_objects_pasted", box_features.data_ptr(), mask_probs.data_ptr(), boxes.data_ptr(), _ptr(n_obj), Kmax, S, H, W,
+          float(threshold), idx.data_ptr(), samp.data_ptr(), slots.slot_of_cell.data_ptr(), E, slots.C, slots.n_cells, slots.S,
+          slots.scratch.data_ptr(), _stream())
 
 
 def flush_slots(frame_cnt: torch.Tensor, slots: ObjectSlots, sums: torch.Tensor) -> None:

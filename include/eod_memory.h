@@ -158,6 +158,25 @@ int eod_write_objects(const float *box_features, const uint8_t *masks, const int
                       const uint8_t *samp, const int32_t *slot_of_cell, int n_episodes, int C, int HW, int64_t n_cells,
                       int n_slots_max, float *scratch, eod_stream_t stream);
 
+/* Mask pasting, detectron2 layers/mask_ops.py paste_masks_in_image as called at custom_rcnn.py:880 (threshold 0.5):
+ * mask_probs (E,Kmax,S,S) f32 (the mask head's probabilities, S = 28), boxes (E,Kmax,4) f32 XYXY in image pixels ->
+ * masks (E,Kmax,H*W) u8 (nullable; planes of objects >= n_obj[e] are all zero) and / or observed (E,H*W) u8 = OR over
+ * the episode's objects (nullable; what eod_masks_observed would return for the pasted masks).  Per object the CPU
+ * code path of the reference's dependency is followed: only pixels of [max(floor(x0)-1,0), min(ceil(x1)+1,W)) x (same
+ * in y) are sampled, pixel centre -> box-normalised coordinate -> F.grid_sample(bilinear, zero padding,
+ * align_corners=False) -> value >= threshold, in the fp32 operation order of ATen's vectorised CPU sampler.
+ * Bit-exact with torch-CPU on the pasted bools.  threshold must be >= 0. */
+int eod_paste_masks(const float *mask_probs, const float *boxes, const int32_t *n_obj, int n_episodes, int Kmax, int S, int H,
+                    int W, float threshold, uint8_t *masks, uint8_t *observed, eod_stream_t stream);
+
+/* eod_write_objects with the pasted-mask test evaluated on the fly for the sampled pixels (samp from
+ * eod_sample_mask(observed of eod_paste_masks)): the (K,H,W) masks are never built.  Same result, bit for bit, as
+ * eod_paste_masks followed by eod_write_objects. */
+int eod_write_objects_pasted(const float *box_features, const float *mask_probs, const float *boxes, const int32_t *n_obj,
+                             int Kmax, int S, int H, int W, float threshold, const int32_t *idx, const uint8_t *samp,
+                             const int32_t *slot_of_cell, int n_episodes, int C, int64_t n_cells, int n_slots_max,
+                             float *scratch, eod_stream_t stream);
+
 /* sums[cell] += scratch[slot] / n_cell for every claimed slot (the per-cell mean of custom_rcnn.py:931-934 added
  * once, :696-697,742); scratch rows, slot_of_cell entries and n_slots return to zero.  Run before
  * eod_finalize_counts (which clears frame_cnt). */

@@ -2,6 +2,7 @@
 
 CPU restatement of the reference's spatial-feature-memory path:
   * ``oracle/geometry.c``      plain-C back-projection / quantisation / pooling / sequential cell sums
+  * ``oracle/paste.c``         plain-C mask pasting (detectron2 paste_masks_in_image as called at custom_rcnn.py:880)
   * ``oracle/reference_ops.py`` torch-CPU restatement of the cited reference lines
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference``
@@ -28,8 +29,8 @@ _lib: Optional[ctypes.CDLL] = None
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "geometry.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("geometry.c", "paste.c", "Makefile")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return _SO
 
@@ -92,3 +93,15 @@ def cell_sums_seq(feat_chw: np.ndarray, idx: np.ndarray, samp: Optional[np.ndarr
     sm = None if samp is None else np.ascontiguousarray(samp, np.uint8).reshape(-1)
     lib().oracle_cell_sums_seq(_p(feat), C, HW, _p(idx), _p(sm), _p(s), _p(n))
     return s, n
+
+
+def paste_masks(probs: np.ndarray, boxes: np.ndarray, H: int, W: int, thr: float = 0.5, want_values: bool = False):
+    """probs (K,S,S) f32, boxes (K,4) f32 XYXY -> masks (K,H,W) bool [, sampled values (K,H,W) f32] (oracle/paste.c)."""
+    probs = np.ascontiguousarray(probs, np.float32)
+    boxes = np.ascontiguousarray(boxes, np.float32)
+    K, S = probs.shape[0], probs.shape[1]
+    masks = np.zeros((K, H, W), np.uint8)
+    values = np.zeros((K, H, W), np.float32) if want_values else None
+    if K:
+        lib().oracle_paste_masks(_p(probs), _p(boxes), K, S, H, W, ctypes.c_float(thr), _p(masks), _p(values))
+    return (masks.astype(bool), values) if want_values else masks.astype(bool)

@@ -102,6 +102,38 @@ def quantize_flat_index(world_xyz: torch.Tensor, map_world_shift: torch.Tensor, 
 # --------------------------------------------------------------------------------------------------
 
 
+def paste_masks_in_image(masks: torch.Tensor, boxes: torch.Tensor, image_shape, threshold: float = 0.5, want_values: bool = False):
+    """detectron2 layers/mask_ops.py paste_masks_in_image + _do_paste_mask as executed on the CPU (call site
+    custom_rcnn.py:880): one chunk per mask, skip_empty=True, F.grid_sample(align_corners=False), ``>= threshold``.
+    detectron2 is not vendored in /root/reference (README :36-39, git master): this is a restatement of its published
+    source; the arithmetic that decides the result (grid construction + grid_sample) is executed by torch itself.
+    masks (K,S,S) f32 probabilities, boxes (K,4) f32 XYXY -> (K,H,W) bool."""
+    img_h, img_w = image_shape
+    N = masks.shape[0]
+    img_masks = torch.zeros(N, img_h, img_w, dtype=torch.bool)
+    values = torch.zeros(N, img_h, img_w) if want_values else None
+    for i in range(N):
+        m, b = masks[i:i + 1, None], boxes[i:i + 1]
+        x0_int, y0_int = torch.clamp(b.min(dim=0).values.floor()[:2] - 1, min=0).to(dtype=torch.int32)
+        x1_int = torch.clamp(b[:, 2].max().ceil() + 1, max=img_w).to(dtype=torch.int32)
+        y1_int = torch.clamp(b[:, 3].max().ceil() + 1, max=img_h).to(dtype=torch.int32)
+        x0, y0, x1, y1 = torch.split(b, 1, dim=1)
+        img_y = torch.arange(y0_int, y1_int, dtype=torch.float32) + 0.5
+        img_x = torch.arange(x0_int, x1_int, dtype=torch.float32) + 0.5
+        img_y = (img_y - y0) / (y1 - y0) * 2 - 1
+        img_x = (img_x - x0) / (x1 - x0) * 2 - 1
+        gx = img_x[:, None, :].expand(1, img_y.size(1), img_x.size(1))
+        gy = img_y[:, :, None].expand(1, img_y.size(1), img_x.size(1))
+        grid = torch.stack([gx, gy], dim=3)
+        if grid.numel() == 0:
+            continue
+        v = F.grid_sample(m.float(), grid, align_corners=False)[:, 0]
+        img_masks[i, int(y0_int):int(y1_int), int(x0_int):int(x1_int)] = (v >= threshold)[0]
+        if want_values:
+            values[i, int(y0_int):int(y1_int), int(x0_int):int(x1_int)] = v[0]
+    return (img_masks, values) if want_values else img_masks
+
+
 def box_to_image_features(box_features: torch.Tensor, masks: torch.Tensor):
     """custom_rcnn.py:884-901.  box_features (K,C) f32, masks (K,H,W) bool ->
     image_features (1,C,H,W) f32, observed_pixels (H,W) bool."""

@@ -134,6 +134,31 @@ def gen_write():
     np.savez_compressed(os.path.join(HERE, "write_mean.npz"), map_w=mw, map_h=mh, **out)
 
 
+def gen_paste():
+    """paste.npz: detectron2's paste_masks_in_image is absent here (unpinned git dependency), so its published CPU
+    algorithm is restated in oracle/reference_ops.py; the arithmetic that decides every output bit - the grid
+    construction ops and F.grid_sample - is executed by torch-CPU (AVX2 / AVX-512 ATen build) at generation time."""
+    sys.path.insert(0, ROOT)
+    from oracle import reference_ops as R
+    rng = np.random.default_rng(77)
+    H, W = 480, 640
+    out = {}
+    for name, edge in (("plain", False), ("edge", True)):
+        _, probs, boxes = eod_episodes.make_mask_head_detections(rng, H, W, 8, (10, 10), 28, edge_cases=edge)
+        masks, values = R.paste_masks_in_image(torch.from_numpy(probs), torch.from_numpy(boxes), (H, W), 0.5, want_values=True)
+        out[name + "_probs"], out[name + "_boxes"] = probs, boxes
+        out[name + "_masks_bits"] = np.packbits(masks.numpy().reshape(-1))
+        # sampled values of the first two objects only (bit pattern pin of the sampler arithmetic), cropped to their region
+        for k in range(2):
+            ys, xs = np.nonzero(values[k].numpy() != 0)
+            y0, y1, x0, x1 = (ys.min(), ys.max() + 1, xs.min(), xs.max() + 1) if ys.size else (0, 1, 0, 1)
+            out[f"{name}_val{k}_yx"] = np.array([y0, y1, x0, x1], np.int32)
+            out[f"{name}_val{k}"] = values[k, y0:y1, x0:x1].numpy()
+        print(name, "pasted pixels per object:", masks.reshape(masks.shape[0], -1).sum(1).tolist())
+    out["cpu_capability"] = np.array(torch.backends.cpu.get_cpu_capability())
+    np.savez_compressed(os.path.join(HERE, "paste.npz"), H=H, W=W, thr=0.5, **out)
+
+
 def gen_read():
     patch_cpu()
     lines = open(os.path.join(REF, "detic/modeling/backbone/timm.py")).read().splitlines()
@@ -256,10 +281,14 @@ if __name__ == "__main__":
     if "--only-semmap" in sys.argv:
         gen_semmap()
         sys.exit(0)
+    if "--only-paste" in sys.argv:
+        gen_paste()
+        sys.exit(0)
     gen_geometry()
     gen_write()
     gen_read()
     gen_semmap()
+    gen_paste()
     gen_loader_order()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

@@ -492,6 +492,98 @@ def test_batched_fused_object_write_vs_oracle(eod, cuda):
         assert sum(int(f.abs().sum()) for f in batch._frame_cnt2) == 0
 
 
+# --------------------------------------------------------------------------------------------------------
+# mask pasting (custom_rcnn.py:880, detectron2 paste_masks_in_image) and the write fused with it
+# --------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["plain", "edge"])
+def test_paste_masks_matches_torch_golden(eod, cuda, golden, name):
+    """eod_paste_masks against the fixture torch-CPU produced at 480x640 (10 objects; 'edge': sub-pixel box, saturated mask
+    whose box-edge value is exactly the threshold, box larger than the image): every pasted bool identical."""
+    g = golden("paste")
+    H, W = int(g["H"]), int(g["W"])
+    probs, boxes = g[name + "_probs"], g[name + "_boxes"]
+    K = probs.shape[0]
+    ref = _unpack(g[name + "_masks_bits"], (K, H, W))
+    masks, observed = eod.ops.paste_masks(_t(probs[None], cuda), _t(boxes[None], cuda), (H, W), float(g["thr"]), want_observed=True)
+    assert np.array_equal(masks[0].cpu().numpy(), ref)
+    assert np.array_equal(observed[0].cpu().numpy().astype(bool), ref.any(0).reshape(-1))
+    mem = eod.SpatialFeatureMemory(128, cuda)
+    assert np.array_equal(mem.paste_masks_in_image(torch.from_numpy(probs), torch.from_numpy(boxes), (H, W)).cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("H,W,S", [(96, 128, 28), (77, 125, 28), (64, 64, 14), (50, 70, 7)])
+def test_paste_masks_randomised_vs_oracle(eod, cuda, H, W, S):
+    """Ragged object counts per episode, image sizes that are not multiples of 4, odd mask sizes, thresholds other than 0.5,
+    degenerate (zero-extent) boxes: bit-exact against oracle/paste.c; planes beyond n_obj are all False."""
+    rng = np.random.default_rng(H * 1000 + W)
+    E, Kmax = 3, 9
+    n_obj = np.array([Kmax, 4, 0], np.int32)
+    probs = rng.uniform(0, 1, (E, Kmax, S, S)).astype(np.float32)
+    boxes = np.zeros((E, Kmax, 4), np.float32)
+    for e in range(E):
+        _, p, b = eod.episodes.make_mask_head_detections(rng, H, W, 8, (Kmax, Kmax), S, edge_cases=(e == 0))
+        probs[e], boxes[e] = p, b
+    boxes[1, 1] = (10.5, 20.0, 10.5, 40.0)                 # x1 == x0: division by zero -> nothing pasted
+    boxes[1, 2] = (30.0, 12.0, 20.0, 5.0)                  # inverted box
+    for thr in (0.5, 0.3, 0.0):
+        masks, observed = eod.ops.paste_masks(_t(probs, cuda), _t(boxes, cuda), (H, W), thr, _t(n_obj, cuda), want_observed=True)
+        masks = masks.cpu().numpy()
+        for e in range(E):
+            ref = oracle.paste_masks(probs[e, : n_obj[e]], boxes[e, : n_obj[e]], H, W, thr)
+            assert np.array_equal(masks[e, : n_obj[e]], ref), (thr, e, int((masks[e, : n_obj[e]] != ref).sum()))
+            assert not masks[e, n_obj[e]:].any()
+            assert np.array_equal(observed[e].cpu().numpy().astype(bool), ref.any(0).reshape(-1) if n_obj[e] else np.zeros(H * W, bool))
+    with pytest.raises(eod.EodError):
+        eod.ops.paste_masks(_t(probs, cuda), _t(boxes, cuda), (H, W), -1.0)
+
+
+def test_fused_detection_write_vs_oracle(eod, cuda):
+    """EpisodeBatch.write_detections / SpatialFeatureMemory.update_implicit_memory fed with the UN-pasted mask-head output
+    (28x28 probabilities + boxes): against oracle paste -> box_to_image_features -> project_image_features -> accumulate.
+    Touched-cell sets and visibility counts exact, sums within the fp32 tolerance; identical sets to the two-step path
+    (eod_paste_masks -> eod_write_objects)."""
+    E, C, H, W, mw, mh, Kmax = 3, 128, 96, 128, 40, 30, 8
+    cells = mw * mh
+    rng = np.random.default_rng(33)
+    batch = eod.EpisodeBatch(E, mw, mh, C, H, W, cuda)
+    twostep = eod.EpisodeBatch(E, mw, mh, C, H, W, cuda)
+    single = eod.SpatialFeatureMemory(C, cuda, height=H, width=W)
+    single.reset(cells)
+    sums = [torch.zeros(cells, C) for _ in range(E)]
+    counts = [torch.zeros(cells) for _ in range(E)]
+    for t in range(3):
+        idx = (rng.integers(0, cells, (E, H // 4 + 1, W // 8 + 1)).repeat(4, 1).repeat(8, 2)[:, :H, :W]).astype(np.int32)
+        n_obj = np.array([Kmax, 0, 5], np.int32) if t != 1 else np.array([2, Kmax, 0], np.int32)
+        bf = np.full((E, Kmax, C), 1e6, np.float32)
+        probs = np.ones((E, Kmax, 28, 28), np.float32)                  # garbage beyond n_obj must be ignored
+        boxes = np.tile(np.array([0, 0, W, H], np.float32), (E, Kmax, 1))
+        for e in range(E):
+            if n_obj[e]:
+                f, p, b = eod.episodes.make_mask_head_detections(rng, H, W, C, (int(n_obj[e]), int(n_obj[e])), 28, edge_cases=(e == 2))
+                bf[e, : n_obj[e]], probs[e, : n_obj[e]], boxes[e, : n_obj[e]] = f, p, b
+        for b_ in (batch, twostep):
+            b_.set_indices(_t(idx, cuda))
+        batch.write_detections(_t(bf, cuda), _t(probs, cuda), _t(boxes, cuda), _t(n_obj, cuda))
+        pasted, _ = eod.ops.paste_masks(_t(probs, cuda), _t(boxes, cuda), (H, W), 0.5, _t(n_obj, cuda))
+        twostep.write_objects(_t(bf, cuda), pasted, _t(n_obj, cuda))
+        if n_obj[0]:
+            single.update_implicit_memory((_t(boxes[0, : n_obj[0]], cuda), _t(bf[0, : n_obj[0]], cuda), _t(probs[0, : n_obj[0]], cuda), None),
+                                          _t(idx[0], cuda).long(), single.implicit_memory, {})
+        torch.cuda.synchronize()
+        for e in range(E):
+            if n_obj[e]:
+                masks = torch.from_numpy(oracle.paste_masks(probs[e, : n_obj[e]], boxes[e, : n_obj[e]], H, W, 0.5))
+                img, obs = R.box_to_image_features(torch.from_numpy(bf[e, : n_obj[e]]), masks)
+                sums[e], counts[e] = R.write_mean_frame(sums[e], counts[e], img, obs, torch.from_numpy(idx[e]).long(), stride=8)
+            ref = sums[e].numpy()
+            for got in (batch.sums[e].cpu().numpy(), twostep.sums[e].cpu().numpy()) + ((single.implicit_memory.cpu().numpy(),) if e == 0 else ()):
+                assert np.abs(got - ref).max() <= SUM_TOL * max(np.abs(ref).max(), 1e-30), (t, e)
+                assert np.array_equal(got == 0, ref == 0)                                 # touched-cell set: exact
+            assert np.array_equal(batch.counts[e].cpu().numpy(), counts[e].numpy()), (t, e)
+        assert np.array_equal(single.observations.cpu().numpy(), counts[0].numpy())
+    assert sums[0].abs().max() > 0 and sums[1].abs().max() > 0
+
+
 def test_dense_backbone_write_vs_oracle(eod, cuda):
     """A7'' (bytecode-only lineage): bilinear lattice samples bit-exact vs torch-CPU F.interpolate, per-cell means of the
     projected samples within the fp32 tolerance, observed set exact, memory REPLACED (zeros elsewhere)."""

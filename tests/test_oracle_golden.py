@@ -134,3 +134,34 @@ def test_explicit_semmap_restatement_matches_reference(golden):
         sem, inten, _ = R.explicit_semmap(torch.from_numpy(g["sums"]), torch.from_numpy(g["counts"]), torch.from_numpy(g["zs_weight"]), th)
         assert np.array_equal(inten.numpy(), g["intensity"])
         assert np.array_equal(sem.numpy(), g[f"semmap_{th}"])
+
+
+@pytest.mark.parametrize("name", ["plain", "edge"])
+def test_paste_masks_c_oracle_matches_torch_golden(golden, name):
+    """oracle/paste.c against the fixture produced by torch-CPU (restated paste_masks_in_image, executed F.grid_sample):
+    pasted bools identical, sampled values identical bit for bit (pins the fma order of the sampler)."""
+    g = golden("paste")
+    H, W = int(g["H"]), int(g["W"])
+    probs, boxes = g[name + "_probs"], g[name + "_boxes"]
+    ref = _unpack(g[name + "_masks_bits"], (probs.shape[0], H, W))
+    masks, values = oracle.paste_masks(probs, boxes, H, W, float(g["thr"]), want_values=True)
+    assert np.array_equal(masks, ref)
+    for k in range(2):
+        y0, y1, x0, x1 = g[f"{name}_val{k}_yx"]
+        assert np.array_equal(values[k, y0:y1, x0:x1].view(np.uint32), g[f"{name}_val{k}"].view(np.uint32))
+
+
+def test_paste_masks_torch_restatement_matches_c_oracle_randomised():
+    """The torch restatement (executes ATen's grid_sample on this host) and the C restatement agree on seeded detections,
+    including boxes that leave the image; skipped on hosts whose ATen build takes the non-vectorised sampler."""
+    if torch.backends.cpu.get_cpu_capability() == "DEFAULT":
+        pytest.skip("scalar ATen grid_sample rounds differently (no fma); canonical is the AVX2 / AVX-512 build")
+    import importlib
+    episodes = importlib.import_module("embodied-object-detection_b200.episodes")
+    rng = np.random.default_rng(5)
+    H, W = 120, 160
+    for edge in (False, True):
+        _, probs, boxes = episodes.make_mask_head_detections(rng, H, W, 8, (6, 9), 28, edge_cases=edge)
+        ref = R.paste_masks_in_image(torch.from_numpy(probs), torch.from_numpy(boxes), (H, W), 0.5).numpy()
+        assert np.array_equal(oracle.paste_masks(probs, boxes, H, W, 0.5), ref)
+        assert ref.any()
