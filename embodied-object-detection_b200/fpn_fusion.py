@@ -8,9 +8,11 @@ Mirrors the memory block of ``CustomRecurrentFPN`` (detic/modeling/backbone/timm
   * MODEL.MEMORY_TYPE image_only | implicit_memory, MODEL.MAP_FEAT_FUSION sum | mem_only | image_only,
     MODEL.MAP_FEATURE_WEIGHT (timm.py:142,177-186).
 
-The gather -> avg-pool 4 -> (avg-pool 2 -> half) x3 chain runs as ONE kernel (eod_read_pool); the 1x1
-projection is a library GEMM (torch conv2d on the channels-last levels) and the ``* weight`` / ``+ res``
-epilogue is eod_fuse.  The dense backbone itself is out of scope and supplied by the caller.
+The gather -> avg-pool 4 -> (avg-pool 2 -> half) x3 chain runs as ONE kernel (eod_read_pool).  In inference the
+1x1 projection, the ``* weight`` and the ``+ res`` run as ONE tensor-core kernel per level (eod_project_fuse: fp16
+levels x hi/lo-split fp32 weights on tcgen05, fp32-GEMM accuracy).  When gradients are needed (training un-freezes the
+``map_merge`` parameters, custom_rcnn.py:609-613) the projection is the library GEMM under autograd and the epilogue is
+eod_fuse with a hand-written backward.  The dense backbone itself is out of scope and supplied by the caller.
 """
 from __future__ import annotations
 
@@ -26,11 +28,29 @@ from ._lib import FUSE_IMAGE_ONLY, FUSE_MEM_ONLY, FUSE_SUM
 _FUSE_MODES = {"sum": FUSE_SUM, "mem_only": FUSE_MEM_ONLY, "image_only": FUSE_IMAGE_ONLY}
 
 
+class _FuseFn(torch.autograd.Function):
+    """eod_fuse with its backward: out = res + w * mem | w * mem  =>  d res = g (sum only), d mem = w * g."""
+
+    @staticmethod
+    def forward(ctx, res, mem, weight: float, mode: int):
+        ctx.weight, ctx.mode = weight, mode
+        return ops.fuse(res, mem, weight, mode)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        g_res = g if (ctx.mode == FUSE_SUM and ctx.needs_input_grad[0]) else None
+        g_mem = ops.fuse(None, g, ctx.weight, FUSE_MEM_ONLY) if ctx.needs_input_grad[1] else None
+        return g_res, g_mem, None, None
+
+
 class MemoryFusion(nn.Module):
     def __init__(self, memory_type: str = "implicit_memory", fusion: str = "sum", map_feature_weight: float = 500.0,
                  memory_feature_weight: float = 100.0, merge_type: str = "", mem_feat_dim: int = 512,
-                 ego_feat_dim: int = 256):
+                 ego_feat_dim: int = 256, tensor_core: bool = True):
         super().__init__()
+        self.tensor_core = tensor_core      # False: library fp32 GEMM + eod_fuse also in inference
+        self._w_split = {}                  # level -> ((weight ptr, version), (2N,K) f16 hi/lo split)
         self.memory_type, self.feat_fusion, self.merge_type = memory_type, fusion, merge_type
         self.map_feature_weight, self.memory_feature_weight = map_feature_weight, memory_feature_weight
         self.memory_dim = mem_feat_dim
@@ -68,16 +88,28 @@ class MemoryFusion(nn.Module):
             raise UnboundLocalError("new_res")        # the reference leaves new_res unbound here (timm.py:181-189)
         levels = self.read(map_memory, proj_indices, observations)
         out = []
-        for lvl, res, conv in zip(levels, results, self.merge_map_projections):
+        mode = _FUSE_MODES[self.feat_fusion]
+        for k, (lvl, res, conv) in enumerate(zip(levels, results, self.merge_map_projections)):
             if self.feat_fusion == "image_only":
                 out.append(res)
+                continue
+            N, K = conv.weight.shape[0], conv.weight.shape[1]
+            needs_grad = torch.is_grad_enabled() and (res.requires_grad or any(p.requires_grad for p in conv.parameters()))
+            if self.tensor_core and not needs_grad and N % 128 == 0 and K % 64 == 0:
+                key = (conv.weight.data_ptr(), conv.weight._version)
+                if self._w_split.get(k, (None,))[0] != key:
+                    self._w_split[k] = (key, ops.project_split_weights(conv.weight.detach().to(torch.float32).contiguous()))
+                bias = None if conv.bias is None else conv.bias.detach().to(torch.float32).contiguous()
+                fused = ops.project_fuse(lvl, self._w_split[k][1], bias, res.detach().to(torch.float32).contiguous(),
+                                         float(self.map_feature_weight), mode)
+                out.append(fused.to(res.dtype))
                 continue
             # timm.py:174: 1x1 conv in fp32 (eval, no autocast) == per-pixel GEMM on the channels-last level
             x = lvl.permute(0, 2, 3, 1).to(torch.float32)                             # (B, h, w, C) contiguous
             mem = torch.matmul(x, conv.weight.view(conv.weight.shape[0], -1).t()) + conv.bias
             mem = mem.permute(0, 3, 1, 2).contiguous()                               # NCHW like res
             res32 = res.to(torch.float32).contiguous()
-            fused = ops.fuse(res32, mem, float(self.map_feature_weight), _FUSE_MODES[self.feat_fusion])
+            fused = _FuseFn.apply(res32, mem, float(self.map_feature_weight), mode)
             out.append(fused.to(res.dtype))
         return out
 

@@ -17,7 +17,7 @@ launch_count = 0
 
 _LAUNCHES = {"eod_backproject_quantize": 1, "eod_quantize_world": 1, "eod_sample_mask": 1, "eod_frame_count": 1, "eod_expand_counts": 1, "eod_write_mean": 1, "eod_write_mean_det": 7,
              "eod_finalize_counts": 1, "eod_box_to_image_features": 1, "eod_masks_observed": 1, "eod_paste_masks": 1, "eod_write_objects_pasted": 1, "eod_bilinear_lattice": 1, "eod_write_objects": 1, "eod_flush_slots": 2, "eod_write_max": 2, "eod_read_pool": 1,
-             "eod_fuse": 1, "eod_normalize_memory": 1, "eod_reset_touched": 1, "eod_semmap_update": 1, "eod_semmap_decode": 2}
+             "eod_fuse": 1, "eod_project_split_weights": 1, "eod_project_fuse": 1, "eod_normalize_memory": 1, "eod_reset_touched": 1, "eod_semmap_update": 1, "eod_semmap_decode": 2}
 
 
 def _call(name: str, *args) -> None:
@@ -411,4 +411,45 @@ def normalize_memory(sums: torch.Tensor, counts: torch.Tensor, half: bool = Fals
     C = sums.shape[-1]
     out = torch.empty(sums.shape, dtype=torch.float16 if half else torch.float32, device=sums.device)
     _call("eod_normalize_memory", sums.data_ptr(), counts.data_ptr(), sums.numel() // C, C, out.data_ptr(), int(half), _stream())
+    return out
+
+
+def project_split_weights(weight: torch.Tensor) -> torch.Tensor:
+    """weight (N,K) or (N,K,1,1) f32 -> (2N,K) f16 hi/lo split consumed by project_fuse (N % 128 == 0, K % 64 == 0)."""
+    _dev(weight, torch.float32, "weight")
+    N = weight.shape[0]
+    K = weight.numel() // N
+    out = torch.empty((2 * N, K), dtype=torch.float16, device=weight.device)
+    _call("eod_project_split_weights", weight.data_ptr(), N, K, out.data_ptr(), _stream())
+    return out
+
+
+def project_fuse(level: torch.Tensor, w_split: torch.Tensor, bias: Optional[torch.Tensor], res: Optional[torch.Tensor],
+                 weight: float, mode: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """level: logical (E,K,h,w) f16 in channels-last memory (what read_pool returns) or (E,h,w,K) contiguous;
+    w_split (2N,K) f16; bias (N) f32 | None; res (E,N,h,w) f32 NCHW | None (mem_only) -> out (E,N,h,w) f32 NCHW."""
+    if level.dim() != 4 or level.dtype != torch.float16 or not level.is_cuda:
+        raise TypeError("level must be a 4-d CUDA float16 tensor")
+    K = w_split.shape[1]
+    if level.shape[1] == K and level.permute(0, 2, 3, 1).is_contiguous():
+        E, _, h, w = level.shape
+    elif level.shape[3] == K and level.is_contiguous():
+        E, h, w, _ = level.shape
+    else:
+        raise ValueError("level must be channels-last (E,h,w,K) memory with K matching w_split")
+    _dev(w_split, torch.float16, "w_split")
+    N = w_split.shape[0] // 2
+    if bias is not None:
+        _dev(bias, torch.float32, "bias")
+        if bias.numel() != N:
+            raise ValueError("bias must have N elements")
+    if mode not in (FUSE_SUM, FUSE_MEM_ONLY):
+        raise ValueError("project_fuse: mode must be FUSE_SUM or FUSE_MEM_ONLY")
+    if res is not None:
+        _dev(res, torch.float32, "res")
+        if tuple(res.shape) != (E, N, h, w):
+            raise ValueError(f"res must be (E,N,h,w) = {(E, N, h, w)}")
+    out = torch.empty((E, N, h, w), dtype=torch.float32, device=level.device) if out is None else _dev(out, torch.float32, "out")
+    _call("eod_project_fuse", level.data_ptr(), w_split.data_ptr(), _ptr(bias), _ptr(res), float(weight), int(mode), E, h * w, K, N,
+          out.data_ptr(), _stream())
     return out

@@ -248,6 +248,19 @@ int eod_reset_touched(float *counts, float *sums, void *norm16, int64_t n_rows, 
  * FMA contraction, as torch computes it).  n elements, fp32. */
 int eod_fuse(const float *res, const float *mem, float weight, int mode, int64_t n, float *out, eod_stream_t stream);
 
+/* 1x1 projection + fusion in one tensor-core kernel (timm.py:170-189 with the modules of :78-86):
+ *   out = res + weight * (level . W^T + bias)   (EOD_FUSE_SUM)   |   weight * (level . W^T + bias)   (EOD_FUSE_MEM_ONLY)
+ * level   (E, h*w, K) f16  - a pooled level exactly as eod_read_pool stores it (channels-last), K = memory feature dim
+ * w_split (2N, K) f16      - eod_project_split_weights(weight (N,K) f32): W = W_hi + 2^-11 * W_lo, two fp16 terms per weight,
+ *                            so that the fp16 tensor-core products reproduce the fp32 GEMM (every product exact in fp32;
+ *                            |error| <= ~2^-22 |W| per weight).  Re-run it whenever the weights change.
+ * bias    (N) f32 nullable; res, out (E, N, h*w) f32 NCHW (res nullable for MEM_ONLY).  N % 128 == 0, K % 64 == 0.
+ * The conv output, the scaling and the sum are rounded separately, as torch does (no contraction across the three ops).
+ * Accumulated fp32: within 1e-5 of scale of the fp32 reference (tolerance stated in the tests), not bit-exact. */
+int eod_project_split_weights(const float *weight, int N, int K, void *w_split, eod_stream_t stream);
+int eod_project_fuse(const void *level, const void *w_split, const float *bias, const float *res, float weight, int mode,
+                     int n_episodes, int hw, int K, int N, float *out, eod_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

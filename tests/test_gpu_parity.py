@@ -179,6 +179,79 @@ def test_memory_fusion_module_matches_reference_golden(eod, cuda, golden):
         bad([_t(g[f"res0_{k}"], cuda, torch.float32) for k in range(3)], [mem16.to(cuda)], [_t(g["idx0"], cuda).long()], [None])
 
 
+@pytest.mark.parametrize("E,h,w,K,N", [(2, 60, 80, 512, 256), (3, 15, 20, 512, 256), (1, 30, 40, 256, 128), (5, 7, 9, 64, 128)])
+def test_project_fuse_tensor_core_vs_fp64(eod, cuda, E, h, w, K, N):
+    """eod_project_fuse (tcgen05, fp16 level x hi/lo-split fp32 weight) against the fp64 evaluation of timm.py:174-184.
+    Tolerance: 1e-5 of the output scale (north star, fp32 accumulations); it must also be as accurate as the fp32 library
+    path (torch-CPU matmul of the same operands) up to a small factor - i.e. the split loses nothing that fp32 keeps.
+    Tiles with a ragged tail (M % 128 != 0), rows that straddle episodes, bias on/off, sum / mem_only."""
+    rng = np.random.default_rng(E * 100 + K)
+    x16 = (rng.standard_normal((E, h, w, K)) * 3).astype(np.float16)
+    W = (rng.uniform(-1, 1, (N, K)) / math.sqrt(K)).astype(np.float32)
+    W[0, :8] = [1e-6, -3e-7, 0.0, 6e-5, 123.456, -1e-3, 2 ** -14, 65504.0]      # sub-fp16-normal, large, exact powers
+    b = rng.standard_normal(N).astype(np.float32)
+    res = (rng.standard_normal((E, N, h, w)) * 2).astype(np.float32)
+    wsplit = eod.ops.project_split_weights(_t(W, cuda))
+    lvl = _t(x16, cuda).permute(0, 3, 1, 2)                                      # logical NCHW, channels-last memory
+    x64 = torch.from_numpy(x16.astype(np.float64)).reshape(-1, K)
+    for weight in (5.0, 500.0):
+        for mode, bias in ((0, b), (1, b), (0, None)):
+            got = eod.ops.project_fuse(lvl, wsplit, None if bias is None else _t(bias, cuda), _t(res, cuda) if mode == 0 else None, weight, mode)
+            mem64 = x64 @ torch.from_numpy(W.astype(np.float64)).t() + (0 if bias is None else torch.from_numpy(bias.astype(np.float64)))
+            mem64 = mem64.reshape(E, h, w, N).permute(0, 3, 1, 2) * weight
+            ref64 = (mem64 + torch.from_numpy(res.astype(np.float64))) if mode == 0 else mem64
+            mem32 = torch.from_numpy(x16.astype(np.float32)).reshape(-1, K) @ torch.from_numpy(W).t()
+            if bias is not None:
+                mem32 = mem32 + torch.from_numpy(bias)
+            mem32 = mem32.reshape(E, h, w, N).permute(0, 3, 1, 2) * weight
+            ref32 = (mem32 + torch.from_numpy(res)) if mode == 0 else mem32
+            scale = ref64.abs().max().item()
+            err = (got.cpu().double() - ref64).abs().max().item()
+            err32 = (ref32.double() - ref64).abs().max().item()
+            assert err <= SUM_TOL * scale, (weight, mode, err / scale)
+            assert err <= 4 * err32 + 1e-7 * scale, (weight, mode, err, err32)
+    with pytest.raises(eod.EodError):
+        eod.ops.project_fuse(lvl, wsplit, None, None, 5.0, 0)                    # sum needs res
+
+
+def test_memory_fusion_tensor_core_and_library_paths_agree(eod, cuda):
+    """MemoryFusion forward: the tcgen05 path (inference) and the library-GEMM + eod_fuse path (tensor_core=False) agree
+    to the fp32 tolerance on all three levels; with gradients enabled the module takes the autograd path and the
+    gradients of the map_merge parameters match a plain-torch restatement (custom_rcnn.py:609-613 trains them)."""
+    rng = np.random.default_rng(12)
+    C, CO, H, W, cells = 512, 256, 96, 128, 900
+    mem16 = _t((rng.standard_normal((cells, C)) * 4).astype(np.float16), cuda)
+    idx = _t(rng.integers(0, cells, (H, W)).astype(np.int64), cuda)
+    res = [_t(rng.standard_normal((1, CO, H >> s, W >> s)).astype(np.float32), cuda) for s in (3, 4, 5)]
+    tc = eod.MemoryFusion("implicit_memory", "sum", 5, mem_feat_dim=C, ego_feat_dim=CO).to(cuda)
+    lib = eod.MemoryFusion("implicit_memory", "sum", 5, mem_feat_dim=C, ego_feat_dim=CO, tensor_core=False).to(cuda)
+    lib.load_state_dict(tc.state_dict())
+    before = eod.ops.launch_count
+    with torch.no_grad():
+        a = tc(res, [mem16], [idx], [None])
+        assert eod.ops.launch_count - before == 1 + 3 + 3        # read + 3 weight splits + 3 fused projections
+        a2 = tc(res, [mem16], [idx], [None])                     # weights unchanged: split cached
+        assert eod.ops.launch_count - before == 1 + 3 + 3 + 1 + 3
+        b = lib(res, [mem16], [idx], [None])
+    for k in range(3):
+        assert torch.equal(a[k], a2[k])
+        assert (a[k] - b[k]).abs().max().item() <= SUM_TOL * b[k].abs().max().item(), k
+    # training path: gradients flow to the projection parameters and to res
+    res_g = [r.clone().requires_grad_(True) for r in res]
+    out = tc(res_g, [mem16], [idx], [None])
+    loss = sum((o * o).sum() for o in out)
+    loss.backward()
+    levels = tc.read([mem16], [idx], [None])
+    for k, conv in enumerate(tc.merge_map_projections):                       # plain-torch restatement on the CPU in fp64
+        w = conv.weight.detach().cpu().double().requires_grad_(True)
+        bb = conv.bias.detach().cpu().double().requires_grad_(True)
+        r = res[k].cpu().double().requires_grad_(True)
+        o = r + 5.0 * torch.nn.functional.conv2d(levels[k].cpu().double(), w, bb)
+        (o * o).sum().backward()
+        for got, ref in ((conv.weight.grad, w.grad), (conv.bias.grad, bb.grad), (res_g[k].grad, r.grad)):
+            assert (got.cpu().double() - ref).abs().max().item() <= 1e-5 * ref.abs().max().item(), k
+
+
 # --------------------------------------------------------------------------------------------------------
 # write, mean mode (A6-A8)
 # --------------------------------------------------------------------------------------------------------
