@@ -47,6 +47,7 @@ SIGNATURES = {
     "eod_semmap_decode": [_P, _P, c_int, c_int64, c_float, _P, _P, _P],
     "eod_reset_touched": [_P, _P, _P, c_int64, c_int, _P],
     "eod_project_split_weights": [_P, c_int, c_int, _P, _P],
+    "eod_project_fuse_levels": [c_int, _P, _P, _P, _P, _P, _P, c_float, c_int, c_int, c_int, c_int, c_int, _P],
     "eod_project_fuse": [_P, _P, _P, _P, c_float, c_int, c_int, c_int, c_int, c_int, _P, _P],
     "eod_fuse": [_P, _P, c_float, c_int, c_int64, _P, _P],
 }

@@ -86,24 +86,25 @@ class MemoryFusion(nn.Module):
             return list(results)
         if self.feat_fusion not in _FUSE_MODES:
             raise UnboundLocalError("new_res")        # the reference leaves new_res unbound here (timm.py:181-189)
-        levels = self.read(map_memory, proj_indices, observations)
-        out = []
         mode = _FUSE_MODES[self.feat_fusion]
-        for k, (lvl, res, conv) in enumerate(zip(levels, results, self.merge_map_projections)):
-            if self.feat_fusion == "image_only":
-                out.append(res)
-                continue
-            N, K = conv.weight.shape[0], conv.weight.shape[1]
-            needs_grad = torch.is_grad_enabled() and (res.requires_grad or any(p.requires_grad for p in conv.parameters()))
-            if self.tensor_core and not needs_grad and N % 128 == 0 and K % 64 == 0:
+        if self.feat_fusion == "image_only":
+            return list(results)
+        levels = self.read(map_memory, proj_indices, observations)
+        convs = self.merge_map_projections
+        N, K = convs[0].weight.shape[0], convs[0].weight.shape[1]
+        needs_grad = torch.is_grad_enabled() and (any(r.requires_grad for r in results) or any(p.requires_grad for p in self.parameters()))
+        if self.tensor_core and not needs_grad and N % 128 == 0 and K % 64 == 0:
+            # inference: projection, scaling and sum of all three levels in ONE persistent tcgen05 launch
+            for k, conv in enumerate(convs):
                 key = (conv.weight.data_ptr(), conv.weight._version)
                 if self._w_split.get(k, (None,))[0] != key:
                     self._w_split[k] = (key, ops.project_split_weights(conv.weight.detach().to(torch.float32).contiguous()))
-                bias = None if conv.bias is None else conv.bias.detach().to(torch.float32).contiguous()
-                fused = ops.project_fuse(lvl, self._w_split[k][1], bias, res.detach().to(torch.float32).contiguous(),
-                                         float(self.map_feature_weight), mode)
-                out.append(fused.to(res.dtype))
-                continue
+            biases = [None if c.bias is None else c.bias.detach().to(torch.float32).contiguous() for c in convs]
+            res32 = [r.detach().to(torch.float32).contiguous() for r in results[:3]] if mode == FUSE_SUM else None
+            fused = ops.project_fuse_levels(levels, [self._w_split[k][1] for k in range(3)], biases, res32, float(self.map_feature_weight), mode)
+            return [f.to(r.dtype) for f, r in zip(fused, results)]
+        out = []
+        for k, (lvl, res, conv) in enumerate(zip(levels, results, convs)):
             # timm.py:174: 1x1 conv in fp32 (eval, no autocast) == per-pixel GEMM on the channels-last level
             x = lvl.permute(0, 2, 3, 1).to(torch.float32)                             # (B, h, w, C) contiguous
             mem = torch.matmul(x, conv.weight.view(conv.weight.shape[0], -1).t()) + conv.bias

@@ -17,7 +17,7 @@ launch_count = 0
 
 _LAUNCHES = {"eod_backproject_quantize": 1, "eod_quantize_world": 1, "eod_sample_mask": 1, "eod_frame_count": 1, "eod_expand_counts": 1, "eod_write_mean": 1, "eod_write_mean_det": 7,
              "eod_finalize_counts": 1, "eod_box_to_image_features": 1, "eod_masks_observed": 1, "eod_paste_masks": 1, "eod_write_objects_pasted": 1, "eod_bilinear_lattice": 1, "eod_write_objects": 1, "eod_flush_slots": 2, "eod_write_max": 2, "eod_read_pool": 1,
-             "eod_fuse": 1, "eod_project_split_weights": 1, "eod_project_fuse": 1, "eod_normalize_memory": 1, "eod_reset_touched": 1, "eod_semmap_update": 1, "eod_semmap_decode": 2}
+             "eod_fuse": 1, "eod_project_split_weights": 1, "eod_project_fuse": 1, "eod_project_fuse_levels": 1, "eod_normalize_memory": 1, "eod_reset_touched": 1, "eod_semmap_update": 1, "eod_semmap_decode": 2}
 
 
 def _call(name: str, *args) -> None:
@@ -453,3 +453,52 @@ def project_fuse(level: torch.Tensor, w_split: torch.Tensor, bias: Optional[torc
     _call("eod_project_fuse", level.data_ptr(), w_split.data_ptr(), _ptr(bias), _ptr(res), float(weight), int(mode), E, h * w, K, N,
           out.data_ptr(), _stream())
     return out
+
+
+def _level_dims(level: torch.Tensor, K: int):
+    if level.dim() != 4 or level.dtype != torch.float16 or not level.is_cuda:
+        raise TypeError("level must be a 4-d CUDA float16 tensor")
+    if level.shape[1] == K and level.permute(0, 2, 3, 1).is_contiguous():
+        E, _, h, w = level.shape
+    elif level.shape[3] == K and level.is_contiguous():
+        E, h, w, _ = level.shape
+    else:
+        raise ValueError("level must be channels-last (E,h,w,K) memory with K matching w_split")
+    return E, h, w
+
+
+def project_fuse_levels(levels: Sequence[torch.Tensor], w_splits: Sequence[torch.Tensor], biases: Sequence[Optional[torch.Tensor]],
+                        results: Optional[Sequence[torch.Tensor]], weight: float, mode: int,
+                        outs: Optional[Sequence[torch.Tensor]] = None, variant: int = 0):
+    """project_fuse for up to three pyramid levels in one launch (persistent tcgen05 kernel).  Same per-level contract as
+    project_fuse; all levels share E, K and N."""
+    import ctypes
+    n = len(levels)
+    if not (1 <= n <= 3) or len(w_splits) != n or len(biases) != n or (results is not None and len(results) != n):
+        raise ValueError("project_fuse_levels: 1..3 levels with matching w_splits / biases / results")
+    if mode not in (FUSE_SUM, FUSE_MEM_ONLY):
+        raise ValueError("project_fuse_levels: mode must be FUSE_SUM or FUSE_MEM_ONLY")
+    if mode == FUSE_SUM and results is None:
+        raise EodError("project_fuse_levels: res is required for sum")
+    K = w_splits[0].shape[1]
+    N = w_splits[0].shape[0] // 2
+    dims = [_level_dims(lv, K) for lv in levels]
+    E = dims[0][0]
+    created = outs is None
+    outs = [torch.empty((E, N, h, w), dtype=torch.float32, device=levels[0].device) for _, h, w in dims] if created else list(outs)
+    for k in range(n):
+        _dev(w_splits[k], torch.float16, "w_split"), _dev(outs[k], torch.float32, "out")
+        if dims[k][0] != E or tuple(w_splits[k].shape) != (2 * N, K):
+            raise ValueError("all levels must share E, K and N")
+        if biases[k] is not None:
+            _dev(biases[k], torch.float32, "bias")
+        if results is not None:
+            _dev(results[k], torch.float32, "res")
+            if tuple(results[k].shape) != (E, N, dims[k][1], dims[k][2]):
+                raise ValueError("res must be (E,N,h,w) NCHW")
+    arr = lambda ptrs: (ctypes.c_void_p * n)(*ptrs)
+    hw = (ctypes.c_int * n)(*[h * w for _, h, w in dims])
+    _call("eod_project_fuse_levels", n, arr([lv.data_ptr() for lv in levels]), arr([w.data_ptr() for w in w_splits]),
+          arr([None if b is None else b.data_ptr() for b in biases]), None if results is None else arr([r.data_ptr() for r in results]),
+          arr([o.data_ptr() for o in outs]), hw, float(weight), int(mode), E, K, N, int(variant), _stream())
+    return outs

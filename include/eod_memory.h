@@ -258,6 +258,12 @@ int eod_fuse(const float *res, const float *mem, float weight, int mode, int64_t
  * The conv output, the scaling and the sum are rounded separately, as torch does (no contraction across the three ops).
  * Accumulated fp32: within 1e-5 of scale of the fp32 reference (tolerance stated in the tests), not bit-exact. */
 int eod_project_split_weights(const float *weight, int N, int K, void *w_split, eod_stream_t stream);
+/* All pyramid levels (<= 3) in ONE persistent launch.  level / w_split / bias / res / out / hw are HOST arrays of n_levels
+ * entries (device pointers inside; bias and res arrays nullable, and so is each bias[l]).  variant: 0 = auto (persistent
+ * kernel when every hw[l] % 4 == 0, else one tile-per-CTA launch per level), 1 = tile per CTA, 2 = persistent. */
+int eod_project_fuse_levels(int n_levels, const void *const *level, const void *const *w_split, const float *const *bias,
+                            const float *const *res, float *const *out, const int *hw, float weight, int mode, int n_episodes,
+                            int K, int N, int variant, eod_stream_t stream);
 int eod_project_fuse(const void *level, const void *w_split, const float *bias, const float *res, float weight, int mode,
                      int n_episodes, int hw, int K, int N, float *out, eod_stream_t stream);
 

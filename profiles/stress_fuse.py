@@ -1,0 +1,31 @@
+"""Stress of the persistent projection+fusion kernel against the tile-per-CTA kernel (bit-identical tile arithmetic expected):
+many tiles per CTA, all level combinations, bias on/off, sum / mem_only.  Found the res-ring release race of r3."""
+import importlib, sys, math, numpy as np, torch
+sys.path.insert(0, '/root/repo')
+eod = importlib.import_module("embodied-object-detection_b200")
+ops = eod.ops
+dev = torch.device("cuda:0")
+rng = np.random.default_rng(99)
+E, K, N = 24, 512, 256
+def run(shapes, use_bias, mode):
+    lv = [torch.from_numpy((rng.standard_normal((E, h, w, K)) * 2).astype(np.float16)).to(dev) for h, w in shapes]
+    Ws = [(rng.uniform(-1, 1, (N, K)) / math.sqrt(K)).astype(np.float32) for _ in shapes]
+    ws = [ops.project_split_weights(torch.from_numpy(W).to(dev)) for W in Ws]
+    bs = [torch.from_numpy(rng.standard_normal(N).astype(np.float32)).to(dev) if use_bias else None for _ in shapes]
+    rs = [torch.from_numpy(rng.standard_normal((E, N, h, w)).astype(np.float32)).to(dev) for h, w in shapes]
+    ref = ops.project_fuse_levels(lv, ws, bs, rs if mode == 0 else None, 1.0, mode, variant=1)
+    got = ops.project_fuse_levels(lv, ws, bs, rs if mode == 0 else None, 1.0, mode, variant=2)
+    for k, (h, w) in enumerate(shapes):
+        d = (got[k] - ref[k]).abs()
+        bad = (d > 1e-3).nonzero()
+        print(shapes, "bias", use_bias, "mode", mode, "level", k, "max diff", d.max().item(), "n bad", bad.shape[0], "of", d.numel())
+        if bad.shape[0]:
+            e = bad[:, 0]; n = bad[:, 1]; pix = bad[:, 2] * w + bad[:, 3]
+            tpe = -(-h * w // 256)
+            print("   episodes", torch.unique(e).tolist()[:10], "nblocks", torch.unique(n // 128).tolist(), "ptiles", torch.unique(pix // 256).tolist()[:20], "of", tpe,
+                  "chan%128", (n % 128).min().item(), (n % 128).max().item(), "pix%256", (pix % 256).min().item(), (pix % 256).max().item())
+            b0 = bad[0]; print("   sample", b0.tolist(), got[k][tuple(b0)].item(), ref[k][tuple(b0)].item())
+for shapes in ([(60, 80)], [(30, 40)], [(15, 20)], [(60, 80), (30, 40)], [(60, 80), (30, 40), (15, 20)]):
+    for use_bias in (False, True):
+        for mode in (1, 0):
+            run(shapes, use_bias, mode)

@@ -197,6 +197,11 @@ def test_project_fuse_tensor_core_vs_fp64(eod, cuda, E, h, w, K, N):
     for weight in (5.0, 500.0):
         for mode, bias in ((0, b), (1, b), (0, None)):
             got = eod.ops.project_fuse(lvl, wsplit, None if bias is None else _t(bias, cuda), _t(res, cuda) if mode == 0 else None, weight, mode)
+            variants = [1] + ([2] if (h * w) % 4 == 0 else [])          # tile-per-CTA kernel; persistent kernel (TMA on res: hw % 4 == 0)
+            for variant in variants:
+                alt = eod.ops.project_fuse_levels([lvl], [wsplit], [None if bias is None else _t(bias, cuda)], [_t(res, cuda)] if mode == 0 else None,
+                                                  weight, mode, variant=variant)[0]
+                assert (alt.cpu().double() - got.cpu().double()).abs().max().item() <= 2e-6 * got.abs().max().item(), (variant, weight, mode)
             mem64 = x64 @ torch.from_numpy(W.astype(np.float64)).t() + (0 if bias is None else torch.from_numpy(bias.astype(np.float64)))
             mem64 = mem64.reshape(E, h, w, N).permute(0, 3, 1, 2) * weight
             ref64 = (mem64 + torch.from_numpy(res.astype(np.float64))) if mode == 0 else mem64
@@ -214,6 +219,49 @@ def test_project_fuse_tensor_core_vs_fp64(eod, cuda, E, h, w, K, N):
         eod.ops.project_fuse(lvl, wsplit, None, None, 5.0, 0)                    # sum needs res
 
 
+def test_project_fuse_all_levels_one_launch(eod, cuda):
+    """The persistent kernel over the three pyramid levels of E episodes (tiles never straddle episodes; the last tile of an
+    episode is ragged: 4800 = 18.75 x 256, 1200, 300) against fp64, and the multi-level launch against per-level launches."""
+    rng = np.random.default_rng(99)
+    E, K, N = 5, 512, 256
+    shapes = [(60, 80), (30, 40), (15, 20)]
+    lv = [_t((rng.standard_normal((E, h, w, K)) * 2).astype(np.float16), cuda) for h, w in shapes]
+    Ws = [(rng.uniform(-1, 1, (N, K)) / math.sqrt(K)).astype(np.float32) for _ in shapes]
+    bs = [rng.standard_normal(N).astype(np.float32) for _ in shapes]
+    rs = [rng.standard_normal((E, N, h, w)).astype(np.float32) for h, w in shapes]
+    ws = [eod.ops.project_split_weights(_t(W, cuda)) for W in Ws]
+    for mode in (0, 1):
+        res_d = [_t(r, cuda) for r in rs] if mode == 0 else None
+        outs = eod.ops.project_fuse_levels(lv, ws, [_t(b, cuda) for b in bs], res_d, 5.0, mode, variant=2)
+        for k, (h, w) in enumerate(shapes):
+            x64 = lv[k].cpu().double().reshape(-1, K)
+            ref = (x64 @ torch.from_numpy(Ws[k].astype(np.float64)).t() + torch.from_numpy(bs[k].astype(np.float64))).reshape(E, h, w, N).permute(0, 3, 1, 2) * 5.0
+            if mode == 0:
+                ref = ref + torch.from_numpy(rs[k].astype(np.float64))
+            err = (outs[k].cpu().double() - ref).abs().max().item()
+            assert err <= SUM_TOL * ref.abs().max().item(), (mode, k, err)
+            single = eod.ops.project_fuse_levels([lv[k]], [ws[k]], [_t(bs[k], cuda)], None if mode else [res_d[k]], 5.0, mode, variant=2)[0]
+            assert torch.equal(single, outs[k]), (mode, k)          # same tile arithmetic whether launched alone or together
+
+
+def test_project_fuse_persistent_many_tiles_per_cta_equals_tile_kernel(eod, cuda):
+    """Regression for a ring-release race: with several tiles per CTA the persistent kernel must reproduce the
+    tile-per-CTA kernel BIT FOR BIT (same UMMA sequence per tile, same epilogue arithmetic), for sum and mem_only, repeatedly."""
+    rng = np.random.default_rng(7)
+    E, K, N = 24, 512, 256
+    shapes = [(60, 80), (30, 40), (15, 20)]
+    lv = [_t((rng.standard_normal((E, h, w, K)) * 2).astype(np.float16), cuda) for h, w in shapes]
+    ws = [eod.ops.project_split_weights(_t((rng.uniform(-1, 1, (N, K)) / math.sqrt(K)).astype(np.float32), cuda)) for _ in shapes]
+    bs = [_t(rng.standard_normal(N).astype(np.float32), cuda) for _ in shapes]
+    rs = [_t(rng.standard_normal((E, N, h, w)).astype(np.float32), cuda) for h, w in shapes]
+    for mode in (0, 1):
+        ref = eod.ops.project_fuse_levels(lv, ws, bs, rs if mode == 0 else None, 5.0, mode, variant=1)
+        for rep in range(4):
+            got = eod.ops.project_fuse_levels(lv, ws, bs, rs if mode == 0 else None, 5.0, mode, variant=2)
+            for k in range(3):
+                assert torch.equal(got[k], ref[k]), (mode, rep, k, int((got[k] != ref[k]).sum()))
+
+
 def test_memory_fusion_tensor_core_and_library_paths_agree(eod, cuda):
     """MemoryFusion forward: the tcgen05 path (inference) and the library-GEMM + eod_fuse path (tensor_core=False) agree
     to the fp32 tolerance on all three levels; with gradients enabled the module takes the autograd path and the
@@ -229,9 +277,9 @@ def test_memory_fusion_tensor_core_and_library_paths_agree(eod, cuda):
     before = eod.ops.launch_count
     with torch.no_grad():
         a = tc(res, [mem16], [idx], [None])
-        assert eod.ops.launch_count - before == 1 + 3 + 3        # read + 3 weight splits + 3 fused projections
+        assert eod.ops.launch_count - before == 1 + 3 + 1        # read + 3 weight splits + ONE fused projection launch for all levels
         a2 = tc(res, [mem16], [idx], [None])                     # weights unchanged: split cached
-        assert eod.ops.launch_count - before == 1 + 3 + 3 + 1 + 3
+        assert eod.ops.launch_count - before == 1 + 3 + 1 + 1 + 1
         b = lib(res, [mem16], [idx], [None])
     for k in range(3):
         assert torch.equal(a[k], a2[k])
