@@ -121,37 +121,89 @@ __global__ void __launch_bounds__(256) finalize_cells_kernel(int64_t n_rows, int
                                                              float *__restrict__ counts, uint8_t *__restrict__ touched,
                                                              const float *__restrict__ sums, __half *__restrict__ norm16, int C)
 {
-    const unsigned lane = threadIdx.x & 31;
-    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t base = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; base < n_rows; base += warps * 32) {
-        const int64_t row = base + lane;
-        const uint32_t v = row < n_rows ? frame_cnt[row] : 0u;
-        float n_new = 0.f;
-        if (v) {
-            frame_cnt[row] = 0u;
-            n_new = counts[row] + 1.0f;                          // custom_rcnn.py:699-701,743
-            counts[row] = n_new;
-            if (touched && (v & 0x7fffffffu)) touched[row] = 1;
+    // Visible cells are rare (a few hundred of 250 000 per episode) and clustered (a frustum footprint): a block scans
+    // 2048 cells per trip, 16 bytes per lane (8 KB of frame_cnt in flight per block), collects the visible ones in shared
+    // memory, and then refreshes their fp16 rows with all 8 warps, two rows and up to 8 independent 16-byte loads per lane
+    // in flight - a warp that owns the footprint no longer walks its rows one dependent load at a time.
+    constexpr int kCellsPerTrip = 2048;
+    __shared__ int s_row[kCellsPerTrip];
+    __shared__ float s_new[kCellsPerTrip];
+    __shared__ int s_cnt;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t n_vec = n_rows >> 2;                              // the host guarantees n_rows % 4 == 0 and 16-byte alignment
+    const uint4 *cnt4 = reinterpret_cast<const uint4 *>(frame_cnt);
+    for (int64_t vb = (int64_t)blockIdx.x * (kCellsPerTrip / 4); vb < n_vec; vb += (int64_t)gridDim.x * (kCellsPerTrip / 4)) {
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        uint4 q[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int64_t vi = vb + warp * 64 + u * 32 + lane;
+            q[u] = vi < n_vec ? __ldcs(cnt4 + vi) : make_uint4(0u, 0u, 0u, 0u);
         }
-        if (!norm16) continue;
-        unsigned todo = __ballot_sync(0xffffffffu, v != 0u);
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const float wn = __shfl_sync(0xffffffffu, n_new, src);
-            const size_t r = (size_t)(base + src) * C;
-            const float4 *src_row = reinterpret_cast<const float4 *>(sums + r);
-            uint2 *dst_row = reinterpret_cast<uint2 *>(norm16 + r);
-            for (int k = lane; k < C / 4; k += 32) {
-                float4 x = src_row[k];
-                if (wn > 1.0f) { x.x = __fdiv_rn(x.x, wn); x.y = __fdiv_rn(x.y, wn); x.z = __fdiv_rn(x.z, wn); x.w = __fdiv_rn(x.w, wn); }
-                __half2 a = __floats2half2_rn(x.x, x.y), b = __floats2half2_rn(x.z, x.w);
-                uint2 raw;
-                raw.x = *reinterpret_cast<uint32_t *>(&a);
-                raw.y = *reinterpret_cast<uint32_t *>(&b);
-                dst_row[k] = raw;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if ((q[u].x | q[u].y | q[u].z | q[u].w) == 0u) continue;
+            const int local = (warp * 64 + u * 32 + lane) * 4;
+            const int64_t row0 = vb * 4 + local;
+            const uint32_t v[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+            reinterpret_cast<uint4 *>(frame_cnt)[vb + warp * 64 + u * 32 + lane] = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if (v[b]) {
+                    const float n_new = counts[row0 + b] + 1.0f;     // custom_rcnn.py:699-701,743
+                    counts[row0 + b] = n_new;
+                    if (touched && (v[b] & 0x7fffffffu)) touched[row0 + b] = 1;
+                    if (norm16) {
+                        const int pos = atomicAdd(&s_cnt, 1);
+                        s_row[pos] = local + b;
+                        s_new[pos] = n_new;
+                    }
+                }
+        }
+        __syncthreads();
+        const int n = s_cnt;
+        const int c4 = C >> 2;
+        for (int i0 = warp; i0 < n; i0 += 16) {                      // rows i0 and i0 + 8 together
+            float4 x[2][4];
+            float wn[2];
+            size_t r[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int i = i0 + 8 * h;
+                wn[h] = i < n ? s_new[i] : 0.f;
+                r[h] = i < n ? (size_t)(vb * 4 + s_row[i]) * C : 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (i < n && (int)lane + 32 * k < c4) x[h][k] = reinterpret_cast<const float4 *>(sums + r[h])[lane + 32 * k];
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (i0 + 8 * h >= n) continue;
+                uint2 *dst_row = reinterpret_cast<uint2 *>(norm16 + r[h]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if ((int)lane + 32 * k >= c4) continue;
+                    float4 y = x[h][k];
+                    if (wn[h] > 1.0f) { y.x = __fdiv_rn(y.x, wn[h]); y.y = __fdiv_rn(y.y, wn[h]); y.z = __fdiv_rn(y.z, wn[h]); y.w = __fdiv_rn(y.w, wn[h]); }
+                    __half2 a = __floats2half2_rn(y.x, y.y), b2 = __floats2half2_rn(y.z, y.w);
+                    uint2 raw;
+                    raw.x = *reinterpret_cast<uint32_t *>(&a);
+                    raw.y = *reinterpret_cast<uint32_t *>(&b2);
+                    dst_row[lane + 32 * k] = raw;
+                }
+                for (int k = lane + 128; k < c4; k += 32) {          // C > 512
+                    float4 y = reinterpret_cast<const float4 *>(sums + r[h])[k];
+                    if (wn[h] > 1.0f) { y.x = __fdiv_rn(y.x, wn[h]); y.y = __fdiv_rn(y.y, wn[h]); y.z = __fdiv_rn(y.z, wn[h]); y.w = __fdiv_rn(y.w, wn[h]); }
+                    __half2 a = __floats2half2_rn(y.x, y.y), b2 = __floats2half2_rn(y.z, y.w);
+                    uint2 raw;
+                    raw.x = *reinterpret_cast<uint32_t *>(&a);
+                    raw.y = *reinterpret_cast<uint32_t *>(&b2);
+                    dst_row[k] = raw;
+                }
             }
         }
+        __syncthreads();
     }
 }
 
@@ -210,6 +262,75 @@ __global__ void __launch_bounds__(1024) sample_mask_kernel(const uint8_t *__rest
         if (threadIdx.x == 0) {
             int t = 0;
             for (int w = 0; w < 32; ++w) t += s_warp[w];
+            n_sampled[e] = t;
+        }
+    }
+}
+
+// Same selection, 16 pixels per thread (HW % 16 == 0, 16-byte aligned planes): 16 KB of the plane per block-wide scan step
+// instead of 1 KB - the 480x640 plane takes 19 steps instead of 300.
+__global__ void __launch_bounds__(1024) sample_mask_vec_kernel(const uint8_t *__restrict__ observed, int HW, int stride,
+                                                               uint8_t *__restrict__ samp, int32_t *__restrict__ n_sampled)
+{
+    __shared__ int s_warp[2][32];
+    const int e = blockIdx.x;
+    const uint4 *obs = reinterpret_cast<const uint4 *>(observed + (size_t)e * HW);
+    uint4 *out = reinterpret_cast<uint4 *>(samp + (size_t)e * HW);
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_vec = HW >> 4;
+    int carry = 0, sampled_total = 0, buf = 0;
+    for (int base = 0; base < n_vec; base += 1024, buf ^= 1) {
+        const int vi = base + threadIdx.x;
+        uint4 q = vi < n_vec ? __ldg(obs + vi) : make_uint4(0u, 0u, 0u, 0u);
+        uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        int cnt = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            // per byte: 0x01 where the byte is non-zero
+            uint32_t nz = w[k] | (w[k] >> 4);
+            nz |= nz >> 2;
+            nz |= nz >> 1;
+            w[k] = nz & 0x01010101u;
+            cnt += __popc(w[k]);
+        }
+        int incl = cnt;                                              // inclusive warp scan of the per-thread counts
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += up;
+        }
+        if (lane == 31) s_warp[buf][warp] = incl;
+        __syncthreads();                                             // double-buffered totals: one barrier per step
+        int pre = 0, total = 0;
+#pragma unroll 8
+        for (int x = 0; x < 32; ++x) {
+            const int t = s_warp[buf][x];
+            pre += x < (int)warp ? t : 0;
+            total += t;
+        }
+        int r = (carry + pre + incl - cnt) % stride;                 // rank of this thread's first observed pixel, mod stride
+        carry += total;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t o4 = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if ((w[k] >> (8 * b)) & 1u) {
+                    if (r == 0) { o4 |= 1u << (8 * b); ++sampled_total; }
+                    if (++r == stride) r = 0;
+                }
+            w[k] = o4;
+        }
+        if (vi < n_vec) out[vi] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    if (n_sampled) {
+        for (int o = 16; o > 0; o >>= 1) sampled_total += __shfl_xor_sync(0xffffffffu, sampled_total, o);
+        __syncthreads();
+        if (lane == 0) s_warp[0][warp] = sampled_total;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int x = 0; x < 32; ++x) t += s_warp[0][x];
             n_sampled[e] = t;
         }
     }
@@ -1103,7 +1224,10 @@ extern "C" int eod_sample_mask(const uint8_t *observed, int n_episodes, int HW, 
 {
     EOD_REQUIRE(observed && samp, EOD_ERR_BADARG, "eod_sample_mask: null pointer");
     EOD_REQUIRE(n_episodes > 0 && HW > 0 && stride > 0, EOD_ERR_BADARG, "eod_sample_mask: bad sizes");
-    sample_mask_kernel<<<n_episodes, 1024, 0, (cudaStream_t)stream>>>(observed, HW, stride, samp, n_sampled);
+    if (HW % 16 == 0 && eod_aligned16(observed) && eod_aligned16(samp))
+        sample_mask_vec_kernel<<<n_episodes, 1024, 0, (cudaStream_t)stream>>>(observed, HW, stride, samp, n_sampled);
+    else
+        sample_mask_kernel<<<n_episodes, 1024, 0, (cudaStream_t)stream>>>(observed, HW, stride, samp, n_sampled);
     return eod_check_launch("eod_sample_mask");
 }
 
@@ -1127,10 +1251,10 @@ extern "C" int eod_finalize_counts(const int32_t *idx, int n_episodes, int HW, i
                 "eod_finalize_counts: norm16 needs sums, C %% 4 == 0 and 16-byte aligned pointers");
     EOD_REQUIRE(idx && frame_cnt && counts, EOD_ERR_BADARG, "eod_finalize_counts: null pointer");
     EOD_REQUIRE(n_episodes > 0 && n_episodes <= 65535 && HW > 0 && n_cells > 0, EOD_ERR_BADARG, "eod_finalize_counts: bad sizes");
-    if (n_cells <= 4 * (int64_t)HW) {
+    if (n_cells <= 4 * (int64_t)HW && ((int64_t)n_episodes * n_cells) % 4 == 0 && eod_aligned16(frame_cnt)) {
         // grid comparable to the image: stream the cell plane once, no atomics
         const int64_t n_rows = (int64_t)n_episodes * n_cells;
-        int64_t blocks = (n_rows + 255) / 256;
+        int64_t blocks = (n_rows + 2047) / 2048;                         // 2048 cells per block trip
         const int64_t cap = (int64_t)eod_num_sms() * 16;
         if (blocks > cap) blocks = cap;
         finalize_cells_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(n_rows, n_cells, frame_cnt, counts, touched, sums, (__half *)norm16, C);

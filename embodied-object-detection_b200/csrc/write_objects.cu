@@ -157,9 +157,20 @@ __global__ void __launch_bounds__(256) masks_observed_kernel(const uint8_t *__re
     reinterpret_cast<uint32_t *>(observed + (size_t)e * HW)[p4] = out;
 }
 
-// CTA = 256 consecutive pixels of one episode; a warp takes the CTA's sampled pixels round-robin, lanes own
-// channels c = lane + 32*j.  The per-object adds happen in object-index order (custom_rcnn.py:890-895).
+// CTA = 2048 consecutive pixels of one episode (the sampled ones are ~2 % of them: compacted first, then processed in
+// rounds of up to 256).  Two phases per round, so that the dependent global loads of all sampled pixels of
+// the CTA are in flight together instead of one pixel after the other (the kernel is latency-, not bandwidth-bound):
+//   A  thread per (sampled pixel, object): cover test -> one 32-object bitmask word per warp ballot, kept in shared memory;
+//      thread per sampled pixel: cell index and slot;
+//   B  warp per sampled pixel, lanes own channels c = lane + 32*j: the covering objects' features are added in ascending
+//      object index (custom_rcnn.py:890-895), divided by their number, and reduced into the cell's scratch slot.
 // kPasted: the cover test is paste_covers() on the (Kmax,S,S) probabilities + boxes instead of a byte of the (Kmax,HW) masks.
+// Frames with more than kCoverObjs kept objects (the reference caps at 100, custom_rcnn.py:860) take the
+// one-pixel-at-a-time path at the end of the kernel.
+constexpr int kCoverObjs = 128;
+
+constexpr int kObjSpan = 2048;            // pixels per CTA (8 per thread); ~1/50 of them are sampled in the reference's regime
+
 template <int C, bool kPasted>
 __global__ void __launch_bounds__(256) write_objects_kernel(const float *__restrict__ box_features, const uint8_t *__restrict__ masks,
                                                             const float *__restrict__ probs, const float *__restrict__ boxes, int Sm, int W,
@@ -168,20 +179,143 @@ __global__ void __launch_bounds__(256) write_objects_kernel(const float *__restr
                                                             int64_t n_cells, int S, float *__restrict__ scratch)
 {
     constexpr int J = C / 32;
-    __shared__ int s_list[256];
-    __shared__ int s_n;
+    __shared__ int s_list[kObjSpan];
+    __shared__ int s_slot[256];
+    __shared__ uint32_t s_cover[256][kCoverObjs / 32];
+    __shared__ PasteObj s_obj[kPasted ? kCoverObjs : 1];
+    __shared__ int s_wcnt[8];
     const int e = blockIdx.y;
-    const int p = blockIdx.x * 256 + threadIdx.x;
-    if (threadIdx.x == 0) s_n = 0;
-    __syncthreads();
-    if (p < HW && __ldg(samp + (size_t)e * HW + p)) s_list[atomicAdd(&s_n, 1)] = p;      // order is irrelevant: each pixel is independent
-    __syncthreads();
-    const int n = s_n;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int n;
+    {   // raster-ordered list of the CTA's sampled pixels (neighbours in the list are neighbours in the image row)
+        const int p0 = blockIdx.x * kObjSpan + threadIdx.x * 8;
+        const uint8_t *sp = samp + (size_t)e * HW + p0;
+        uint32_t lo = 0, hi = 0;
+        if (p0 + 7 < HW && (reinterpret_cast<uintptr_t>(sp) & 7u) == 0) {
+            const uint2 q = __ldg(reinterpret_cast<const uint2 *>(sp));
+            lo = q.x; hi = q.y;
+        } else {
+            for (int b = 0; b < 8 && p0 + b < HW; ++b) {
+                const uint32_t v = __ldg(sp + b);
+                if (b < 4) lo |= v << (8 * b); else hi |= v << (8 * (b - 4));
+            }
+        }
+        unsigned bits = 0;                                            // bit b: pixel p0 + b is sampled
+#pragma unroll
+        for (int b = 0; b < 4; ++b) bits |= (((lo >> (8 * b)) & 0xffu) ? 1u : 0u) << b | (((hi >> (8 * b)) & 0xffu) ? 1u : 0u) << (b + 4);
+        const int cnt = __popc(bits);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += up;
+        }
+        if (lane == 31) s_wcnt[warp] = incl;
+        __syncthreads();
+        int pre = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { pre += w < (int)warp ? s_wcnt[w] : 0; tot += s_wcnt[w]; }
+        int pos = pre + incl - cnt;
+        while (bits) {
+            s_list[pos++] = p0 + __ffs(bits) - 1;
+            bits &= bits - 1;
+        }
+        n = tot;
+        __syncthreads();
+    }
     if (n == 0) return;
     const int K = n_obj ? min(__ldg(n_obj + e), Kmax) : Kmax;
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint8_t *m = kPasted ? nullptr : masks + (size_t)e * Kmax * HW;
     const float *f = box_features + (size_t)e * Kmax * C;
+
+    if (K <= kCoverObjs) {
+        if (kPasted) {
+            if ((int)threadIdx.x < K) s_obj[threadIdx.x] = paste_prepare(boxes + ((size_t)e * Kmax + threadIdx.x) * 4, HW / W, W);
+            __syncthreads();
+        }
+        const int Kpad = (K + 31) & ~31;
+        constexpr int J4 = C / 128;
+        const int n_words = Kpad >> 5;
+        for (int base = 0; base < n; base += 256) {                      // rounds of up to 256 sampled pixels
+            const int nn = min(256, n - base);
+            // ---- phase A ----
+            int my_slot = -1;
+            if ((int)threadIdx.x < nn) {
+                const int cell = __ldg(idx + (size_t)e * HW + s_list[base + threadIdx.x]);
+                my_slot = __ldg(slot_of_cell + (size_t)e * n_cells + cell) - 1;
+            }
+            for (int q = threadIdx.x; q < nn * Kpad; q += 256) {         // a warp's 32 consecutive q: one pixel, 32 objects
+                const int i = q / Kpad, k = q - i * Kpad;
+                const int px = s_list[base + i];
+                bool mine = false;
+                if (k < K) {
+                    if (kPasted) mine = paste_covers(probs + ((size_t)e * Kmax + k) * Sm * Sm, s_obj[k], Sm, px % W, px / W, thr);
+                    else mine = __ldg(m + (size_t)k * HW + px) != 0;
+                }
+                const unsigned word = __ballot_sync(0xffffffffu, mine);
+                if (lane == 0) s_cover[i][k >> 5] = word;
+            }
+            if ((int)threadIdx.x < nn) s_slot[threadIdx.x] = my_slot;
+            __syncthreads();
+            // ---- phase B ----
+            // Warp w takes a contiguous piece of the raster-ordered list; lanes own float4 channel groups 4*lane + 128*j.
+            // Consecutive samples that fall into the same cell are summed in registers and leave as ONE 128-bit reduction
+            // per lane and group (the scratch row is an unordered fp32 sum either way).
+            const int chunk = (nn + 7) >> 3;
+            const int i_end = min(nn, ((int)warp + 1) * chunk);
+            float4 agg[J4];
+            int agg_slot = -1;
+            auto flush = [&]() {
+                if (agg_slot >= 0) {
+                    float *dst = scratch + ((size_t)e * S + agg_slot) * C + 4 * lane;
+#pragma unroll
+                    for (int j = 0; j < J4; ++j) red_add_v4(dst + 128 * j, agg[j].x, agg[j].y, agg[j].z, agg[j].w);
+                }
+            };
+            for (int i = warp * chunk; i < i_end; ++i) {
+                float4 acc[J4];
+#pragma unroll
+                for (int j = 0; j < J4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                int cnt = 0;
+                for (int wd = 0; wd < n_words; ++wd) {
+                    unsigned todo = s_cover[i][wd];
+                    cnt += __popc(todo);
+                    while (todo) {                                         // ascending object index
+                        const int kk = wd * 32 + __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        const float4 *row = reinterpret_cast<const float4 *>(f + (size_t)kk * C) + lane;
+#pragma unroll
+                        for (int j = 0; j < J4; ++j) {
+                            const float4 x = __ldg(row + 32 * j);
+                            acc[j].x = __fadd_rn(acc[j].x, x.x); acc[j].y = __fadd_rn(acc[j].y, x.y);
+                            acc[j].z = __fadd_rn(acc[j].z, x.z); acc[j].w = __fadd_rn(acc[j].w, x.w);
+                        }
+                    }
+                }
+                const int slot = s_slot[i];
+                if (cnt == 0 || slot < 0 || slot >= S) continue;           // cnt == 0 cannot happen for a sampled pixel; slot overflow: caller error
+                const float n_px = (float)cnt;
+                if (slot != agg_slot) {
+                    flush();
+                    agg_slot = slot;
+#pragma unroll
+                    for (int j = 0; j < J4; ++j)
+                        agg[j] = make_float4(__fdiv_rn(acc[j].x, n_px), __fdiv_rn(acc[j].y, n_px), __fdiv_rn(acc[j].z, n_px), __fdiv_rn(acc[j].w, n_px));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < J4; ++j) {
+                        agg[j].x = __fadd_rn(agg[j].x, __fdiv_rn(acc[j].x, n_px)); agg[j].y = __fadd_rn(agg[j].y, __fdiv_rn(acc[j].y, n_px));
+                        agg[j].z = __fadd_rn(agg[j].z, __fdiv_rn(acc[j].z, n_px)); agg[j].w = __fadd_rn(agg[j].w, __fdiv_rn(acc[j].w, n_px));
+                    }
+                }
+            }
+            flush();
+            __syncthreads();                                               // s_cover / s_slot are rewritten by the next round
+        }
+        return;
+    }
+
+    // ---- more than kCoverObjs objects: one sampled pixel at a time per warp ----
     for (int i = warp; i < n; i += 8) {
         const int px = s_list[i];
         float acc[J];
@@ -271,7 +405,7 @@ static int launch_write_objects(const char *what, bool pasted, const float *box_
                                 const uint8_t *samp, const int32_t *slot_of_cell, int n_episodes, int C, int HW, int64_t n_cells,
                                 int n_slots_max, float *scratch, cudaStream_t st)
 {
-    dim3 grid((HW + 255) / 256, n_episodes);
+    dim3 grid((HW + kObjSpan - 1) / kObjSpan, n_episodes);
 #define EOD_WO(CC)                                                                                                                      \
     case CC:                                                                                                                            \
         if (pasted)                                                                                                                     \

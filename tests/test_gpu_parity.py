@@ -306,15 +306,18 @@ def test_memory_fusion_tensor_core_and_library_paths_agree(eod, cuda):
 def test_sample_mask_and_box_features_bit_exact(eod, cuda):
     rng = np.random.default_rng(3)
     H, W, C = 48, 80, 64
-    for stride in (1, 3, 8):
-        obs = rng.uniform(size=(3, H * W)) < rng.uniform(0.0, 0.9)
-        obs[2] = False                                                     # empty: nothing observed
-        n = torch.zeros(3, dtype=torch.int32, device=cuda)
-        samp = eod.ops.sample_mask(_t(obs.view(np.uint8), cuda), stride, n_sampled=n)
-        for e in range(3):
-            ref = R.sample_mask(torch.from_numpy(obs[e]), stride).numpy()
-            assert np.array_equal(samp[e].cpu().numpy().astype(bool), ref)
-            assert int(n[e]) == int(ref.sum())
+    # plane sizes: 16-pixel vectorised scan (one and several 16 KB steps, ragged last step) and the scalar kernel (HW % 16 != 0)
+    for hw in (H * W, 480 * 640, 16 * 1025, 47 * 81):
+        for stride in (1, 3, 8):
+            obs = rng.uniform(size=(3, hw)) < rng.uniform(0.0, 0.9)
+            obs[2] = False                                                 # empty: nothing observed
+            obs_u8 = obs.view(np.uint8) * rng.integers(1, 256, obs.shape).astype(np.uint8)      # any non-zero byte counts as observed
+            n = torch.zeros(3, dtype=torch.int32, device=cuda)
+            samp = eod.ops.sample_mask(_t(obs_u8, cuda), stride, n_sampled=n)
+            for e in range(3):
+                ref = R.sample_mask(torch.from_numpy(obs[e]), stride).numpy()
+                assert np.array_equal(samp[e].cpu().numpy(), ref.astype(np.uint8)), (hw, stride, e)
+                assert int(n[e]) == int(ref.sum())
     bf, masks = eod.episodes.make_detections(rng, H, W, C, (7, 9))
     img, observed = eod.ops.box_to_image_features(_t(bf, cuda), _t(masks, cuda))
     ref_img, ref_obs = R.box_to_image_features(torch.from_numpy(bf), torch.from_numpy(masks))
@@ -703,6 +706,30 @@ def test_fused_detection_write_vs_oracle(eod, cuda):
             assert np.array_equal(batch.counts[e].cpu().numpy(), counts[e].numpy()), (t, e)
         assert np.array_equal(single.observations.cpu().numpy(), counts[0].numpy())
     assert sums[0].abs().max() > 0 and sums[1].abs().max() > 0
+
+
+def test_object_write_more_than_128_objects(eod, cuda):
+    """Above 128 kept objects per frame the write takes its one-pixel-at-a-time path (the bitmask phase holds 128):
+    both the byte-mask and the pasted variant against the oracle chain."""
+    E, C, H, W, mw, mh, Kmax = 1, 128, 64, 96, 20, 15, 140
+    cells = mw * mh
+    rng = np.random.default_rng(140)
+    idx = (rng.integers(0, cells, (E, H // 4, W // 8)).repeat(4, 1).repeat(8, 2)).astype(np.int32)
+    f, probs, boxes = eod.episodes.make_mask_head_detections(rng, H, W, C, (Kmax, Kmax), 28)
+    masks = oracle.paste_masks(probs, boxes, H, W, 0.5)
+    img, obs = R.box_to_image_features(torch.from_numpy(f), torch.from_numpy(masks))
+    ref, counts = R.write_mean_frame(torch.zeros(cells, C), torch.zeros(cells), img, obs, torch.from_numpy(idx[0]).long(), stride=8)
+    for pasted in (False, True):
+        batch = eod.EpisodeBatch(E, mw, mh, C, H, W, cuda)
+        batch.set_indices(_t(idx, cuda))
+        if pasted:
+            batch.write_detections(_t(f[None], cuda), _t(probs[None], cuda), _t(boxes[None], cuda))
+        else:
+            batch.write_objects(_t(f[None], cuda), _t(masks[None], cuda))
+        got = batch.sums[0].cpu().numpy()
+        assert np.abs(got - ref.numpy()).max() <= SUM_TOL * np.abs(ref.numpy()).max(), pasted
+        assert np.array_equal(got == 0, ref.numpy() == 0)
+        assert np.array_equal(batch.counts[0].cpu().numpy(), counts.numpy())
 
 
 def test_dense_backbone_write_vs_oracle(eod, cuda):
