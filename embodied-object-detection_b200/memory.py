@@ -245,6 +245,57 @@ class EpisodeBatch:
         return levels
 
 
+    def step_detections(self, depth, pose, shifts, intr, cell, box_features, mask_probs, boxes, n_obj=None, sample_stride: int = 8,
+                        mask_thresh: float = 0.5, order: int = ORDER_ZX) -> List[torch.Tensor]:
+        """One frame of the reference's LIVE regime for all E episodes (custom_rcnn.py:489-515 with :876-936): read of the
+        state left by frame t-1, then the write of this frame's kept detections (un-pasted 28x28 mask probabilities + boxes).
+        Two streams, stream-ordered for the caller on entry and exit:
+
+            geometry stream : project ----------------------------> read
+            write stream    : paste/observed -> sample -> (project) count -> write_objects -> flush -> (read) finalize
+
+        The mask pasting and the sampling scan do not depend on the geometry, and the issue-bound read runs next to the
+        latency-bound object write instead of in front of it."""
+        s0 = torch.cuda.current_stream(self.device)
+        self._k = self._t & 1
+        self._t += 1
+        S = -(-self.H * self.W // sample_stride)
+        if self._slots is None or self._slots.S < S:
+            self._slots = ops.ObjectSlots(self.E, self.n_cells, self.C, S, self.device)
+        e_in = torch.cuda.Event()
+        e_in.record(s0)
+        with torch.cuda.stream(self._geo):
+            self._geo.wait_event(e_in)
+            if self._e_fin is not None:
+                self._geo.wait_event(self._e_fin)
+            self.project(depth, pose, shifts, intr, cell, order)
+            e_geo = torch.cuda.Event()
+            e_geo.record()
+            levels = self.read()
+            e_read = torch.cuda.Event()
+            e_read.record()
+        with torch.cuda.stream(self._wr):
+            self._wr.wait_event(e_in)
+            if self._e_fin is not None:
+                self._wr.wait_event(self._e_fin)
+            _, observed = ops.paste_masks(mask_probs, boxes, (self.H, self.W), mask_thresh, n_obj, want_masks=False, want_observed=True)
+            samp = ops.sample_mask(observed, sample_stride)
+            self._wr.wait_event(e_geo)
+            ops.frame_count(self.idx, samp, self.frame_cnt, n_obj, self._slots)
+            ops.write_objects_pasted(box_features, mask_probs, boxes, n_obj, self.idx, samp, self._slots, mask_thresh)
+            ops.flush_slots(self.frame_cnt, self._slots, self.sums)
+            self._wr.wait_event(e_read)                    # finalize rewrites the norm16 rows the read gathers from
+            self._finalize()
+            e_fin = torch.cuda.Event()
+            e_fin.record()
+            for t in (observed, samp):
+                t.record_stream(self._wr)
+        self._e_read, self._e_fin = e_read, e_fin
+        s0.wait_event(e_read)
+        s0.wait_event(e_fin)
+        return levels
+
+
 class SpatialFeatureMemory:
     """Reference-facing, one episode in flight (like one ``CustomRCNNRecurrent`` instance).
 

@@ -58,4 +58,16 @@ res = {k: sum(x.elapsed_time(y) for x, y in v[2:]) / len(v[2:]) for k, v in stag
 res["frame_step_ms"] = sum(x.elapsed_time(y) for x, y in tot[2:]) / len(tot[2:])
 res["frames_per_s"] = E / res["frame_step_ms"] * 1e3
 res["sampled_px_per_episode"] = float(samp.sum().item()) / E
+# the same frame through EpisodeBatch.step_detections (two streams)
+ov = []
+for t in range(T):
+    bf, pr, bx, n = dets[t & 1]
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    batch.step_detections(depth[t % 4], pose[t % 4], shifts, intr, cell, bf, pr, bx, n)
+    b.record()
+    ov.append((a, b))
+torch.cuda.synchronize()
+res["step_detections_ms"] = sum(x.elapsed_time(y) for x, y in ov[2:]) / len(ov[2:])
+res["step_detections_frames_per_s"] = E / res["step_detections_ms"] * 1e3
 print(json.dumps({"E": E, "Kmax": Kmax, "C": C, **res}))

@@ -708,6 +708,42 @@ def test_fused_detection_write_vs_oracle(eod, cuda):
     assert sums[0].abs().max() > 0 and sums[1].abs().max() > 0
 
 
+def test_step_detections_two_streams_matches_serial(eod, cuda):
+    """EpisodeBatch.step_detections (geometry/read and paste/write on two streams) against the serial composition
+    project -> read -> write_detections, frame by frame: identical indices and fp16 levels (the read sees the state of
+    frame t-1), identical touched sets and counts, sums within the reduction-order tolerance."""
+    E, C, H, W, mw, mh, Kmax, T = 3, 128, 96, 128, 60, 45, 6, 4
+    cell = 0.2
+    rng = np.random.default_rng(77)
+    eps = [eod.episodes.make_episode(500 + e, T, H, W, mw, mh, cell) for e in range(E)]
+    intr = eod.compute_intrinsics(W, H, math.radians(67.5))
+    shifts = _t(np.stack([np.concatenate([np.zeros(3, np.float32), ep.map_world_shift]) for ep in eps]), cuda)
+    a = eod.EpisodeBatch(E, mw, mh, C, H, W, cuda)
+    b = eod.EpisodeBatch(E, mw, mh, C, H, W, cuda)
+    for t in range(T):
+        Tm = eod.transform3d(torch.from_numpy(np.stack([ep.xyzhe[t] for ep in eps])))
+        pose = Tm[:, :3].reshape(E, 12).to(cuda)
+        depth = _t(np.stack([ep.depth[t] for ep in eps]), cuda)
+        n_obj = np.array([Kmax, 0 if t == 1 else 3, 2], np.int32)
+        bf = np.zeros((E, Kmax, C), np.float32); pr = np.zeros((E, Kmax, 28, 28), np.float32); bx = np.zeros((E, Kmax, 4), np.float32)
+        for e in range(E):
+            if n_obj[e]:
+                f, p, bb = eod.episodes.make_mask_head_detections(rng, H, W, C, (int(n_obj[e]), int(n_obj[e])), 28)
+                bf[e, : n_obj[e]], pr[e, : n_obj[e]], bx[e, : n_obj[e]] = f, p, bb
+        args = (_t(bf, cuda), _t(pr, cuda), _t(bx, cuda), _t(n_obj, cuda))
+        la = [l.clone() for l in a.step_detections(depth, pose, shifts, intr, cell, *args)]
+        b.project(depth, pose, shifts, intr, cell)
+        lb = [l.clone() for l in b.read()]
+        b.write_detections(*args)
+        torch.cuda.synchronize()
+        assert torch.equal(a.idx, b.idx)
+        for x, y in zip(la, lb):
+            assert torch.equal(x, y), t
+        assert torch.equal(a.counts, b.counts) and torch.equal(a.sums == 0, b.sums == 0)
+        assert (a.sums - b.sums).abs().max().item() <= SUM_TOL * max(b.sums.abs().max().item(), 1e-30)
+    assert b.counts.max().item() >= 2 and b.sums.abs().max().item() > 0
+
+
 def test_object_write_more_than_128_objects(eod, cuda):
     """Above 128 kept objects per frame the write takes its one-pixel-at-a-time path (the bitmask phase holds 128):
     both the byte-mask and the pasted variant against the oracle chain."""
