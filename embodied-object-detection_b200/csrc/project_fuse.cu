@@ -45,6 +45,11 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const void *tmap, int x, 
                  "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar))
                  : "memory");
 }
+// L2 prefetch of a 3-D tile (no shared-memory destination): takes the DRAM latency out of the small smem rings
+__device__ __forceinline__ void tma_prefetch_3d(const void *tmap, int x, int y, int z)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tmap), "r"(x), "r"(y), "r"(z) : "memory");
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols)
 {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
@@ -206,7 +211,7 @@ constexpr int P2_BM = 256, P2_STAGES = 3, P2_RCH = 16, P2_RSLOTS = 2;
 constexpr int P2_A_BYTES = P2_BM * PF_BK * 2;                 // 32 KB
 constexpr int P2_STAGE_BYTES = P2_A_BYTES + PF_B_BYTES;       // 64 KB
 constexpr int P2_R_BYTES = P2_RCH * P2_BM * 4;                // 16 KB
-constexpr int P2_SMEM_BYTES = P2_STAGES * P2_STAGE_BYTES + P2_RSLOTS * P2_R_BYTES + 1024 + 128;
+constexpr int P2_SMEM_BYTES = P2_STAGES * P2_STAGE_BYTES + P2_RSLOTS * P2_R_BYTES + 1024 + 128 + 2 * PF_BN * 4 /* bias, double buffered */;
 constexpr int P2_THREADS = 12 * 32;                 // 3 warpgroups: 2 x epilogue, 1 x {A/B producer, MMA, res producer, idle}
 constexpr int P2_MAX_LEVELS = 3;
 
@@ -248,6 +253,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) project_fuse_persistent_kernel(
     uint64_t *full = bars, *empty = full + P2_STAGES, *rfull = empty + P2_STAGES, *rempty = rfull + P2_RSLOTS;
     uint64_t *tmem_full = rempty + P2_RSLOTS, *tmem_empty = tmem_full + 1;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 1);
+    float *bias_s = reinterpret_cast<float *>(bars + 16);           // 2 x 128 floats
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 8 && lane == 0) {
@@ -310,6 +316,14 @@ __global__ void __launch_bounds__(P2_THREADS, 1) project_fuse_persistent_kernel(
             uint32_t rc = 0;
             for (int t = blockIdx.x; t < P.n_tiles; t += gridDim.x) {
                 const P2Tile T = p2_decode(P, t);
+                // the ring holds 32 KB; what hides the DRAM latency is the L2 prefetch of the NEXT tile's res block (128 KB)
+                // issued one tile ahead (and of this one, for the first tile)
+                for (int ahead = (t == (int)blockIdx.x ? 0 : 1); ahead < 2; ++ahead) {
+                    const int tn = t + ahead * gridDim.x;
+                    if (tn >= P.n_tiles) break;
+                    const P2Tile Tn = p2_decode(P, tn);
+                    for (int c = 0; c < PF_BN / P2_RCH; ++c) tma_prefetch_3d(&P.tm_r[Tn.l], Tn.p0, Tn.nb * PF_BN + c * P2_RCH, Tn.e);
+                }
                 for (int c = 0; c < PF_BN / P2_RCH; ++c, ++rc) {
                     const int s = rc % P2_RSLOTS;
                     mbar_wait(rempty + s, ((rc / P2_RSLOTS) & 1) ^ 1);
@@ -333,6 +347,12 @@ __global__ void __launch_bounds__(P2_THREADS, 1) project_fuse_persistent_kernel(
             const bool live = pix < hw;
             float *out = P.out[T.l] + ((size_t)T.e * P.N + (size_t)T.nb * PF_BN) * hw + (live ? pix : 0);
             const float *bias_n = P.bias[T.l] ? P.bias[T.l] + T.nb * PF_BN : nullptr;
+            // the tile's 128 bias values go through shared memory (a dependent L1 load per output element was 1/3 of the
+            // epilogue's stalls); the load overlaps the wait for the accumulators.  Double buffered: a warp may be two phases
+            // apart from the slowest one only across the named barrier below.
+            float *bias_t = bias_s + (tile_it & 1) * PF_BN;
+            if (bias_n && threadIdx.x < PF_BN) bias_t[threadIdx.x] = __ldg(bias_n + threadIdx.x);
+            named_bar_sync(1, 256);
             // phase 1: TMEM -> registers (the GEMM result x.W_hi + 2^-11 x.W_lo of this pixel's 128 channels)
             float v[PF_BN];
             mbar_wait(tmem_full, tile_it & 1);
@@ -363,7 +383,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) project_fuse_persistent_kernel(
 #pragma unroll
                 for (int j = 0; j < P2_RCH; ++j) {
                     float x = v[c * P2_RCH + j];
-                    if (bias_n) x = __fadd_rn(x, __ldg(bias_n + c * P2_RCH + j));      // conv bias
+                    if (bias_n) x = __fadd_rn(x, bias_t[c * P2_RCH + j]);              // conv bias
                     x = __fmul_rn(x, P.weight);                                          // timm.py:177
                     if (kSum) x = __fadd_rn(r[j], x);                                    // timm.py:182
                     if (live) out[(size_t)(c * P2_RCH + j) * hw] = x;

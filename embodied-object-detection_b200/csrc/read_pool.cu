@@ -72,8 +72,17 @@ __device__ __forceinline__ void store_half4(__half *dst, float4 v)
     *reinterpret_cast<uint2 *>(dst) = raw;
 }
 
-__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w)); }
-__device__ __forceinline__ float4 scale4(float4 a, float s) { return make_float4(__fmul_rn(a.x, s), __fmul_rn(a.y, s), __fmul_rn(a.z, s), __fmul_rn(a.w, s)); }
+// packed fp32x2 arithmetic (sm_100 FADD2 / FMUL2): two IEEE round-to-nearest operations per instruction, same bits as the scalar ones
+__device__ __forceinline__ float4 add4(float4 a, float4 b)
+{
+    const float2 lo = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y)), hi = __fadd2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ float4 scale4(float4 a, float s)
+{
+    const float2 lo = __fmul2_rn(make_float2(a.x, a.y), make_float2(s, s)), hi = __fmul2_rn(make_float2(a.z, a.w), make_float2(s, s));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
 
 template <int C, typename TableT, typename IdxT>
 __global__ void __launch_bounds__(C, 1024 / C) read_pool_kernel(const TableT *__restrict__ table, const float *__restrict__ counts,

@@ -18,4 +18,13 @@ echo "full rc=$?"
 PROF_E=64 PROF_T=2 python profiles/prof_step.py > $O/prof_plain64_$TAG.log 2>&1 && \
 PROF_E=64 PROF_T=2 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file $O/traffic64_$TAG.csv python profiles/prof_step.py > $O/ncu_traffic_$TAG.log 2>&1
 echo "traffic rc=$?"
+# projection + fusion (tcgen05): timing without a profiler, then one --set full capture of the persistent kernel
+python profiles/prof_fuse.py > $O/prof_fuse_$TAG.json 2>$O/prof_fuse_$TAG.err; echo "fuse rc=$?"; tail -1 $O/prof_fuse_$TAG.json
+PROF_ONLY=tc PROF_ROUNDS=2 ncu --set full --clock-control none --import-source on -k regex:project_fuse_persistent -s 2 -c 1 -f -o $O/prof_fuse_$TAG python profiles/prof_fuse.py > $O/ncu_fuse_$TAG.log 2>&1
+echo "fuse full rc=$?"
+# the other BASELINE configurations and the object-regime stage breakdown (no profiler)
+python profiles/bench_configs.py > $O/configs_$TAG.log 2>$O/configs_$TAG.err; echo "configs rc=$?"
+python profiles/prof_objects.py > $O/objects_$TAG.json 2>$O/objects_$TAG.err; echo "objects rc=$?"
+PROF_E=16 PROF_T=4 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $O/launches_obj_$TAG.csv python profiles/prof_objects.py > $O/ncu_launches_obj_$TAG.log 2>&1
+echo "object launch list rc=$?"
 fi

@@ -34,6 +34,51 @@ def load_metrics(fn):
     return d
 
 
+def rep_section(rep, title, md, extra=()):
+    """Key metrics + stall breakdown of every launch captured in one .ncu-rep (ncu --set full)."""
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    h, units = rows[0], rows[1]
+    want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+            "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+            "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "launch__registers_per_thread", "launch__block_size",
+            "launch__grid_size", "launch__shared_mem_per_block_dynamic", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
+            "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"] + list(extra)
+    md += [f"## {title}", ""]
+    ki = h.index("Kernel Name")
+    md += ["| metric | " + " | ".join(f"`{r[ki].split('(')[0].replace('<unnamed>::', '').replace('void ', '')[:28]}`" for r in rows[2:]) + " |",
+           "|---|" + "---|" * len(rows[2:])]
+    for w in want:
+        if w in h:
+            i = h.index(w)
+            md.append(f"| {w} [{units[i]}] | " + " | ".join(r[i][:14] for r in rows[2:]) + " |")
+    md.append("")
+    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    blocks, names, cur = [], [], None
+    for r in csv.reader(src.splitlines()):
+        if r and r[0] == "Kernel Name":
+            cur = []
+            blocks.append(cur)
+            names.append(r[1].split("(")[0].replace("<unnamed>::", "").replace("void ", ""))
+            continue
+        if cur is not None:
+            cur.append(r)
+    md += ["Warp-stall sampling (source page, all samples), first capture of each kernel:", ""]
+    done = set()
+    for name, b in zip(names, blocks):
+        if name in done or len(b) < 2:
+            continue
+        done.add(name)
+        hh, data = b[0], b[1:]
+        si = hh.index("# Samples")
+        stalls = [c for c in hh if c.startswith("stall_") and "Not Issued" not in c]
+        tot = {s: sum(int(r[hh.index(s)]) for r in data) for s in stalls}
+        total = sum(int(r[si]) for r in data) or 1
+        md.append(f"- `{name}`: " + ", ".join(f"{s[6:]} {v / total:.2f}" for s, v in sorted(tot.items(), key=lambda x: -x[1])[:7])
+                  + f" ({len(data)} SASS instructions)")
+    md.append("")
+
+
 def main():
     tag = sys.argv[1]
     prefix = sys.argv[2] if len(sys.argv) > 2 else tag
@@ -83,46 +128,35 @@ def main():
 
     rep = os.path.join(OUT, f"prof_{tag}.ncu-rep")
     if os.path.exists(rep):
-        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-        rows = list(csv.reader(raw.splitlines()))
-        h, units = rows[0], rows[1]
-        want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-                "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
-                "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "launch__registers_per_thread", "launch__block_size",
-                "launch__grid_size", "launch__shared_mem_per_block_dynamic", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
-                "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
-        md += ["## `ncu --set full` (E=16), key metrics per captured launch", ""]
-        ki = h.index("Kernel Name")
-        md += ["| metric | " + " | ".join(f"`{r[ki].split('(')[0].replace('<unnamed>::', '').replace('void ', '')[:28]}`" for r in rows[2:]) + " |",
-               "|---|" + "---|" * len(rows[2:])]
-        for w in want:
-            if w in h:
-                i = h.index(w)
-                md.append(f"| {w} [{units[i]}] | " + " | ".join(r[i][:14] for r in rows[2:]) + " |")
-        md.append("")
-        src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-        blocks, names, cur = [], [], None
-        for r in csv.reader(src.splitlines()):
-            if r and r[0] == "Kernel Name":
-                cur = []
-                blocks.append(cur)
-                names.append(r[1].split("(")[0].replace("<unnamed>::", "").replace("void ", ""))
-                continue
-            if cur is not None:
-                cur.append(r)
-        md += ["## Warp-stall sampling (source page, all samples), first capture of each kernel", ""]
-        done = set()
-        for name, b in zip(names, blocks):
-            if name in done or len(b) < 2:
-                continue
-            done.add(name)
-            hh, data = b[0], b[1:]
-            si = hh.index("# Samples")
-            stalls = [c for c in hh if c.startswith("stall_") and "Not Issued" not in c]
-            tot = {s: sum(int(r[hh.index(s)]) for r in data) for s in stalls}
-            total = sum(int(r[si]) for r in data) or 1
-            md.append(f"- `{name}`: " + ", ".join(f"{s[6:]} {v / total:.2f}" for s, v in sorted(tot.items(), key=lambda x: -x[1])[:7])
-                      + f" ({len(data)} SASS instructions)")
+        rep_section(rep, "`ncu --set full` of the write and read kernels (E=16), key metrics per captured launch", md)
+
+    fn = os.path.join(OUT, f"prof_fuse_{tag}.json")
+    if os.path.exists(fn):
+        md += ["## Projection + fusion stage (`profiles/prof_fuse.py`, E=64, three levels, K=512 -> N=256; CUDA events, no profiler)", "",
+               "```", open(fn).read().strip().splitlines()[-1], "```", ""]
+    rep = os.path.join(OUT, f"prof_fuse_{tag}.ncu-rep")
+    if os.path.exists(rep):
+        rep_section(rep, "`ncu --set full` of `project_fuse_persistent_kernel` (E=64, all levels in one launch)", md,
+                    extra=["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "l1tex__m_xbar2l1tex_read_bytes.sum", "sm__cycles_elapsed.max"])
+
+    fn = os.path.join(OUT, f"configs_{tag}.log")
+    if os.path.exists(fn):
+        md += ["## Other BASELINE configurations (`profiles/bench_configs.py`; CUDA events, no profiler)", "", "```"] + \
+              [l for l in open(fn).read().strip().splitlines() if l.startswith("{")] + ["```", ""]
+    fn = os.path.join(OUT, f"objects_{tag}.json")
+    if os.path.exists(fn):
+        md += ["## Object regime, stage breakdown (`profiles/prof_objects.py`, E=64, C=512, <=16 detections per frame; ms per launch)", "",
+               "```", open(fn).read().strip().splitlines()[-1], "```", ""]
+    fn = os.path.join(OUT, f"launches_obj_{tag}.csv")
+    if os.path.exists(fn):
+        shutil.copy(fn, os.path.join(ROOT, "profiles", f"{prefix}_launches_objects.csv"))
+        agg = collections.OrderedDict()
+        for (_, k), v in load_metrics(fn).items():
+            agg.setdefault(k, []).append(v["gpu__time_duration.sum"])
+        tot = sum(sum(v) for v in agg.values())
+        md += ["Launch list of the same script under ncu (E=16, cold cache, serialised):", "", "| kernel | launches | mean us | share |", "|---|---|---|---|"]
+        for k, v in agg.items():
+            md.append(f"| `{k[:60]}` | {len(v)} | {sum(v) / len(v) / 1e3:.1f} | {sum(v) / tot:.3f} |")
         md.append("")
 
     fn = os.path.join(OUT, f"bench_{tag}.log")
