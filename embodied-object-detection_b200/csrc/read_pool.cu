@@ -14,176 +14,304 @@
 
 namespace {
 
-template <typename IdxT>
-__device__ __forceinline__ int load_cell(const IdxT *p) { return (int)__ldg(p); }
+// ---- V channels per lane (V = 4 or 8) as packed fp32x2 pairs -------------------------------------------------------
+// FADD2 / FMUL2 (sm_100): two IEEE round-to-nearest operations per instruction, the same bits as the scalar ones.
+template <int V>
+struct Vec { float2 p[V / 2]; };
 
-__device__ __forceinline__ float4 round_to_half(float4 v)
+template <int V>
+__device__ __forceinline__ Vec<V> vzero()
 {
-    v.x = __half2float(__float2half_rn(v.x));
-    v.y = __half2float(__float2half_rn(v.y));
-    v.z = __half2float(__float2half_rn(v.z));
-    v.w = __half2float(__float2half_rn(v.w));
-    return v;
+    Vec<V> r;
+#pragma unroll
+    for (int i = 0; i < V / 2; ++i) r.p[i] = make_float2(0.f, 0.f);
+    return r;
+}
+template <int V>
+__device__ __forceinline__ Vec<V> vadd(const Vec<V> &a, const Vec<V> &b)
+{
+    Vec<V> r;
+#pragma unroll
+    for (int i = 0; i < V / 2; ++i) r.p[i] = __fadd2_rn(a.p[i], b.p[i]);
+    return r;
+}
+template <int V>
+__device__ __forceinline__ Vec<V> vscale(const Vec<V> &a, float s)
+{
+    Vec<V> r;
+#pragma unroll
+    for (int i = 0; i < V / 2; ++i) r.p[i] = __fmul2_rn(a.p[i], make_float2(s, s));
+    return r;
+}
+template <int V>
+__device__ __forceinline__ Vec<V> vround_half(const Vec<V> &a)
+{
+    Vec<V> r;
+#pragma unroll
+    for (int i = 0; i < V / 2; ++i) r.p[i] = __half22float2(__float22half2_rn(a.p[i]));
+    return r;
+}
+// V halves, 2*V bytes, one store
+template <int V>
+__device__ __forceinline__ void vstore_half(__half *dst, const Vec<V> &a)
+{
+    uint32_t w[V / 2];
+#pragma unroll
+    for (int i = 0; i < V / 2; ++i) {
+        const __half2 h = __float22half2_rn(a.p[i]);
+        w[i] = *reinterpret_cast<const uint32_t *>(&h);
+    }
+    if (V == 8) *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3 % (V / 2)]);
+    else *reinterpret_cast<uint2 *>(dst) = make_uint2(w[0], w[1]);
 }
 
-// Split row fetch: the global loads of a batch of pixels are issued first (load_raw, load_n), their
-// consumers (finish: normalise + fp16 rounding) run afterwards, so one memory latency is exposed per batch
-// instead of one per cell change.
-struct RawF32 { float4 v; float n; };
-struct RawF16 { uint2 v; };
+// Split row fetch: the global load of a row is issued (load_raw) before its consumer (finish: normalise + fp16
+// rounding) runs, so the next run's row is in flight under the current run's adds.
+template <int V> struct RawF32 { float4 v[V / 4]; float n; };
+template <int V> struct RawF16 { uint32_t w[V / 2]; };
 
-__device__ __forceinline__ RawF32 load_raw(const float *table, const float *counts, size_t cell, int C, int g)
+template <int V>
+__device__ __forceinline__ RawF32<V> load_raw(const float *table, const float *counts, size_t cell, int C, int g)
 {
-    RawF32 r;
-    r.v = __ldg(reinterpret_cast<const float4 *>(table + cell * C) + g);
+    RawF32<V> r;
+#pragma unroll
+    for (int i = 0; i < V / 4; ++i) r.v[i] = __ldg(reinterpret_cast<const float4 *>(table + cell * C + (size_t)g * V) + i);
     r.n = counts ? __ldg(counts + cell) : 0.f;
     return r;
 }
-__device__ __forceinline__ RawF16 load_raw(const __half *table, const float *, size_t cell, int C, int g)
+template <int V>
+__device__ __forceinline__ RawF16<V> load_raw(const __half *table, const float *, size_t cell, int C, int g)
 {
-    RawF16 r;
-    r.v = __ldg(reinterpret_cast<const uint2 *>(table + cell * C) + g);
+    RawF16<V> r;
+    if (V == 8) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4 *>(table + cell * C) + g);
+        r.w[0] = q.x; r.w[1] = q.y; r.w[2 % (V / 2)] = q.z; r.w[3 % (V / 2)] = q.w;
+    } else {
+        const uint2 q = __ldg(reinterpret_cast<const uint2 *>(table + cell * C) + g);
+        r.w[0] = q.x; r.w[1] = q.y;
+    }
     return r;
 }
-__device__ __forceinline__ float4 finish(const RawF32 &r)
+template <int V>
+__device__ __forceinline__ Vec<V> finish(const RawF32<V> &r)
 {
-    float4 v = r.v;
-    if (r.n > 1.0f) {            // custom_rcnn.py:774 (cells seen once or never are left as-is)
-        v.x = __fdiv_rn(v.x, r.n); v.y = __fdiv_rn(v.y, r.n); v.z = __fdiv_rn(v.z, r.n); v.w = __fdiv_rn(v.w, r.n);
+    Vec<V> v;
+#pragma unroll
+    for (int i = 0; i < V / 4; ++i) {
+        float4 x = r.v[i];
+        if (r.n > 1.0f) {        // custom_rcnn.py:774 (cells seen once or never are left as-is)
+            x.x = __fdiv_rn(x.x, r.n); x.y = __fdiv_rn(x.y, r.n); x.z = __fdiv_rn(x.z, r.n); x.w = __fdiv_rn(x.w, r.n);
+        }
+        v.p[2 * i] = make_float2(x.x, x.y);
+        v.p[2 * i + 1] = make_float2(x.z, x.w);
     }
-    return round_to_half(v);     // custom_rcnn.py:1036
+    return vround_half<V>(v);    // custom_rcnn.py:1036
 }
-__device__ __forceinline__ float4 finish(const RawF16 &r)
+template <int V>
+__device__ __forceinline__ Vec<V> finish(const RawF16<V> &r)
 {
-    const __half2 a = *reinterpret_cast<const __half2 *>(&r.v.x), b = *reinterpret_cast<const __half2 *>(&r.v.y);
-    const float2 fa = __half22float2(a), fb = __half22float2(b);
-    return make_float4(fa.x, fa.y, fb.x, fb.y);
+    Vec<V> v;
+#pragma unroll
+    for (int i = 0; i < V / 2; ++i) v.p[i] = __half22float2(*reinterpret_cast<const __half2 *>(&r.w[i]));
+    return v;
 }
-template <typename T> struct RawOf;
-template <> struct RawOf<float> { using type = RawF32; };
-template <> struct RawOf<__half> { using type = RawF16; };
+template <typename T, int V> struct RawOf;
+template <int V> struct RawOf<float, V> { using type = RawF32<V>; };
+template <int V> struct RawOf<__half, V> { using type = RawF16<V>; };
 
-__device__ __forceinline__ void store_half4(__half *dst, float4 v)
-{
-    __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
-    uint2 raw;
-    raw.x = *reinterpret_cast<uint32_t *>(&a);
-    raw.y = *reinterpret_cast<uint32_t *>(&b);
-    *reinterpret_cast<uint2 *>(dst) = raw;
-}
+// Warp-autonomous read: a work item = one 16x16-pixel quadrant (4 L0 pixels, 1 L1 pixel) x 32*V channels, owned by ONE
+// warp (lane = group of V consecutive channels; V = 8 for C >= 256: the per-run bookkeeping below is scalar work that
+// every lane repeats, so wider lanes halve it per channel).  The warp stages the quadrant's 256 cell ids in its private
+// slice of shared memory, classifies its 16 windows itself (lanes 0-15) and walks them - no CTA barrier anywhere, and the
+// ids of the NEXT item are already in flight (registers) while the current one is processed.  Level 2 needs four L1
+// pixels of different quadrants; it is pooled from the stored L1 by pool_level2_kernel instead of through a CTA-wide
+// exchange.  (The CTA-per-32x32-block version spent 35 % of its stall samples on the index staging latency and on two
+// barriers per block.)
+//
+// Summation order == ATen CPU avg_pool2d: fp32, start from 0, row-major over the window, then / k^2; the fp16 roundings
+// between levels (timm.py:168) are reproduced, so outputs are bit-identical.
+constexpr int kReadWarps = 8;
 
-// packed fp32x2 arithmetic (sm_100 FADD2 / FMUL2): two IEEE round-to-nearest operations per instruction, same bits as the scalar ones
-__device__ __forceinline__ float4 add4(float4 a, float4 b)
+struct QuadIdx { int v[8]; };
+
+template <typename IdxT>
+__device__ __forceinline__ QuadIdx load_quad_idx(const IdxT *idx_e, int W, int qy, int qx, unsigned lane)
 {
-    const float2 lo = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y)), hi = __fadd2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w));
-    return make_float4(lo.x, lo.y, hi.x, hi.y);
-}
-__device__ __forceinline__ float4 scale4(float4 a, float s)
-{
-    const float2 lo = __fmul2_rn(make_float2(a.x, a.y), make_float2(s, s)), hi = __fmul2_rn(make_float2(a.z, a.w), make_float2(s, s));
-    return make_float4(lo.x, lo.y, hi.x, hi.y);
+    // lane -> row lane>>1 of the quadrant, columns (lane&1)*8 .. +7
+    const IdxT *src = idx_e + (size_t)(qy * 16 + (lane >> 1)) * W + qx * 16 + (lane & 1) * 8;
+    QuadIdx q;
+    if (sizeof(IdxT) == 4) {
+        const int4 a = __ldg(reinterpret_cast<const int4 *>(src)), b = __ldg(reinterpret_cast<const int4 *>(src) + 1);
+        q.v[0] = a.x; q.v[1] = a.y; q.v[2] = a.z; q.v[3] = a.w; q.v[4] = b.x; q.v[5] = b.y; q.v[6] = b.z; q.v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const longlong2 a = __ldg(reinterpret_cast<const longlong2 *>(src) + k);
+            q.v[2 * k] = (int)a.x; q.v[2 * k + 1] = (int)a.y;
+        }
+    }
+    return q;
 }
 
 template <int C, typename TableT, typename IdxT>
-__global__ void __launch_bounds__(C, 1024 / C) read_pool_kernel(const TableT *__restrict__ table, const float *__restrict__ counts,
-                                                      const IdxT *__restrict__ idx, int H, int W, int64_t n_cells,
-                                                      __half *__restrict__ L0, __half *__restrict__ L1, __half *__restrict__ L2)
+__global__ void __launch_bounds__(kReadWarps * 32, (C >= 256 ? 3 : 4)) read_pool_kernel(const TableT *__restrict__ table, const float *__restrict__ counts,
+                                                                                        const IdxT *__restrict__ idx, int H, int W, int64_t n_cells, int E,
+                                                                                        __half *__restrict__ L0, __half *__restrict__ L1)
 {
-    constexpr int G = C / 4;                 // channel groups == threads per quadrant
-    __shared__ int s_idx[32 * 32];
-    __shared__ int s_wcell[64];              // per 4x4 window (8x8 of them): the cell id if all 16 pixels agree, else -1
-    __shared__ float4 s_l1[4][G];
+    constexpr int V = C >= 256 ? 8 : 4;      // channels per lane
+    constexpr int NC = C / (32 * V);         // channel chunks per quadrant
+    using Raw = typename RawOf<TableT, V>::type;
+    __shared__ __align__(16) int s_idx[kReadWarps][16 * 16];
+    __shared__ int s_wcell[kReadWarps][16];                    // per 4x4 window: the cell id if all 16 pixels agree, else -1
+    __shared__ int s_run_cell[kReadWarps][16][16];             // mixed windows: runs of equal cell id in row-major (= summation) order ...
+    __shared__ __align__(16) unsigned char s_run_len[kReadWarps][16][16];   // ... their lengths ...
+    __shared__ int s_nruns[kReadWarps][16];                    // ... and how many there are
 
-    const int e = blockIdx.z, by = blockIdx.y, bx = blockIdx.x;
-    const int q = threadIdx.x / G, g = threadIdx.x % G;
-    const int qy = q >> 1, qx = q & 1;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nqy = H / 16, nqx = W / 16;
+    const int64_t n_items = (int64_t)E * nqy * nqx * NC;
+    const int64_t stride = (int64_t)gridDim.x * kReadWarps;
+    const int h0 = H / 8, w0 = W / 8, h1 = H / 16, w1 = W / 16;
 
-    const IdxT *idx_e = idx + (size_t)e * H * W;
-    for (int i = threadIdx.x; i < 1024; i += C) {
-        const int r = i >> 5, c = i & 31;
-        s_idx[i] = load_cell(idx_e + (size_t)(by * 32 + r) * W + bx * 32 + c);
-    }
-    __syncthreads();
-    if (threadIdx.x < 64) {
-        const int wy = threadIdx.x >> 3, wx = threadIdx.x & 7;
-        const int4 r0 = *reinterpret_cast<const int4 *>(&s_idx[(wy * 4 + 0) * 32 + wx * 4]);
-        const int4 r1 = *reinterpret_cast<const int4 *>(&s_idx[(wy * 4 + 1) * 32 + wx * 4]);
-        const int4 r2 = *reinterpret_cast<const int4 *>(&s_idx[(wy * 4 + 2) * 32 + wx * 4]);
-        const int4 r3 = *reinterpret_cast<const int4 *>(&s_idx[(wy * 4 + 3) * 32 + wx * 4]);
-        const int c0 = r0.x;
-        const bool u = (r0.y == c0) & (r0.z == c0) & (r0.w == c0) & (r1.x == c0) & (r1.y == c0) & (r1.z == c0) & (r1.w == c0) &
-                       (r2.x == c0) & (r2.y == c0) & (r2.z == c0) & (r2.w == c0) & (r3.x == c0) & (r3.y == c0) & (r3.z == c0) & (r3.w == c0);
-        s_wcell[threadIdx.x] = u ? c0 : -1;
-    }
-    __syncthreads();
+    auto decode = [&](int64_t item, int &e, int &qy, int &qx, int &chunk) {
+        chunk = (int)(item % NC);
+        int64_t q = item / NC;
+        qx = (int)(q % nqx); q /= nqx;
+        qy = (int)(q % nqy);
+        e = (int)(q / nqy);
+    };
 
-    const TableT *table_e = table + (size_t)e * n_cells * C;
-    const float *counts_e = counts ? counts + (size_t)e * n_cells : nullptr;
-    const int h0 = H / 8, w0 = W / 8, h1 = H / 16, w1 = W / 16, h2 = H / 32, w2 = W / 32;
+    int64_t item = (int64_t)blockIdx.x * kReadWarps + warp;
+    if (item >= n_items) return;
+    int e, qy, qx, chunk;
+    decode(item, e, qy, qx, chunk);
+    QuadIdx nxt = load_quad_idx<IdxT>(idx + (size_t)e * H * W, W, qy, qx, lane);
 
-    int cur_cell = -1;
-    float4 cur = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 l1acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 1
-    for (int l0 = 0; l0 < 4; ++l0) {                       // L0 pixels of the quadrant, row-major
-        const int l0y = l0 >> 1, l0x = l0 & 1;
-        // The four 4x4 windows of this L0 pixel.  A window whose 16 pixels hit ONE cell needs no additions: the
-        // gathered value x is an fp16 number, so the sequential fp32 sum x+x+...+x is exact at every step
-        // (k*x, k <= 16, has at most 15 significant bits) and avg_pool2d(4) returns x itself.
-        const int wbase = (qy * 4 + l0y * 2) * 8 + qx * 4 + l0x * 2;
-        const int w00 = s_wcell[wbase];
-        float4 v0;
-        if (w00 >= 0 && w00 == s_wcell[wbase + 1] && w00 == s_wcell[wbase + 8] && w00 == s_wcell[wbase + 9]) {
-            // whole 8x8 block in one cell: pool(4), pool(2) and the fp16 rounding all return the gathered value
-            if (w00 != cur_cell) cur = finish(load_raw(table_e, counts_e, (size_t)w00, C, g));
-            cur_cell = w00;
-            v0 = cur;
-        } else {
-            float4 s2 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 1
-            for (int win = 0; win < 4; ++win) {            // 4x4 windows of the avg_pool2d(4) (timm.py:152)
-                const int wc = s_wcell[wbase + (win >> 1) * 8 + (win & 1)];
-                if (wc >= 0) {
-                    if (wc != cur_cell) cur = finish(load_raw(table_e, counts_e, (size_t)wc, C, g));
-                    cur_cell = wc;
-                    s2 = add4(s2, cur);
-                    continue;
-                }
-                const int row0 = qy * 16 + l0y * 8 + (win >> 1) * 4, col0 = qx * 16 + l0x * 8 + (win & 1) * 4;
-                float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {     // two rows (8 pixels) per batch of loads
-                    const int4 ca = *reinterpret_cast<const int4 *>(&s_idx[(row0 + 2 * half) * 32 + col0]);
-                    const int4 cb = *reinterpret_cast<const int4 *>(&s_idx[(row0 + 2 * half + 1) * 32 + col0]);
-                    const int cc[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
-                    typename RawOf<TableT>::type raw[8];
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)             // warp-uniform predicates; all loads in flight together
-                        if (cc[k] != (k == 0 ? cur_cell : cc[k - 1])) raw[k] = load_raw(table_e, counts_e, (size_t)cc[k], C, g);
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        if (cc[k] != (k == 0 ? cur_cell : cc[k - 1])) cur = finish(raw[k]);
-                        s4 = add4(s4, cur);
-                    }
-                    cur_cell = cc[7];
-                }
-                s2 = add4(s2, scale4(s4, 0.0625f));        // / 16 (exact)
-            }
-            v0 = round_to_half(scale4(s2, 0.25f));         // avg_pool2d(2) -> half (timm.py:168, level 0)
+    for (; item < n_items; item += stride) {
+        decode(item, e, qy, qx, chunk);
+        // stage this item's ids, start the next item's loads
+        {
+            int4 *dst = reinterpret_cast<int4 *>(&s_idx[warp][(lane >> 1) * 16 + (lane & 1) * 8]);
+            dst[0] = make_int4(nxt.v[0], nxt.v[1], nxt.v[2], nxt.v[3]);
+            dst[1] = make_int4(nxt.v[4], nxt.v[5], nxt.v[6], nxt.v[7]);
         }
-        const int y0 = by * 4 + qy * 2 + l0y, x0 = bx * 4 + qx * 2 + l0x;
-        store_half4(L0 + (((size_t)e * h0 + y0) * w0 + x0) * C + 4 * g, v0);
-        l1acc = add4(l1acc, v0);
-    }
-    const float4 v1 = round_to_half(scale4(l1acc, 0.25f));  // level 1
-    store_half4(L1 + (((size_t)e * h1 + by * 2 + qy) * w1 + bx * 2 + qx) * C + 4 * g, v1);
-    s_l1[q][g] = v1;
-    __syncthreads();
-    if (q == 0) {                                           // level 2: quadrants in row-major order
-        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (item + stride < n_items) {
+            int e2, qy2, qx2, c2;
+            decode(item + stride, e2, qy2, qx2, c2);
+            nxt = load_quad_idx<IdxT>(idx + (size_t)e2 * H * W, W, qy2, qx2, lane);
+        }
+        __syncwarp();
+        if (lane < 16) {                                   // classify window (lane>>2, lane&3) of the quadrant
+            const int wy = lane >> 2, wx = lane & 3;
+            const int4 r0 = *reinterpret_cast<const int4 *>(&s_idx[warp][(wy * 4 + 0) * 16 + wx * 4]);
+            const int4 r1 = *reinterpret_cast<const int4 *>(&s_idx[warp][(wy * 4 + 1) * 16 + wx * 4]);
+            const int4 r2 = *reinterpret_cast<const int4 *>(&s_idx[warp][(wy * 4 + 2) * 16 + wx * 4]);
+            const int4 r3 = *reinterpret_cast<const int4 *>(&s_idx[warp][(wy * 4 + 3) * 16 + wx * 4]);
+            const int c0 = r0.x;
+            const bool u = (r0.y == c0) & (r0.z == c0) & (r0.w == c0) & (r1.x == c0) & (r1.y == c0) & (r1.z == c0) & (r1.w == c0) &
+                           (r2.x == c0) & (r2.y == c0) & (r2.z == c0) & (r2.w == c0) & (r3.x == c0) & (r3.y == c0) & (r3.z == c0) & (r3.w == c0);
+            s_wcell[warp][lane] = u ? c0 : -1;
+            if (!u) {
+                // a mixed window is typically an edge between two or three cells: 2-8 runs instead of 16 pixels; the walk below
+                // pays the fetch / fp16->fp32 conversion / bookkeeping per RUN and V/2 packed adds per pixel
+                const int cells[16] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w};
+                int prev = c0, len = 1, nr = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) s = add4(s, s_l1[k][g]);
-        store_half4(L2 + (((size_t)e * h2 + by) * w2 + bx) * C + 4 * g, scale4(s, 0.25f));
+                for (int k = 1; k < 16; ++k) {
+                    if (cells[k] != prev) {
+                        s_run_cell[warp][lane][nr] = prev;
+                        s_run_len[warp][lane][nr] = (unsigned char)len;
+                        ++nr;
+                        prev = cells[k];
+                        len = 1;
+                    } else {
+                        ++len;
+                    }
+                }
+                s_run_cell[warp][lane][nr] = prev;
+                s_run_len[warp][lane][nr] = (unsigned char)len;
+                s_nruns[warp][lane] = nr + 1;
+            }
+        }
+        __syncwarp();
+
+        const int g = chunk * 32 + (int)lane;               // group of V channels
+        const TableT *table_e = table + (size_t)e * n_cells * C;
+        const float *counts_e = counts ? counts + (size_t)e * n_cells : nullptr;
+        int cur_cell = -1;
+        Vec<V> cur = vzero<V>();
+        Vec<V> l1acc = vzero<V>();
+#pragma unroll 1
+        for (int l0 = 0; l0 < 4; ++l0) {                   // L0 pixels of the quadrant, row-major
+            const int l0y = l0 >> 1, l0x = l0 & 1;
+            // The four 4x4 windows of this L0 pixel.  A window whose 16 pixels hit ONE cell needs no additions: the
+            // gathered value x is an fp16 number, so the sequential fp32 sum x+x+...+x is exact at every step
+            // (k*x, k <= 16, has at most 15 significant bits) and avg_pool2d(4) returns x itself.
+            const int wbase = (l0y * 2) * 4 + l0x * 2;
+            const int w00 = s_wcell[warp][wbase];
+            Vec<V> v0;
+            if (w00 >= 0 && w00 == s_wcell[warp][wbase + 1] && w00 == s_wcell[warp][wbase + 4] && w00 == s_wcell[warp][wbase + 5]) {
+                // whole 8x8 block in one cell: pool(4), pool(2) and the fp16 rounding all return the gathered value
+                if (w00 != cur_cell) cur = finish<V>(load_raw<V>(table_e, counts_e, (size_t)w00, C, g));
+                cur_cell = w00;
+                v0 = cur;
+            } else {
+                Vec<V> s2 = vzero<V>();
+#pragma unroll 1
+                for (int win = 0; win < 4; ++win) {        // 4x4 windows of the avg_pool2d(4) (timm.py:152)
+                    const int wi = wbase + (win >> 1) * 4 + (win & 1);
+                    const int wc = s_wcell[warp][wi];
+                    if (wc >= 0) {
+                        if (wc != cur_cell) cur = finish<V>(load_raw<V>(table_e, counts_e, (size_t)wc, C, g));
+                        cur_cell = wc;
+                        s2 = vadd<V>(s2, cur);
+                        continue;
+                    }
+                    const int nr = s_nruns[warp][wi];
+                    Vec<V> s4 = vzero<V>();
+                    Raw raw = load_raw<V>(table_e, counts_e, (size_t)s_run_cell[warp][wi][0], C, g);
+#pragma unroll 1
+                    for (int r = 0; r < nr; ++r) {
+                        cur = finish<V>(raw);
+                        if (r + 1 < nr) raw = load_raw<V>(table_e, counts_e, (size_t)s_run_cell[warp][wi][r + 1], C, g);   // next run's row in flight under the adds
+                        int len = s_run_len[warp][wi][r];   // 1..15, warp-uniform
+                        // sequential fp32 sum: `len` times + cur
+#pragma unroll 1
+                        for (; len >= 4; len -= 4) { s4 = vadd<V>(s4, cur); s4 = vadd<V>(s4, cur); s4 = vadd<V>(s4, cur); s4 = vadd<V>(s4, cur); }
+                        if (len & 2) { s4 = vadd<V>(s4, cur); s4 = vadd<V>(s4, cur); }
+                        if (len & 1) s4 = vadd<V>(s4, cur);
+                    }
+                    cur_cell = s_run_cell[warp][wi][nr - 1];
+                    s2 = vadd<V>(s2, vscale<V>(s4, 0.0625f));    // / 16 (exact)
+                }
+                v0 = vround_half<V>(vscale<V>(s2, 0.25f));      // avg_pool2d(2) -> half (timm.py:168, level 0)
+            }
+            const int y0 = qy * 2 + l0y, x0 = qx * 2 + l0x;
+            vstore_half<V>(L0 + (((size_t)e * h0 + y0) * w0 + x0) * C + V * g, v0);
+            l1acc = vadd<V>(l1acc, v0);
+        }
+        const Vec<V> v1 = vround_half<V>(vscale<V>(l1acc, 0.25f));  // level 1
+        vstore_half<V>(L1 + (((size_t)e * h1 + qy) * w1 + qx) * C + V * g, v1);
+        __syncwarp();                                       // the slice is rewritten by the next item
+    }
+}
+
+// level 2 = avg_pool2d(level 1, 2) -> half (timm.py:168): the four L1 pixels in row-major order, fp32, then / 4
+__global__ void __launch_bounds__(256) pool_level2_kernel(const __half *__restrict__ L1, int E, int h1, int w1, int C4, __half *__restrict__ L2)
+{
+    const int h2 = h1 / 2, w2 = w1 / 2;
+    const int64_t total = (int64_t)E * h2 * w2 * C4, step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
+        const int g = (int)(i % C4);
+        int64_t p = i / C4;
+        const int x = (int)(p % w2); p /= w2;
+        const int y = (int)(p % h2);
+        const int e = (int)(p / h2);
+        Vec<4> s = vzero<4>();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            s = vadd<4>(s, finish<4>(load_raw<4>(L1, nullptr, ((size_t)e * h1 + 2 * y + (k >> 1)) * w1 + 2 * x + (k & 1), C4 * 4, g)));
+        vstore_half<4>(L2 + (((size_t)e * h2 + y) * w2 + x) * C4 * 4 + 4 * g, vscale<4>(s, 0.25f));
     }
 }
 
@@ -212,16 +340,26 @@ template <int C>
 int launch(const void *table, int mem_is_f16, const float *counts, const void *idx, int idx_is_i64, int E, int H, int W,
            int64_t n_cells, void *L0, void *L1, void *L2, cudaStream_t st)
 {
-    dim3 grid(W / 32, H / 32, E), block(C);
+    const int64_t n_items = (int64_t)E * (H / 16) * (W / 16) * (C >= 256 ? C / 256 : 1);
+    int64_t blocks = (n_items + kReadWarps - 1) / kReadWarps;
+    const int64_t cap = (int64_t)eod_num_sms() * 4 * 4;          // 3-4 resident CTAs per SM, a few waves: each warp walks several items with prefetch
+    if (blocks > cap) blocks = cap;
+    dim3 grid((unsigned)blocks), block(kReadWarps * 32);
     __half *l0 = (__half *)L0, *l1 = (__half *)L1, *l2 = (__half *)L2;
     if (mem_is_f16) {
-        if (idx_is_i64) read_pool_kernel<C, __half, int64_t><<<grid, block, 0, st>>>((const __half *)table, nullptr, (const int64_t *)idx, H, W, n_cells, l0, l1, l2);
-        else read_pool_kernel<C, __half, int32_t><<<grid, block, 0, st>>>((const __half *)table, nullptr, (const int32_t *)idx, H, W, n_cells, l0, l1, l2);
+        if (idx_is_i64) read_pool_kernel<C, __half, int64_t><<<grid, block, 0, st>>>((const __half *)table, nullptr, (const int64_t *)idx, H, W, n_cells, E, l0, l1);
+        else read_pool_kernel<C, __half, int32_t><<<grid, block, 0, st>>>((const __half *)table, nullptr, (const int32_t *)idx, H, W, n_cells, E, l0, l1);
     } else {
-        if (idx_is_i64) read_pool_kernel<C, float, int64_t><<<grid, block, 0, st>>>((const float *)table, counts, (const int64_t *)idx, H, W, n_cells, l0, l1, l2);
-        else read_pool_kernel<C, float, int32_t><<<grid, block, 0, st>>>((const float *)table, counts, (const int32_t *)idx, H, W, n_cells, l0, l1, l2);
+        if (idx_is_i64) read_pool_kernel<C, float, int64_t><<<grid, block, 0, st>>>((const float *)table, counts, (const int64_t *)idx, H, W, n_cells, E, l0, l1);
+        else read_pool_kernel<C, float, int32_t><<<grid, block, 0, st>>>((const float *)table, counts, (const int32_t *)idx, H, W, n_cells, E, l0, l1);
     }
-    return eod_check_launch("eod_read_pool");
+    int rc = eod_check_launch("eod_read_pool");
+    if (rc) return rc;
+    const int64_t total = (int64_t)E * (H / 32) * (W / 32) * (C / 4);
+    int64_t b2 = (total + 255) / 256;
+    if (b2 > (int64_t)eod_num_sms() * 8) b2 = (int64_t)eod_num_sms() * 8;
+    pool_level2_kernel<<<(unsigned)b2, 256, 0, st>>>(l1, E, H / 16, W / 16, C / 4, l2);
+    return eod_check_launch("eod_read_pool[level 2]");
 }
 
 }  // namespace
