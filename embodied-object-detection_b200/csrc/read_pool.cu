@@ -1,12 +1,13 @@
 // Memory read: normalise (sum/count where count>1) -> fp16 -> gather to the
-// image plane -> avg-pool 4 -> three times (avg-pool 2 -> fp16), fused into one kernel.
+// image plane -> avg-pool 4 -> three times (avg-pool 2 -> fp16): one kernel for levels 0 and 1 (the (480,640,C)
+// image-plane tensors are never materialised) and a small second one that pools level 2 from level 1.
 //
-// Work decomposition: one CTA per 32x32-pixel block of one episode's frame (= one L2 output pixel, four L1,
-// sixteen L0).  Thread (q, g): q = 16x16 quadrant of the block, g = group of 4 consecutive channels, so a
-// warp is 32 channel groups of the SAME quadrant and walks the SAME pixels: the cell id is warp-uniform,
-// every table access is one coalesced 512 B (fp32) / 256 B (fp16) segment of a cell row, and consecutive
-// pixels that hit the same cell reuse the value from registers.  The 1.2 MB int index plane is read once;
-// table rows come from L1/L2 after the first touch (a frame sees ~5k distinct cells).
+// Work decomposition: a warp owns one 16x16-pixel quadrant of one episode's frame (= four L0 pixels, one L1 pixel)
+// and ALL channels (lane = C/32 consecutive channels), so the cell id is warp-uniform, every table access is one
+// coalesced C*2-byte (fp16) / C*4-byte (fp32) cell row, and consecutive pixels that hit the same cell reuse the value
+// from registers.  The 1.2 MB index plane is read once; table rows come from L1/L2 after the first touch (a frame sees a
+// few hundred to a few thousand distinct cells).  The kernel is instruction-issue bound, not bandwidth bound: what it
+// optimises is scalar bookkeeping per gathered row (see read_pool_kernel).
 //
 // Summation order == ATen CPU avg_pool2d: fp32, start from 0, row-major over the window, then / k^2;
 // the fp16 roundings between levels (timm.py:168) are reproduced, so outputs are bit-identical.
@@ -61,8 +62,12 @@ __device__ __forceinline__ void vstore_half(__half *dst, const Vec<V> &a)
         const __half2 h = __float22half2_rn(a.p[i]);
         w[i] = *reinterpret_cast<const uint32_t *>(&h);
     }
-    if (V == 8) *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3 % (V / 2)]);
-    else *reinterpret_cast<uint2 *>(dst) = make_uint2(w[0], w[1]);
+    if (V >= 8) {
+#pragma unroll
+        for (int i = 0; i < V / 8; ++i) reinterpret_cast<uint4 *>(dst)[i] = make_uint4(w[(4 * i) % (V / 2)], w[(4 * i + 1) % (V / 2)], w[(4 * i + 2) % (V / 2)], w[(4 * i + 3) % (V / 2)]);
+    } else {
+        *reinterpret_cast<uint2 *>(dst) = make_uint2(w[0], w[1]);
+    }
 }
 
 // Split row fetch: the global load of a row is issued (load_raw) before its consumer (finish: normalise + fp16
@@ -83,9 +88,12 @@ template <int V>
 __device__ __forceinline__ RawF16<V> load_raw(const __half *table, const float *, size_t cell, int C, int g)
 {
     RawF16<V> r;
-    if (V == 8) {
-        const uint4 q = __ldg(reinterpret_cast<const uint4 *>(table + cell * C) + g);
-        r.w[0] = q.x; r.w[1] = q.y; r.w[2 % (V / 2)] = q.z; r.w[3 % (V / 2)] = q.w;
+    if (V >= 8) {
+#pragma unroll
+        for (int i = 0; i < V / 8; ++i) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4 *>(table + cell * C + (size_t)g * V) + i);
+            r.w[(4 * i) % (V / 2)] = q.x; r.w[(4 * i + 1) % (V / 2)] = q.y; r.w[(4 * i + 2) % (V / 2)] = q.z; r.w[(4 * i + 3) % (V / 2)] = q.w;
+        }
     } else {
         const uint2 q = __ldg(reinterpret_cast<const uint2 *>(table + cell * C) + g);
         r.w[0] = q.x; r.w[1] = q.y;
@@ -119,9 +127,10 @@ template <typename T, int V> struct RawOf;
 template <int V> struct RawOf<float, V> { using type = RawF32<V>; };
 template <int V> struct RawOf<__half, V> { using type = RawF16<V>; };
 
-// Warp-autonomous read: a work item = one 16x16-pixel quadrant (4 L0 pixels, 1 L1 pixel) x 32*V channels, owned by ONE
-// warp (lane = group of V consecutive channels; V = 8 for C >= 256: the per-run bookkeeping below is scalar work that
-// every lane repeats, so wider lanes halve it per channel).  The warp stages the quadrant's 256 cell ids in its private
+// Warp-autonomous read: a work item = one 16x16-pixel quadrant (4 L0 pixels, 1 L1 pixel) x all C channels, owned by ONE
+// warp (lane = group of V = C/32 consecutive channels: the per-run bookkeeping below is scalar work that every lane
+// repeats, so wider lanes amortise it over more channels - V = 4 -> 8 took C=256 from 0.40 to 0.27 ms, V = 8 -> 16 took
+// C=512 from 0.51 to 0.40 ms at E=64).  The warp stages the quadrant's 256 cell ids in its private
 // slice of shared memory, classifies its 16 windows itself (lanes 0-15) and walks them - no CTA barrier anywhere, and the
 // ids of the NEXT item are already in flight (registers) while the current one is processed.  Level 2 needs four L1
 // pixels of different quadrants; it is pooled from the stored L1 by pool_level2_kernel instead of through a CTA-wide
@@ -154,11 +163,11 @@ __device__ __forceinline__ QuadIdx load_quad_idx(const IdxT *idx_e, int W, int q
 }
 
 template <int C, typename TableT, typename IdxT>
-__global__ void __launch_bounds__(kReadWarps * 32, (C >= 256 ? 3 : 4)) read_pool_kernel(const TableT *__restrict__ table, const float *__restrict__ counts,
+__global__ void __launch_bounds__(kReadWarps * 32, (C >= 512 ? 2 : (C >= 256 ? 3 : 4))) read_pool_kernel(const TableT *__restrict__ table, const float *__restrict__ counts,
                                                                                         const IdxT *__restrict__ idx, int H, int W, int64_t n_cells, int E,
                                                                                         __half *__restrict__ L0, __half *__restrict__ L1)
 {
-    constexpr int V = C >= 256 ? 8 : 4;      // channels per lane
+    constexpr int V = C >= 512 ? 16 : (C >= 256 ? 8 : 4);      // channels per lane
     constexpr int NC = C / (32 * V);         // channel chunks per quadrant
     using Raw = typename RawOf<TableT, V>::type;
     __shared__ __align__(16) int s_idx[kReadWarps][16 * 16];
@@ -340,7 +349,7 @@ template <int C>
 int launch(const void *table, int mem_is_f16, const float *counts, const void *idx, int idx_is_i64, int E, int H, int W,
            int64_t n_cells, void *L0, void *L1, void *L2, cudaStream_t st)
 {
-    const int64_t n_items = (int64_t)E * (H / 16) * (W / 16) * (C >= 256 ? C / 256 : 1);
+    const int64_t n_items = (int64_t)E * (H / 16) * (W / 16);      // C in {128, 256, 512}: one warp covers all channels of a quadrant (V = C / 32 per lane)
     int64_t blocks = (n_items + kReadWarps - 1) / kReadWarps;
     const int64_t cap = (int64_t)eod_num_sms() * 4 * 4;          // 3-4 resident CTAs per SM, a few waves: each warp walks several items with prefetch
     if (blocks > cap) blocks = cap;
