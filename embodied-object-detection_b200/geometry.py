@@ -17,8 +17,9 @@ from . import ops
 from ._lib import ORDER_XZ, ORDER_ZX
 
 
-def transform3d(xyzhe: torch.Tensor) -> torch.Tensor:
-    """(N,5) x,y,z,heading,elevation -> (N,4,4) camera-to-world, fp32 on the host (core.py:6-34)."""
+def transform3d(xyzhe: torch.Tensor, axis_swap: bool = False) -> torch.Tensor:
+    """(N,5) x,y,z,heading,elevation -> (N,4,4) camera-to-world, fp32 on the host (core.py:6-34).
+    axis_swap: the online robot variant (robot_demo.py:40-90), T @ R with R exchanging the camera's x and z axes."""
     xyzhe = xyzhe.detach().to("cpu", torch.float32)
     cx, sx = torch.cos(xyzhe[:, 4]), torch.sin(xyzhe[:, 4])
     cy, sy = torch.cos(xyzhe[:, 3]), torch.sin(xyzhe[:, 3])
@@ -35,6 +36,11 @@ def transform3d(xyzhe: torch.Tensor) -> torch.Tensor:
     T[:, 2, 2] = cy * cx
     T[:, 2, 3] = xyzhe[:, 2]
     T[:, 3, 3] = 1
+    if axis_swap:
+        # torch.matmul(T, R) with the 0/1 permutation R of robot_demo.py:68-88: columns 0 and 2 change places.  Every
+        # product with a 0/1 entry and every sum with the resulting +0 is exact, so the column swap is bit-identical
+        # (tests/golden/robot.npz holds the matmul's own output).
+        T = T[:, :, [2, 1, 0, 3]].contiguous()
     return T
 
 
@@ -57,14 +63,17 @@ class Projector:
 
     def __init__(self, vfov: float, batch_size: int, feature_map_height: int, feature_map_width: int, output_height: int,
                  output_width: int, gridcellsize: float, world_shift_origin, z_clip_threshold: float,
-                 device: torch.device = torch.device("cuda")):
+                 device: torch.device = torch.device("cuda"), intrinsics: Optional[Sequence[float]] = None):
         self.vfov, self.batch_size = vfov, batch_size
         self.fmh, self.fmw = feature_map_height, feature_map_width
         self.output_height, self.output_width = output_height, output_width
         self.gridcellsize, self.z_clip_threshold = gridcellsize, z_clip_threshold
         self.device = torch.device(device)
         self.world_shift_origin = torch.as_tensor(world_shift_origin, dtype=torch.float32).reshape(3).cpu()
-        self.intrinsics = compute_intrinsics(feature_map_width, feature_map_height, vfov)
+        # intrinsics: (fx, fy, cx, cy) of a calibrated camera instead of the vfov model - the robot demo hard-codes its K
+        # (robot_demo.py:123-125); rounded to fp32 as torch.tensor(K) holds them
+        self.intrinsics = compute_intrinsics(feature_map_width, feature_map_height, vfov) if intrinsics is None else \
+            tuple(float(v) for v in torch.tensor([float(x) for x in intrinsics], dtype=torch.float32))
 
     def _run(self, depth: torch.Tensor, T: torch.Tensor, map_world_shift=None, order: int = ORDER_ZX, **want):
         assert depth.shape[2] == self.fmh and depth.shape[3] == self.fmw

@@ -96,6 +96,42 @@ def gen_geometry():
         print(name, "unique cells/frame", [len(np.unique(f)) for f in flat], "outliers", np.stack(outl).mean())
 
 
+def gen_robot():
+    """robot.npz: the online robot geometry (robot_demo.py:40-90 _transform3D with the axis swap, :92-225 ProjectorUtils with the
+    hard-coded K, :514-534 millimetre depth -> world -> column-major flat index), executed from the reference's own source:
+    the two definitions are extracted with ast (the module itself imports detectron2), lines 518-534 are exec'd verbatim."""
+    path = os.path.join(REF, "robot_demo.py")
+    src = open(path).read()
+    tree = ast.parse(src)
+    ns = {"torch": torch, "np": np, "math": math}
+    for node in tree.body:
+        if (isinstance(node, ast.FunctionDef) and node.name == "_transform3D") or (isinstance(node, ast.ClassDef) and node.name == "ProjectorUtils"):
+            exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+    lines = src.splitlines()
+    device = torch.device("cpu")
+    H, W = 480, 640
+    res = 0.2
+    map_w = map_h = math.ceil(40 / res)                                   # robot_demo.py:471-474
+    rng = np.random.default_rng(31)
+    projector = ns["ProjectorUtils"](vfov=math.radians(58), hfov=math.radians(87), batch_size=1, feature_map_height=H, feature_map_width=W,
+                                     output_height=map_h, output_width=map_w, gridcellsize=res,
+                                     world_shift_origin=torch.zeros(3), z_clip_threshold=3, device=device)
+    out = {"K": np.array([380.3127746582031, 379.828857421875, 315.81829833984375, 250.9555206298828], np.float64),
+           "map_world_shift": np.array([-13, 0, -13], np.float32), "res": res, "map_w": map_w, "map_h": map_h}
+    depth_mm, poses, Ts, flats = [], [], [], []
+    for t in range(3):
+        ep = eod_episodes.make_episode(900 + t, 1, H, W, map_w, map_h, res)
+        depth_image = np.round(ep.depth[0] * 1000.0).astype(np.uint16)   # RealSense-style millimetres (16-bit png in the demo)
+        pose_val = np.array([rng.uniform(-8, 8), rng.uniform(-8, 8), rng.uniform(-3.1, 3.1)])
+        u = {"np": np, "torch": torch, "device": device, "depth_image": depth_image, "pose_val": pose_val, "projector": projector,
+             "_transform3D": ns["_transform3D"], "map_world_shift": torch.FloatTensor([-13, 0, -13]), "res": res, "map_h": map_h, "map_w": map_w}
+        exec_lines(lines, 514, 534, u)                                    # depth_var .. proj_indices, verbatim
+        depth_mm.append(depth_image); poses.append(pose_val); Ts.append(u["T"].numpy()); flats.append(u["proj_indices"][..., 0].astype(np.int32))
+    out.update(depth_mm=np.stack(depth_mm), pose_val=np.stack(poses), T=np.concatenate(Ts), flat=np.stack(flats))
+    np.savez_compressed(os.path.join(HERE, "robot.npz"), **out)
+    print("robot: unique cells/frame", [len(np.unique(f)) for f in flats])
+
+
 def gen_write():
     patch_cpu()
     ns, lines = ref_methods()
@@ -281,6 +317,9 @@ if __name__ == "__main__":
     if "--only-semmap" in sys.argv:
         gen_semmap()
         sys.exit(0)
+    if "--only-robot" in sys.argv:
+        gen_robot()
+        sys.exit(0)
     if "--only-paste" in sys.argv:
         gen_paste()
         sys.exit(0)
@@ -289,6 +328,7 @@ if __name__ == "__main__":
     gen_read()
     gen_semmap()
     gen_paste()
+    gen_robot()
     gen_loader_order()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

@@ -62,6 +62,22 @@ def test_quantize_world_matches_reference_golden(eod, cuda, golden, name):
     assert np.array_equal(got[..., 0].cpu().numpy(), g["flat"])
 
 
+def test_robot_demo_geometry_matches_reference_golden(eod, cuda, golden):
+    """The online robot path (robot_demo.py:514-534 executed from source): millimetre depth, axis-swapped pose, calibrated K,
+    flat = q_x * map_h + q_z - through the Projector mirror with explicit intrinsics."""
+    g = golden("robot")
+    n, H, W = g["depth_mm"].shape
+    proj = eod.Projector(math.radians(58), 1, H, W, int(g["map_h"]), int(g["map_w"]), float(g["res"]), np.zeros(3, np.float32), 3,
+                         device=cuda, intrinsics=g["K"])
+    for t in range(n):
+        pv = g["pose_val"][t]
+        T = eod.transform3d(torch.FloatTensor(np.array([[pv[0], 0.65, pv[1], -1 * pv[2], np.pi + 0.06]])), axis_swap=True)
+        depth = torch.FloatTensor(g["depth_mm"][t] / 1000)[None, None]
+        flat = proj.flat_indices(depth, T, g["map_world_shift"], order="xz")
+        assert flat.shape == (1, H, W, 1) and flat.dtype == torch.int32
+        assert np.array_equal(flat[0, ..., 0].cpu().numpy(), g["flat"][t])
+
+
 def test_backproject_randomised_vs_oracle(eod, cuda):
     rng = np.random.default_rng(42)
     H, W, E = 60, 100, 5                                           # ragged: not multiples of the block size

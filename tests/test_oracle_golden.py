@@ -165,3 +165,20 @@ def test_paste_masks_torch_restatement_matches_c_oracle_randomised():
         ref = R.paste_masks_in_image(torch.from_numpy(probs), torch.from_numpy(boxes), (H, W), 0.5).numpy()
         assert np.array_equal(oracle.paste_masks(probs, boxes, H, W, 0.5), ref)
         assert ref.any()
+
+
+def test_robot_demo_geometry_oracle_and_host_pose_match_reference(eod, golden):
+    """Online robot variant (robot_demo.py:40-90,92-225,514-534 executed from source -> robot.npz): the host pose with the axis
+    swap is bit-identical to the reference's matmul(T, R), and the C oracle reproduces the column-major flat indices."""
+    g = golden("robot")
+    H, W = g["depth_mm"].shape[1:]
+    K = tuple(float(np.float32(v)) for v in g["K"])
+    for t in range(g["depth_mm"].shape[0]):
+        pv = g["pose_val"][t]
+        xyzhe = torch.FloatTensor(np.array([[pv[0], 0.65, pv[1], -1 * pv[2], np.pi + 0.06]]))       # robot_demo.py:518-519
+        T = eod.transform3d(xyzhe, axis_swap=True)
+        assert np.array_equal(T.numpy().view(np.uint32), g["T"][t:t + 1].view(np.uint32))
+        depth = torch.FloatTensor(g["depth_mm"][t] / 1000).numpy()                                   # :514-516
+        out = oracle.backproject_quantize(depth, g["T"][t], K, np.zeros(3, np.float32), g["map_world_shift"], np.float32(g["res"]),
+                                          int(g["map_w"]), int(g["map_h"]), 1, 3.0, want=("idx",))
+        assert np.array_equal(out["idx"], g["flat"][t])
