@@ -871,11 +871,16 @@ __device__ __forceinline__ bool det_run_sampled(unsigned heads, unsigned samps, 
 }
 
 __global__ void __launch_bounds__(256) det_tile_runs_kernel(const int32_t *__restrict__ idx, const uint8_t *__restrict__ samp, int HW,
-                                                            int tiles_per_ep, int32_t *__restrict__ tile_off, int32_t *__restrict__ n_list)
+                                                            int tiles_per_ep, int32_t *__restrict__ tile_off, int32_t *__restrict__ n_list,
+                                                            int32_t *__restrict__ chunk_rows, int32_t *__restrict__ n_long)
 {
     const int e = blockIdx.y, tile = blockIdx.x * 8 + (threadIdx.x >> 5);
     const unsigned lane = threadIdx.x & 31;
-    if (blockIdx.x == 0 && threadIdx.x == 0) n_list[e] = 0;        // consumed by the previous call's reduce, refilled by det_cell_runs
+    if (blockIdx.x == 0 && threadIdx.x == 0) {                     // consumed by the previous call's reduce, refilled by this one's
+        n_list[e] = 0;
+        chunk_rows[e] = 0;
+        n_long[e] = 0;
+    }
     if (tile >= tiles_per_ep) return;
     int cell;
     unsigned heads, samps;
@@ -992,15 +997,64 @@ __device__ __forceinline__ void bitonic_sort_warp(int *buf, int n2, unsigned lan
         }
 }
 
-constexpr int DET_SORT_MAX = 2048;       // segment length a warp sorts in shared memory; longer ones use selection
+constexpr int DET_SORT_MAX = 2048;       // segment length a warp sorts in shared memory (bitonic); longer ones are bitmap-sorted
 constexpr int DET_WARPS = 4;
+constexpr int DET_DIRECT = 256;          // segments up to this length are summed by the warp that sorted them
+constexpr int DET_CHUNK = 128;           // longer ones are cut into chunks of this many runs, summed by separate warps
 
-// warp per listed cell
+// Long segments (a cell that takes a large part of the frame has 10^3-10^4 runs): their sorted positions, the chunk tasks
+// and the per-chunk partial sums.  The chunking is relative to the segment's own sorted order, so the summation tree of a
+// cell is fixed: chunk c = sorted runs [128c, 128c + 128) added in order, then the chunk sums added in order.
+struct DetLong {
+    int32_t *seg2;          // (E, cap)  sorted positions of long segments, at the segment's own offsets
+    int32_t *task_start;    // (E, rows) start of a chunk in seg2 (episode-relative)
+    int32_t *task_len;      // (E, rows)
+    int32_t *long_i;        // (E, rows) index into cell_list of a long cell ...
+    int32_t *long_base;     // (E, rows) ... and its first chunk row
+    int32_t *chunk_rows;    // (E) rows handed out this frame
+    int32_t *n_long;        // (E) long cells this frame
+    float *cparts;          // (E, rows, C) chunk sums
+    int rows;
+};
+
+// rows of `count` positions (kGlobal: read-only global memory, else shared), U rows in flight, added strictly in order
+template <int J, bool kGlobal>
+__device__ __forceinline__ void det_sum_sorted(const float *part_e, int C, const int *sorted, int count, float (&acc)[J])
+{
+    constexpr int U = (J <= 8) ? 8 : 4;
+    int it = 0;
+#pragma unroll 1
+    for (; it + U <= count; it += U) {
+        int pos[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) pos[u] = kGlobal ? __ldg(sorted + it + u) : sorted[it + u];
+        float r[U][J];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const float *row = part_e + (size_t)pos[u] * C;
+#pragma unroll
+            for (int j = 0; j < J; ++j) r[u][j] = __ldg(row + 32 * j);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int j = 0; j < J; ++j) acc[j] = __fadd_rn(acc[j], r[u][j]);
+    }
+    for (; it < count; ++it) {
+        const float *row = part_e + (size_t)(kGlobal ? __ldg(sorted + it) : sorted[it]) * C;
+#pragma unroll
+        for (int j = 0; j < J; ++j) acc[j] = __fadd_rn(acc[j], __ldg(row + 32 * j));
+    }
+}
+
+// warp per listed cell: sort the segment by run position; short segments are summed and finished here, long ones are
+// written out sorted and cut into chunk tasks for det_chunk_kernel / det_final_kernel
 template <int C>
 __global__ void __launch_bounds__(32 * DET_WARPS) det_reduce_kernel(const int32_t *__restrict__ cell_list, const int32_t *__restrict__ list_off,
                                                                     const int32_t *__restrict__ n_list, const int32_t *__restrict__ n_runs, int cap,
-                                                                    int64_t n_cells, int32_t *__restrict__ seg, const float *__restrict__ partials,
-                                                                    const uint32_t *__restrict__ frame_cnt, float *__restrict__ sums)
+                                                                    int64_t n_cells, const int32_t *__restrict__ seg, const float *__restrict__ partials,
+                                                                    const uint32_t *__restrict__ frame_cnt, float *__restrict__ sums, const DetLong L,
+                                                                    int32_t *__restrict__ status)
 {
     constexpr int J = C / 32;
     __shared__ int s_sort[DET_WARPS][DET_SORT_MAX];
@@ -1015,35 +1069,11 @@ __global__ void __launch_bounds__(32 * DET_WARPS) det_reduce_kernel(const int32_
         const int s0 = __ldg(list_off + (size_t)e * cap + i);
         const int s1 = (i + 1 < n) ? __ldg(list_off + (size_t)e * cap + i + 1) : total;
         const int k = s1 - s0;
-        int32_t *sg = seg + (size_t)e * cap + s0;
+        const int32_t *sg = seg + (size_t)e * cap + s0;
         float acc[J];
 #pragma unroll
         for (int j = 0; j < J; ++j) acc[j] = 0.f;
-
-        auto add_row = [&](int pos) {
-            const float *row = part_e + (size_t)pos * C;
-#pragma unroll
-            for (int j = 0; j < J; ++j) acc[j] = __fadd_rn(acc[j], __ldg(row + 32 * j));
-        };
-        // rows of `count` sorted positions, U rows in flight, added strictly in order
-        auto sum_sorted = [&](const int *sorted, int count) {
-            constexpr int U = (J <= 8) ? 8 : 4;
-            int it = 0;
-            for (; it + U <= count; it += U) {
-                float r[U][J];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const float *row = part_e + (size_t)sorted[it + u] * C;
-#pragma unroll
-                    for (int j = 0; j < J; ++j) r[u][j] = __ldg(row + 32 * j);
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-#pragma unroll
-                    for (int j = 0; j < J; ++j) acc[j] = __fadd_rn(acc[j], r[u][j]);
-            }
-            for (; it < count; ++it) add_row(sorted[it]);
-        };
+        bool finish_here = true;
 
         if (k <= DET_SORT_MAX) {
             int n2 = 32;
@@ -1051,54 +1081,83 @@ __global__ void __launch_bounds__(32 * DET_WARPS) det_reduce_kernel(const int32_
             for (int q = lane; q < n2; q += 32) buf[q] = q < k ? sg[q] : 0x7fffffff;
             __syncwarp();
             bitonic_sort_warp(buf, n2, lane);
-            sum_sorted(buf, k);
-        } else if (k <= 64 * DET_SORT_MAX) {
-            // long segment (a cell that fills much of the frame): sort it chunk by chunk in shared memory, write the
-            // sorted chunks back in place, then merge them (lane l feeds chunks l and l + 32) 2048 positions at a time
-            const int m = (k + DET_SORT_MAX - 1) / DET_SORT_MAX;
-            for (int c = 0; c < m; ++c) {
-                int32_t *chunk = sg + c * DET_SORT_MAX;
-                const int len = min(DET_SORT_MAX, k - c * DET_SORT_MAX);
-                int n2 = 32;
-                while (n2 < len) n2 <<= 1;
-                for (int q = lane; q < n2; q += 32) buf[q] = q < len ? chunk[q] : 0x7fffffff;
-                __syncwarp();
-                bitonic_sort_warp(buf, n2, lane);
-                for (int q = lane; q < len; q += 32) chunk[q] = buf[q];
-                __syncwarp();
-            }
-            const int c0 = (int)lane, c1 = (int)lane + 32;
-            const int len0 = c0 < m ? min(DET_SORT_MAX, k - c0 * DET_SORT_MAX) : 0;
-            const int len1 = c1 < m ? min(DET_SORT_MAX, k - c1 * DET_SORT_MAX) : 0;
-            int ptr0 = 0, ptr1 = 0;
-            int head0 = len0 > 0 ? sg[c0 * DET_SORT_MAX] : 0x7fffffff;
-            int head1 = len1 > 0 ? sg[c1 * DET_SORT_MAX] : 0x7fffffff;
-            for (int done = 0; done < k; done += DET_SORT_MAX) {
-                const int cnt = min(DET_SORT_MAX, k - done);
-                for (int it = 0; it < cnt; ++it) {
-                    int best = min(head0, head1);
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
-                    if (head0 == best) { ++ptr0; head0 = ptr0 < len0 ? sg[c0 * DET_SORT_MAX + ptr0] : 0x7fffffff; }
-                    else if (head1 == best) { ++ptr1; head1 = ptr1 < len1 ? sg[c1 * DET_SORT_MAX + ptr1] : 0x7fffffff; }
-                    if (lane == 0) buf[it] = best;
-                }
-                __syncwarp();
-                sum_sorted(buf, cnt);
-                __syncwarp();
+            if (k <= DET_DIRECT) det_sum_sorted<J, false>(part_e, C, buf, k, acc);
+            else {
+                int32_t *out = L.seg2 + (size_t)e * cap + s0;
+                for (int q = lane; q < k; q += 32) out[q] = buf[q];
+                finish_here = false;
             }
         } else {
-            int last = -1;                                         // last resort: smallest position greater than the last one
-            for (int it = 0; it < k; ++it) {
-                int best = 0x7fffffff;
+            // bitmap sort: positions are distinct integers below `total`; 65 536 of them per pass fit the warp's 8 KB slice.
+            // Every pass streams the whole segment (coalesced) and emits the range's members in ascending order.
+            int32_t *out = L.seg2 + (size_t)e * cap + s0;
+            int written = 0;
+            for (int r0 = 0; r0 < total && written < k; r0 += DET_SORT_MAX * 32) {
+                for (int q = lane; q < DET_SORT_MAX; q += 32) buf[q] = 0;
+                __syncwarp();
                 for (int q = lane; q < k; q += 32) {
-                    const int v = sg[q];
-                    if (v > last && v < best) best = v;
+                    const int v = sg[q] - r0;
+                    if (v >= 0 && v < DET_SORT_MAX * 32) atomicOr(reinterpret_cast<unsigned *>(buf) + (v >> 5), 1u << (v & 31));
                 }
+                __syncwarp();
+                for (int w0 = 0; w0 < DET_SORT_MAX; w0 += 32) {
+                    unsigned word = (unsigned)buf[w0 + lane];
+                    const int cnt = __popc(word);
+                    int incl = cnt;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
-                last = best;
-                add_row(best);
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                        if ((int)lane >= o) incl += up;
+                    }
+                    int at = written + incl - cnt;
+                    while (word) {
+                        out[at++] = r0 + (w0 + (int)lane) * 32 + __ffs(word) - 1;
+                        word &= word - 1;
+                    }
+                    written += __shfl_sync(0xffffffffu, incl, 31);
+                }
+                __syncwarp();
+            }
+            finish_here = false;
+        }
+
+        if (!finish_here) {
+            // hand the sorted segment to the chunk pass
+            const int nch = (k + DET_CHUNK - 1) / DET_CHUNK;
+            int base = 0, j = 0;
+            if (lane == 0) {
+                base = atomicAdd(L.chunk_rows + e, nch);           // which rows a cell gets is arbitrary; what is summed into them is not
+                j = atomicAdd(L.n_long + e, 1);
+            }
+            base = __shfl_sync(0xffffffffu, base, 0);
+            j = __shfl_sync(0xffffffffu, j, 0);
+            if (base + nch <= L.rows && j < L.rows) {
+                for (int c = lane; c < nch; c += 32) {
+                    L.task_start[(size_t)e * L.rows + base + c] = s0 + c * DET_CHUNK;
+                    L.task_len[(size_t)e * L.rows + base + c] = min(DET_CHUNK, k - c * DET_CHUNK);
+                }
+                if (lane == 0) {
+                    L.long_i[(size_t)e * L.rows + j] = i;
+                    L.long_base[(size_t)e * L.rows + j] = base;
+                }
+                __syncwarp();
+                continue;
+            }
+            // chunk rows exhausted (cannot happen with the rows sized by det_carve): same tree, walked by this warp alone
+            if (lane == 0) {
+                L.long_i[(size_t)e * L.rows + min(j, L.rows - 1)] = -1;
+                *status = 2;
+            }
+            __threadfence();
+            __syncwarp();
+            const int *sorted = L.seg2 + (size_t)e * cap + s0;
+            for (int c = 0; c < nch; ++c) {
+                float ch[J];
+#pragma unroll
+                for (int jj = 0; jj < J; ++jj) ch[jj] = 0.f;
+                det_sum_sorted<J, true>(part_e, C, sorted + c * DET_CHUNK, min(DET_CHUNK, k - c * DET_CHUNK), ch);
+#pragma unroll
+                for (int jj = 0; jj < J; ++jj) acc[jj] = __fadd_rn(acc[jj], ch[jj]);
             }
         }
         const float nn = (float)(__ldg(frame_cnt + (size_t)e * n_cells + cell) & 0x7fffffffu);
@@ -1109,13 +1168,75 @@ __global__ void __launch_bounds__(32 * DET_WARPS) det_reduce_kernel(const int32_
     }
 }
 
+// warp per chunk task: cparts[row] = sum of the chunk's partial rows, in sorted order
+template <int C>
+__global__ void __launch_bounds__(256) det_chunk_kernel(const float *__restrict__ partials, int cap, const DetLong L)
+{
+    constexpr int J = C / 32;
+    const int e = blockIdx.y;
+    const unsigned lane = threadIdx.x & 31;
+    const int n_rows = min(__ldg(L.chunk_rows + e), L.rows);
+    const float *part_e = partials + (size_t)e * cap * C + lane;
+    for (int r = blockIdx.x * 8 + (threadIdx.x >> 5); r < n_rows; r += gridDim.x * 8) {
+        const int len = __ldg(L.task_len + (size_t)e * L.rows + r);
+        if (len <= 0) continue;                                  // a row of a cell that fell back (stale task)
+        const int start = __ldg(L.task_start + (size_t)e * L.rows + r);
+        float acc[J];
+#pragma unroll
+        for (int j = 0; j < J; ++j) acc[j] = 0.f;
+        det_sum_sorted<J, true>(part_e, C, L.seg2 + (size_t)e * cap + start, len, acc);
+        float *dst = L.cparts + ((size_t)e * L.rows + r) * C + lane;
+#pragma unroll
+        for (int j = 0; j < J; ++j) dst[32 * j] = acc[j];
+    }
+}
+
+// warp per long cell: add its chunk sums in chunk order, divide by n, add ONCE to sums[cell]
+template <int C>
+__global__ void __launch_bounds__(256) det_final_kernel(const int32_t *__restrict__ cell_list, const int32_t *__restrict__ list_off,
+                                                        const int32_t *__restrict__ n_list, const int32_t *__restrict__ n_runs, int cap,
+                                                        int64_t n_cells, const uint32_t *__restrict__ frame_cnt, float *__restrict__ sums,
+                                                        const DetLong L)
+{
+    constexpr int J = C / 32;
+    const int e = blockIdx.y;
+    const unsigned lane = threadIdx.x & 31;
+    const int n = __ldg(n_list + e), total = min(__ldg(n_runs + e), cap);
+    const int n_long = min(__ldg(L.n_long + e), L.rows);
+    for (int jl = blockIdx.x * 8 + (threadIdx.x >> 5); jl < n_long; jl += gridDim.x * 8) {
+        const int i = __ldg(L.long_i + (size_t)e * L.rows + jl);
+        if (i < 0) continue;                                     // finished by the sorting warp (row overflow)
+        const int base = __ldg(L.long_base + (size_t)e * L.rows + jl);
+        const int cell = __ldg(cell_list + (size_t)e * cap + i);
+        const int s0 = __ldg(list_off + (size_t)e * cap + i);
+        const int s1 = (i + 1 < n) ? __ldg(list_off + (size_t)e * cap + i + 1) : total;
+        const int nch = (s1 - s0 + DET_CHUNK - 1) / DET_CHUNK;
+        float acc[J];
+#pragma unroll
+        for (int j = 0; j < J; ++j) acc[j] = 0.f;
+        const float *rows = L.cparts + ((size_t)e * L.rows + base) * C + lane;
+        for (int c = 0; c < nch; ++c)
+#pragma unroll
+            for (int j = 0; j < J; ++j) acc[j] = __fadd_rn(acc[j], rows[(size_t)c * C + 32 * j]);
+        const float nn = (float)(__ldg(frame_cnt + (size_t)e * n_cells + cell) & 0x7fffffffu);
+        float *dst = sums + ((size_t)e * n_cells + cell) * C + lane;
+#pragma unroll
+        for (int j = 0; j < J; ++j) dst[32 * j] = __fadd_rn(dst[32 * j], __fdiv_rn(acc[j], nn));     // custom_rcnn.py:934, :742
+    }
+}
+
 struct DetWorkspace {
     int32_t *tile_off, *n_runs, *n_list, *status, *cell_runs, *cell_off, *run_cell, *seg, *cell_list, *list_off;
     float *partials;
+    DetLong L;
     int cap;
 };
 
 size_t det_align(size_t x) { return (x + 255) & ~size_t(255); }
+
+// chunk rows per episode: every long segment (> DET_DIRECT runs) needs ceil(k / DET_CHUNK) <= k / DET_CHUNK + 1 rows and there
+// are fewer than cap / DET_DIRECT of them
+int det_rows(int cap) { return cap / DET_CHUNK + cap / DET_DIRECT + 8; }
 
 // Carves the caller's workspace.  cell_runs must be all-zero between frames (the library leaves it so; the caller
 // zero-fills the workspace once).  Returns the bytes needed for `cap` runs per episode.
@@ -1124,17 +1245,27 @@ size_t det_carve(void *ws, int E, int C, int tiles_per_ep, int64_t n_cells, int 
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t at = o; o += det_align(bytes); return ws ? (char *)ws + at : (char *)nullptr; };
     DetWorkspace w;
+    const int rows = det_rows(cap);
     w.cell_runs = (int32_t *)take((size_t)E * n_cells * 4);
     w.status = (int32_t *)take(256);
     w.n_runs = (int32_t *)take((size_t)E * 4);
     w.n_list = (int32_t *)take((size_t)E * 4);
     w.tile_off = (int32_t *)take((size_t)E * tiles_per_ep * 4);
     w.cell_off = (int32_t *)take((size_t)E * n_cells * 4);
+    w.L.chunk_rows = (int32_t *)take((size_t)E * 4);
+    w.L.n_long = (int32_t *)take((size_t)E * 4);
     w.run_cell = (int32_t *)take((size_t)E * cap * 4);
     w.seg = (int32_t *)take((size_t)E * cap * 4);
     w.cell_list = (int32_t *)take((size_t)E * cap * 4);
     w.list_off = (int32_t *)take((size_t)E * cap * 4);
+    w.L.seg2 = (int32_t *)take((size_t)E * cap * 4);
+    w.L.task_start = (int32_t *)take((size_t)E * rows * 4);
+    w.L.task_len = (int32_t *)take((size_t)E * rows * 4);
+    w.L.long_i = (int32_t *)take((size_t)E * rows * 4);
+    w.L.long_base = (int32_t *)take((size_t)E * rows * 4);
+    w.L.cparts = (float *)take((size_t)E * rows * C * 4);
     w.partials = (float *)take((size_t)E * cap * C * 4);
+    w.L.rows = rows;
     w.cap = cap;
     if (out) *out = w;
     return o;
@@ -1151,7 +1282,9 @@ int launch_det(const float *feat, const int32_t *idx, const uint8_t *samp, const
     // capacity: whatever the workspace holds beyond the fixed planes (at most one run per pixel)
     const size_t fixed = det_carve(nullptr, E, C, tiles_per_ep, n_cells, 0, nullptr);
     EOD_REQUIRE(ws && eod_aligned16(ws) && ws_bytes > fixed + 4096, EOD_ERR_BADARG, "eod_write_mean_det: workspace missing or too small (see eod_write_mean_det_workspace_bytes)");
-    int64_t cap = (int64_t)((ws_bytes - fixed - 6 * 256) / ((size_t)E * (C * 4 + 16)));
+    // per run: partial row + 5 ints; per chunk row (cap / 128 + cap / 256 of them): a partial row + 4 ints
+    const size_t per_run = (size_t)C * 4 + 20 + ((size_t)C * 4 + 16) * 3 / 256 + 1;
+    int64_t cap = ws_bytes > fixed + 16 * 256 ? (int64_t)((ws_bytes - fixed - 16 * 256) / ((size_t)E * per_run)) : 0;
     if (cap > HW) cap = HW;
     EOD_REQUIRE(cap >= 1, EOD_ERR_BADARG, "eod_write_mean_det: workspace too small");
     DetWorkspace w;
@@ -1160,7 +1293,7 @@ int launch_det(const float *feat, const int32_t *idx, const uint8_t *samp, const
     int rc = make_feature_tmap<C>(feat, E, HW, &tmap);
     if (rc) return rc;
     dim3 gt((tiles_per_ep + 7) / 8, E);
-    det_tile_runs_kernel<<<gt, 256, 0, st>>>(idx, samp, HW, tiles_per_ep, w.tile_off, w.n_list);
+    det_tile_runs_kernel<<<gt, 256, 0, st>>>(idx, samp, HW, tiles_per_ep, w.tile_off, w.n_list, w.L.chunk_rows, w.L.n_long);
     det_scan_tiles_kernel<<<E, 1024, 0, st>>>(w.tile_off, tiles_per_ep, w.n_runs);
     det_cell_runs_kernel<<<gt, 256, 0, st>>>(idx, samp, HW, tiles_per_ep, n_cells, w.tile_off, w.cap, w.cell_runs, w.cell_list, w.n_list);
     det_scan_list_kernel<<<E, 1024, 0, st>>>(w.cell_runs, w.cell_list, w.n_list, w.cap, n_cells, w.list_off, w.cell_off);
@@ -1174,7 +1307,13 @@ int launch_det(const float *feat, const int32_t *idx, const uint8_t *samp, const
     const int64_t max_list = n_cells < (int64_t)w.cap ? n_cells : (int64_t)w.cap;
     const int64_t want_blocks = (max_list + DET_WARPS - 1) / DET_WARPS;
     dim3 gr((unsigned)(want_blocks < 128 ? want_blocks : 128), E);          // warps stride over the episode's cell list
-    det_reduce_kernel<C><<<gr, 32 * DET_WARPS, 0, st>>>(w.cell_list, w.list_off, w.n_list, w.n_runs, w.cap, n_cells, w.seg, w.partials, frame_cnt, sums);
+    det_reduce_kernel<C><<<gr, 32 * DET_WARPS, 0, st>>>(w.cell_list, w.list_off, w.n_list, w.n_runs, w.cap, n_cells, w.seg, w.partials, frame_cnt, sums,
+                                                        w.L, w.status);
+    const int chunk_blocks = (w.L.rows + 7) / 8;
+    dim3 gk((unsigned)(chunk_blocks < 64 ? chunk_blocks : 64), E);
+    det_chunk_kernel<C><<<gk, 256, 0, st>>>(w.partials, w.cap, w.L);
+    dim3 gf(8, E);
+    det_final_kernel<C><<<gf, 256, 0, st>>>(w.cell_list, w.list_off, w.n_list, w.n_runs, w.cap, n_cells, frame_cnt, sums, w.L);
     return eod_check_launch("eod_write_mean_det[reduce]");
 }
 

@@ -444,8 +444,8 @@ def test_write_mean_det_reproducible_and_correct(eod, cuda, C, with_samp):
 
 
 def test_write_mean_det_very_long_segment(eod, cuda):
-    """A cell with more runs than a warp sorts in shared memory at once (2048) takes the chunk-sort + merge path of
-    det_reduce."""
+    """A cell with more runs than a warp sorts in shared memory at once (2048) takes the bitmap-sort path of det_reduce and the
+    chunked summation (det_chunk / det_final)."""
     rng = np.random.default_rng(77)
     E, C, H, W, cells = 1, 128, 64, 96, 50
     feat = rng.standard_normal((E, C, H, W)).astype(np.float32)
@@ -466,6 +466,37 @@ def test_write_mean_det_very_long_segment(eod, cuda):
     ref = np.where(n[:, None] > 0, s_ / np.maximum(n, 1)[:, None].astype(np.float32), 0).astype(np.float32)
     assert n[7] == 2400
     assert np.abs(outs[0][0].cpu().numpy() - ref).max() <= SUM_TOL * np.abs(ref).max()
+
+
+def test_write_mean_det_bitmap_sort_many_passes_and_batch_independence(eod, cuda):
+    """More than 65 536 runs in one episode (the bitmap sort of a long segment needs several passes), two cells with ~77 k runs
+    each and a third long one; the result must be bitwise identical run to run AND when the episode sits at another place of
+    a larger batch (fixed per-cell summation tree: sorted runs -> chunks of 128 -> chunk sums in order)."""
+    rng = np.random.default_rng(5)
+    C, H, W, cells = 128, 480, 640, 40
+    feat = rng.standard_normal((1, C, H, W)).astype(np.float32)
+    idx = np.empty((1, H, W), np.int32)
+    idx[0] = 3 + ((np.arange(W) // 2) % 2)[None, :]                          # runs of 2 px alternating cells 3 / 4: 153 600 runs
+    idx[0, 100:140, ::4] = 9                                                  # + 6 400 isolated pixels of cell 9
+    ref_s, n = oracle.cell_sums_seq(feat[0], idx[0], None, cells)
+    ref = np.where(n[:, None] > 0, ref_s / np.maximum(n, 1)[:, None].astype(np.float32), 0).astype(np.float32)
+    outs = []
+    for E, slot in ((1, 0), (1, 0), (3, 2)):
+        f = rng.standard_normal((E, C, H, W)).astype(np.float32)
+        ix = rng.integers(10, cells, (E, H, W)).astype(np.int32)
+        f[slot], ix[slot] = feat[0], idx[0]
+        d_idx, d_feat = _t(ix, cuda), _t(f, cuda)
+        d_cnt = torch.zeros((E, cells), dtype=torch.int32, device=cuda)
+        eod.ops.frame_count(d_idx, None, d_cnt)
+        ws = eod.ops.DetWorkspace(E, C, H * W, cells, cuda, H * W)            # one run per pixel fits
+        d_sums = torch.zeros((E, cells, C), device=cuda)
+        eod.ops.write_mean_det(d_feat, d_idx, None, d_cnt, d_sums, ws)
+        torch.cuda.synchronize()
+        assert not ws.overflowed()
+        outs.append(d_sums[slot].clone())
+        del ws, d_feat
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    assert np.abs(outs[0].cpu().numpy() - ref).max() <= SUM_TOL * np.abs(ref).max()
 
 
 def test_episode_batch_deterministic_variant(eod, cuda):
