@@ -1060,3 +1060,60 @@ def test_tma_and_ldg_variants_agree_full_size(eod, cuda):
     s, n = oracle.cell_sums_seq(feat[0].cpu().numpy(), idx[0].cpu().numpy(), None, cells)
     ref = np.where(n[:, None] > 0, s / np.maximum(n, 1)[:, None].astype(np.float32), 0)
     assert np.abs(outs[1][0].cpu().numpy() - ref).max() <= SUM_TOL * np.abs(ref).max()
+
+
+def test_new_kernels_stay_inside_their_output_buffers(eod, cuda):
+    """compute-sanitizer is not available on the pool, so the kernels written this round get a canary check: every output
+    tensor is a window of a larger buffer filled with a sentinel, and the bytes on both sides must survive the launch
+    (ragged sizes on purpose: partial tiles, partial vectors, last-episode tails)."""
+    rng = np.random.default_rng(123)
+
+    def window(shape, dtype, pad=4096):
+        n = int(np.prod(shape))
+        item = torch.empty((), dtype=dtype).element_size()
+        padn = pad // item
+        buf = torch.empty(n + 2 * padn, dtype=dtype, device=cuda)
+        buf.view(torch.uint8).fill_(0xA5)
+        return buf, buf[padn:padn + n].view(shape), padn
+
+    def intact(buf, padn):
+        b = buf.view(torch.uint8)
+        item = buf.element_size()
+        return bool((b[: padn * item] == 0xA5).all()) and bool((b[-padn * item:] == 0xA5).all())
+
+    # read: E=3, 96x160, C=256 / 512 (lanes own 8 / 16 channels)
+    for C in (128, 256, 512):
+        E, H, W, cells = 3, 96, 160, 700
+        table = _t((rng.standard_normal((E, cells, C))).astype(np.float16), cuda)
+        idx = _t(rng.integers(0, cells, (E, H, W)).astype(np.int32), cuda)
+        bufs = [window((E, H >> s, W >> s, C), torch.float16) for s in (3, 4, 5)]
+        eod.ops.read_pool(table, None, idx, out=[b[1] for b in bufs])
+        torch.cuda.synchronize()
+        assert all(intact(b[0], b[2]) for b in bufs), C
+    # paste: odd image size, masks + observed
+    E, K, H, W = 2, 5, 77, 125
+    probs = _t(rng.uniform(0, 1, (E, K, 28, 28)).astype(np.float32), cuda)
+    boxes = _t(np.tile(np.array([-5.0, -3.0, W + 4.0, H + 2.0], np.float32), (E, K, 1)), cuda)
+    mb, mv, mp = window((E, K, H * W), torch.uint8)
+    ob, ov, op_ = window((E, H * W), torch.uint8)
+    eod._lib.check(eod._lib.lib().eod_paste_masks(probs.data_ptr(), boxes.data_ptr(), None, E, K, 28, H, W, 0.5, mv.data_ptr(), ov.data_ptr(),
+                                                  torch.cuda.current_stream().cuda_stream), "eod_paste_masks")
+    torch.cuda.synchronize()
+    assert intact(mb, mp) and intact(ob, op_) and bool(mv.any())
+    # projection + fusion: ragged tiles in both kernels
+    for variant, (h, w) in ((1, (7, 9)), (2, (15, 20)), (2, (30, 40))):
+        E, Kc, N = 3, 128, 128
+        lvl = _t(rng.standard_normal((E, h, w, Kc)).astype(np.float16), cuda)
+        ws = eod.ops.project_split_weights(_t(rng.standard_normal((N, Kc)).astype(np.float32), cuda))
+        res = _t(rng.standard_normal((E, N, h, w)).astype(np.float32), cuda)
+        ob, ov, op_ = window((E, N, h, w), torch.float32)
+        eod.ops.project_fuse_levels([lvl], [ws], [None], [res], 5.0, 0, outs=[ov], variant=variant)
+        torch.cuda.synchronize()
+        assert intact(ob, op_), (variant, h, w)
+    # sampling scan: vectorised (HW % 16 == 0) and scalar planes
+    for hw in (16 * 1025, 47 * 81):
+        obs = _t((rng.uniform(size=(2, hw)) < 0.3).astype(np.uint8), cuda)
+        sb, sv, sp = window((2, hw), torch.uint8)
+        eod.ops.sample_mask(obs, 8, samp=sv)
+        torch.cuda.synchronize()
+        assert intact(sb, sp), hw
