@@ -61,32 +61,45 @@ __device__ __forceinline__ float paste_coord(int c, float b0, float extent, floa
     return __fmaf_rn(__fadd_rn(g, 1.f), half_S, -0.5f);
 }
 
+// one axis of the bilinear tap: source coordinate i -> near tap floor(i) with weight 1 - frac, far tap floor(i) + 1 with weight frac
+struct PasteAxis {
+    float w_near, w_far;
+    int i_near, i_far;
+    bool in_near, in_far;
+};
+__device__ __forceinline__ PasteAxis paste_axis(int c, float b0, float extent, int S)
+{
+    const float fS = (float)S;
+    const float i = paste_coord(c, b0, extent, fS * 0.5f);
+    const float f = floorf(i), f1 = __fadd_rn(f, 1.f);
+    PasteAxis a;
+    a.w_far = __fsub_rn(i, f);
+    a.w_near = __fsub_rn(1.f, a.w_far);
+    a.in_near = f > -1.f && f < fS;                     // comparisons in the float domain: false for inf / NaN coordinates
+    a.in_far = f1 > -1.f && f1 < fS;
+    a.i_near = a.in_near ? (int)f : 0;
+    a.i_far = a.in_far ? (int)f1 : 0;
+    return a;
+}
+// sampled value >= thr, in the operation order of ATen's vectorised CPU grid_sample; padding taps contribute 0 * weight
+// (NaN for non-finite coordinates, which then compares false)
+__device__ __forceinline__ bool paste_eval(const float *__restrict__ m, int S, const PasteAxis &x, const PasteAxis &y, float thr)
+{
+    const float v_nw = (x.in_near && y.in_near) ? __ldg(m + y.i_near * S + x.i_near) : 0.f;
+    const float v_ne = (x.in_far && y.in_near) ? __ldg(m + y.i_near * S + x.i_far) : 0.f;
+    const float v_sw = (x.in_near && y.in_far) ? __ldg(m + y.i_far * S + x.i_near) : 0.f;
+    const float v_se = (x.in_far && y.in_far) ? __ldg(m + y.i_far * S + x.i_far) : 0.f;
+    float acc = __fmul_rn(v_nw, __fmul_rn(y.w_near, x.w_near));
+    acc = __fmaf_rn(v_ne, __fmul_rn(y.w_near, x.w_far), acc);
+    acc = __fmaf_rn(v_sw, __fmul_rn(y.w_far, x.w_near), acc);
+    acc = __fmaf_rn(v_se, __fmul_rn(y.w_far, x.w_far), acc);
+    return acc >= thr;
+}
 // pasted-mask value test for one (object, pixel); m = the object's (S,S) probabilities
 __device__ __forceinline__ bool paste_covers(const float *__restrict__ m, const PasteObj &o, int S, int px, int py, float thr)
 {
     if (px < o.rx0 || px >= o.rx1 || py < o.ry0 || py >= o.ry1) return false;
-    const float half_S = (float)S * 0.5f, fS = (float)S;
-    const float ix = paste_coord(px, o.x0, o.dx, half_S), iy = paste_coord(py, o.y0, o.dy, half_S);
-    const float xw = floorf(ix), yn = floorf(iy);
-    const float xe = __fadd_rn(xw, 1.f), ys = __fadd_rn(yn, 1.f);
-    const float w = __fsub_rn(ix, xw), e = __fsub_rn(1.f, w), n = __fsub_rn(iy, yn), s = __fsub_rn(1.f, n);
-    const bool in_w = xw > -1.f && xw < fS, in_e = xe > -1.f && xe < fS, in_n = yn > -1.f && yn < fS, in_s = ys > -1.f && ys < fS;
-    if (!((in_w || in_e) && (in_n || in_s))) {
-        // every tap is padding: the sampler returns 0 * weights (NaN for non-finite coordinates): covered only if 0 >= thr
-        const float z = __fmul_rn(0.f, __fmul_rn(s, e));
-        return __fmaf_rn(0.f, __fmul_rn(n, w), __fmaf_rn(0.f, __fmul_rn(n, e), __fmaf_rn(0.f, __fmul_rn(s, w), z))) >= thr;
-    }
-    const int jx = in_w ? (int)xw : 0, jy = in_n ? (int)yn : 0;
-    const int kx = in_e ? (int)xe : 0, ky = in_s ? (int)ys : 0;
-    const float v_nw = (in_w && in_n) ? __ldg(m + jy * S + jx) : 0.f;
-    const float v_ne = (in_e && in_n) ? __ldg(m + jy * S + kx) : 0.f;
-    const float v_sw = (in_w && in_s) ? __ldg(m + ky * S + jx) : 0.f;
-    const float v_se = (in_e && in_s) ? __ldg(m + ky * S + kx) : 0.f;
-    float acc = __fmul_rn(v_nw, __fmul_rn(s, e));
-    acc = __fmaf_rn(v_ne, __fmul_rn(s, w), acc);
-    acc = __fmaf_rn(v_sw, __fmul_rn(n, e), acc);
-    acc = __fmaf_rn(v_se, __fmul_rn(n, w), acc);
-    return acc >= thr;
+    return paste_eval(m, S, paste_axis(px, o.x0, o.dx, S), paste_axis(py, o.y0, o.dy, S), thr);
 }
 
 constexpr int kPasteChunk = 128;      // objects staged in shared memory at a time
@@ -118,9 +131,17 @@ __global__ void __launch_bounds__(256) paste_masks_kernel(const float *__restric
                 // whole quad outside the object's rows / columns: skip (the common case)
                 if (!(py[3] < o.ry0 || py[0] >= o.ry1 || (py[0] == py[3] && (px[3] < o.rx0 || px[0] >= o.rx1)))) {
                     const float *m = probs + ((size_t)e * Kmax + k) * S * S;
+                    if (py[0] == py[3]) {                      // the usual case (W % 4 == 0): one row, the y axis is shared
+                        const PasteAxis ay = paste_axis(py[0], o.y0, o.dy, S);
 #pragma unroll
-                    for (int b = 0; b < 4; ++b)
-                        if (p0 + b < HW && paste_covers(m, o, S, px[b], py[b], thr)) bits |= 1u << (8 * b);
+                        for (int b = 0; b < 4; ++b)
+                            if (p0 + b < HW && px[b] >= o.rx0 && px[b] < o.rx1 && paste_eval(m, S, paste_axis(px[b], o.x0, o.dx, S), ay, thr))
+                                bits |= 1u << (8 * b);
+                    } else {
+#pragma unroll
+                        for (int b = 0; b < 4; ++b)
+                            if (p0 + b < HW && paste_covers(m, o, S, px[b], py[b], thr)) bits |= 1u << (8 * b);
+                    }
                 }
             }
             any |= bits;
