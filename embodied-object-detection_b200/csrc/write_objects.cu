@@ -259,31 +259,41 @@ __global__ void __launch_bounds__(256) write_objects_kernel(const float *__restr
         const int n_words = Kpad >> 5;
         for (int base = 0; base < n; base += 256) {                      // rounds of up to 256 sampled pixels
             const int nn = min(256, n - base);
-            // ---- phase A ----
-            int my_slot = -1;
+            // ---- phase A: thread per sampled pixel ----
+            // Cell and slot of the pixel, then the objects one after the other: an integer box-region test from shared memory and,
+            // for the one or two objects that pass it, the sampler.  (The first version spent a warp trip per (pixel, 32 objects)
+            // - 53 trips per CTA with one or two useful lanes each, an integer division per lane and trip; this is ~3 trips.)
             if ((int)threadIdx.x < nn) {
-                const int cell = __ldg(idx + (size_t)e * HW + s_list[base + threadIdx.x]);
-                my_slot = __ldg(slot_of_cell + (size_t)e * n_cells + cell) - 1;
-            }
-            for (int q = threadIdx.x; q < nn * Kpad; q += 256) {         // a warp's 32 consecutive q: one pixel, 32 objects
-                const int i = q / Kpad, k = q - i * Kpad;
-                const int px = s_list[base + i];
-                bool mine = false;
-                if (k < K) {
-                    if (kPasted) mine = paste_covers(probs + ((size_t)e * Kmax + k) * Sm * Sm, s_obj[k], Sm, px % W, px / W, thr);
-                    else mine = __ldg(m + (size_t)k * HW + px) != 0;
+                const int px = s_list[base + threadIdx.x];
+                const int cell = __ldg(idx + (size_t)e * HW + px);
+                const int my_slot = __ldg(slot_of_cell + (size_t)e * n_cells + cell) - 1;
+                const int x = px % W, y = px / W;
+                static_assert(kCoverObjs == 128, "four cover words");
+                unsigned w0 = 0u, w1 = 0u, w2 = 0u, w3 = 0u;
+                for (int k = 0; k < K; ++k) {
+                    bool mine;
+                    if (kPasted) {
+                        const PasteObj &o = s_obj[k];
+                        mine = x >= o.rx0 && x < o.rx1 && y >= o.ry0 && y < o.ry1 &&
+                               paste_eval(probs + ((size_t)e * Kmax + k) * Sm * Sm, Sm, paste_axis(x, o.x0, o.dx, Sm), paste_axis(y, o.y0, o.dy, Sm), thr);
+                    } else {
+                        mine = __ldg(m + (size_t)k * HW + px) != 0;
+                    }
+                    if (mine) {
+                        const unsigned bit = 1u << (k & 31);
+                        const int wd = k >> 5;
+                        w0 |= wd == 0 ? bit : 0u; w1 |= wd == 1 ? bit : 0u; w2 |= wd == 2 ? bit : 0u; w3 |= wd == 3 ? bit : 0u;
+                    }
                 }
-                const unsigned word = __ballot_sync(0xffffffffu, mine);
-                if (lane == 0) s_cover[i][k >> 5] = word;
+                s_cover[threadIdx.x][0] = w0; s_cover[threadIdx.x][1] = w1; s_cover[threadIdx.x][2] = w2; s_cover[threadIdx.x][3] = w3;
+                s_slot[threadIdx.x] = my_slot;
             }
-            if ((int)threadIdx.x < nn) s_slot[threadIdx.x] = my_slot;
             __syncthreads();
+            const int chunk = (nn + 7) >> 3;                              // warp w owns pixels [w*chunk, i_end)
+            const int i_beg = (int)warp * chunk, i_end = min(nn, ((int)warp + 1) * chunk);
             // ---- phase B ----
-            // Warp w takes a contiguous piece of the raster-ordered list; lanes own float4 channel groups 4*lane + 128*j.
-            // Consecutive samples that fall into the same cell are summed in registers and leave as ONE 128-bit reduction
-            // per lane and group (the scratch row is an unordered fp32 sum either way).
-            const int chunk = (nn + 7) >> 3;
-            const int i_end = min(nn, ((int)warp + 1) * chunk);
+            // Lanes own float4 channel groups 4*lane + 128*j.  Consecutive samples that fall into the same cell are summed in
+            // registers and leave as ONE 128-bit reduction per lane and group (the scratch row is an unordered fp32 sum either way).
             float4 agg[J4];
             int agg_slot = -1;
             auto flush = [&]() {
@@ -293,7 +303,7 @@ __global__ void __launch_bounds__(256) write_objects_kernel(const float *__restr
                     for (int j = 0; j < J4; ++j) red_add_v4(dst + 128 * j, agg[j].x, agg[j].y, agg[j].z, agg[j].w);
                 }
             };
-            for (int i = warp * chunk; i < i_end; ++i) {
+            for (int i = i_beg; i < i_end; ++i) {
                 float4 acc[J4];
 #pragma unroll
                 for (int j = 0; j < J4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -315,18 +325,31 @@ __global__ void __launch_bounds__(256) write_objects_kernel(const float *__restr
                 }
                 const int slot = s_slot[i];
                 if (cnt == 0 || slot < 0 || slot >= S) continue;           // cnt == 0 cannot happen for a sampled pixel; slot overflow: caller error
-                const float n_px = (float)cnt;
+                // / number of covering objects (custom_rcnn.py:899).  Almost always 1 or 2: a power of two divides exactly like the
+                // multiplication by its (exact) reciprocal, so the 4*J4 IEEE divides are only paid for 3, 5, 6, 7, ... objects
+                if (cnt > 1) {
+                    if ((cnt & (cnt - 1)) == 0) {
+                        const float r = 1.0f / (float)cnt;
+#pragma unroll
+                        for (int j = 0; j < J4; ++j)
+                            acc[j] = make_float4(__fmul_rn(acc[j].x, r), __fmul_rn(acc[j].y, r), __fmul_rn(acc[j].z, r), __fmul_rn(acc[j].w, r));
+                    } else {
+                        const float n_px = (float)cnt;
+#pragma unroll
+                        for (int j = 0; j < J4; ++j)
+                            acc[j] = make_float4(__fdiv_rn(acc[j].x, n_px), __fdiv_rn(acc[j].y, n_px), __fdiv_rn(acc[j].z, n_px), __fdiv_rn(acc[j].w, n_px));
+                    }
+                }
                 if (slot != agg_slot) {
                     flush();
                     agg_slot = slot;
 #pragma unroll
-                    for (int j = 0; j < J4; ++j)
-                        agg[j] = make_float4(__fdiv_rn(acc[j].x, n_px), __fdiv_rn(acc[j].y, n_px), __fdiv_rn(acc[j].z, n_px), __fdiv_rn(acc[j].w, n_px));
+                    for (int j = 0; j < J4; ++j) agg[j] = acc[j];
                 } else {
 #pragma unroll
                     for (int j = 0; j < J4; ++j) {
-                        agg[j].x = __fadd_rn(agg[j].x, __fdiv_rn(acc[j].x, n_px)); agg[j].y = __fadd_rn(agg[j].y, __fdiv_rn(acc[j].y, n_px));
-                        agg[j].z = __fadd_rn(agg[j].z, __fdiv_rn(acc[j].z, n_px)); agg[j].w = __fadd_rn(agg[j].w, __fdiv_rn(acc[j].w, n_px));
+                        agg[j].x = __fadd_rn(agg[j].x, acc[j].x); agg[j].y = __fadd_rn(agg[j].y, acc[j].y);
+                        agg[j].z = __fadd_rn(agg[j].z, acc[j].z); agg[j].w = __fadd_rn(agg[j].w, acc[j].w);
                     }
                 }
             }
