@@ -114,8 +114,16 @@ __global__ void __launch_bounds__(256) paste_masks_kernel(const float *__restric
     const int p0 = (blockIdx.x * 256 + threadIdx.x) * 4;
     const int K = n_obj ? max(0, min(__ldg(n_obj + e), Kmax)) : Kmax;
     int px[4], py[4];
+    {
+        const int v = p0 / W, u0 = p0 - v * W;                 // one integer division per thread; the quad rarely wraps a row
+        if (u0 + 3 < W) {
 #pragma unroll
-    for (int b = 0; b < 4; ++b) { px[b] = (p0 + b) % W; py[b] = (p0 + b) / W; }
+            for (int b = 0; b < 4; ++b) { px[b] = u0 + b; py[b] = v; }
+        } else {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) { px[b] = (p0 + b) % W; py[b] = (p0 + b) / W; }
+        }
+    }
     uint32_t any = 0;
     for (int k0 = 0; k0 < Kmax; k0 += kPasteChunk) {
         const int kn = min(kPasteChunk, Kmax - k0);
