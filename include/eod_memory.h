@@ -205,8 +205,9 @@ int eod_write_max(const float *height, const int32_t *idx, const uint8_t *outlie
 
 /* ---------------------------------------------------------------------------------------------------
  * (3) Read.  Replaces create_implicit_memory (custom_rcnn.py:764-774), the fp16 cast (:1036) and
- * timm.py:147-168 (gather to the image plane, avg-pool 4, then per level avg-pool 2 -> half) in ONE
- * kernel; the (480,640,C) image-plane tensors are never materialised.
+ * timm.py:147-168 (gather to the image plane, avg-pool 4, then per level avg-pool 2 -> half) in one
+ * kernel for levels 0 and 1 plus a small second one that pools level 2 from level 1; the (480,640,C)
+ * image-plane tensors are never materialised.
  *   table: mem_is_f16 == 0: sums (E,cells,C) f32 with counts (E,cells) f32 (nullable = no normalise);
  *          mem_is_f16 == 1: already normalised fp16 table (E,cells,C) (reference API: map_memory list)
  *   idx (E,H,W) int32 or int64.  H, W multiples of 32.
