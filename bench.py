@@ -108,6 +108,32 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Pin this rank's CPU threads - and with them the first-touch placement of its pinned staging buffers - to the NUMA node
+    its GPU hangs off.  Unbound, the 8 ranks of a box stream most of their H2D traffic across the socket interconnect and the
+    e2e arm is host-memory bound at less than half of 8 x PCIe.  Best effort: returns the node, or None when sysfs says nothing."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(index)], capture_output=True,
+                             text=True, timeout=20).stdout.strip().lower()
+        if not bus:
+            return None
+        dom, rest = bus.split(":", 1)
+        node = int(open(f"/sys/bus/pci/devices/{dom[-4:]}:{rest}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -219,6 +245,7 @@ def main_gpu(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     eod._lib.lib()                                                   # fail loudly when the extension is missing
+    numa_node = None if args.no_numa else bind_to_gpu_numa_node(local_rank)
 
     E = N_EPISODES
     my_eps = [rank + world * i for i in range(E)]                    # weak scaling: 64 episodes per GPU
@@ -280,7 +307,7 @@ def main_gpu(args, rank, local_rank, world):
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": workload_config(world), "clocks": clocks, "gpu_launches": int(launches),
+        "data": "synthetic", "config": dict(workload_config(world), host_numa_node=numa_node), "clocks": clocks, "gpu_launches": int(launches),
         "e2e": e2e,
         "roofline": {"bound": "hbm", "kernel": "write_mean_chw_tma_kernel<256>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "frac_of_nominal_8TBs": (achieved / 8000.0) if achieved else None,
@@ -376,6 +403,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--write-variant", type=int, default=0, help="diagnostics: 0 auto, 1 LDG, 2 TMA, 3 TMA dry (no result)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-numa", action="store_true", help="diagnostics: do not bind the rank to its GPU's NUMA node")
     ap.add_argument("--no-pipeline", action="store_true", help="diagnostics: stream-ordered EpisodeBatch.step (no cross-frame overlap)")
     args = ap.parse_args()
     rank, local_rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
