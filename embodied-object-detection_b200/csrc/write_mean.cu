@@ -711,8 +711,32 @@ write_mean_chw_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int32_
 // ------------------------------------------------------------------------------------------------------
 // main pass, HWC: warp per strip of 32 pixels, lanes own float4 channel groups
 // ------------------------------------------------------------------------------------------------------
-template <int C>
-__global__ void __launch_bounds__(256) write_mean_hwc_kernel(const float *__restrict__ feat, const int32_t *__restrict__ idx,
+// four consecutive channels of one pixel as fp32: fp32 features (16 B), or bf16 / fp16 features (8 B) widened exactly
+enum { FEAT_F32 = 0, FEAT_BF16 = 1, FEAT_F16 = 2 };
+template <int F> struct FeatRaw { uint2 q; };
+template <> struct FeatRaw<FEAT_F32> { float4 q; };
+template <int F>
+__device__ __forceinline__ FeatRaw<F> load_feat_raw(const void *row, int k)       // k-th group of 4 channels of the pixel row
+{
+    FeatRaw<F> r;
+    if constexpr (F == FEAT_F32) r.q = ldg_stream_f4(reinterpret_cast<const float *>(row) + 4 * k);
+    else asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.q.x), "=r"(r.q.y) : "l"(reinterpret_cast<const uint2 *>(row) + k));
+    return r;
+}
+template <int F>
+__device__ __forceinline__ float4 widen_feat(const FeatRaw<F> &r)
+{
+    if constexpr (F == FEAT_F32) return r.q;
+    else if constexpr (F == FEAT_BF16)
+        return make_float4(__uint_as_float(r.q.x << 16), __uint_as_float(r.q.x & 0xffff0000u), __uint_as_float(r.q.y << 16), __uint_as_float(r.q.y & 0xffff0000u));
+    else {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&r.q.x)), b = __half22float2(*reinterpret_cast<const __half2 *>(&r.q.y));
+        return make_float4(a.x, a.y, b.x, b.y);
+    }
+}
+
+template <int C, int F>
+__global__ void __launch_bounds__(256, 3) write_mean_hwc_kernel(const void *__restrict__ feat, const int32_t *__restrict__ idx,
                                                              const uint8_t *__restrict__ samp, const uint32_t *__restrict__ frame_cnt,
                                                              int HW, int64_t n_cells, int strips_per_ep, int n_strips,
                                                              float *__restrict__ sums)
@@ -743,24 +767,41 @@ __global__ void __launch_bounds__(256) write_mean_hwc_kernel(const float *__rest
                                __fdiv_rn(acc[v].z, n), __fdiv_rn(acc[v].w, n));
             }
         };
-#pragma unroll 4
-        for (int p = 0; p < pvalid; ++p) {
-            const int cell = __shfl_sync(0xffffffffu, my_cell, p);
-            if (cell != cur) {
-                flush();
-                cur = cell;
-                any = false;
+        // batches of PB pixels: the batch's rows are requested first (32 registers of raw data per lane: 4 fp32 pixels or
+        // 8 sixteen-bit ones at C=256), then walked - the same bytes in flight whatever the feature type
+        constexpr int PB = (F == FEAT_F32 ? 8 : 16) / V > 0 ? (F == FEAT_F32 ? 8 : 16) / V : 1;
+#pragma unroll 1
+        for (int pb = 0; pb < pvalid; pb += PB) {
+            FeatRaw<F> raw[PB][V];
 #pragma unroll
-                for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int b = 0; b < PB; ++b) {
+                const int p = pb + b;
+                if (p < pvalid && ((samps >> p) & 1u)) {
+                    const char *row = reinterpret_cast<const char *>(feat) + (pix0 + p) * C * (F == FEAT_F32 ? 4 : 2);
+#pragma unroll
+                    for (int v = 0; v < V; ++v) raw[b][v] = load_feat_raw<F>(row, v * 32 + (int)lane);
+                }
             }
-            if ((samps >> p) & 1u) {
-                any = true;
-                const float *row = feat + (pix0 + p) * C;
 #pragma unroll
-                for (int v = 0; v < V; ++v) {
-                    const float4 f = ldg_stream_f4(row + v * 128 + 4 * lane);
-                    acc[v].x = __fadd_rn(acc[v].x, f.x); acc[v].y = __fadd_rn(acc[v].y, f.y);
-                    acc[v].z = __fadd_rn(acc[v].z, f.z); acc[v].w = __fadd_rn(acc[v].w, f.w);
+            for (int b = 0; b < PB; ++b) {
+                const int p = pb + b;
+                if (p >= pvalid) break;
+                const int cell = __shfl_sync(0xffffffffu, my_cell, p);
+                if (cell != cur) {
+                    flush();
+                    cur = cell;
+                    any = false;
+#pragma unroll
+                    for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                if ((samps >> p) & 1u) {
+                    any = true;
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        const float4 f = widen_feat<F>(raw[b][v]);
+                        acc[v].x = __fadd_rn(acc[v].x, f.x); acc[v].y = __fadd_rn(acc[v].y, f.y);
+                        acc[v].z = __fadd_rn(acc[v].z, f.z); acc[v].w = __fadd_rn(acc[v].w, f.w);
+                    }
                 }
             }
         }
@@ -1335,12 +1376,14 @@ int launch_ldg(const float *feat, const int32_t *idx, const uint8_t *samp, const
 }
 
 template <int C>
-int launch_hwc(const float *feat, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt, int E, int HW,
+int launch_hwc(const void *feat, int feat_type, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt, int E, int HW,
                int64_t n_cells, float *sums, cudaStream_t st)
 {
     const int strips_per_ep = (HW + TILE_PX - 1) / TILE_PX, n_strips = strips_per_ep * E;
     const int blocks = min((n_strips + 7) / 8, eod_num_sms() * 8);
-    write_mean_hwc_kernel<C><<<blocks, 256, 0, st>>>(feat, idx, samp, frame_cnt, HW, n_cells, strips_per_ep, n_strips, sums);
+    if (feat_type == FEAT_BF16) write_mean_hwc_kernel<C, FEAT_BF16><<<blocks, 256, 0, st>>>(feat, idx, samp, frame_cnt, HW, n_cells, strips_per_ep, n_strips, sums);
+    else if (feat_type == FEAT_F16) write_mean_hwc_kernel<C, FEAT_F16><<<blocks, 256, 0, st>>>(feat, idx, samp, frame_cnt, HW, n_cells, strips_per_ep, n_strips, sums);
+    else write_mean_hwc_kernel<C, FEAT_F32><<<blocks, 256, 0, st>>>(feat, idx, samp, frame_cnt, HW, n_cells, strips_per_ep, n_strips, sums);
     return eod_check_launch("eod_write_mean[hwc]");
 }
 
@@ -1348,7 +1391,9 @@ template <int C>
 int dispatch(const float *feat, int layout, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt, const float *pix_n, int E, int HW,
              int64_t n_cells, float *sums, int variant, cudaStream_t st)
 {
-    if (layout == EOD_LAYOUT_HWC) return launch_hwc<C>(feat, idx, samp, frame_cnt, E, HW, n_cells, sums, st);
+    if (layout == EOD_LAYOUT_HWC) return launch_hwc<C>(feat, FEAT_F32, idx, samp, frame_cnt, E, HW, n_cells, sums, st);
+    if (layout == EOD_LAYOUT_HWC_BF16) return launch_hwc<C>(feat, FEAT_BF16, idx, samp, frame_cnt, E, HW, n_cells, sums, st);
+    if (layout == EOD_LAYOUT_HWC_F16) return launch_hwc<C>(feat, FEAT_F16, idx, samp, frame_cnt, E, HW, n_cells, sums, st);
     const bool tma_ok = (HW % TILE_PX == 0) && (!samp || (reinterpret_cast<uintptr_t>(samp) % 16 == 0));
     if (variant == EOD_WRITE_TMA || variant == EOD_WRITE_TMA_DRY) EOD_REQUIRE(tma_ok, EOD_ERR_UNSUPPORTED, "eod_write_mean: TMA variant needs HW %% 32 == 0");
     if (variant == EOD_WRITE_TMA_DRY) return launch_tma<C, true>(feat, idx, samp, frame_cnt, pix_n, E, HW, n_cells, sums, st);
@@ -1443,17 +1488,18 @@ extern "C" int eod_expand_counts(const int32_t *idx, const uint32_t *frame_cnt, 
     return eod_check_launch("eod_expand_counts");
 }
 
-extern "C" int eod_write_mean(const float *feat, int layout, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt,
+extern "C" int eod_write_mean(const void *feat_any, int layout, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt,
                               int n_episodes, int C, int HW, int64_t n_cells, float *sums, int variant, const float *pix_inv_n,
                               eod_stream_t stream)
 {
+    const float *feat = reinterpret_cast<const float *>(feat_any);
     EOD_REQUIRE(!pix_inv_n || eod_aligned16(pix_inv_n), EOD_ERR_ALIGN, "eod_write_mean: pix_inv_n must be 16-byte aligned");
     EOD_REQUIRE(feat && idx && frame_cnt && sums, EOD_ERR_BADARG, "eod_write_mean: null pointer");
     EOD_REQUIRE(n_episodes > 0 && HW > 0 && n_cells > 0, EOD_ERR_BADARG, "eod_write_mean: bad sizes");
-    EOD_REQUIRE(layout == EOD_LAYOUT_CHW || layout == EOD_LAYOUT_HWC, EOD_ERR_BADARG, "eod_write_mean: bad layout");
+    EOD_REQUIRE(layout >= EOD_LAYOUT_CHW && layout <= EOD_LAYOUT_HWC_F16, EOD_ERR_BADARG, "eod_write_mean: bad layout");
     EOD_REQUIRE(variant >= EOD_WRITE_AUTO && variant <= EOD_WRITE_TMA_DRY, EOD_ERR_BADARG, "eod_write_mean: bad variant");
     EOD_REQUIRE(eod_aligned16(feat) && eod_aligned16(sums) && eod_aligned16(idx), EOD_ERR_ALIGN, "eod_write_mean: pointers must be 16-byte aligned");
-    EOD_REQUIRE(layout == EOD_LAYOUT_HWC || HW % 4 == 0, EOD_ERR_ALIGN, "eod_write_mean: CHW rows must be 16-byte aligned (HW %% 4 == 0)");
+    EOD_REQUIRE(layout != EOD_LAYOUT_CHW || HW % 4 == 0, EOD_ERR_ALIGN, "eod_write_mean: CHW rows must be 16-byte aligned (HW %% 4 == 0)");
     cudaStream_t st = (cudaStream_t)stream;
     switch (C) {
     case 128: return dispatch<128>(feat, layout, idx, samp, frame_cnt, pix_inv_n, n_episodes, HW, n_cells, sums, variant, st);

@@ -9,7 +9,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import (FUSE_IMAGE_ONLY, FUSE_MEM_ONLY, FUSE_SUM, LAYOUT_CHW, LAYOUT_HWC, ORDER_XZ, ORDER_ZX, WRITE_AUTO,
+from ._lib import (FUSE_IMAGE_ONLY, FUSE_MEM_ONLY, FUSE_SUM, LAYOUT_CHW, LAYOUT_HWC, LAYOUT_HWC_BF16, LAYOUT_HWC_F16, ORDER_XZ, ORDER_ZX, WRITE_AUTO,
                    WRITE_DET, WRITE_LDG, WRITE_TMA, EodError, check)
 
 # kernels launched through this module since import (bench.py reports it as gpu_launches)
@@ -139,9 +139,10 @@ def expand_counts(idx: torch.Tensor, frame_cnt: torch.Tensor, pix_inv_n: torch.T
 def write_mean(feat: torch.Tensor, idx: torch.Tensor, samp: Optional[torch.Tensor], frame_cnt: torch.Tensor,
                sums: torch.Tensor, layout: int = LAYOUT_CHW, variant: int = WRITE_AUTO,
                pix_inv_n: Optional[torch.Tensor] = None) -> None:
-    """feat (E,C,HW) [CHW] or (E,HW,C) [HWC] f32; sums (E,cells,C) f32 accumulated in place.
-    pix_inv_n: output of expand_counts for this frame (optional, faster)."""
-    _dev(feat, torch.float32, "feat"), _dev(idx, torch.int32, "idx"), _dev(sums, torch.float32, "sums")
+    """feat (E,C,HW) [CHW] or (E,HW,C) [HWC] f32, or (E,HW,C) bf16 / fp16 [LAYOUT_HWC_BF16 / _F16]; sums (E,cells,C) f32
+    accumulated in place.  pix_inv_n: output of expand_counts for this frame (optional, faster)."""
+    feat_dtype = {LAYOUT_HWC_BF16: torch.bfloat16, LAYOUT_HWC_F16: torch.float16}.get(int(layout), torch.float32)
+    _dev(feat, feat_dtype, "feat"), _dev(idx, torch.int32, "idx"), _dev(sums, torch.float32, "sums")
     _dev(frame_cnt, torch.int32, "frame_cnt")
     E, n_cells, C = sums.shape
     HW = idx[0].numel()

@@ -41,6 +41,8 @@ extern "C" {
 
 #define EOD_LAYOUT_CHW 0 /* features (E, C, H*W): the reference's image_features, custom_rcnn.py:886 */
 #define EOD_LAYOUT_HWC 1 /* features (E, H*W, C): channels-last                                         */
+#define EOD_LAYOUT_HWC_BF16 2 /* channels-last bf16 features (a bf16 backbone's output): widened exactly, summed in fp32 */
+#define EOD_LAYOUT_HWC_F16 3  /* channels-last fp16 features                                                             */
 
 #define EOD_FUSE_SUM 0        /* res + w*mem   timm.py:181-182 */
 #define EOD_FUSE_MEM_ONLY 1   /* w*mem         timm.py:183-184 */
@@ -108,8 +110,10 @@ int eod_expand_counts(const int32_t *idx, const uint32_t *frame_cnt, int n_episo
 /* Main pass: sums[cell] += (sum of the sampled pixels' feature vectors) / n_cell, i.e. the per-cell mean
  * of custom_rcnn.py:917-934 accumulated as in :696-697,742.  Warp-aggregated fp32 reductions
  * (red.global.add.f32, one per run of equal cell id and channel): run-to-run results agree to ~1e-7 of
- * scale, not bitwise.  pix_inv_n: nullable, output of eod_expand_counts for this frame. */
-int eod_write_mean(const float *feat, int layout, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt,
+ * scale, not bitwise.  pix_inv_n: nullable, output of eod_expand_counts for this frame.
+ * feat is fp32 for EOD_LAYOUT_CHW / _HWC and bf16 / fp16 for EOD_LAYOUT_HWC_BF16 / _HWC_F16 (half the bytes of the dominant
+ * stream: the 16-bit values are widened exactly and everything downstream is the fp32 arithmetic of the fp32 layouts). */
+int eod_write_mean(const void *feat, int layout, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt,
                    int n_episodes, int C, int HW, int64_t n_cells, float *sums, int variant, const float *pix_inv_n,
                    eod_stream_t stream);
 

@@ -24,6 +24,7 @@ PROF_ONLY=tc PROF_ROUNDS=2 ncu --set full --clock-control none --import-source o
 echo "fuse full rc=$?"
 # the other BASELINE configurations and the object-regime stage breakdown (no profiler)
 python profiles/bench_configs.py > $O/configs_$TAG.log 2>$O/configs_$TAG.err; echo "configs rc=$?"
+python profiles/prof_layouts.py > $O/layouts_$TAG.json 2>$O/layouts_$TAG.err; echo "layouts rc=$?"
 python profiles/prof_objects.py > $O/objects_$TAG.json 2>$O/objects_$TAG.err; echo "objects rc=$?"
 PROF_E=16 PROF_T=4 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $O/launches_obj_$TAG.csv python profiles/prof_objects.py > $O/ncu_launches_obj_$TAG.log 2>&1
 echo "object launch list rc=$?"

@@ -143,6 +143,10 @@ def main():
     if os.path.exists(fn):
         md += ["## Other BASELINE configurations (`profiles/bench_configs.py`; CUDA events, no profiler)", "", "```"] + \
               [l for l in open(fn).read().strip().splitlines() if l.startswith("{")] + ["```", ""]
+    fn = os.path.join(OUT, f"layouts_{tag}.json")
+    if os.path.exists(fn):
+        md += ["## Dense write by feature layout (`profiles/prof_layouts.py`, E=64, C=256; CUDA events, no profiler)", "",
+               "```", open(fn).read().strip().splitlines()[-1], "```", ""]
     fn = os.path.join(OUT, f"objects_{tag}.json")
     if os.path.exists(fn):
         md += ["## Object regime, stage breakdown (`profiles/prof_objects.py`, E=64, C=512, <=16 detections per frame; ms per launch)", "",

@@ -345,6 +345,8 @@ def _write_case(eod, cuda, C, E, H, W, cells, layout, variant, with_samp, seed, 
     rng = np.random.default_rng(seed)
     HW = H * W
     feat = rng.standard_normal((E, C, H, W)).astype(np.float32) * 3
+    if layout in (2, 3):        # 16-bit channels-last features: the oracle sums the exactly widened values
+        feat = torch.from_numpy(feat).to(torch.bfloat16 if layout == 2 else torch.float16).float().numpy()
     idx = (rng.integers(0, cells, (E, H // 2 + 1, W // 16 + 1)).repeat(2, 1).repeat(16, 2)[:, :H, :W]).astype(np.int32)
     idx[:, ::5, ::3] = rng.integers(0, cells, idx[:, ::5, ::3].shape)
     samp = (rng.uniform(size=(E, H, W)) < 0.3).astype(np.uint8) if with_samp else None
@@ -358,6 +360,8 @@ def _write_case(eod, cuda, C, E, H, W, cells, layout, variant, with_samp, seed, 
     d_idx = _t(idx, cuda)
     d_samp = None if samp is None else _t(samp, cuda)
     f_dev = _t(feat if layout == 0 else feat.transpose(0, 2, 3, 1), cuda)
+    if layout in (2, 3):
+        f_dev = f_dev.to(torch.bfloat16 if layout == 2 else torch.float16)
     eod.ops.frame_count(d_idx, d_samp, d_cnt)
     pix = eod.ops.expand_counts(d_idx, d_cnt, torch.empty((E, H, W), device=cuda)) if expand else None
     eod.ops.write_mean(f_dev, d_idx, d_samp, d_cnt, d_sums, layout, variant, pix)
@@ -540,9 +544,10 @@ def test_write_mean_chw_ragged_tail_ldg(eod, cuda):
 
 
 @pytest.mark.parametrize("C", [128, 256, 512])
-def test_write_mean_hwc_vs_oracle(eod, cuda, C):
-    _write_case(eod, cuda, C, 2, 30, 52, 90, 1, 0, True, seed=C)
-    _write_case(eod, cuda, C, 2, 64, 96, 200, 1, 0, False, seed=C + 1)
+@pytest.mark.parametrize("layout", [1, 2, 3], ids=["f32", "bf16", "f16"])      # EOD_LAYOUT_HWC, _HWC_BF16, _HWC_F16
+def test_write_mean_hwc_vs_oracle(eod, cuda, C, layout):
+    _write_case(eod, cuda, C, 2, 30, 52, 90, layout, 0, True, seed=C)
+    _write_case(eod, cuda, C, 2, 64, 96, 200, layout, 0, False, seed=C + 1)
 
 
 @pytest.mark.parametrize("fused", [True, False], ids=["fused", "image-buffer"])
