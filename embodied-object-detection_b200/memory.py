@@ -150,7 +150,7 @@ class EpisodeBatch:
 
     def _count(self, samp: Optional[torch.Tensor]) -> None:
         self._timed("count", ops.frame_count, self.idx, samp, self.frame_cnt)
-        if self.variant != WRITE_DET:                      # the deterministic write divides once per cell, from frame_cnt
+        if self.variant != WRITE_DET and self.layout == LAYOUT_CHW:      # only the TMA-staged CHW kernel takes per-pixel divisors
             self._timed("expand", ops.expand_counts, self.idx, self.frame_cnt, self.pix_inv_n)
 
     def _write(self, feat: torch.Tensor, samp: Optional[torch.Tensor]) -> None:
@@ -160,13 +160,14 @@ class EpisodeBatch:
             self._timed("write", ops.write_mean_det, feat, self.idx, samp, self.frame_cnt, self.sums, self._det_ws)
             return
         self._timed("write", ops.write_mean, feat, self.idx, samp, self.frame_cnt, self.sums, self.layout, self.variant,
-                    self.pix_inv_n)
+                    self.pix_inv_n if self.layout == LAYOUT_CHW else None)
 
     def _finalize(self) -> None:
         self._timed("finalize", ops.finalize_counts, self.idx, self.frame_cnt, self.counts, None, self.sums, self.norm16)
 
     def write(self, feat: torch.Tensor, samp: Optional[torch.Tensor] = None) -> None:
-        """A7 + A8 for one frame of every episode: feat (E,C,H,W) [CHW] or (E,H,W,C) [HWC] fp32;
+        """A7 + A8 for one frame of every episode: feat (E,C,H,W) [CHW] or (E,H,W,C) [HWC] fp32, or (E,H,W,C) bf16 / fp16
+        [LAYOUT_HWC_BF16 / LAYOUT_HWC_F16];
         samp (E,H,W) u8 selects the contributing pixels (None = all)."""
         self._count(samp)
         self._write(feat, samp)
