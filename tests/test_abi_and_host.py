@@ -198,3 +198,24 @@ def test_store_round_trip_and_episode_dataset(eod, tmp_path):
     assert np.array_equal(ds2[1][5]["memory_features"], mem) and np.array_equal(ds2[1][5]["observations"], obs)
     with pytest.raises(F.StoreError):
         F.open_store(str(tmp_path / "nope.h5"))                             # no silent zero-memory fallback
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` runs on the host alone (the oracle port timed on the CPU) and prints ONE JSON line with the
+    keys the driver reads; under torchrun every rank but 0 exits without work."""
+    import json
+    import subprocess
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "config",
+                "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    idle = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                          capture_output=True, text=True, timeout=120, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
+    assert idle.returncode == 0 and idle.stdout.strip() == ""
