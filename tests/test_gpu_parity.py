@@ -1122,3 +1122,48 @@ def test_new_kernels_stay_inside_their_output_buffers(eod, cuda):
         eod.ops.sample_mask(obs, 8, samp=sv)
         torch.cuda.synchronize()
         assert intact(sb, sp), hw
+
+
+def test_edge_frames_through_step(eod, cuda):
+    """Degenerate frames through the public step APIs against the oracle: the smallest image the read accepts (32x32, one L2
+    pixel), a single episode, a frame without depth (every pixel is clipped onto one border cell: a single 1024-pixel run), a
+    frame in which no episode has a detection (nothing may change), and a reset in the middle."""
+    H = W = 32
+    C, mw, mh, cell, E = 128, 9, 7, 0.5, 1
+    cells = mw * mh
+    intr = eod.compute_intrinsics(W, H, math.radians(67.5))
+    rng = np.random.default_rng(3)
+    batch = eod.EpisodeBatch(E, mw, mh, C, H, W, cuda)
+    shifts = _t(np.array([[0, 0, 0, -2.0, 0, -1.5]], np.float32), cuda)
+    sums, counts = torch.zeros(cells, C), torch.zeros(cells)
+    xyzhe = np.array([[0.3, 1.25, 0.2, 0.7, math.pi]], np.float32)
+    Tm = eod.transform3d(torch.from_numpy(xyzhe))
+    pose = Tm[:, :3].reshape(1, 12).to(cuda)
+    for t, depth in enumerate((rng.uniform(0.3, 3.0, (1, H, W)).astype(np.float32), np.zeros((1, H, W), np.float32),
+                               rng.uniform(0.3, 3.0, (1, H, W)).astype(np.float32))):
+        feat = rng.standard_normal((1, C, H, W)).astype(np.float32)
+        before = (batch.sums[0].cpu(), batch.counts[0].cpu())
+        levels = [l.clone() for l in batch.step(_t(depth, cuda), pose, shifts, intr, cell, _t(feat, cuda))]
+        torch.cuda.synchronize()
+        idx = oracle.backproject_quantize(depth[0], Tm[0].numpy(), intr, np.zeros(3, np.float32), np.array([-2.0, 0, -1.5], np.float32),
+                                          np.float32(cell), mw, mh, 0, 0.5, want=("idx",))["idx"]
+        assert np.array_equal(batch.idx[0].cpu().numpy(), idx)
+        if t == 1:
+            assert len(np.unique(idx)) == 1                                  # no depth: one cell for the whole frame
+        ref_levels = R.read_frame(before[0], before[1], torch.from_numpy(idx).long())
+        for k in range(3):
+            assert np.array_equal(levels[k][0].contiguous().cpu().numpy().view(np.uint16), ref_levels[k][0].numpy().view(np.uint16)), (t, k)
+        sums, counts = R.write_mean_frame(sums, counts, torch.from_numpy(feat), torch.ones(H, W, dtype=torch.bool), torch.from_numpy(idx).long(), stride=1)
+        assert (batch.sums[0].cpu() - sums).abs().max().item() <= SUM_TOL * sums.abs().max().item(), t
+        assert torch.equal(batch.counts[0].cpu(), counts)
+    # a frame without any detection: the object write must leave sums, counts and the fp16 table alone
+    snap = (batch.sums.clone(), batch.counts.clone(), batch.norm16.clone())
+    n_obj = _t(np.zeros(1, np.int32), cuda)
+    batch.step_detections(_t(rng.uniform(0.3, 3.0, (1, H, W)).astype(np.float32), cuda), pose, shifts, intr, cell,
+                          torch.zeros((1, 4, C), device=cuda), torch.ones((1, 4, 28, 28), device=cuda),
+                          _t(np.tile(np.array([0, 0, W, H], np.float32), (1, 4, 1)), cuda), n_obj)
+    torch.cuda.synchronize()
+    assert torch.equal(batch.sums, snap[0]) and torch.equal(batch.counts, snap[1]) and torch.equal(batch.norm16, snap[2])
+    batch.reset()
+    torch.cuda.synchronize()
+    assert not batch.sums.any() and not batch.counts.any() and not batch.norm16.any()
