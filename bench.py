@@ -12,6 +12,8 @@ is  back-project+quantise -> read (normalise, fp16, gather, pool x3) -> write (c
   roofline     dominant kernel (eod_write_mean): algorithmic bytes per launch / mean CUDA-event duration of that
                launch inside the timed region, vs MEASURED_PEAKS.json hbm_gbs
   cpu_baseline the oracle port of the same path (torch-CPU restatement of the reference ops) on the host cores
+  extras       (not part of `value`) two more stages of the path on the same batch: the tcgen05 projection + fusion of the
+               three levels, and the object regime (detections as mask probabilities + boxes) through step_detections
 
 `--impl reference` times that CPU implementation alone (the reference cannot run as committed: hard-coded
 .cuda() and detectron2 imports), on a bounded sample of the same workload per step.
@@ -301,6 +303,9 @@ def main_gpu(args, rank, local_rank, world):
     achieved = wbytes / (stage_ms["write"] * 1e-3) / 1e9 if stage_ms.get("write") else None
     path_gbs = frame_bytes(vis_per_frame) * (value / world) / 1e9
 
+    extras = run_extras(eod, batch, dev, depth, pose, shifts, intr) if (rank == 0 and not args.no_extras) else None
+    if world > 1:
+        torch.distributed.barrier()
     # ---- e2e through the plugin API with host buffers (rank-local, then max over ranks) ----
     e2e = None if args.no_e2e else run_e2e(eod, batch, dev, depth_h, pose.cpu(), shifts, intr, args, world, sharding, slabs)
 
@@ -308,7 +313,7 @@ def main_gpu(args, rank, local_rank, world):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": dict(workload_config(world), host_numa_node=numa_node), "clocks": clocks, "gpu_launches": int(launches),
-        "e2e": e2e,
+        "e2e": e2e, "extras": extras,
         "roofline": {"bound": "hbm", "kernel": "write_mean_chw_tma_kernel<256>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "frac_of_nominal_8TBs": (achieved / 8000.0) if achieved else None,
                      "traffic": measured_traffic(E), "peak_source": peak_src, "bytes_per_launch": wbytes, "launch_ms": stage_ms.get("write"),
@@ -324,6 +329,59 @@ def main_gpu(args, rank, local_rank, world):
                                              f"+ sparse-equivalent (index_add_) write; the literal one-hot matmul of the reference needs "
                                              f"{N_PIX * MAP_W * MAP_H / 1e9:.0f} GB at stride 1"}
         print(json.dumps(out))
+
+
+def run_extras(eod, batch, dev, depth, pose, shifts, intr):
+    """Two more stages of the same path, timed on the bench batch after the headline loop (CUDA events, resident inputs; not part
+    of `value`): the tensor-core projection + fusion of the three read levels and the reference's live object
+    regime (kept detections as 28x28 mask probabilities + boxes; mask pasting folded into the write).  Best effort."""
+    out = {}
+    try:
+        E = batch.E
+        ops = eod.ops
+        g = torch.Generator(device=dev).manual_seed(5)
+        levels = [l.permute(0, 3, 1, 2) for l in batch.levels]                        # the last frame's pooled levels, channels-last memory
+        N = 256
+        ws = [ops.project_split_weights(torch.randn((N, C), device=dev, generator=g) / C ** 0.5) for _ in range(3)]
+        bias = [torch.randn((N,), device=dev, generator=g) for _ in range(3)]
+        res = [torch.randn((E, N, l.shape[2], l.shape[3]), device=dev, generator=g) for l in levels]
+        outs = [torch.empty_like(r) for r in res]
+        for _ in range(3):
+            ops.project_fuse_levels(levels, ws, bias, res, 5.0, 0, outs)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            ops.project_fuse_levels(levels, ws, bias, res, 5.0, 0, outs)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 10
+        nbytes = sum(l.numel() * 2 for l in levels) + 2 * sum(r.numel() * 4 for r in res)
+        out["project_fuse"] = {"ms_per_frame_step": ms, "GBps": nbytes / ms / 1e6, "kernel": "project_fuse_persistent_kernel (tcgen05)",
+                               "shape": f"E={E}, K={C} -> N={N}, levels 60x80/30x40/15x20"}
+        del res, outs
+        rng = np.random.default_rng(0)
+        Kmax = 16
+        bf = np.zeros((E, Kmax, C), np.float32); pr = np.zeros((E, Kmax, 28, 28), np.float32); bx = np.zeros((E, Kmax, 4), np.float32)
+        n = np.zeros(E, np.int32)
+        for e in range(E):
+            f, p_, b_ = eod.episodes.make_mask_head_detections(rng, H, W, C, (4, Kmax), 28)
+            n[e] = f.shape[0]; bf[e, : n[e]], pr[e, : n[e]], bx[e, : n[e]] = f, p_, b_
+        det = [torch.from_numpy(x).to(dev) for x in (bf, pr, bx, n)]
+        batch.join()
+        for t in range(3):
+            batch.step_detections(depth[t], pose[t], shifts, intr, float(CELL), *det)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for t in range(N_FRAMES):
+            batch.step_detections(depth[t], pose[t], shifts, intr, float(CELL), *det)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / N_FRAMES
+        out["object_regime"] = {"ms_per_frame_step": ms, "frames_per_s": E / ms * 1e3,
+                                "shape": f"E={E}, C={C}, <= {Kmax} detections per frame, 28x28 mask probabilities + boxes, every 8th observed pixel"}
+    except Exception as exc:                                                          # never lose the headline line to an extra
+        out["error"] = repr(exc)[:200]
+    return out
 
 
 def run_e2e(eod, batch, dev, depth_h, pose_h, shifts, intr, args, world, sharding, slabs):
@@ -403,6 +461,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--write-variant", type=int, default=0, help="diagnostics: 0 auto, 1 LDG, 2 TMA, 3 TMA dry (no result)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the projection+fusion and object-regime stage timings")
     ap.add_argument("--no-numa", action="store_true", help="diagnostics: do not bind the rank to its GPU's NUMA node")
     ap.add_argument("--no-pipeline", action="store_true", help="diagnostics: stream-ordered EpisodeBatch.step (no cross-frame overlap)")
     args = ap.parse_args()
