@@ -211,7 +211,11 @@ constexpr int P2_BM = 256, P2_STAGES = 3, P2_RCH = 16, P2_RSLOTS = 2;
 constexpr int P2_A_BYTES = P2_BM * PF_BK * 2;                 // 32 KB
 constexpr int P2_STAGE_BYTES = P2_A_BYTES + PF_B_BYTES;       // 64 KB
 constexpr int P2_R_BYTES = P2_RCH * P2_BM * 4;                // 16 KB
-constexpr int P2_SMEM_BYTES = P2_STAGES * P2_STAGE_BYTES + P2_RSLOTS * P2_R_BYTES + 1024 + 128 + 2 * PF_BN * 4 /* bias, double buffered */;
+constexpr int P2_BAR_BYTES = 128;                               // 12 mbarriers (96 B) + the TMEM base address (4 B), padded
+constexpr int P2_BIAS_BYTES = 2 * PF_BN * 4;                    // the tile's bias values, double buffered
+constexpr int P2_SMEM_BYTES = P2_STAGES * P2_STAGE_BYTES + P2_RSLOTS * P2_R_BYTES + P2_BAR_BYTES + P2_BIAS_BYTES + 1024 /* alignment slack */;
+static_assert((2 * P2_STAGES + 2 * P2_RSLOTS + 2) * 8 + 4 <= P2_BAR_BYTES, "barrier block too small");
+static_assert(P2_SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
 constexpr int P2_THREADS = 12 * 32;                 // 3 warpgroups: 2 x epilogue, 1 x {A/B producer, MMA, res producer, idle}
 constexpr int P2_MAX_LEVELS = 3;
 
@@ -253,7 +257,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) project_fuse_persistent_kernel(
     uint64_t *full = bars, *empty = full + P2_STAGES, *rfull = empty + P2_STAGES, *rempty = rfull + P2_RSLOTS;
     uint64_t *tmem_full = rempty + P2_RSLOTS, *tmem_empty = tmem_full + 1;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 1);
-    float *bias_s = reinterpret_cast<float *>(bars + 16);           // 2 x 128 floats
+    float *bias_s = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(bars) + P2_BAR_BYTES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 8 && lane == 0) {
