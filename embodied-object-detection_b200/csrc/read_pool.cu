@@ -254,8 +254,9 @@ __global__ void __launch_bounds__(kReadWarps * 32, (C >= 512 ? 2 : (C >= 256 ? 3
         for (int l0 = 0; l0 < 4; ++l0) {                   // L0 pixels of the quadrant, row-major
             const int l0y = l0 >> 1, l0x = l0 & 1;
             // The four 4x4 windows of this L0 pixel.  A window whose 16 pixels hit ONE cell needs no additions: the
-            // gathered value x is an fp16 number, so the sequential fp32 sum x+x+...+x is exact at every step
-            // (k*x, k <= 16, has at most 15 significant bits) and avg_pool2d(4) returns x itself.
+            // gathered value x is an fp16 number, so the sequential fp32 sum 0+x+x+...+x is exact at every step
+            // (k*x, k <= 16, has at most 15 significant bits) and avg_pool2d(4) returns x itself - except that -0.0
+            // becomes +0.0 (0 + -0 = +0), which the shortcuts reproduce by adding +0 (found by profiles/stress_read.py).
             const int wbase = (l0y * 2) * 4 + l0x * 2;
             const int w00 = s_wcell[warp][wbase];
             Vec<V> v0;
@@ -263,7 +264,8 @@ __global__ void __launch_bounds__(kReadWarps * 32, (C >= 512 ? 2 : (C >= 256 ? 3
                 // whole 8x8 block in one cell: pool(4), pool(2) and the fp16 rounding all return the gathered value
                 if (w00 != cur_cell) cur = finish<V>(load_raw<V>(table_e, counts_e, (size_t)w00, C, g));
                 cur_cell = w00;
-                v0 = cur;
+                v0 = vadd<V>(cur, vzero<V>());               // the reference's sums start from +0: a gathered -0.0 comes out as +0.0
+
             } else {
                 Vec<V> s2 = vzero<V>();
 #pragma unroll 1

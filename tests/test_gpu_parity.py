@@ -160,6 +160,27 @@ def test_read_pool_randomised_vs_oracle(eod, cuda, C, E, H, W):
             assert np.array_equal(a, b), (e, k, np.mean(a != b))
 
 
+def test_read_pool_signed_zeros_and_adversarial_patterns(eod, cuda):
+    """Patterns the randomised test does not reach (from profiles/stress_read.py): a table holding -0.0 (what a tiny negative
+    feature becomes in fp16), subnormals and +-65504 in cells that fill whole 8x8 blocks - the reference's window sums start
+    from +0, so a gathered -0.0 must come out as +0.0 -, checkerboards (16 runs per window) and 1-pixel stripes."""
+    rng = np.random.default_rng(9)
+    for C in (128, 256, 512):
+        H, W, cells, E = 96, 128, 37, 2
+        yy, xx = np.mgrid[0:H, 0:W]
+        pats = [(yy // 24) * 7 % cells + (xx // 40) % 3, ((yy + xx) % 2) * (cells - 1), xx % cells, yy % cells]
+        table = rng.standard_normal((E, cells, C)).astype(np.float16)
+        table[:, :, :8] = np.array([0.0, -0.0, 6e-8, -6e-8, 65504.0, -65504.0, 1.0, -1.0], np.float16)
+        table[:, :, 8:16] = np.float16(-1e-9)                               # underflows to -0.0
+        for pat in pats:
+            idx = np.stack([np.roll(pat, 5 * e, axis=1) for e in range(E)]).astype(np.int32) % cells
+            got = eod.ops.read_pool(_t(table, cuda), None, _t(idx, cuda))
+            for e in range(E):
+                ref = oracle.read_pool_f16(table[e], idx[e])
+                for k in range(3):
+                    assert np.array_equal(got[k][e].contiguous().cpu().numpy().view(np.uint16), ref[k].view(np.uint16)), (C, e, k)
+
+
 def test_fuse_bit_exact(eod, cuda):
     rng = np.random.default_rng(1)
     for n in (1, 3, 4, 1000, 256 * 60 * 80 + 3):
