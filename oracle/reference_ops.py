@@ -118,6 +118,8 @@ def paste_masks_in_image(masks: torch.Tensor, boxes: torch.Tensor, image_shape, 
         x1_int = torch.clamp(b[:, 2].max().ceil() + 1, max=img_w).to(dtype=torch.int32)
         y1_int = torch.clamp(b[:, 3].max().ceil() + 1, max=img_h).to(dtype=torch.int32)
         x0, y0, x1, y1 = torch.split(b, 1, dim=1)
+        if int(y0_int) >= int(y1_int) or int(x0_int) >= int(x1_int):
+            continue        # box entirely outside the image: torch.arange would raise upstream; fast_rcnn_inference clips boxes, so it cannot occur
         img_y = torch.arange(y0_int, y1_int, dtype=torch.float32) + 0.5
         img_x = torch.arange(x0_int, x1_int, dtype=torch.float32) + 0.5
         img_y = (img_y - y0) / (y1 - y0) * 2 - 1

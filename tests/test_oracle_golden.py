@@ -182,3 +182,35 @@ def test_robot_demo_geometry_oracle_and_host_pose_match_reference(eod, golden):
         out = oracle.backproject_quantize(depth, g["T"][t], K, np.zeros(3, np.float32), g["map_world_shift"], np.float32(g["res"]),
                                           int(g["map_w"]), int(g["map_h"]), 1, 3.0, want=("idx",))
         assert np.array_equal(out["idx"], g["flat"][t])
+
+
+def test_paste_masks_c_oracle_vs_torch_on_threshold_knife_edges():
+    """Masks that sit exactly on the threshold (constant 0.5, {0, 0.5, 1} lattices, +-1e-5 around 0.5), NaN / Inf probabilities,
+    integer / half-integer / sub-pixel / oversized boxes: the C restatement and torch-CPU's grid_sample must agree on every pasted
+    bool - this is where a different fma order would show."""
+    if torch.backends.cpu.get_cpu_capability() == "DEFAULT":
+        pytest.skip("scalar ATen grid_sample rounds differently (no fma); canonical is the AVX2 / AVX-512 build")
+    rng = np.random.default_rng(1)
+    H, W, K = 60, 80, 5
+    for case in range(18):
+        S = int(rng.choice([28, 14, 7]))
+        kind = case % 6
+        if kind == 0:   probs = np.full((K, S, S), 0.5, np.float32)
+        elif kind == 1: probs = rng.choice([0.0, 0.5, 1.0], (K, S, S)).astype(np.float32)
+        elif kind == 2: probs = (rng.integers(0, 3, (K, S, S)) * 0.25 + 0.25).astype(np.float32)
+        elif kind == 3: probs = rng.uniform(0.49999, 0.50001, (K, S, S)).astype(np.float32)
+        elif kind == 4: probs = rng.uniform(0, 1, (K, S, S)).astype(np.float32)
+        else:
+            probs = rng.uniform(0, 1, (K, S, S)).astype(np.float32)
+            probs[0, 3, 3] = np.nan; probs[1, 2, 2] = np.inf; probs[2, 1, 1] = -np.inf
+        boxes = np.zeros((K, 4), np.float32)
+        for k in range(K):
+            t = k % 5
+            if t == 0:   x0, y0 = rng.integers(0, W - 30), rng.integers(0, H - 30); boxes[k] = (x0, y0, x0 + rng.integers(1, 30), y0 + rng.integers(1, 30))
+            elif t == 1: x0, y0 = rng.integers(0, W - 30) + 0.5, rng.integers(0, H - 30) + 0.5; boxes[k] = (x0, y0, x0 + 28, y0 + 28)
+            elif t == 2: x0, y0 = rng.uniform(-5, W - 4), rng.uniform(-5, H - 4); boxes[k] = (x0, y0, x0 + rng.uniform(0.01, 3), y0 + rng.uniform(0.01, 3))
+            elif t == 3: boxes[k] = (rng.uniform(-50, 0), rng.uniform(-50, 0), W + rng.uniform(0, 50), H + rng.uniform(0, 50))
+            else:        x0, y0 = rng.uniform(0, W - 40), rng.uniform(0, H - 40); boxes[k] = (x0, y0, x0 + rng.uniform(5, 40), y0 + rng.uniform(5, 40))
+        for thr in (0.5, 0.25):
+            ref = R.paste_masks_in_image(torch.from_numpy(probs), torch.from_numpy(boxes), (H, W), thr).numpy()
+            assert np.array_equal(oracle.paste_masks(probs, boxes, H, W, thr), ref), (case, thr)
