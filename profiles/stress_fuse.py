@@ -7,6 +7,7 @@ ops = eod.ops
 dev = torch.device("cuda:0")
 rng = np.random.default_rng(99)
 E, K, N = 24, 512, 256
+n_bad_total = [0]
 def run(shapes, use_bias, mode):
     lv = [torch.from_numpy((rng.standard_normal((E, h, w, K)) * 2).astype(np.float16)).to(dev) for h, w in shapes]
     Ws = [(rng.uniform(-1, 1, (N, K)) / math.sqrt(K)).astype(np.float32) for _ in shapes]
@@ -19,6 +20,7 @@ def run(shapes, use_bias, mode):
         d = (got[k] - ref[k]).abs()
         bad = (d > 1e-3).nonzero()
         print(shapes, "bias", use_bias, "mode", mode, "level", k, "max diff", d.max().item(), "n bad", bad.shape[0], "of", d.numel())
+        n_bad_total[0] += int(bad.shape[0])
         if bad.shape[0]:
             e = bad[:, 0]; n = bad[:, 1]; pix = bad[:, 2] * w + bad[:, 3]
             tpe = -(-h * w // 256)
@@ -29,3 +31,5 @@ for shapes in ([(60, 80)], [(30, 40)], [(15, 20)], [(60, 80), (30, 40)], [(60, 8
     for use_bias in (False, True):
         for mode in (1, 0):
             run(shapes, use_bias, mode)
+print("fuse stress:", n_bad_total[0], "bad elements")
+sys.exit(1 if n_bad_total[0] else 0)
