@@ -10,6 +10,15 @@
 
 namespace {
 
+// build_memory_data.py:136-142 / robot_demo.py:527-530: q.round().long() and THEN the clip.  On the x86 hosts the reference runs on,
+// float -> int64 of NaN, +-inf or anything beyond +-2^63 yields INT64_MIN, which clips to cell 0; finite values clip as usual.
+// (The outlier mask of core.py:253-256 compares the rounded FLOATS, so it needs no such rule.)
+__device__ __forceinline__ bool q_overflows(float q) { return !(fabsf(q) < 9.223372036854775808e18f); }
+__device__ __forceinline__ int clip_cell(float q, int n)
+{
+    return q_overflows(q) ? 0 : (int)fminf(fmaxf(q, 0.0f), (float)(n - 1));
+}
+
 struct BackprojectParams {
     const float *depth;
     const float *pose;
@@ -68,8 +77,7 @@ __global__ void __launch_bounds__(256) backproject_quantize_kernel(const Backpro
     }
     if (P.height) P.height[g] = p1y;
     if (P.idx) {
-        const int ix = (int)fminf(fmaxf(qx, 0.0f), (float)(P.map_w - 1));
-        const int iz = (int)fminf(fmaxf(qz, 0.0f), (float)(P.map_h - 1));
+        const int ix = clip_cell(qx, P.map_w), iz = clip_cell(qz, P.map_h);
         P.idx[g] = P.order == EOD_ORDER_XZ ? ix * P.map_h + iz : iz * P.map_w + ix;
     }
 }
@@ -116,11 +124,11 @@ __global__ void __launch_bounds__(256) backproject_quantize_vec4_kernel(const Ba
         const float qx = rintf(__fdiv_rn(p1x, P.cell));
         const float qz = rintf(__fdiv_rn(p1z, P.cell));
         q2v[2 * k] = (int32_t)qx; q2v[2 * k + 1] = (int32_t)qz;
-        const bool out = (qx >= (float)P.map_w) || (qz >= (float)P.map_h) || (qx < 0.0f) || (qz < 0.0f) || (p1y > thr) || (z == 0.0f);
+        const bool out = (qx >= (float)P.map_w) || (qz >= (float)P.map_h) || (qx < 0.0f) || (qz < 0.0f) ||
+                         (p1y > thr) || (z == 0.0f);
         out4 |= (out ? 1u : 0u) << (8 * k);
         h4[k] = p1y;
-        const int ix = (int)fminf(fmaxf(qx, 0.0f), (float)(P.map_w - 1));
-        const int iz = (int)fminf(fmaxf(qz, 0.0f), (float)(P.map_h - 1));
+        const int ix = clip_cell(qx, P.map_w), iz = clip_cell(qz, P.map_h);
         idx4[k] = P.order == EOD_ORDER_XZ ? ix * P.map_h + iz : iz * P.map_w + ix;
     }
     if (P.world) {
@@ -149,8 +157,7 @@ __global__ void __launch_bounds__(256) quantize_world_kernel(const float *__rest
     const float x = __ldg(world + 3 * i), z = __ldg(world + 3 * i + 2);
     const float qx = rintf(__fdiv_rn(__fsub_rn(x, sx), cell));
     const float qz = rintf(__fdiv_rn(__fsub_rn(z, sz), cell));
-    const int ix = (int)fminf(fmaxf(qx, 0.0f), (float)(map_w - 1));
-    const int iz = (int)fminf(fmaxf(qz, 0.0f), (float)(map_h - 1));
+    const int ix = clip_cell(qx, map_w), iz = clip_cell(qz, map_h);
     idx[i] = order == EOD_ORDER_XZ ? ix * map_h + iz : iz * map_w + ix;
 }
 

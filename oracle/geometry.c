@@ -29,6 +29,10 @@
 #define ORACLE_ORDER_COLMAJOR 1 /* flat = q_x * map_h + q_z   (robot_demo.py:533)        */
 
 static float clipf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
+/* build_memory_data.py:136-142: q.round().long() and THEN the clip.  On x86 (the hosts the reference runs on) float -> int64 of NaN,
+ * +-inf or anything beyond +-2^63 is INT64_MIN, which clips to cell 0.  (core.py:253-256 compares the rounded floats: no such rule.) */
+static int q_overflows(float q) { return !(fabsf(q) < 9.223372036854775808e18f); }
+static int32_t clip_cell(float q, int n) { return q_overflows(q) ? 0 : (int32_t)clipf(q, 0.0f, (float)(n - 1)); }
 
 /*
  * depth   (H*W) f32 metres, 0 == no depth
@@ -72,8 +76,8 @@ void oracle_backproject_quantize(const float *depth, int H, int W, const float *
             }
             if (height) height[p] = p1y;
             if (idx) {
-                const int32_t ix = (int32_t)clipf(qx, 0.0f, (float)(map_w - 1));
-                const int32_t iz = (int32_t)clipf(qz, 0.0f, (float)(map_h - 1));
+                const int32_t ix = clip_cell(qx, map_w);
+                const int32_t iz = clip_cell(qz, map_h);
                 idx[p] = order == ORACLE_ORDER_COLMAJOR ? ix * map_h + iz : iz * map_w + ix;
             }
         }
