@@ -78,6 +78,33 @@ def test_robot_demo_geometry_matches_reference_golden(eod, cuda, golden):
         assert np.array_equal(flat[0, ..., 0].cpu().numpy(), g["flat"][t])
 
 
+def test_backproject_non_finite_depths_follow_torch(eod, cuda):
+    """Depth values a sensor should never emit (inf, NaN, 3e38, 1e6): the clipped flat index and the outlier mask must still be what
+    the reference's torch-CPU ops return - `.round().long()` of a non-finite / out-of-range float is INT64_MIN on x86, which the
+    clip of build_memory_data.py:141-142 turns into cell 0; the outlier test of core.py:253-256 compares the rounded floats."""
+    rng = np.random.default_rng(2)
+    H, W, mw, mh, cell = 32, 64, 120, 90, 0.1
+    depth = rng.uniform(0.3, 9.0, (H, W)).astype(np.float32)
+    depth[0, :8] = [np.inf, np.nan, 3e38, 1e6, -np.inf, 0.0, 1e-30, 65504.0]
+    xyzhe = np.array([[1.0, 1.25, -2.0, 0.9, math.pi + 0.1]], np.float32)
+    T = eod.transform3d(torch.from_numpy(xyzhe))
+    vf = math.radians(67.5)
+    intr = eod.compute_intrinsics(W, H, vf)
+    shift = np.array([-6.0, 0.0, -4.5], np.float32)
+    world = R.pixel_to_world(torch.from_numpy(depth[None]), T, vf, torch.zeros(3))
+    ref_idx = R.quantize_flat_index(world, torch.from_numpy(shift), cell, mw, mh).numpy().reshape(H, W)
+    _, ref_out, _ = R.projector_forward(torch.from_numpy(depth[None, None]), T, vf, mh, mw, cell, torch.from_numpy(shift), 0.5)
+    sh = _t(np.concatenate([np.zeros(3, np.float32), shift])[None], cuda)
+    got = eod.ops.backproject_quantize(_t(depth[None], cuda), T[:, :3].reshape(1, 12).to(cuda), sh, intr, cell, mw, mh)
+    assert np.array_equal(got["idx"][0].cpu().numpy(), ref_idx)
+    sh2 = _t(np.concatenate([shift, np.zeros(3, np.float32)])[None], cuda)
+    got2 = eod.ops.backproject_quantize(_t(depth[None], cuda), T[:, :3].reshape(1, 12).to(cuda), sh2, intr, cell, mw, mh, want_idx=False, want_outlier=True)
+    assert np.array_equal(got2["outlier"][0].cpu().numpy().astype(bool), ref_out[0].numpy())
+    for name, d_np in (("oracle", None),):
+        o = oracle.backproject_quantize(depth, T[0].numpy(), intr, np.zeros(3, np.float32), shift, np.float32(cell), mw, mh, 0, 0.5, want=("idx",))
+        assert np.array_equal(o["idx"], ref_idx)
+
+
 def test_backproject_randomised_vs_oracle(eod, cuda):
     rng = np.random.default_rng(42)
     H, W, E = 60, 100, 5                                           # ragged: not multiples of the block size
