@@ -163,6 +163,14 @@ def main():
             md.append(f"| `{k[:60]}` | {len(v)} | {sum(v) / len(v) / 1e3:.1f} | {sum(v) / tot:.3f} |")
         md.append("")
 
+    stress = [(k, os.path.join(OUT, f"stress_{k}_{tag}.log")) for k in ("read", "paste", "geometry", "dense_write", "fuse")]
+    if any(os.path.exists(f) for _, f in stress):
+        md += ["## Adversarial / randomised sweeps against the oracle (`profiles/stress_*.py`)", ""]
+        for k, f in stress:
+            if os.path.exists(f):
+                md.append(f"- `stress_{k}.py`: " + open(f).read().strip().splitlines()[-1])
+        md.append("")
+
     fn = os.path.join(OUT, f"bench_{tag}.log")
     if os.path.exists(fn):
         line = open(fn).read().strip().splitlines()[-1]
