@@ -163,7 +163,7 @@ def main():
             md.append(f"| `{k[:60]}` | {len(v)} | {sum(v) / len(v) / 1e3:.1f} | {sum(v) / tot:.3f} |")
         md.append("")
 
-    stress = [(k, os.path.join(OUT, f"stress_{k}_{tag}.log")) for k in ("read", "paste", "geometry", "dense_write", "fuse")]
+    stress = [(k, os.path.join(OUT, f"stress_{k}_{tag}.log")) for k in ("read", "paste", "geometry", "dense_write", "objects", "fuse")]
     if any(os.path.exists(f) for _, f in stress):
         md += ["## Adversarial / randomised sweeps against the oracle (`profiles/stress_*.py`)", ""]
         for k, f in stress:
