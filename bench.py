@@ -12,8 +12,14 @@ is  back-project+quantise -> read (normalise, fp16, gather, pool x3) -> write (c
   roofline     dominant kernel (eod_write_mean): algorithmic bytes per launch / mean CUDA-event duration of that
                launch inside the timed region, vs MEASURED_PEAKS.json hbm_gbs
   cpu_baseline the oracle port of the same path (torch-CPU restatement of the reference ops) on the host cores
-  extras       (not part of `value`) two more stages of the path on the same batch: the tcgen05 projection + fusion of the
-               three levels, and the object regime (detections as mask probabilities + boxes) through step_detections
+  value_with_fusion   the same timed loop with the tcgen05 projection + fusion of the three levels inside every frame-step
+  write_alone  the dominant kernel timed back to back with nothing else on the GPU, right after the timed loop (same power
+               state): splits the in-bench roofline loss into concurrency and clock
+  roofline_1000  the same workload on the north-star 1000x1000 grid (0.2 m cells), timed the same way
+  parity_check   after the timed region: the bench's own batch / inputs, a few frames of 2 episodes against the CPU oracle
+                 (oracle/path_check.py) - the oracle is the checker here, never the thing measured
+  extras       (not part of `value`) more stages of the path on the same batch: the tcgen05 projection + fusion of the
+               three levels alone, and the object regime (detections as mask probabilities + boxes) through step_detections
 
 `--impl reference` times that CPU implementation alone (the reference cannot run as committed: hard-coded
 .cuda() and detectron2 imports), on a bounded sample of the same workload per step.
@@ -241,6 +247,42 @@ def workload_config(world):
 # ---------------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------
+def timed_steps(batch, n_steps, one_step, barrier, sharding, dev):
+    """K steps bracketed by barrier + synchronize, CUDA events on the caller's stream, max over ranks -> total ms."""
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(n_steps):
+        one_step()
+    ev1.record()
+    barrier()
+    return sharding.max_over_ranks(ev0.elapsed_time(ev1), dev)
+
+
+def run_parity_check(batch, depth, pose, shifts, intr, cell, slabs, depth_h, T_h, shift_h, my_eps, n_frames=3, checked=(0, 37)):
+    """Outside the timed region: the bench's own EpisodeBatch (E=64, pipeline=True) and its own resident inputs, n_frames
+    frames, two episodes against the CPU oracle - synchronised pass (levels bit-exact on the downloaded state), then the same
+    frames back to back as the timed loop enqueues them (final state of all 64 episodes must agree)."""
+    from oracle import path_check
+    host = {e: dict(depth=depth_h[e], T=T_h[e], shift=shift_h[e]) for e in checked}
+    frames = [dict(depth=depth[t], pose=pose[t], feat=slabs[t & 1]) for t in range(n_frames)]
+    t0 = time.perf_counter()
+    res = path_check.check_dense_steps(batch, frames, shifts, intr, cell, host, synced=True)
+    state = (batch.sums[list(checked)].clone(), batch.counts.clone())
+    res2 = path_check.check_dense_steps(batch, frames, shifts, intr, cell, host, synced=False)
+    all_counts_equal = bool(torch.equal(batch.counts, state[1]))
+    scale = float(state[0].abs().max())
+    sums_drift = float((batch.sums[list(checked)] - state[0]).abs().max()) / max(scale, 1e-30)
+    out = {"checked_episodes": [int(my_eps[e]) for e in checked], "frames": n_frames, "grid": [batch.map_w, batch.map_h],
+           "synced": {k: v for k, v in path_check.summary(res).items() if k not in ("episodes", "frames", "synced")},
+           "back_to_back": {k: v for k, v in path_check.summary(res2).items() if k not in ("episodes", "frames", "synced")},
+           "back_to_back_counts_equal_all_episodes": all_counts_equal, "back_to_back_sums_drift_over_scale": sums_drift,
+           "tolerance": {"indices/counts/levels": "bit-exact", "sums": "max|a-b| <= 1e-5 * max|ref|"},
+           "seconds": round(time.perf_counter() - t0, 2)}
+    out["ok"] = bool(res["ok"] and res2["ok"] and all_counts_equal and sums_drift <= 1e-6)
+    return out
+
+
 def main_gpu(args, rank, local_rank, world):
     eod = importlib.import_module("embodied-object-detection_b200")
     sharding = eod.sharding
@@ -280,15 +322,8 @@ def main_gpu(args, rank, local_rank, world):
     barrier()
     launches0 = eod.ops.launch_count
     batch.profile(True)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        one_step()
-    ev1.record()
-    barrier()
+    ms_total = timed_steps(batch, args.steps, one_step, barrier, sharding, dev)
     clocks = sampler.stop()
-    ms_total = sharding.max_over_ranks(ev0.elapsed_time(ev1), dev)
     launches = eod.ops.launch_count - launches0
     stage_ms = batch.stage_ms()
     batch.profile(False)
@@ -303,17 +338,87 @@ def main_gpu(args, rank, local_rank, world):
     achieved = wbytes / (stage_ms["write"] * 1e-3) / 1e9 if stage_ms.get("write") else None
     path_gbs = frame_bytes(vis_per_frame) * (value / world) / 1e9
 
+    # ---- the dominant kernel alone, back to back, in the power state the timed loop left behind ----
+    write_alone = None
+    if not args.no_extras:
+        batch.join()
+        batch.project(depth[0], pose[0], shifts, intr, float(CELL))
+        batch._count(None)
+        n_alone = 20
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        batch._write(slabs[1], None)
+        a.record()
+        for i in range(n_alone):
+            batch._write(slabs[i & 1], None)
+        b.record()
+        torch.cuda.synchronize()
+        batch._finalize()
+        ms_alone = a.elapsed_time(b) / n_alone
+        write_alone = {"launch_ms": ms_alone, "GBps": wbytes / ms_alone / 1e6, "frac": wbytes / ms_alone / 1e6 / peak, "launches": n_alone,
+                       "note": "same kernel, same batch, nothing else resident: in-bench loss = overlap with read/count/expand/project of the "
+                               "neighbouring frames + SM clock under the power cap"}
+        batch.reset()
+
+    # ---- the same loop with projection + fusion of the three levels in every frame-step (north-star subsystem 4) ----
+    with_fusion = None
+    if not args.no_extras:
+        g = torch.Generator(device=dev).manual_seed(5 + rank)
+        N_OUT = 256
+        ws = [eod.ops.project_split_weights(torch.randn((N_OUT, C), device=dev, generator=g) / C ** 0.5) for _ in range(3)]
+        bias = [torch.randn((N_OUT,), device=dev, generator=g) for _ in range(3)]
+        res = [torch.randn((E, N_OUT, H >> s_, W >> s_), device=dev, generator=g) for s_ in (3, 4, 5)]   # the FPN's p3-p5 (timm.py:170-189)
+        outs = [torch.empty_like(r) for r in res]
+
+        def one_step_fused():
+            batch.reset()
+            for t in range(N_FRAMES):
+                levels = batch.step(depth[t], pose[t], shifts, intr, float(CELL), slabs[t & 1])
+                eod.ops.project_fuse_levels(levels, ws, bias, res, 5.0, 0, outs)
+            batch.join()
+
+        one_step_fused()
+        ms_f = timed_steps(batch, args.steps, one_step_fused, barrier, sharding, dev)
+        with_fusion = {"value": world * args.steps * E * N_FRAMES / (ms_f / 1e3), "unit": UNIT, "ms_per_step": ms_f / args.steps,
+                       "stages": "back-project -> read -> project+fuse (tcgen05, MAP_FEAT_FUSION sum, weight 5) -> write, every frame-step",
+                       "extra_bytes_per_frame": int(6300 * (C * 2 + 2 * N_OUT * 4))}
+        del res, outs
+
+    parity = None
+    if rank == 0 and not args.no_parity:
+        try:
+            parity = run_parity_check(batch, depth, pose, shifts, intr, float(CELL), slabs, depth_h, T.numpy(), shift_h, my_eps)
+        except Exception as exc:                                     # a failed check must be visible, never silently dropped
+            parity = {"ok": False, "error": repr(exc)[:300]}
+
     extras = run_extras(eod, batch, dev, depth, pose, shifts, intr) if (rank == 0 and not args.no_extras) else None
     if world > 1:
         torch.distributed.barrier()
     # ---- e2e through the plugin API with host buffers (rank-local, then max over ranks) ----
     e2e = None if args.no_e2e else run_e2e(eod, batch, dev, depth_h, pose.cpu(), shifts, intr, args, world, sharding, slabs)
+    e2e_variants = None
+    if not args.no_e2e and not args.no_extras:
+        try:
+            e2e_variants = run_e2e_variants(eod, batch, dev, depth_h, pose.cpu(), shifts, intr, args, world, sharding, slabs)
+        except Exception as exc:
+            e2e_variants = {"error": repr(exc)[:300]}
+
+    # ---- the north-star grid: 1000 x 1000 cells (0.2 m), same episodes, same timing method ----
+    roofline_1000 = None
+    if not args.no_extras:
+        try:
+            del batch
+            torch.cuda.empty_cache()
+            roofline_1000 = run_grid_1000(eod, dev, depth, pose, shift_h, intr, slabs, depth_h, T.numpy(), my_eps, args, barrier, sharding,
+                                          world, rank, peak)
+        except Exception as exc:
+            roofline_1000 = {"error": repr(exc)[:300]}
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": dict(workload_config(world), host_numa_node=numa_node), "clocks": clocks, "gpu_launches": int(launches),
-        "e2e": e2e, "extras": extras,
+        "data": "synthetic", "config": workload_config(world), "clocks": clocks, "gpu_launches": int(launches),
+        "e2e": e2e, "e2e_variants": e2e_variants, "value_with_fusion": with_fusion, "write_alone": write_alone, "parity_check": parity,
+        "roofline_1000": roofline_1000, "extras": extras, "host": {"numa_node": numa_node, "cpus": os.cpu_count()},
         "roofline": {"bound": "hbm", "kernel": "write_mean_chw_tma_kernel<256>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "frac_of_nominal_8TBs": (achieved / 8000.0) if achieved else None,
                      "traffic": measured_traffic(E), "peak_source": peak_src, "bytes_per_launch": wbytes, "launch_ms": stage_ms.get("write"),
@@ -329,6 +434,47 @@ def main_gpu(args, rank, local_rank, world):
                                              f"+ sparse-equivalent (index_add_) write; the literal one-hot matmul of the reference needs "
                                              f"{N_PIX * MAP_W * MAP_H / 1e9:.0f} GB at stride 1"}
         print(json.dumps(out))
+
+
+def run_grid_1000(eod, dev, depth, pose, shift_h, intr, slabs, depth_h, T_h, my_eps, args, barrier, sharding, world, rank, peak):
+    """BASELINE north-star target: 480x640, C=256 on a 1000x1000 grid.  Same 64 episodes per GPU (the depth maps are replayed
+    into the larger map: only map_world_shift changes), 0.2 m cells as everywhere in the reference's implicit memory
+    (SMNet/build_memory_data.py:136), same pipelined loop, CUDA events, stage events for the write launch."""
+    E, mw, mh = N_EPISODES, 1000, 1000
+    shift_1k = shift_h.copy()
+    shift_1k[:, 0] -= np.float32((mw - MAP_W) * float(CELL) / 2)
+    shift_1k[:, 2] -= np.float32((mh - MAP_H) * float(CELL) / 2)
+    shifts = torch.from_numpy(np.concatenate([np.zeros_like(shift_1k), shift_1k], 1)).to(dev)
+    batch = eod.EpisodeBatch(E, mw, mh, C, H, W, dev, pipeline=not args.no_pipeline)
+
+    def one_step():
+        batch.reset()
+        for t in range(N_FRAMES):
+            batch.step(depth[t], pose[t], shifts, intr, float(CELL), slabs[t & 1])
+        batch.join()
+
+    one_step()
+    one_step()
+    steps = max(2, min(args.steps, 5))
+    batch.profile(True)
+    ms = timed_steps(batch, steps, one_step, barrier, sharding, dev)
+    stage_ms = batch.stage_ms()
+    batch.profile(False)
+    vis = float(batch.counts.sum().item()) / (E * N_FRAMES)
+    wbytes = write_launch_bytes(E, vis * E)
+    value = world * steps * E * N_FRAMES / (ms / 1e3)
+    achieved = wbytes / stage_ms["write"] / 1e6
+    out = {"grid": [mw, mh], "cell_m": float(CELL), "channels": C, "episodes_per_gpu": E, "value": value, "unit": UNIT, "steps": steps,
+           "ms_per_step": ms / steps, "kernel": "write_mean_chw_tma_kernel<256>", "achieved": achieved, "peak": peak, "frac": achieved / peak,
+           "bytes_per_launch": wbytes, "launch_ms": stage_ms["write"], "stage_ms": stage_ms, "visible_cells_per_frame": vis,
+           "whole_path_frac": frame_bytes(vis) * (value / world) / 1e9 / peak,
+           "resident_bytes": int(batch.sums.numel() * 4 + batch.norm16.numel() * 2 + batch.counts.numel() * 4)}
+    if rank == 0 and not args.no_parity:
+        try:
+            out["parity_check"] = run_parity_check(batch, depth, pose, shifts, intr, float(CELL), slabs, depth_h, T_h, shift_1k, my_eps, n_frames=2)
+        except Exception as exc:
+            out["parity_check"] = {"ok": False, "error": repr(exc)[:300]}
+    return out
 
 
 def run_extras(eod, batch, dev, depth, pose, shifts, intr):
@@ -445,8 +591,129 @@ def run_e2e(eod, batch, dev, depth_h, pose_h, shifts, intr, args, world, shardin
     return {"value": world * frames_per_step * args.e2e_steps / sec, "unit": UNIT,
             "h2d_bytes_per_step": int(h2d * args.e2e_frames), "d2h_bytes_per_step": int(d2h * args.e2e_frames),
             "frames_per_step": frames_per_step, "steps": args.e2e_steps,
+            "h2d_GBps_per_rank": h2d * args.e2e_frames * args.e2e_steps / sec / 1e9,
             "note": "bounded: e2e step = %d frame-steps of the 64-episode batch; PCIe-bound (features cross the bus, which the "
                     "reference never does: its features are produced on the device)" % args.e2e_frames}
+
+
+def h2d_ceiling(dev, world, sharding, nbytes=1 << 30, reps=6):
+    """What this rank's PCIe link + host memory deliver while EVERY rank copies at once: plain cudaMemcpyAsync of a pinned
+    1 GiB buffer, all ranks started together.  The dense e2e arm cannot beat this number; it explains N-GPU e2e scaling."""
+    pin = torch.empty((nbytes,), dtype=torch.uint8).pin_memory()
+    dst = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+    dst.copy_(pin, non_blocking=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        dst.copy_(pin, non_blocking=True)
+    torch.cuda.synchronize()
+    sec = sharding.max_over_ranks(time.perf_counter() - t0, dev)
+    return nbytes * reps / sec / 1e9
+
+
+def run_e2e_variants(eod, batch, dev, depth_h, pose_h, shifts, intr, args, world, sharding, slabs):
+    """Two more end-to-end arms through the public API with HOST inputs (wall clock, max over ranks), plus the H2D ceiling:
+      dense_bf16_hwc  features uploaded as channels-last bf16 (EOD_LAYOUT_HWC_BF16: what a bf16 backbone emits, BASELINE
+                      configs[3]); the arithmetic stays fp32 after an exact widening - half the bytes on the bus;
+      object_regime   the reference's live regime through step_detections: per frame-step depth, pose, <=16 kept detections
+                      ((K,C) features, 28x28 mask probabilities, boxes) go up, the coarsest pooled level comes back."""
+    E = batch.E
+    out = {"h2d_ceiling_GBps_per_rank_all_ranks_busy": h2d_ceiling(dev, world, sharding)}
+    comp_s = torch.cuda.current_stream(dev)
+    copy_s = torch.cuda.Stream(device=dev)
+    n_fr = args.e2e_frames
+    pin_depth = torch.from_numpy(depth_h).permute(1, 0, 2, 3).contiguous().pin_memory()      # (T, E, H, W)
+    pin_pose = pose_h.contiguous().pin_memory()
+    dev_depth = [torch.empty((E, H, W), device=dev) for _ in range(2)]
+    dev_pose = [torch.empty((E, 12), device=dev) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+
+    def run(upload_extra, step_fn, d2h_fn, n_frames):
+        def upload(t, b):
+            with torch.cuda.stream(copy_s):
+                copy_s.wait_event(freed[b])
+                dev_depth[b].copy_(pin_depth[t % N_FRAMES], non_blocking=True)
+                dev_pose[b].copy_(pin_pose[t % N_FRAMES], non_blocking=True)
+                upload_extra(t, b)
+                ready[b].record(copy_s)
+
+        def one():
+            batch.reset()
+            upload(0, 0)
+            for t in range(n_frames):
+                b = t & 1
+                if t + 1 < n_frames:
+                    upload(t + 1, b ^ 1)
+                comp_s.wait_event(ready[b])
+                step_fn(b)
+                d2h_fn()
+                freed[b].record(comp_s)
+            torch.cuda.synchronize()
+
+        for f in freed:
+            f.record(comp_s)
+        one()
+        if world > 1:
+            torch.distributed.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            one()
+        return sharding.max_over_ranks(time.perf_counter() - t0, dev)
+
+    batch.join()
+    batch.pipeline = False
+    # ---- dense, bf16 channels-last upload ----
+    g = torch.Generator().manual_seed(11)
+    n_slots = 4
+    pin_feat = torch.randn((n_slots, H, W, C), generator=g).to(torch.bfloat16).pin_memory()
+    dev_feat = [torch.empty((E, H, W, C), dtype=torch.bfloat16, device=dev) for _ in range(2)]
+    host_levels = [torch.empty(l.shape, dtype=l.dtype).pin_memory() for l in batch.levels]
+    layout0 = batch.layout
+    batch.layout = eod._lib.LAYOUT_HWC_BF16
+
+    def up_feat(t, b):
+        for e in range(E):
+            dev_feat[b][e].copy_(pin_feat[(e + t) % n_slots], non_blocking=True)
+
+    def d2h_levels():
+        for hl, l in zip(host_levels, batch.levels):
+            hl.copy_(l, non_blocking=True)
+
+    sec = run(up_feat, lambda b: batch.step(dev_depth[b], dev_pose[b], shifts, intr, float(CELL), dev_feat[b]), d2h_levels, n_fr)
+    batch.layout = layout0
+    h2d = E * (C * H * W * 2 + H * W * 4 + 48)
+    out["dense_bf16_hwc"] = {"value": world * E * n_fr * args.e2e_steps / sec, "unit": UNIT, "h2d_bytes_per_step": int(h2d * n_fr),
+                             "d2h_bytes_per_step": int(sum(l.numel() * 2 for l in batch.levels) * n_fr),
+                             "h2d_GBps_per_rank": h2d * n_fr * args.e2e_steps / sec / 1e9}
+    del dev_feat, pin_feat
+    # ---- object regime ----
+    rng = np.random.default_rng(3)
+    Kmax, n_var = 16, 4
+    bf = np.zeros((n_var, E, Kmax, C), np.float32); pr = np.zeros((n_var, E, Kmax, 28, 28), np.float32); bx = np.zeros((n_var, E, Kmax, 4), np.float32)
+    n = np.zeros((n_var, E), np.int32)
+    for v in range(n_var):
+        for e in range(E):
+            f, p_, b_ = eod.episodes.make_mask_head_detections(rng, H, W, C, (4, Kmax), 28)
+            n[v, e] = f.shape[0]; bf[v, e, : n[v, e]], pr[v, e, : n[v, e]], bx[v, e, : n[v, e]] = f, p_, b_
+    pin_det = [torch.from_numpy(x).pin_memory() for x in (bf, pr, bx, n)]
+    dev_det = [[torch.empty(x.shape[1:], dtype=x.dtype, device=dev) for x in pin_det] for _ in range(2)]
+    host_l2 = torch.empty(batch.levels[2].shape, dtype=torch.float16).pin_memory()
+
+    def up_det(t, b):
+        for d, p_ in zip(dev_det[b], pin_det):
+            d.copy_(p_[t % n_var], non_blocking=True)
+
+    n_fr_obj = 5 * n_fr
+    sec = run(up_det, lambda b: batch.step_detections(dev_depth[b], dev_pose[b], shifts, intr, float(CELL), *dev_det[b]),
+              lambda: host_l2.copy_(batch.levels[2], non_blocking=True), n_fr_obj)
+    h2d = E * (H * W * 4 + 48) + sum(int(x[0].numel() * x.element_size()) for x in pin_det)
+    out["object_regime"] = {"value": world * E * n_fr_obj * args.e2e_steps / sec, "unit": UNIT, "ms_per_frame_step": 1e3 * sec / (n_fr_obj * args.e2e_steps),
+                            "h2d_bytes_per_step": int(h2d * n_fr_obj), "d2h_bytes_per_step": int(host_l2.numel() * 2 * n_fr_obj),
+                            "shape": f"E={E}, C={C}, <= {Kmax} detections per frame; D2H = the coarsest pooled level (15x20) per frame-step"}
+    return out
 
 
 def main():
@@ -461,6 +728,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--write-variant", type=int, default=0, help="diagnostics: 0 auto, 1 LDG, 2 TMA, 3 TMA dry (no result)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the post-run oracle check of the benchmarked path")
     ap.add_argument("--no-extras", action="store_true", help="skip the projection+fusion and object-regime stage timings")
     ap.add_argument("--no-numa", action="store_true", help="diagnostics: do not bind the rank to its GPU's NUMA node")
     ap.add_argument("--no-pipeline", action="store_true", help="diagnostics: stream-ordered EpisodeBatch.step (no cross-frame overlap)")

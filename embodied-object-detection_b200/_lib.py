@@ -28,7 +28,7 @@ SIGNATURES = {
     "eod_sample_mask": [_P, c_int, c_int, c_int, _P, _P, _P],
     "eod_frame_count": [_P, _P, _P, c_int, c_int, c_int64, _P, _P, _P, _P, c_int, _P],
     "eod_expand_counts": [_P, _P, c_int, c_int, c_int64, _P, _P],
-    "eod_write_mean": [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int64, _P, c_int, _P, _P],
+    "eod_write_mean": [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int64, _P, c_int, _P, _P, _P],
     "eod_write_mean_det_workspace_bytes": [c_int, c_int, c_int, c_int64, c_int],
     "eod_write_mean_det_status_offset": [c_int, c_int64],
     "eod_write_mean_det": [_P, _P, _P, _P, c_int, c_int, c_int, c_int64, _P, _P, c_int64, _P],
@@ -46,6 +46,9 @@ SIGNATURES = {
     "eod_semmap_update": [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int64, _P, _P, _P],
     "eod_semmap_decode": [_P, _P, c_int, c_int64, c_float, _P, _P, _P],
     "eod_reset_touched": [_P, _P, _P, c_int64, c_int, _P],
+    "eod_reset_episodes": [_P, _P, _P, _P, c_int, c_int64, c_int, _P],
+    "eod_refresh_norm16": [_P, _P, _P, _P, c_int, c_int64, c_int, _P],
+    "eod_check_indices": [_P, c_int, c_int64, c_int64, _P, _P, _P],
     "eod_project_split_weights": [_P, c_int, c_int, _P, _P],
     "eod_project_fuse_levels": [c_int, _P, _P, _P, _P, _P, _P, c_float, c_int, c_int, c_int, c_int, c_int, _P],
     "eod_project_fuse": [_P, _P, _P, _P, c_float, c_int, c_int, c_int, c_int, c_int, _P, _P],

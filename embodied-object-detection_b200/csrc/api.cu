@@ -26,11 +26,13 @@ int eod_check_launch(const char *what)
 
 int eod_num_sms()
 {
-    static int n = 0;
+    static int cache[64] = {0};                 // per device ordinal (a process may drive several GPUs)
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    int &n = cache[dev & 63];
     if (!n) {
-        int dev = 0, v = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) n = v;
-        else n = EOD_NUM_SMS_FALLBACK;
+        int v = 0;
+        n = (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) ? v : EOD_NUM_SMS_FALLBACK;
     }
     return n;
 }

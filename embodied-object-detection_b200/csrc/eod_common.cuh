@@ -23,6 +23,25 @@ int eod_num_sms();
 
 static inline bool eod_aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: `done` is a per-kernel bitmask over device
+// ordinals (one bit per device of the process), so a second GPU used from the same process gets the attribute too.
+// Returns EOD_OK or EOD_ERR_LAUNCH (message set).  Racing threads at worst set the attribute twice.
+template <typename F>
+static inline int eod_ensure_dyn_smem(F func, int bytes, unsigned long long *done, const char *what)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (__atomic_load_n(done, __ATOMIC_ACQUIRE) & bit) return EOD_OK;
+    const cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) {
+        eod_set_error("%s: cannot raise dynamic shared memory to %d bytes: %s", what, bytes, cudaGetErrorString(e));
+        return EOD_ERR_LAUNCH;
+    }
+    __atomic_fetch_or(done, bit, __ATOMIC_RELEASE);
+    return EOD_OK;
+}
+
 // ---- device helpers -------------------------------------------------------------------------------
 
 // 128-bit fp32 reduction to global memory (sm_90+): one L2 atomic transaction for four floats.

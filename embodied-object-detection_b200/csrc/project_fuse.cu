@@ -491,12 +491,9 @@ int pf_launch_v1(const void *level, const void *w_split, const float *bias, cons
     if (rc) return rc;
     rc = pf_make_tmap(w_split, 2 * (int64_t)N, K, 2 * PF_BN, &tm_b);
     if (rc) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(project_fuse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM_BYTES);
-        cudaFuncSetAttribute(project_fuse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM_BYTES);
-        attr_set = true;
-    }
+    static unsigned long long attr_done[2] = {0ull, 0ull};
+    if (int rc_attr = eod_ensure_dyn_smem(project_fuse_kernel<true>, PF_SMEM_BYTES, &attr_done[0], "eod_project_fuse")) return rc_attr;
+    if (int rc_attr = eod_ensure_dyn_smem(project_fuse_kernel<false>, PF_SMEM_BYTES, &attr_done[1], "eod_project_fuse")) return rc_attr;
     const unsigned grid = (unsigned)((M + PF_BM - 1) / PF_BM) * (unsigned)(N / PF_BN);
     if (mode == EOD_FUSE_SUM)
         project_fuse_kernel<true><<<grid, 128, PF_SMEM_BYTES, st>>>(tm_a, tm_b, bias, res, out, weight, M, hw, N, K / PF_BK);
@@ -566,12 +563,9 @@ extern "C" int eod_project_fuse_levels(int n_levels, const void *const *level, c
     }
     for (int l = n_levels; l <= P2_MAX_LEVELS; ++l) P.tile_start[l] = tiles;
     P.n_tiles = tiles;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(project_fuse_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES);
-        cudaFuncSetAttribute(project_fuse_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES);
-        attr_set = true;
-    }
+    static unsigned long long attr_done[2] = {0ull, 0ull};
+    if (int rc_attr = eod_ensure_dyn_smem(project_fuse_persistent_kernel<true>, P2_SMEM_BYTES, &attr_done[0], "eod_project_fuse_levels")) return rc_attr;
+    if (int rc_attr = eod_ensure_dyn_smem(project_fuse_persistent_kernel<false>, P2_SMEM_BYTES, &attr_done[1], "eod_project_fuse_levels")) return rc_attr;
     const int grid = tiles < eod_num_sms() ? tiles : eod_num_sms();
     if (mode == EOD_FUSE_SUM) project_fuse_persistent_kernel<true><<<grid, P2_THREADS, P2_SMEM_BYTES, st>>>(P);
     else project_fuse_persistent_kernel<false><<<grid, P2_THREADS, P2_SMEM_BYTES, st>>>(P);

@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(256) max_pass1_kernel(const float *__restrict_
     const size_t g = (size_t)e * H * W + p;
     if (outlier && __ldg(outlier + g)) return;
     const float h = __fadd_rn(__ldg(height + g), 1000.0f);
+    if (h != h) return;          // NaN never satisfies `src >= out`: it may neither raise the cell nor shadow the finite candidates
     const unsigned long long key = ((unsigned long long)orderable(h) << 32) | (unsigned)(p + 1);
     atomicMax(key64 + (size_t)e * n_cells + __ldg(idx + g), key);
 }

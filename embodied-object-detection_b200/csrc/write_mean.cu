@@ -6,13 +6,14 @@
 //
 // The main pass streams the per-pixel feature tensor exactly once (N*C*4 bytes per frame - the term that
 // bounds the whole path) and is written for HBM bandwidth:
-//   * CHW features (the reference's (1,C,480,640) layout): a persistent CTA per SM walks 32-pixel tiles;
-//     a producer warp issues ONE 3-D TMA box load (32 px x C channels, 128B-swizzled) + a 128 B bulk copy
-//     of the tile's cell indices per stage into a 3..6-deep mbarrier ring; consumer thread c owns channel
-//     c, reads its pixels with conflict-free LDS.128, and accumulates each run of equal cell id in a
-//     register (neighbouring pixels fall into the same map cell); a run leaves the SM as one
-//     red.global.add.f32 per channel (a warp covers 128 contiguous bytes of the cell row) - one L2
-//     reduction per run instead of one per pixel.
+//   * CHW features (the reference's (1,C,480,640) layout): a persistent CTA per SM, 12 consumer warps + 1 producer
+//     warp.  Unit of work = (32-pixel tile, 128-channel block) = one 16 KB 3-D TMA box (128B-swizzled) plus bulk
+//     copies of the tile's cell ids / sample mask / reciprocal divisors; unit u lands in ring stage u % 12 and is
+//     consumed by warp u % 12 (every consumer warp owns one stage: the full/empty mbarrier pair of the stage is the
+//     only synchronisation).  Lane l sums channels l, l+32, l+64, l+96 over each run of equal cell id with
+//     conflict-free LDS.128 (neighbouring pixels fall into the same map cell) and the run leaves the SM as four
+//     warp-wide red.global.add.f32 (128 contiguous bytes of the cell row each) - one L2 reduction per run and
+//     channel instead of one per pixel.  Details and measurements: DESIGN.md 3.1.
 //   * an LDG-staged variant of the same algorithm (padded smem tile) handles shapes the TMA path does
 //     not (HW % 32 != 0) and is the bring-up comparator (variant = EOD_WRITE_LDG).
 //   * HWC features: a warp walks a strip of pixels, lanes own float4 channel groups, runs accumulate in
@@ -442,7 +443,7 @@ __device__ __forceinline__ void tile_masks(const int *s_cells, const uint8_t *s_
 template <int C>
 __global__ void __launch_bounds__(C) write_mean_chw_ldg_kernel(const float *__restrict__ feat, const int32_t *__restrict__ idx,
                                                                const uint8_t *__restrict__ samp, const uint32_t *__restrict__ frame_cnt,
-                                                               int HW, int64_t n_cells, int tiles_per_ep, int n_tiles,
+                                                               const int32_t *__restrict__ active, int HW, int64_t n_cells, int tiles_per_ep, int n_tiles,
                                                                float *__restrict__ sums)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -454,6 +455,7 @@ __global__ void __launch_bounds__(C) write_mean_chw_ldg_kernel(const float *__re
 
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const int e = t / tiles_per_ep, p0 = (t - e * tiles_per_ep) * TILE_PX;
+        if (active && __ldg(active + e) <= 0) continue;              // CTA-uniform: an idle slot of the batch is not even read
         const int pvalid = min(TILE_PX, HW - p0);
         const float *feat_e = feat + (size_t)e * C * HW;
         // coalesced 128 B row segments: warp w loads channels w, w+NW, ...
@@ -572,8 +574,8 @@ struct DetArgs {
 template <int C, bool kDry, bool kPixN, bool kDet>
 __global__ void __launch_bounds__(TmaCfg<C>::kThreads, 1)
 write_mean_chw_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t *__restrict__ idx, const uint8_t *__restrict__ samp,
-                          const uint32_t *__restrict__ frame_cnt, const float *__restrict__ pix_n, int HW, int64_t n_cells,
-                          int tiles_per_ep, int n_tiles, int group, float *__restrict__ sums, const DetArgs det)
+                          const uint32_t *__restrict__ frame_cnt, const float *__restrict__ pix_n, const int32_t *__restrict__ active, int HW,
+                          int64_t n_cells, int tiles_per_ep, int n_tiles, int group, float *__restrict__ sums, const DetArgs det)
 {
     using Cfg = TmaCfg<C>;
     extern __shared__ unsigned char smem_dyn[];
@@ -623,11 +625,16 @@ write_mean_chw_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int32_
                 const int e = t / tiles_per_ep, p0 = (t - e * tiles_per_ep) * TILE_PX;
                 const uint32_t fullb = full0 + 8 * stage, aux = aux0 + stage * Cfg::kAuxBytes;
                 mbar_wait_s(empty0 + 8 * stage, phase ^ 1);
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fullb), "r"(tx) : "memory");
-                tma_load_3d_hint(base + stage * Cfg::kUnitBytes, &tmap, p0, cb * Cfg::kChanBlk, e, fullb, pol);
-                bulk_load_1d_s(aux + Cfg::kAuxCells, idx + (size_t)e * HW + p0, TILE_PX * 4, fullb);
-                if (has_samp) bulk_load_1d_s(aux + Cfg::kAuxSamp, samp + (size_t)e * HW + p0, TILE_PX, fullb);
-                if (kPixN) bulk_load_1d_s(aux + Cfg::kAuxPixN, pix_n + (size_t)e * HW + p0, TILE_PX * 4, fullb);
+                if (active && __ldg(active + e) <= 0) {
+                    // idle slot of the batch: the stage is handed over empty (keeps the unit -> stage mapping), nothing is fetched
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fullb) : "memory");
+                } else {
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fullb), "r"(tx) : "memory");
+                    tma_load_3d_hint(base + stage * Cfg::kUnitBytes, &tmap, p0, cb * Cfg::kChanBlk, e, fullb, pol);
+                    bulk_load_1d_s(aux + Cfg::kAuxCells, idx + (size_t)e * HW + p0, TILE_PX * 4, fullb);
+                    if (has_samp) bulk_load_1d_s(aux + Cfg::kAuxSamp, samp + (size_t)e * HW + p0, TILE_PX, fullb);
+                    if (kPixN) bulk_load_1d_s(aux + Cfg::kAuxPixN, pix_n + (size_t)e * HW + p0, TILE_PX * 4, fullb);
+                }
                 if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
             }
         }
@@ -644,8 +651,9 @@ write_mean_chw_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int32_
         int t, cb;
         unit_of(u, t, cb);
         int run_pos = kDet ? __ldg(det.tile_off + t) : 0;          // issued before the wait: its latency hides behind the TMA load
+        const bool idle = active && __ldg(active + t / tiles_per_ep) <= 0;
         mbar_wait_s(fullb, phase);
-        if (!kDry) {
+        if (!kDry && !idle) {
             const int e = t / tiles_per_ep;
             // run structure of the tile: lane p looks at pixel p
             const int cell = (int)lds32(aux + Cfg::kAuxCells + 4 * lane);
@@ -738,14 +746,15 @@ __device__ __forceinline__ float4 widen_feat(const FeatRaw<F> &r)
 template <int C, int F>
 __global__ void __launch_bounds__(256, 3) write_mean_hwc_kernel(const void *__restrict__ feat, const int32_t *__restrict__ idx,
                                                              const uint8_t *__restrict__ samp, const uint32_t *__restrict__ frame_cnt,
-                                                             int HW, int64_t n_cells, int strips_per_ep, int n_strips,
-                                                             float *__restrict__ sums)
+                                                             const int32_t *__restrict__ active, int HW, int64_t n_cells, int strips_per_ep,
+                                                             int n_strips, float *__restrict__ sums)
 {
     constexpr int V = C / 128;                 // float4 per lane per pixel
     const unsigned lane = threadIdx.x & 31;
     const int warps_total = gridDim.x * (blockDim.x >> 5);
     for (int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); s < n_strips; s += warps_total) {
         const int e = s / strips_per_ep, p0 = (s - e * strips_per_ep) * TILE_PX;
+        if (active && __ldg(active + e) <= 0) continue;              // warp-uniform: idle slot of the batch
         const int pvalid = min(TILE_PX, HW - p0);
         const size_t pix0 = (size_t)e * HW + p0;
         const int my_cell = (int)lane < pvalid ? __ldg(idx + pix0 + lane) : -1;
@@ -830,21 +839,18 @@ PFN_encodeTiled get_encode_fn()
 
 template <int C, bool kDry, bool kPixN, bool kDet = false>
 int launch_tma_kernel(const CUtensorMap &tmap, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt, const float *pix_n,
-                      int E, int HW, int64_t n_cells, float *sums, cudaStream_t st, const DetArgs det = DetArgs{})
+                      const int32_t *active, int E, int HW, int64_t n_cells, float *sums, cudaStream_t st, const DetArgs det = DetArgs{})
 {
     using Cfg = TmaCfg<C>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(write_mean_chw_tma_kernel<C, kDry, kPixN, kDet>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-        attr_set = true;
-    }
+    static unsigned long long attr_done = 0ull;
+    if (int rc_attr = eod_ensure_dyn_smem(write_mean_chw_tma_kernel<C, kDry, kPixN, kDet>, Cfg::kSmemBytes, &attr_done, "eod_write_mean[tma]")) return rc_attr;
     const int tiles_per_ep = HW / TILE_PX, n_tiles = tiles_per_ep * E;
     static const int group_env = [] { const char *v = getenv("EOD_TMA_TILE_GROUP"); return v ? atoi(v) : 2; }();   // tuning knob: 1 | 2 | 4 | 8
     int group = (group_env == 1 || group_env == 2 || group_env == 4 || group_env == 8) ? group_env : 2;
     while (group > 1 && n_tiles % group) group >>= 1;
     const int n_groups = n_tiles / group;
     const int grid = n_groups < eod_num_sms() ? n_groups : eod_num_sms();
-    write_mean_chw_tma_kernel<C, kDry, kPixN, kDet><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmap, idx, samp, frame_cnt, pix_n, HW, n_cells, tiles_per_ep, n_tiles, group, sums, det);
+    write_mean_chw_tma_kernel<C, kDry, kPixN, kDet><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmap, idx, samp, frame_cnt, pix_n, active, HW, n_cells, tiles_per_ep, n_tiles, group, sums, det);
     return eod_check_launch("eod_write_mean[tma]");
 }
 
@@ -868,14 +874,14 @@ int make_feature_tmap(const float *feat, int E, int HW, CUtensorMap *tmap)
 }
 
 template <int C, bool kDry>
-int launch_tma(const float *feat, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt, const float *pix_n, int E, int HW,
-               int64_t n_cells, float *sums, cudaStream_t st)
+int launch_tma(const float *feat, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt, const float *pix_n, const int32_t *active,
+               int E, int HW, int64_t n_cells, float *sums, cudaStream_t st)
 {
     CUtensorMap tmap;
     const int rc = make_feature_tmap<C>(feat, E, HW, &tmap);
     if (rc) return rc;
-    if (pix_n) return launch_tma_kernel<C, kDry, true>(tmap, idx, samp, frame_cnt, pix_n, E, HW, n_cells, sums, st);
-    return launch_tma_kernel<C, kDry, false>(tmap, idx, samp, frame_cnt, nullptr, E, HW, n_cells, sums, st);
+    if (pix_n) return launch_tma_kernel<C, kDry, true>(tmap, idx, samp, frame_cnt, pix_n, active, E, HW, n_cells, sums, st);
+    return launch_tma_kernel<C, kDry, false>(tmap, idx, samp, frame_cnt, nullptr, active, E, HW, n_cells, sums, st);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -1340,7 +1346,7 @@ int launch_det(const float *feat, const int32_t *idx, const uint8_t *samp, const
     det_scan_list_kernel<<<E, 1024, 0, st>>>(w.cell_runs, w.cell_list, w.n_list, w.cap, n_cells, w.list_off, w.cell_off);
     if ((rc = eod_check_launch("eod_write_mean_det[prepass]"))) return rc;
     DetArgs det{w.tile_off, w.partials, w.run_cell, w.status, w.cap};
-    rc = launch_tma_kernel<C, false, false, true>(tmap, idx, samp, frame_cnt, nullptr, E, HW, n_cells, sums, st, det);
+    rc = launch_tma_kernel<C, false, false, true>(tmap, idx, samp, frame_cnt, nullptr, nullptr, E, HW, n_cells, sums, st, det);
     if (rc) return rc;
     dim3 gc((w.cap + 255) / 256, E);
     det_claim_kernel<<<gc, 256, 0, st>>>(w.run_cell, w.n_runs, w.cap, n_cells, w.cell_off, w.cell_runs, w.seg);
@@ -1359,46 +1365,43 @@ int launch_det(const float *feat, const int32_t *idx, const uint8_t *samp, const
 }
 
 template <int C>
-int launch_ldg(const float *feat, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt, int E, int HW,
+int launch_ldg(const float *feat, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt, const int32_t *active, int E, int HW,
                int64_t n_cells, float *sums, cudaStream_t st)
 {
     const int smem = C * TILE_PX * 4 + TILE_PX * 4 + TILE_PX;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(write_mean_chw_ldg_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        attr_set = true;
-    }
+    static unsigned long long attr_done = 0ull;
+    if (int rc_attr = eod_ensure_dyn_smem(write_mean_chw_ldg_kernel<C>, smem, &attr_done, "eod_write_mean[ldg]")) return rc_attr;
     const int tiles_per_ep = (HW + TILE_PX - 1) / TILE_PX, n_tiles = tiles_per_ep * E;
     const int per_sm = (C >= 512) ? 3 : (C == 256 ? 6 : 8);
     const int grid = min(n_tiles, eod_num_sms() * per_sm);
-    write_mean_chw_ldg_kernel<C><<<grid, C, smem, st>>>(feat, idx, samp, frame_cnt, HW, n_cells, tiles_per_ep, n_tiles, sums);
+    write_mean_chw_ldg_kernel<C><<<grid, C, smem, st>>>(feat, idx, samp, frame_cnt, active, HW, n_cells, tiles_per_ep, n_tiles, sums);
     return eod_check_launch("eod_write_mean[ldg]");
 }
 
 template <int C>
-int launch_hwc(const void *feat, int feat_type, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt, int E, int HW,
-               int64_t n_cells, float *sums, cudaStream_t st)
+int launch_hwc(const void *feat, int feat_type, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt, const int32_t *active, int E,
+               int HW, int64_t n_cells, float *sums, cudaStream_t st)
 {
     const int strips_per_ep = (HW + TILE_PX - 1) / TILE_PX, n_strips = strips_per_ep * E;
     const int blocks = min((n_strips + 7) / 8, eod_num_sms() * 8);
-    if (feat_type == FEAT_BF16) write_mean_hwc_kernel<C, FEAT_BF16><<<blocks, 256, 0, st>>>(feat, idx, samp, frame_cnt, HW, n_cells, strips_per_ep, n_strips, sums);
-    else if (feat_type == FEAT_F16) write_mean_hwc_kernel<C, FEAT_F16><<<blocks, 256, 0, st>>>(feat, idx, samp, frame_cnt, HW, n_cells, strips_per_ep, n_strips, sums);
-    else write_mean_hwc_kernel<C, FEAT_F32><<<blocks, 256, 0, st>>>(feat, idx, samp, frame_cnt, HW, n_cells, strips_per_ep, n_strips, sums);
+    if (feat_type == FEAT_BF16) write_mean_hwc_kernel<C, FEAT_BF16><<<blocks, 256, 0, st>>>(feat, idx, samp, frame_cnt, active, HW, n_cells, strips_per_ep, n_strips, sums);
+    else if (feat_type == FEAT_F16) write_mean_hwc_kernel<C, FEAT_F16><<<blocks, 256, 0, st>>>(feat, idx, samp, frame_cnt, active, HW, n_cells, strips_per_ep, n_strips, sums);
+    else write_mean_hwc_kernel<C, FEAT_F32><<<blocks, 256, 0, st>>>(feat, idx, samp, frame_cnt, active, HW, n_cells, strips_per_ep, n_strips, sums);
     return eod_check_launch("eod_write_mean[hwc]");
 }
 
 template <int C>
-int dispatch(const float *feat, int layout, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt, const float *pix_n, int E, int HW,
-             int64_t n_cells, float *sums, int variant, cudaStream_t st)
+int dispatch(const float *feat, int layout, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt, const float *pix_n,
+             const int32_t *active, int E, int HW, int64_t n_cells, float *sums, int variant, cudaStream_t st)
 {
-    if (layout == EOD_LAYOUT_HWC) return launch_hwc<C>(feat, FEAT_F32, idx, samp, frame_cnt, E, HW, n_cells, sums, st);
-    if (layout == EOD_LAYOUT_HWC_BF16) return launch_hwc<C>(feat, FEAT_BF16, idx, samp, frame_cnt, E, HW, n_cells, sums, st);
-    if (layout == EOD_LAYOUT_HWC_F16) return launch_hwc<C>(feat, FEAT_F16, idx, samp, frame_cnt, E, HW, n_cells, sums, st);
+    if (layout == EOD_LAYOUT_HWC) return launch_hwc<C>(feat, FEAT_F32, idx, samp, frame_cnt, active, E, HW, n_cells, sums, st);
+    if (layout == EOD_LAYOUT_HWC_BF16) return launch_hwc<C>(feat, FEAT_BF16, idx, samp, frame_cnt, active, E, HW, n_cells, sums, st);
+    if (layout == EOD_LAYOUT_HWC_F16) return launch_hwc<C>(feat, FEAT_F16, idx, samp, frame_cnt, active, E, HW, n_cells, sums, st);
     const bool tma_ok = (HW % TILE_PX == 0) && (!samp || (reinterpret_cast<uintptr_t>(samp) % 16 == 0));
     if (variant == EOD_WRITE_TMA || variant == EOD_WRITE_TMA_DRY) EOD_REQUIRE(tma_ok, EOD_ERR_UNSUPPORTED, "eod_write_mean: TMA variant needs HW %% 32 == 0");
-    if (variant == EOD_WRITE_TMA_DRY) return launch_tma<C, true>(feat, idx, samp, frame_cnt, pix_n, E, HW, n_cells, sums, st);
-    if (variant == EOD_WRITE_LDG || !tma_ok) return launch_ldg<C>(feat, idx, samp, frame_cnt, E, HW, n_cells, sums, st);
-    return launch_tma<C, false>(feat, idx, samp, frame_cnt, pix_n, E, HW, n_cells, sums, st);
+    if (variant == EOD_WRITE_TMA_DRY) return launch_tma<C, true>(feat, idx, samp, frame_cnt, pix_n, active, E, HW, n_cells, sums, st);
+    if (variant == EOD_WRITE_LDG || !tma_ok) return launch_ldg<C>(feat, idx, samp, frame_cnt, active, E, HW, n_cells, sums, st);
+    return launch_tma<C, false>(feat, idx, samp, frame_cnt, pix_n, active, E, HW, n_cells, sums, st);
 }
 
 }  // namespace
@@ -1490,7 +1493,7 @@ extern "C" int eod_expand_counts(const int32_t *idx, const uint32_t *frame_cnt, 
 
 extern "C" int eod_write_mean(const void *feat_any, int layout, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt,
                               int n_episodes, int C, int HW, int64_t n_cells, float *sums, int variant, const float *pix_inv_n,
-                              eod_stream_t stream)
+                              const int32_t *active, eod_stream_t stream)
 {
     const float *feat = reinterpret_cast<const float *>(feat_any);
     EOD_REQUIRE(!pix_inv_n || eod_aligned16(pix_inv_n), EOD_ERR_ALIGN, "eod_write_mean: pix_inv_n must be 16-byte aligned");
@@ -1502,9 +1505,9 @@ extern "C" int eod_write_mean(const void *feat_any, int layout, const int32_t *i
     EOD_REQUIRE(layout != EOD_LAYOUT_CHW || HW % 4 == 0, EOD_ERR_ALIGN, "eod_write_mean: CHW rows must be 16-byte aligned (HW %% 4 == 0)");
     cudaStream_t st = (cudaStream_t)stream;
     switch (C) {
-    case 128: return dispatch<128>(feat, layout, idx, samp, frame_cnt, pix_inv_n, n_episodes, HW, n_cells, sums, variant, st);
-    case 256: return dispatch<256>(feat, layout, idx, samp, frame_cnt, pix_inv_n, n_episodes, HW, n_cells, sums, variant, st);
-    case 512: return dispatch<512>(feat, layout, idx, samp, frame_cnt, pix_inv_n, n_episodes, HW, n_cells, sums, variant, st);
+    case 128: return dispatch<128>(feat, layout, idx, samp, frame_cnt, pix_inv_n, active, n_episodes, HW, n_cells, sums, variant, st);
+    case 256: return dispatch<256>(feat, layout, idx, samp, frame_cnt, pix_inv_n, active, n_episodes, HW, n_cells, sums, variant, st);
+    case 512: return dispatch<512>(feat, layout, idx, samp, frame_cnt, pix_inv_n, active, n_episodes, HW, n_cells, sums, variant, st);
     default:
         eod_set_error("eod_write_mean: C=%d not compiled in (128, 256, 512)", C);
         return EOD_ERR_UNSUPPORTED;

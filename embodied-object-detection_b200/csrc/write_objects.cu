@@ -40,7 +40,11 @@ struct PasteObj {
     int rx0, ry0, rx1, ry1;    // integer region [rx0, rx1) x [ry0, ry1) outside of which the pasted mask is False
 };
 
-__device__ __forceinline__ PasteObj paste_prepare(const float *__restrict__ box, int H, int W)
+// thr >= 0.5: the integer neighbourhood of the box (detectron2's skip_empty=True CPU path) - for probabilities <= 1 the bilinear value
+// outside it is below 0.5, so this is also what the skip_empty=False path the reference takes on CUDA tensors (custom_rcnn.py:880)
+// produces.  thr < 0.5: the two paths differ up to extent/(2S) pixels outside the box, so the WHOLE image is sampled, as the
+// reference's CUDA path does.
+__device__ __forceinline__ PasteObj paste_prepare(const float *__restrict__ box, int H, int W, float thr)
 {
     PasteObj o;
     const float x0 = __ldg(box), y0 = __ldg(box + 1), x1 = __ldg(box + 2), y1 = __ldg(box + 3);
@@ -51,6 +55,7 @@ __device__ __forceinline__ PasteObj paste_prepare(const float *__restrict__ box,
     o.ry0 = (int)fminf(fmaxf(__fsub_rn(floorf(y0), 1.f), 0.f), (float)H);
     o.rx1 = (int)fmaxf(fminf(__fadd_rn(ceilf(x1), 1.f), (float)W), 0.f);
     o.ry1 = (int)fmaxf(fminf(__fadd_rn(ceilf(y1), 1.f), (float)H), 0.f);
+    if (!(thr >= 0.5f)) { o.rx0 = 0; o.ry0 = 0; o.rx1 = W; o.ry1 = H; }
     return o;
 }
 
@@ -128,7 +133,7 @@ __global__ void __launch_bounds__(256) paste_masks_kernel(const float *__restric
     for (int k0 = 0; k0 < Kmax; k0 += kPasteChunk) {
         const int kn = min(kPasteChunk, Kmax - k0);
         __syncthreads();
-        if ((int)threadIdx.x < kn && k0 + (int)threadIdx.x < K) s_obj[threadIdx.x] = paste_prepare(boxes + ((size_t)e * Kmax + k0 + threadIdx.x) * 4, H, W);
+        if ((int)threadIdx.x < kn && k0 + (int)threadIdx.x < K) s_obj[threadIdx.x] = paste_prepare(boxes + ((size_t)e * Kmax + k0 + threadIdx.x) * 4, H, W, thr);
         __syncthreads();
         if (p0 >= HW) continue;
         for (int j = 0; j < kn; ++j) {
@@ -259,7 +264,7 @@ __global__ void __launch_bounds__(256) write_objects_kernel(const float *__restr
 
     if (K <= kCoverObjs) {
         if (kPasted) {
-            if ((int)threadIdx.x < K) s_obj[threadIdx.x] = paste_prepare(boxes + ((size_t)e * Kmax + threadIdx.x) * 4, HW / W, W);
+            if ((int)threadIdx.x < K) s_obj[threadIdx.x] = paste_prepare(boxes + ((size_t)e * Kmax + threadIdx.x) * 4, HW / W, W, thr);
             __syncthreads();
         }
         const int Kpad = (K + 31) & ~31;
@@ -379,7 +384,7 @@ __global__ void __launch_bounds__(256) write_objects_kernel(const float *__restr
             bool mine = false;
             if (k < K) {
                 if (kPasted) {
-                    const PasteObj o = paste_prepare(boxes + ((size_t)e * Kmax + k) * 4, HW / W, W);
+                    const PasteObj o = paste_prepare(boxes + ((size_t)e * Kmax + k) * 4, HW / W, W, thr);
                     mine = paste_covers(probs + ((size_t)e * Kmax + k) * Sm * Sm, o, Sm, px % W, px / W, thr);
                 } else {
                     mine = __ldg(m + (size_t)k * HW + px) != 0;

@@ -132,9 +132,84 @@ def make_episode(seed: int, n_frames: int = 20, H: int = 480, W: int = 640, map_
             holes = rng.uniform(size=(H // 8 + 1, W // 8 + 1)) < zero_frac      # 8x8 no-depth patches
             d = np.where(np.kron(holes, np.ones((8, 8), bool))[:H, :W], np.float32(0), d)
         depth[t] = d
+    return Episode(depth, poses, map_shift(room, map_w, map_h, cell), float(cell), map_w, map_h, room, seed)
+
+
+def map_shift(room: Room, map_w: int, map_h: int, cell: float) -> np.ndarray:
+    """map_world_shift (3,) f32 that centres the room in a map_w x map_h grid of ``cell`` metres (the same depth maps can be
+    replayed into grids of another size or resolution: only this shift changes)."""
     span_x, span_z = map_w * cell, map_h * cell
-    shift = np.array([(room.x0 + room.x1) / 2 - span_x / 2, 0.0, (room.z0 + room.z1) / 2 - span_z / 2], np.float32)
-    return Episode(depth, poses, shift, float(cell), map_w, map_h, room, seed)
+    return np.array([(room.x0 + room.x1) / 2 - span_x / 2, 0.0, (room.z0 + room.z1) / 2 - span_z / 2], np.float32)
+
+
+class DeviceEpisodes:
+    """Synthetic episodes rendered ON THE DEVICE, one frame-step at a time (torch, fp32): for workloads whose depth maps would
+    not fit or would take minutes to ray-cast on the host (BASELINE configs[4]: 512 episodes x 100 frames).  Same scene model
+    as ``make_episode`` (room + boxes + random walk + 8x8 no-depth patches); values differ from the numpy renderer in the
+    last bits (fp32 vs fp64 ray parameters), which is irrelevant for synthetic inputs.  Input generation, not the hot path."""
+
+    def __init__(self, n_episodes: int, n_frames: int, device, H: int = 480, W: int = 640, map_w: int = 500, map_h: int = 500,
+                 cell: float = 0.2, seed0: int = 1234, zero_frac: float = 0.02, vfov: float = math.radians(VFOV_DEG), n_boxes: int = 5):
+        import torch
+        self.torch, self.device = torch, torch.device(device)
+        self.n, self.T, self.H, self.W, self.zero_frac = n_episodes, n_frames, H, W, zero_frac
+        rooms, poses = [], []
+        for e in range(n_episodes):
+            rng = np.random.default_rng(seed0 + e)
+            room = make_room(rng, n_boxes=n_boxes)
+            rooms.append(room)
+            poses.append(random_walk(rng, room, n_frames))
+        self.xyzhe = np.stack(poses)                                                       # (n, T, 5) f32
+        self.shift = np.stack([map_shift(r, map_w, map_h, cell) for r in rooms])           # (n, 3) f32
+        self.walls = torch.tensor([[r.x0, r.x1, r.z0, r.z1, r.ceil] for r in rooms], dtype=torch.float32, device=self.device)
+        self.boxes = torch.tensor(np.stack([r.boxes for r in rooms]), dtype=torch.float32, device=self.device)      # (n, nb, 6)
+        hfov = W / H * vfov
+        fx, fy = W / (2.0 * math.tan(hfov / 2.0)), H / (2.0 * math.tan(vfov / 2.0))
+        xs = (torch.arange(W, device=self.device, dtype=torch.float32) + 0.5 - W / 2.0) / fx
+        ys = (torch.arange(H, device=self.device, dtype=torch.float32) + 0.5 - H / 2.0) / fy
+        self.X, self.Y = xs[None, None, :], ys[None, :, None]
+        self.gen = torch.Generator(device=self.device).manual_seed(seed0)
+
+    def render(self, episodes, frames, out=None):
+        """depth (R,H,W) f32 for slot s = frame frames[s] of episode episodes[s]."""
+        torch = self.torch
+        ep = torch.as_tensor(np.asarray(episodes, np.int64), device=self.device)
+        pose = torch.from_numpy(self.xyzhe[np.asarray(episodes), np.asarray(frames)]).to(self.device)            # (R,5)
+        px, py, pz, h = (pose[:, k, None, None] for k in range(4))
+        ch, sh = torch.cos(h), torch.sin(h)
+        dx, dy, dz = ch * self.X - sh, (-self.Y).expand(len(episodes), -1, self.W), -sh * self.X - ch
+        big = torch.tensor(1e30, device=self.device)
+        wl = self.walls[ep]
+
+        def plane(num, den):
+            tt = num / den
+            return torch.where((den != 0) & (tt > 1e-6), tt, big)
+
+        t = plane(0.0 - py, dy)
+        t = torch.minimum(t, plane(wl[:, 4, None, None] - py, dy))
+        t = torch.minimum(t, plane(wl[:, 0, None, None] - px, dx))
+        t = torch.minimum(t, plane(wl[:, 1, None, None] - px, dx))
+        t = torch.minimum(t, plane(wl[:, 2, None, None] - pz, dz))
+        t = torch.minimum(t, plane(wl[:, 3, None, None] - pz, dz))
+        bx = self.boxes[ep]
+        for b in range(bx.shape[1]):
+            c = [bx[:, b, k, None, None] for k in range(6)]
+            tx0, tx1 = (c[0] - px) / dx, (c[1] - px) / dx
+            ty0, ty1 = (c[2] - py) / dy, (c[3] - py) / dy
+            tz0, tz1 = (c[4] - pz) / dz, (c[5] - pz) / dz
+            tn = torch.maximum(torch.maximum(torch.minimum(tx0, tx1), torch.minimum(ty0, ty1)), torch.minimum(tz0, tz1))
+            tf = torch.minimum(torch.minimum(torch.maximum(tx0, tx1), torch.maximum(ty0, ty1)), torch.maximum(tz0, tz1))
+            hit = (tf >= tn) & (tn > 1e-6) & torch.isfinite(tn)
+            t = torch.where(hit, torch.minimum(t, tn), t)
+        d = torch.clamp(t, max=MAX_DEPTH)
+        if self.zero_frac > 0:
+            holes = torch.rand((len(episodes), self.H // 8 + 1, self.W // 8 + 1), device=self.device, generator=self.gen) < self.zero_frac
+            holes = holes.repeat_interleave(8, 1).repeat_interleave(8, 2)[:, : self.H, : self.W]
+            d = torch.where(holes, torch.zeros((), device=self.device), d)
+        if out is not None:
+            out.copy_(d)
+            return out
+        return d.contiguous()
 
 
 def make_detections(rng: np.random.Generator, H: int = 480, W: int = 640, C: int = 512, k_range=(4, 16)):

@@ -50,6 +50,7 @@ class MemoryFusion(nn.Module):
                  ego_feat_dim: int = 256, tensor_core: bool = True):
         super().__init__()
         self.tensor_core = tensor_core      # False: library fp32 GEMM + eod_fuse also in inference
+        self.validate_indices = True        # range-check proj_indices against the memory table before the gather
         self._w_split = {}                  # level -> ((weight ptr, version), (2N,K) f16 hi/lo split)
         self.memory_type, self.feat_fusion, self.merge_type = memory_type, fusion, merge_type
         self.map_feature_weight, self.memory_feature_weight = map_feature_weight, memory_feature_weight
@@ -75,7 +76,10 @@ class MemoryFusion(nn.Module):
             idx = proj_indices[i]
             if idx.dim() == 3 and idx.shape[-1] == 1:
                 idx = idx.squeeze(2)
-            per_image.append(ops.read_pool(mem.unsqueeze(0).contiguous(), counts, idx.unsqueeze(0).contiguous()))
+            idx = idx.unsqueeze(0).contiguous()
+            if self.validate_indices:                     # the reference's gather raises on a bad id (timm.py:147)
+                ops.check_indices(idx, mem.shape[0])
+            per_image.append(ops.read_pool(mem.unsqueeze(0).contiguous(), counts, idx))
         if len(per_image) == 1:
             return per_image[0]
         return [torch.cat([lv[k] for lv in per_image], dim=0) for k in range(3)]
@@ -107,7 +111,9 @@ class MemoryFusion(nn.Module):
         for k, (lvl, res, conv) in enumerate(zip(levels, results, convs)):
             # timm.py:174: 1x1 conv in fp32 (eval, no autocast) == per-pixel GEMM on the channels-last level
             x = lvl.permute(0, 2, 3, 1).to(torch.float32)                             # (B, h, w, C) contiguous
-            mem = torch.matmul(x, conv.weight.view(conv.weight.shape[0], -1).t()) + conv.bias
+            mem = torch.matmul(x, conv.weight.view(conv.weight.shape[0], -1).t())
+            if conv.bias is not None:
+                mem = mem + conv.bias
             mem = mem.permute(0, 3, 1, 2).contiguous()                               # NCHW like res
             res32 = res.to(torch.float32).contiguous()
             fused = _FuseFn.apply(res32, mem, float(self.map_feature_weight), mode)
@@ -122,9 +128,12 @@ class CustomRecurrentFPN(nn.Module):
     def __init__(self, fpn_body: Callable, top_block: Optional[Callable], fusion: MemoryFusion,
                  out_features=("p3", "p4", "p5", "p6", "p7")):
         super().__init__()
-        self.fpn_body, self.top_block, self.fusion = fpn_body, top_block, fusion
+        self.fpn_body, self.top_block = fpn_body, top_block
+        # ``fusion`` is held OUTSIDE the module tree: its three 1x1 convs are registered once, directly on the backbone under
+        # the reference's state-dict names (timm.py:78-86), so state_dict() carries exactly `map_merge_projection{1,2,3}.*`
+        # and a reference checkpoint loads with strict=True (no duplicate `fusion.*` keys)
+        object.__setattr__(self, "fusion", fusion)
         self._out_features = list(out_features)
-        # reference state-dict names live directly on the backbone (timm.py:78-86)
         if fusion.memory_type == "implicit_memory":
             self.map_merge_projection1 = fusion.map_merge_projection1
             self.map_merge_projection2 = fusion.map_merge_projection2

@@ -42,9 +42,16 @@ class EpisodeBatch:
     ``pipeline=False`` (default): fully stream-ordered for the caller - on return the caller's stream has been made
     to wait for everything ``step`` enqueued.
     ``pipeline=True``: the caller promises that depth / pose / shifts / samp of a step are ready when ``step`` is
-    called and stay untouched until the next ``step`` (or ``join``) - they are consumed ahead of the caller's stream.
-    The returned levels are ordered on the caller's stream; grid state (``sums``, ``counts``, ``norm16``) must be read
-    after ``join()``.
+    called and stay untouched until the next ``step`` (or ``join``) - they are consumed ahead of the caller's stream
+    (``step(..., inputs_ready=False)`` drops the promise for one step: the geometry then waits for the caller's stream,
+    the write of the previous frame still overlaps).  The returned levels are ordered on the caller's stream; grid state
+    (``sums``, ``counts``, ``norm16``) must be read after ``join()``.
+
+    Lock-step batches of RAGGED episodes (the reference iterates sequences of different lengths one after the other,
+    custom_rcnn.py:441-443): ``step(..., active=, reset_mask=, refresh_mask=)`` - slots whose episode has ended are
+    skipped by the write (their grid is left alone), a slot that starts a sequence flagged ``memory_reset`` is cleared
+    on its own (:470-477), and with ``read_frozen = True`` (TEST_TYPE longterm, :482-486) the fp16 read table is a
+    snapshot that only ``refresh_mask`` brings up to date.
     """
 
     def __init__(self, n_episodes: int, map_w: int, map_h: int, channels: int, height: int = 480, width: int = 640,
@@ -77,6 +84,7 @@ class EpisodeBatch:
         self._slots: Optional[ops.ObjectSlots] = None      # workspace of write_objects, created on first use
         self._det_ws: Optional[ops.DetWorkspace] = None    # workspace of the deterministic write (variant=WRITE_DET)
         self.det_runs_per_episode = 0                      # 0: HW/4 runs per episode and frame
+        self.read_frozen = False      # True: finalize leaves norm16 alone (longterm snapshot read); refresh_read() updates it
         self.stage_events = None      # dict(stage -> [(start, end) CUDA events]) when profiling is on
 
     # current frame's planes
@@ -117,12 +125,15 @@ class EpisodeBatch:
             if ev is not None:
                 s0.wait_event(ev)
 
-    def reset(self, full: bool = False) -> None:
-        """memory_reset (custom_rcnn.py:470-477) for every episode of the batch.  Only rows of cells seen since the
-        last reset can be non-zero, so by default just those are cleared (eod_reset_touched); ``full=True`` rewrites
-        the whole grid (use it if the state tensors were modified from outside)."""
+    def reset(self, full: bool = False, mask: Optional[torch.Tensor] = None) -> None:
+        """memory_reset (custom_rcnn.py:470-477) for every episode of the batch, or - ``mask`` (E) i32 - for the slots
+        with mask[e] != 0 only.  Only rows of cells seen since the last reset can be non-zero, so by default just those
+        are cleared (eod_reset_touched / eod_reset_episodes); ``full=True`` rewrites the whole grid (use it if the state
+        tensors were modified from outside)."""
         self.join()
-        if full:
+        if mask is not None:
+            ops.reset_episodes(self.counts, self.sums, self.norm16, mask)
+        elif full:
             self.sums.zero_()
             self.counts.zero_()
             self.norm16.zero_()
@@ -140,37 +151,62 @@ class EpisodeBatch:
                     out={"idx": self.idx})
         return self.idx
 
-    def set_indices(self, idx: torch.Tensor) -> None:
-        """Use precomputed proj_indices (E,H,W) int32, as the reference does from memory_data/*.h5."""
-        self.idx.copy_(idx)
+    def _geometry(self, depth, pose, shifts, intr, cell, order, proj_indices) -> None:
+        if proj_indices is None:
+            self.project(depth, pose, shifts, intr, cell, order)
+        else:
+            self._timed("project", self.idx.copy_, proj_indices.reshape(self.E, self.H, self.W))
+
+    def set_indices(self, idx: torch.Tensor, validate: bool = True) -> None:
+        """Use precomputed proj_indices (E,H,W) int32 / int64, as the reference does from memory_data/*.h5.  The plane is
+        range-checked against this batch's grid (IndexError, one 4-byte read-back); validate=False only for planes that
+        eod_backproject_quantize produced for this grid (they are clipped already)."""
+        idx = idx.reshape(self.E, self.H, self.W)
+        if validate:
+            self.idx.copy_(ops.check_indices(idx.contiguous(), self.n_cells, want_i32=True))
+        else:
+            self.idx.copy_(idx)
+
+    def refresh_read(self, mask: Optional[torch.Tensor] = None) -> None:
+        """Bring the fp16 read table up to date with sums / counts for the slots with mask[e] != 0 (None = all): the
+        'updated_memory = self.implicit_memory' of custom_rcnn.py:482-486 at the first frame of a sequence."""
+        self.join()
+        ops.refresh_norm16(self.counts, self.sums, self.norm16, mask)
+        self._sync_next = True
 
     def read(self) -> List[torch.Tensor]:
         """A10-A12 fused: [L0 (E,C,H/8,W/8), L1, L2] fp16 (channels_last memory)."""
         return self._timed("read", ops.read_pool, self.norm16, None, self.idx, out=self.levels)
 
-    def _count(self, samp: Optional[torch.Tensor]) -> None:
-        self._timed("count", ops.frame_count, self.idx, samp, self.frame_cnt)
+    def _count(self, samp: Optional[torch.Tensor], active: Optional[torch.Tensor] = None) -> None:
+        self._timed("count", ops.frame_count, self.idx, samp, self.frame_cnt, active)
         if self.variant != WRITE_DET and self.layout == LAYOUT_CHW:      # only the TMA-staged CHW kernel takes per-pixel divisors
             self._timed("expand", ops.expand_counts, self.idx, self.frame_cnt, self.pix_inv_n)
 
-    def _write(self, feat: torch.Tensor, samp: Optional[torch.Tensor]) -> None:
+    def _write(self, feat: torch.Tensor, samp: Optional[torch.Tensor], active: Optional[torch.Tensor] = None) -> None:
         if self.variant == WRITE_DET:
+            if active is not None:
+                raise EodError("the deterministic write does not take an active mask (advance ragged episodes with the default variant)")
             if self._det_ws is None:
                 self._det_ws = ops.DetWorkspace(self.E, self.C, self.H * self.W, self.n_cells, self.device, self.det_runs_per_episode)
             self._timed("write", ops.write_mean_det, feat, self.idx, samp, self.frame_cnt, self.sums, self._det_ws)
             return
         self._timed("write", ops.write_mean, feat, self.idx, samp, self.frame_cnt, self.sums, self.layout, self.variant,
-                    self.pix_inv_n if self.layout == LAYOUT_CHW else None)
+                    self.pix_inv_n if self.layout == LAYOUT_CHW else None, active)
 
     def _finalize(self) -> None:
-        self._timed("finalize", ops.finalize_counts, self.idx, self.frame_cnt, self.counts, None, self.sums, self.norm16)
+        # read_frozen (TEST_TYPE longterm): counts only - the fp16 table the read gathers from is a snapshot
+        if self.read_frozen:
+            self._timed("finalize", ops.finalize_counts, self.idx, self.frame_cnt, self.counts)
+        else:
+            self._timed("finalize", ops.finalize_counts, self.idx, self.frame_cnt, self.counts, None, self.sums, self.norm16)
 
-    def write(self, feat: torch.Tensor, samp: Optional[torch.Tensor] = None) -> None:
+    def write(self, feat: torch.Tensor, samp: Optional[torch.Tensor] = None, active: Optional[torch.Tensor] = None) -> None:
         """A7 + A8 for one frame of every episode: feat (E,C,H,W) [CHW] or (E,H,W,C) [HWC] fp32, or (E,H,W,C) bf16 / fp16
         [LAYOUT_HWC_BF16 / LAYOUT_HWC_F16];
-        samp (E,H,W) u8 selects the contributing pixels (None = all)."""
-        self._count(samp)
-        self._write(feat, samp)
+        samp (E,H,W) u8 selects the contributing pixels (None = all); active (E) i32: slots with active <= 0 are skipped."""
+        self._count(samp, active)
+        self._write(feat, samp, active)
         self._finalize()
 
     def write_objects(self, box_features: torch.Tensor, masks: torch.Tensor, n_obj: Optional[torch.Tensor] = None,
@@ -205,34 +241,52 @@ class EpisodeBatch:
         self._finalize()
 
     # ---- one frame, overlapped -------------------------------------------------------------------------------
-    def step(self, depth, pose, shifts, intr, cell, feat, samp=None, order: int = ORDER_ZX) -> List[torch.Tensor]:
+    def step(self, depth, pose, shifts, intr, cell, feat, samp=None, order: int = ORDER_ZX, *, active: Optional[torch.Tensor] = None,
+             reset_mask: Optional[torch.Tensor] = None, refresh_mask: Optional[torch.Tensor] = None,
+             inputs_ready: bool = True, proj_indices: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
         """One frame of the hot path for all E episodes, in the reference's order: the read of frame t sees
-        the state written by frame t-1 (custom_rcnn.py:489-515).  See the class docstring for the stream layout."""
+        the state written by frame t-1 (custom_rcnn.py:489-515).  See the class docstring for the stream layout.
+        active / reset_mask / refresh_mask: (E) i32 device tensors ordered on the caller's stream (ragged lock-step batches):
+        reset_mask clears those slots BEFORE this frame's read (frame['memory_reset'], :470-477), refresh_mask then brings
+        their fp16 read table up to date (read_frozen mode, :482-486), active <= 0 slots are not written.
+        proj_indices (E,H,W) int32: precomputed, range-checked cell indices (memory_data/*.h5) used instead of depth / pose."""
         s0 = torch.cuda.current_stream(self.device)
         self._k = self._t & 1
         self._t += 1
-        strict = (not self.pipeline) or self._sync_next
+        strict = (not self.pipeline) or self._sync_next or not inputs_ready
         self._sync_next = False
         e_in = torch.cuda.Event()
         e_in.record(s0)
+        e_state = None
+        if reset_mask is not None or refresh_mask is not None:
+            with torch.cuda.stream(self._wr):              # behind finalize of frame t-1 (same stream), ahead of this frame's read
+                self._wr.wait_event(e_in)
+                if reset_mask is not None:
+                    ops.reset_episodes(self.counts, self.sums, self.norm16, reset_mask)
+                if refresh_mask is not None:
+                    ops.refresh_norm16(self.counts, self.sums, self.norm16, refresh_mask)
+                e_state = torch.cuda.Event()
+                e_state.record()
         with torch.cuda.stream(self._geo):
             if strict:
                 self._geo.wait_event(e_in)                 # inputs (and a preceding reset) are ordered on the caller's stream
-            self.project(depth, pose, shifts, intr, cell, order)
-            self._count(samp)
+            self._geometry(depth, pose, shifts, intr, cell, order, proj_indices)
+            self._count(samp, active)
             e_geo = torch.cuda.Event()
             e_geo.record()
             if not strict:
                 self._geo.wait_event(e_in)                 # the caller has consumed the previous frame's levels
             if self._e_fin is not None:
                 self._geo.wait_event(self._e_fin)          # norm16 as finalised by frame t-1
+            if e_state is not None:
+                self._geo.wait_event(e_state)
             levels = self.read()
             e_read = torch.cuda.Event()
             e_read.record()
         with torch.cuda.stream(self._wr):
             self._wr.wait_event(e_in)                      # feat is ordered on the caller's stream
             self._wr.wait_event(e_geo)
-            self._write(feat, samp)
+            self._write(feat, samp, active)
             self._wr.wait_event(e_read)                    # finalize rewrites the norm16 rows the read gathers from
             self._finalize()
             e_fin = torch.cuda.Event()
@@ -247,7 +301,8 @@ class EpisodeBatch:
 
 
     def step_detections(self, depth, pose, shifts, intr, cell, box_features, mask_probs, boxes, n_obj=None, sample_stride: int = 8,
-                        mask_thresh: float = 0.5, order: int = ORDER_ZX) -> List[torch.Tensor]:
+                        mask_thresh: float = 0.5, order: int = ORDER_ZX, *, reset_mask: Optional[torch.Tensor] = None,
+                        refresh_mask: Optional[torch.Tensor] = None, proj_indices: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
         """One frame of the reference's LIVE regime for all E episodes (custom_rcnn.py:489-515 with :876-936): read of the
         state left by frame t-1, then the write of this frame's kept detections (un-pasted 28x28 mask probabilities + boxes).
         Two streams, stream-ordered for the caller on entry and exit:
@@ -256,7 +311,8 @@ class EpisodeBatch:
             write stream    : paste/observed -> sample -> (project) count -> write_objects -> flush -> (read) finalize
 
         The mask pasting and the sampling scan do not depend on the geometry, and the issue-bound read runs next to the
-        latency-bound object write instead of in front of it."""
+        latency-bound object write instead of in front of it.  Slots whose episode has ended pass n_obj == 0 (nothing is
+        written, :686); reset_mask / refresh_mask as in ``step``."""
         s0 = torch.cuda.current_stream(self.device)
         self._k = self._t & 1
         self._t += 1
@@ -265,13 +321,25 @@ class EpisodeBatch:
             self._slots = ops.ObjectSlots(self.E, self.n_cells, self.C, S, self.device)
         e_in = torch.cuda.Event()
         e_in.record(s0)
+        e_state = None
+        if reset_mask is not None or refresh_mask is not None:
+            with torch.cuda.stream(self._wr):              # behind finalize of frame t-1 (same stream), ahead of this frame's read
+                self._wr.wait_event(e_in)
+                if reset_mask is not None:
+                    ops.reset_episodes(self.counts, self.sums, self.norm16, reset_mask)
+                if refresh_mask is not None:
+                    ops.refresh_norm16(self.counts, self.sums, self.norm16, refresh_mask)
+                e_state = torch.cuda.Event()
+                e_state.record()
         with torch.cuda.stream(self._geo):
             self._geo.wait_event(e_in)
             if self._e_fin is not None:
                 self._geo.wait_event(self._e_fin)
-            self.project(depth, pose, shifts, intr, cell, order)
+            self._geometry(depth, pose, shifts, intr, cell, order, proj_indices)
             e_geo = torch.cuda.Event()
             e_geo.record()
+            if e_state is not None:
+                self._geo.wait_event(e_state)
             levels = self.read()
             e_read = torch.cuda.Event()
             e_read.record()
@@ -319,6 +387,7 @@ class SpatialFeatureMemory:
         self._cls: Optional[torch.Tensor] = None
         self.semmap_gt_info, self.replica_map_info = semmap_gt_info or {}, replica_map_info or {}
         self.downsample, self.sample_stride, self.H, self.W = downsample, sample_stride, height, width
+        self.validate_indices = True                            # range-check externally supplied proj_indices (see _idx32)
         self.implicit_memory: Optional[torch.Tensor] = None     # (cells, C) f32 sums        (custom_rcnn.py:476,759)
         self.observations: Optional[torch.Tensor] = None        # (cells,)  f32 counts      (:477,760)
         self._frame_cnt: Optional[torch.Tensor] = None
@@ -409,13 +478,15 @@ class SpatialFeatureMemory:
         counts = self.observations if memory is None else observations
         if table.dtype == torch.float16:
             counts = None
-        idx = proj_indices.to(self.device)
+        idx = torch.as_tensor(proj_indices).to(self.device)
         if idx.dim() == 3 and idx.shape[-1] == 1:
             idx = idx.squeeze(2)
         if idx.dtype not in (torch.int32, torch.int64):
             idx = idx.to(torch.int64)
-        return ops.read_pool(table.unsqueeze(0).contiguous(), None if counts is None else counts.unsqueeze(0).contiguous(),
-                             idx.unsqueeze(0).contiguous())
+        idx = idx.unsqueeze(0).contiguous()
+        if self.validate_indices:
+            ops.check_indices(idx, table.shape[0])
+        return ops.read_pool(table.unsqueeze(0).contiguous(), None if counts is None else counts.unsqueeze(0).contiguous(), idx)
 
     # ---- write ---------------------------------------------------------------------------------------
     def box_to_image_features(self, box_features: torch.Tensor, masks: torch.Tensor):
@@ -423,10 +494,17 @@ class SpatialFeatureMemory:
         return ops.box_to_image_features(box_features.to(self.device, torch.float32).contiguous(),
                                          masks.to(self.device).contiguous())
 
-    def _idx32(self, proj_indices: torch.Tensor) -> torch.Tensor:
-        p = proj_indices.to(self.device)
+    def _idx32(self, proj_indices: torch.Tensor, n_cells: Optional[int] = None) -> torch.Tensor:
+        """(1, HW) int32 view of an externally supplied plane (h5 / npz proj_indices, int32 or int64).  With n_cells the ids are
+        range-checked on the device (IndexError like the reference's gather, one 4-byte read-back); ``validate_indices =
+        False`` on the instance skips that for callers whose planes come from eod_backproject_quantize for this very grid."""
+        p = torch.as_tensor(proj_indices).to(self.device)
         if p.dim() == 3 and p.shape[-1] == 1:
             p = p.squeeze(2)
+        if p.dtype not in (torch.int32, torch.int64):
+            p = p.to(torch.int64)
+        if n_cells is not None and self.validate_indices:
+            return ops.check_indices(p.contiguous(), n_cells, want_i32=True).reshape(1, -1)
         return p.to(torch.int32).reshape(1, -1).contiguous()
 
     def project_image_features(self, image_features: torch.Tensor, observed_pixels: torch.Tensor,
@@ -434,7 +512,7 @@ class SpatialFeatureMemory:
         """custom_rcnn.py:903-936: (mean (M,C) f32 in ascending cell order, observed_mem (cells,) bool)."""
         n_cells = memory[0].shape[0]
         C = image_features.shape[1]
-        idx = self._idx32(proj_indices[0])
+        idx = self._idx32(proj_indices[0], n_cells)
         samp = ops.sample_mask(observed_pixels.to(self.device).reshape(1, -1).view(torch.uint8).contiguous(), self.sample_stride)
         scratch = torch.zeros((1, n_cells, C), dtype=torch.float32, device=self.device)
         cnt = torch.zeros((1, n_cells), dtype=torch.int32, device=self.device)
@@ -485,7 +563,7 @@ class SpatialFeatureMemory:
                          proj_indices: torch.Tensor, mask_thresh: float = 0.5) -> None:
         """custom_rcnn.py:876-880 + 690-701,738-743 in one go: the kept detections' (K,S,S) mask probabilities and boxes are
         pasted on the fly (no (K,H,W) masks, no (1,C,H,W) image)."""
-        idx = self._idx32(proj_indices).view(1, self.H, self.W)
+        idx = self._idx32(proj_indices, self.implicit_memory.shape[0]).view(1, self.H, self.W)
         bf = box_features.to(self.device, torch.float32).contiguous().unsqueeze(0)
         mp = mask_probs.to(self.device, torch.float32).contiguous().unsqueeze(0)
         bx = boxes.to(self.device, torch.float32).contiguous().unsqueeze(0)
@@ -505,7 +583,7 @@ class SpatialFeatureMemory:
     def write_object_features(self, box_features: torch.Tensor, masks: torch.Tensor, proj_indices: torch.Tensor) -> None:
         """A6 + A7 + A8 without the (1,C,H,W) image (custom_rcnn.py:690-701,738-743): the per-pixel object mean is
         formed only for the every-``sample_stride``-th observed pixels, on the fly."""
-        idx = self._idx32(proj_indices)
+        idx = self._idx32(proj_indices, self.implicit_memory.shape[0])
         bf = box_features.to(self.device, torch.float32).contiguous().unsqueeze(0)
         m = masks.to(self.device).contiguous().unsqueeze(0)
         HW = masks.shape[-2] * masks.shape[-1]
@@ -542,7 +620,7 @@ class SpatialFeatureMemory:
             f, C, layout = f.unsqueeze(0).contiguous(), w2.shape[0], LAYOUT_HWC
         else:
             f = f.reshape(1, C, -1).contiguous()
-        idx = idx_full[::step, ::step].to(torch.int32).reshape(1, -1).contiguous()
+        idx = self._idx32(idx_full[::step, ::step].contiguous(), n_cells)
         table = torch.zeros((1, n_cells, C), dtype=torch.float32, device=self.device)
         cnt = torch.zeros((1, n_cells), dtype=torch.int32, device=self.device)
         touched = torch.zeros((1, n_cells), dtype=torch.uint8, device=self.device)
@@ -556,7 +634,7 @@ class SpatialFeatureMemory:
                              proj_indices: torch.Tensor, layout: int = LAYOUT_CHW) -> None:
         """A7 + A8 on the live state: per-cell mean of every ``sample_stride``-th observed pixel, sums +=,
         counts += 1 for all visible cells."""
-        idx = self._idx32(proj_indices)
+        idx = self._idx32(proj_indices, self.implicit_memory.shape[0])
         samp = None
         if observed_pixels is not None:
             samp = ops.sample_mask(observed_pixels.to(self.device).reshape(1, -1).view(torch.uint8).contiguous(), self.sample_stride)

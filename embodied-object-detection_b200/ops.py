@@ -17,7 +17,8 @@ launch_count = 0
 
 _LAUNCHES = {"eod_backproject_quantize": 1, "eod_quantize_world": 1, "eod_sample_mask": 1, "eod_frame_count": 1, "eod_expand_counts": 1, "eod_write_mean": 1, "eod_write_mean_det": 9,
              "eod_finalize_counts": 1, "eod_box_to_image_features": 1, "eod_masks_observed": 1, "eod_paste_masks": 1, "eod_write_objects_pasted": 1, "eod_bilinear_lattice": 1, "eod_write_objects": 1, "eod_flush_slots": 2, "eod_write_max": 2, "eod_read_pool": 2,
-             "eod_fuse": 1, "eod_project_split_weights": 1, "eod_project_fuse": 1, "eod_project_fuse_levels": 1, "eod_normalize_memory": 1, "eod_reset_touched": 1, "eod_semmap_update": 1, "eod_semmap_decode": 2}
+             "eod_fuse": 1, "eod_project_split_weights": 1, "eod_project_fuse": 1, "eod_project_fuse_levels": 1, "eod_normalize_memory": 1, "eod_reset_touched": 1, "eod_semmap_update": 1, "eod_semmap_decode": 2,
+             "eod_reset_episodes": 1, "eod_refresh_norm16": 1, "eod_check_indices": 1}
 
 
 def _call(name: str, *args) -> None:
@@ -31,6 +32,9 @@ def _dev(t: torch.Tensor, dtype: torch.dtype, name: str) -> torch.Tensor:
         raise TypeError(f"{name}: expected a torch.Tensor")
     if not t.is_cuda:
         raise EodError(f"{name}: tensor is on {t.device}; the spatial memory runs on CUDA only (no CPU fallback)")
+    if t.device.index != torch.cuda.current_device():
+        raise EodError(f"{name}: tensor is on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()} "
+                       f"(kernels launch on the current device: wrap the call in torch.cuda.device(...))")
     if t.dtype != dtype:
         raise TypeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
     if not t.is_contiguous():
@@ -42,7 +46,12 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
-def _stream() -> int:
+def _stream(ref: Optional[torch.Tensor] = None) -> int:
+    """The current stream of the device the operands live on.  The library launches on the CUDA context's current device, so
+    a tensor on another device than torch's current one is an error (wrap the call in ``torch.cuda.device(t.device)``)."""
+    if ref is not None and ref.device.index is not None and ref.device.index != torch.cuda.current_device():
+        raise EodError(f"operands live on {ref.device} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+                       f"wrap the call in torch.cuda.device({str(ref.device)!r})")
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -138,9 +147,10 @@ def expand_counts(idx: torch.Tensor, frame_cnt: torch.Tensor, pix_inv_n: torch.T
 
 def write_mean(feat: torch.Tensor, idx: torch.Tensor, samp: Optional[torch.Tensor], frame_cnt: torch.Tensor,
                sums: torch.Tensor, layout: int = LAYOUT_CHW, variant: int = WRITE_AUTO,
-               pix_inv_n: Optional[torch.Tensor] = None) -> None:
+               pix_inv_n: Optional[torch.Tensor] = None, active: Optional[torch.Tensor] = None) -> None:
     """feat (E,C,HW) [CHW] or (E,HW,C) [HWC] f32, or (E,HW,C) bf16 / fp16 [LAYOUT_HWC_BF16 / _F16]; sums (E,cells,C) f32
-    accumulated in place.  pix_inv_n: output of expand_counts for this frame (optional, faster)."""
+    accumulated in place.  pix_inv_n: output of expand_counts for this frame (optional, faster).
+    active (E) i32 | None: slots with active <= 0 are skipped (give frame_count the same mask)."""
     feat_dtype = {LAYOUT_HWC_BF16: torch.bfloat16, LAYOUT_HWC_F16: torch.float16}.get(int(layout), torch.float32)
     _dev(feat, feat_dtype, "feat"), _dev(idx, torch.int32, "idx"), _dev(sums, torch.float32, "sums")
     _dev(frame_cnt, torch.int32, "frame_cnt")
@@ -154,8 +164,12 @@ def write_mean(feat: torch.Tensor, idx: torch.Tensor, samp: Optional[torch.Tenso
         _dev(pix_inv_n, torch.float32, "pix_inv_n")
         if pix_inv_n.numel() < E * HW:
             raise ValueError("pix_inv_n must hold E*HW floats")
+    if active is not None:
+        _dev(active, torch.int32, "active")
+        if active.numel() != E:
+            raise ValueError("active must hold one int32 per episode")
     _call("eod_write_mean", feat.data_ptr(), int(layout), idx.data_ptr(), _ptr(samp), frame_cnt.data_ptr(), E, C, HW,
-          n_cells, sums.data_ptr(), int(variant), _ptr(pix_inv_n), _stream())
+          n_cells, sums.data_ptr(), int(variant), _ptr(pix_inv_n), _ptr(active), _stream())
 
 
 def semmap_update(frame_cnt: torch.Tensor, counts: torch.Tensor, sums: torch.Tensor, zs_weight: torch.Tensor, n_cls: int,
@@ -188,6 +202,46 @@ def reset_touched(counts: torch.Tensor, sums: torch.Tensor, norm16: Optional[tor
         _dev(norm16, torch.float16, "norm16")
     C = sums.shape[-1]
     _call("eod_reset_touched", counts.data_ptr(), sums.data_ptr(), _ptr(norm16), counts.numel(), C, _stream())
+
+
+def reset_episodes(counts: torch.Tensor, sums: torch.Tensor, norm16: Optional[torch.Tensor], mask: torch.Tensor) -> None:
+    """Per-slot memory_reset: clears the touched rows of the episodes with mask[e] != 0.  counts (E,cells), sums (E,cells,C)."""
+    _dev(counts, torch.float32, "counts"), _dev(sums, torch.float32, "sums"), _dev(mask, torch.int32, "mask")
+    if norm16 is not None:
+        _dev(norm16, torch.float16, "norm16")
+    E, n_cells, C = sums.shape
+    if mask.numel() != E:
+        raise ValueError("mask must hold one int32 per episode")
+    _call("eod_reset_episodes", counts.data_ptr(), sums.data_ptr(), _ptr(norm16), mask.data_ptr(), E, n_cells, C, _stream())
+
+
+def refresh_norm16(counts: torch.Tensor, sums: torch.Tensor, norm16: torch.Tensor, mask: Optional[torch.Tensor] = None) -> None:
+    """norm16[e] := half(sums / counts where counts > 1) for every touched cell of the episodes with mask[e] != 0 (None = all):
+    the read table of TEST_TYPE longterm, refreshed at the first frame of a sequence (custom_rcnn.py:482-486)."""
+    _dev(counts, torch.float32, "counts"), _dev(sums, torch.float32, "sums"), _dev(norm16, torch.float16, "norm16")
+    E, n_cells, C = sums.shape
+    if mask is not None:
+        _dev(mask, torch.int32, "mask")
+        if mask.numel() != E:
+            raise ValueError("mask must hold one int32 per episode")
+    _call("eod_refresh_norm16", counts.data_ptr(), sums.data_ptr(), norm16.data_ptr(), _ptr(mask), E, n_cells, C, _stream())
+
+
+def check_indices(idx: torch.Tensor, n_cells: int, want_i32: bool = False) -> Optional[torch.Tensor]:
+    """Range check of an externally supplied index plane (int32 / int64, any shape): raises IndexError - like the reference's
+    gather does (timm.py:147) - if any id is outside [0, n_cells).  Synchronises (one 4-byte read-back).  want_i32: also return
+    the plane as int32 (same shape)."""
+    if idx.dtype not in (torch.int32, torch.int64):
+        raise TypeError("idx must be int32 or int64")
+    _dev(idx, idx.dtype, "idx")
+    err = torch.zeros((1,), dtype=torch.int32, device=idx.device)
+    out = torch.empty(idx.shape, dtype=torch.int32, device=idx.device) if want_i32 else None
+    if idx.numel():
+        _call("eod_check_indices", idx.data_ptr(), int(idx.dtype == torch.int64), idx.numel(), int(n_cells), _ptr(out), err.data_ptr(), _stream())
+    bad = int(err.item())
+    if bad:
+        raise IndexError(f"{bad} cell indices are outside [0, {int(n_cells)}): proj_indices do not belong to this map")
+    return out
 
 
 class DetWorkspace:

@@ -112,10 +112,12 @@ int eod_expand_counts(const int32_t *idx, const uint32_t *frame_cnt, int n_episo
  * (red.global.add.f32, one per run of equal cell id and channel): run-to-run results agree to ~1e-7 of
  * scale, not bitwise.  pix_inv_n: nullable, output of eod_expand_counts for this frame.
  * feat is fp32 for EOD_LAYOUT_CHW / _HWC and bf16 / fp16 for EOD_LAYOUT_HWC_BF16 / _HWC_F16 (half the bytes of the dominant
- * stream: the 16-bit values are widened exactly and everything downstream is the fp32 arithmetic of the fp32 layouts). */
+ * stream: the 16-bit values are widened exactly and everything downstream is the fp32 arithmetic of the fp32 layouts).
+ * active (E) i32 nullable: the same mask eod_frame_count takes - slots of the lock-step batch with active[e] <= 0 (an episode
+ * that has ended, custom_rcnn.py:441-443 iterates ragged sequences) are skipped without reading their features. */
 int eod_write_mean(const void *feat, int layout, const int32_t *idx, const uint8_t *samp, const uint32_t *frame_cnt,
                    int n_episodes, int C, int HW, int64_t n_cells, float *sums, int variant, const float *pix_inv_n,
-                   eod_stream_t stream);
+                   const int32_t *active, eod_stream_t stream);
 
 /* Deterministic variant of the main pass (CHW features, HW %% 32 == 0): run sums are stored in raster run order
  * (no atomics), then every touched cell adds the partial sums of its runs in ascending run position, divides by
@@ -169,7 +171,11 @@ int eod_write_objects(const float *box_features, const uint8_t *masks, const int
  * code path of the reference's dependency is followed: only pixels of [max(floor(x0)-1,0), min(ceil(x1)+1,W)) x (same
  * in y) are sampled, pixel centre -> box-normalised coordinate -> F.grid_sample(bilinear, zero padding,
  * align_corners=False) -> value >= threshold, in the fp32 operation order of ATen's vectorised CPU sampler.
- * Bit-exact with torch-CPU on the pasted bools.  threshold must be >= 0. */
+ * Bit-exact with torch-CPU on the pasted bools.  The reference calls the function on CUDA tensors, where the dependency
+ * samples the WHOLE image (skip_empty=False); for probabilities <= 1 and threshold >= 0.5 (the reference's 0.5) the value
+ * outside the integer neighbourhood is below the threshold and both paths give the same bools.  For 0 <= threshold < 0.5 they
+ * differ up to extent/(2S) pixels outside the box, and this library then samples the whole image like the CUDA path.
+ * threshold must be >= 0 (negative = detectron2's uint8 soft masks: EOD_ERR_UNSUPPORTED). */
 int eod_paste_masks(const float *mask_probs, const float *boxes, const int32_t *n_obj, int n_episodes, int Kmax, int S, int H,
                     int W, float threshold, uint8_t *masks, uint8_t *observed, eod_stream_t stream);
 
@@ -247,6 +253,25 @@ int eod_semmap_decode(const float *intensity, const int32_t *cls, int n_episodes
  * (if given) the norm16 row of every cell whose count is non-zero - equivalent to zero-filling the grid because
  * rows of never-visible cells are zero already.  n_rows = E*cells. */
 int eod_reset_touched(float *counts, float *sums, void *norm16, int64_t n_rows, int C, eod_stream_t stream);
+
+/* Per-slot memory_reset of a lock-step batch: the same as eod_reset_touched for the episodes with mask[e] != 0 only
+ * (frame['memory_reset'] is per sequence: custom_rcnn.py:470-477, SMNet/loader.py:289-293).  mask (E) i32. */
+int eod_reset_episodes(float *counts, float *sums, void *norm16, const int32_t *mask, int n_episodes, int64_t n_cells, int C,
+                       eod_stream_t stream);
+
+/* Re-derive the normalised fp16 rows (custom_rcnn.py:764-774,1036) of every cell with a non-zero count from the current
+ * sums / counts, for the episodes with mask[e] != 0 (mask nullable = all).  TEST_TYPE 'longterm' reads a snapshot of the
+ * memory taken at the first frame of each sequence (custom_rcnn.py:482-486): the write then runs eod_finalize_counts WITHOUT
+ * norm16 and this refresh runs once per sequence start. */
+int eod_refresh_norm16(const float *counts, const float *sums, void *norm16, const int32_t *mask, int n_episodes, int64_t n_cells,
+                       int C, eod_stream_t stream);
+
+/* Range check of an externally supplied index plane (proj_indices of memory_data/*.h5, SMNet/loader.py:185-186; the reference
+ * raises IndexError on a bad id, timm.py:147).  Every kernel here uses a cell id as a row offset, so ids outside [0, n_cells)
+ * must not reach them: err[0] (device int32, caller zeroes it) += number of out-of-range ids; idx32_out (nullable, n int32)
+ * receives the ids with out-of-range ones clamped into the grid.  idx: n ids, int32 or int64 (idx_is_i64). */
+int eod_check_indices(const void *idx, int idx_is_i64, int64_t n, int64_t n_cells, int32_t *idx32_out, int32_t *err,
+                      eod_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * (4) Fusion epilogue, timm.py:177-189: out = res + weight*mem | weight*mem | res (two roundings, no

@@ -95,13 +95,15 @@ def cell_sums_seq(feat_chw: np.ndarray, idx: np.ndarray, samp: Optional[np.ndarr
     return s, n
 
 
-def paste_masks(probs: np.ndarray, boxes: np.ndarray, H: int, W: int, thr: float = 0.5, want_values: bool = False):
-    """probs (K,S,S) f32, boxes (K,4) f32 XYXY -> masks (K,H,W) bool [, sampled values (K,H,W) f32] (oracle/paste.c)."""
+def paste_masks(probs: np.ndarray, boxes: np.ndarray, H: int, W: int, thr: float = 0.5, want_values: bool = False, skip_empty: bool = True):
+    """probs (K,S,S) f32, boxes (K,4) f32 XYXY -> masks (K,H,W) bool [, sampled values (K,H,W) f32] (oracle/paste.c).
+    skip_empty=True: detectron2's CPU path (integer neighbourhood of the box); False: its CUDA path (whole image), which
+    is what the library follows for thresholds below 0.5."""
     probs = np.ascontiguousarray(probs, np.float32)
     boxes = np.ascontiguousarray(boxes, np.float32)
     K, S = probs.shape[0], probs.shape[1]
     masks = np.zeros((K, H, W), np.uint8)
     values = np.zeros((K, H, W), np.float32) if want_values else None
     if K:
-        lib().oracle_paste_masks(_p(probs), _p(boxes), K, S, H, W, ctypes.c_float(thr), _p(masks), _p(values))
+        lib().oracle_paste_masks2(_p(probs), _p(boxes), K, S, H, W, ctypes.c_float(thr), int(bool(skip_empty)), _p(masks), _p(values))
     return (masks.astype(bool), values) if want_values else masks.astype(bool)

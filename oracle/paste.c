@@ -21,7 +21,17 @@
 #include <stdint.h>
 
 /* probs (K,S,S) f32, boxes (K,4) f32 -> masks (K,H*W) u8; values (K,H*W) f32 nullable (sampled value inside the region, 0 outside) */
+void oracle_paste_masks2(const float *probs, const float *boxes, int K, int S, int H, int W, float thr, int skip_empty, uint8_t *masks, float *values);
+
 void oracle_paste_masks(const float *probs, const float *boxes, int K, int S, int H, int W, float thr, uint8_t *masks, float *values)
+{
+    oracle_paste_masks2(probs, boxes, K, S, H, W, thr, 1, masks, values);
+}
+
+/* skip_empty = 1: the CPU path above (integer neighbourhood of the box).  skip_empty = 0: what _do_paste_mask does for CUDA
+ * tensors - the path the reference actually takes (custom_rcnn.py:880 is called on .cuda() tensors): the whole image is sampled.
+ * The two agree for probabilities <= 1 and thr >= 0.5 (outside the neighbourhood the bilinear value is < 0.5). */
+void oracle_paste_masks2(const float *probs, const float *boxes, int K, int S, int H, int W, float thr, int skip_empty, uint8_t *masks, float *values)
 {
     const float half_S = (float)S / 2.0f;
     for (int k = 0; k < K; ++k) {
@@ -29,10 +39,11 @@ void oracle_paste_masks(const float *probs, const float *boxes, int K, int S, in
         const float x0 = boxes[4 * k], y0 = boxes[4 * k + 1], x1 = boxes[4 * k + 2], y1 = boxes[4 * k + 3];
         const float dx = x1 - x0, dy = y1 - y0;
         float f;
-        f = floorf(x0) - 1.0f; const int rx0 = (int)(f < 0 ? 0 : (f > W ? W : f));
-        f = floorf(y0) - 1.0f; const int ry0 = (int)(f < 0 ? 0 : (f > H ? H : f));
-        f = ceilf(x1) + 1.0f;  const int rx1 = (int)(f > W ? W : (f < 0 ? 0 : f));
-        f = ceilf(y1) + 1.0f;  const int ry1 = (int)(f > H ? H : (f < 0 ? 0 : f));
+        f = floorf(x0) - 1.0f; int rx0 = (int)(f < 0 ? 0 : (f > W ? W : f));
+        f = floorf(y0) - 1.0f; int ry0 = (int)(f < 0 ? 0 : (f > H ? H : f));
+        f = ceilf(x1) + 1.0f;  int rx1 = (int)(f > W ? W : (f < 0 ? 0 : f));
+        f = ceilf(y1) + 1.0f;  int ry1 = (int)(f > H ? H : (f < 0 ? 0 : f));
+        if (!skip_empty) { rx0 = 0; ry0 = 0; rx1 = W; ry1 = H; }
         for (long p = 0; p < (long)H * W; ++p) { masks[(long)k * H * W + p] = 0; if (values) values[(long)k * H * W + p] = 0.0f; }
         for (int py = ry0; py < ry1; ++py) {
             float gy = ((float)py + 0.5f) - y0; gy = gy / dy; gy = gy * 2.0f; gy = gy - 1.0f;

@@ -102,12 +102,15 @@ def quantize_flat_index(world_xyz: torch.Tensor, map_world_shift: torch.Tensor, 
 # --------------------------------------------------------------------------------------------------
 
 
-def paste_masks_in_image(masks: torch.Tensor, boxes: torch.Tensor, image_shape, threshold: float = 0.5, want_values: bool = False):
+def paste_masks_in_image(masks: torch.Tensor, boxes: torch.Tensor, image_shape, threshold: float = 0.5, want_values: bool = False,
+                         skip_empty: bool = True):
     """detectron2 layers/mask_ops.py paste_masks_in_image + _do_paste_mask as executed on the CPU (call site
     custom_rcnn.py:880): one chunk per mask, skip_empty=True, F.grid_sample(align_corners=False), ``>= threshold``.
     detectron2 is not vendored in /root/reference (README :36-39, git master): this is a restatement of its published
     source; the arithmetic that decides the result (grid construction + grid_sample) is executed by torch itself.
-    masks (K,S,S) f32 probabilities, boxes (K,4) f32 XYXY -> (K,H,W) bool."""
+    masks (K,S,S) f32 probabilities, boxes (K,4) f32 XYXY -> (K,H,W) bool.
+    skip_empty=False restates the branch _do_paste_mask takes for CUDA tensors (the reference's live path): the whole image
+    is sampled instead of the box's integer neighbourhood."""
     img_h, img_w = image_shape
     N = masks.shape[0]
     img_masks = torch.zeros(N, img_h, img_w, dtype=torch.bool)
@@ -117,6 +120,8 @@ def paste_masks_in_image(masks: torch.Tensor, boxes: torch.Tensor, image_shape, 
         x0_int, y0_int = torch.clamp(b.min(dim=0).values.floor()[:2] - 1, min=0).to(dtype=torch.int32)
         x1_int = torch.clamp(b[:, 2].max().ceil() + 1, max=img_w).to(dtype=torch.int32)
         y1_int = torch.clamp(b[:, 3].max().ceil() + 1, max=img_h).to(dtype=torch.int32)
+        if not skip_empty:
+            x0_int, y0_int, x1_int, y1_int = 0, 0, img_w, img_h
         x0, y0, x1, y1 = torch.split(b, 1, dim=1)
         if int(y0_int) >= int(y1_int) or int(x0_int) >= int(x1_int):
             continue        # box entirely outside the image: torch.arange would raise upstream; fast_rcnn_inference clips boxes, so it cannot occur
@@ -257,15 +262,18 @@ def scatter_max_canonical(src: torch.Tensor, index: torch.Tensor, out: torch.Ten
     s, ix = src.numpy(), index.numpy()
     # vectorised equivalent of the sequential loop: stable sort by (cell, value, position)
     import numpy as np
+    keep = ~np.isnan(s)                      # `NaN >= x` is false: a NaN height never raises a cell and never shadows a finite one
+    pos = np.arange(s.shape[0])[keep]
+    s, ix = s[keep], ix[keep]
     if s.shape[0]:
-        order = np.lexsort((np.arange(s.shape[0]), s, ix))
+        order = np.lexsort((pos, s, ix))
         ixs = ix[order]
         last = np.r_[ixs[1:] != ixs[:-1], True]
         win = order[last]
         cells = ix[win]
         raise_ = s[win] >= o[cells]
         o[cells[raise_]] = s[win][raise_]
-        arg[cells[raise_]] = win[raise_]
+        arg[cells[raise_]] = pos[win[raise_]]
     return torch.from_numpy(o), torch.from_numpy(arg)
 
 

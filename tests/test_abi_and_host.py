@@ -89,6 +89,22 @@ def test_config_keys_and_defaults(eod):
     assert f2(res, None, None, None)[0] is res[0]        # image_only: FPN results untouched (timm.py:194-196)
 
 
+def test_backbone_state_dict_is_the_reference_key_set(eod):
+    """the three 1x1 convs must appear ONCE, under the reference's names (timm.py:78-86), so that a reference
+    checkpoint loads with strict=True and saved checkpoints carry no keys the reference does not know."""
+    fusion = eod.MemoryFusion("implicit_memory", "sum", 5.0)
+    body = torch.nn.Conv2d(3, 8, 1)
+    bb = eod.CustomRecurrentFPN(lambda x: [body(x)] * 3, None, fusion)
+    bb.body = body
+    keys = sorted(bb.state_dict().keys())
+    assert keys == sorted(["body.weight", "body.bias"] + [f"map_merge_projection{i}.{p}" for i in (1, 2, 3) for p in ("bias", "weight")])
+    ref_ckpt = {k: torch.randn_like(v) for k, v in bb.state_dict().items()}
+    bb.load_state_dict(ref_ckpt, strict=True)
+    assert torch.equal(fusion.map_merge_projection2.weight, ref_ckpt["map_merge_projection2.weight"])       # shared parameters
+    assert sum(p.numel() for p in bb.parameters()) == sum(v.numel() for v in ref_ckpt.values())
+    assert any("map_merge" in n for n, _ in bb.named_parameters())                                        # the LR / un-freeze rule still matches
+
+
 def test_map_dims_lookup(eod):
     info = {"17DRP5sb8fy_0": {"dim": [1094, 1, 569]}}
     rep = {"apartment_0": {"dim": [120, 1, 80]}}

@@ -753,7 +753,9 @@ def test_paste_masks_randomised_vs_oracle(eod, cuda, H, W, S):
         masks, observed = eod.ops.paste_masks(_t(probs, cuda), _t(boxes, cuda), (H, W), thr, _t(n_obj, cuda), want_observed=True)
         masks = masks.cpu().numpy()
         for e in range(E):
-            ref = oracle.paste_masks(probs[e, : n_obj[e]], boxes[e, : n_obj[e]], H, W, thr)
+            # thr >= 0.5: detectron2's CPU path (integer box neighbourhood) == its CUDA path; below 0.5 the library follows the
+            # CUDA path the reference takes (whole image sampled, skip_empty=False)
+            ref = oracle.paste_masks(probs[e, : n_obj[e]], boxes[e, : n_obj[e]], H, W, thr, skip_empty=thr >= 0.5)
             assert np.array_equal(masks[e, : n_obj[e]], ref), (thr, e, int((masks[e, : n_obj[e]] != ref).sum()))
             assert not masks[e, n_obj[e]:].any()
             assert np.array_equal(observed[e].cpu().numpy().astype(bool), ref.any(0).reshape(-1) if n_obj[e] else np.zeros(H * W, bool))
@@ -915,6 +917,10 @@ def test_write_max_vs_oracle(eod, cuda, layout, stride):
         heights = (np.round(rng.uniform(-1.5, 1.0, (H, W)) * 4) / 4).astype(np.float32)        # quantised -> many exact ties
         if t == 2:
             heights[:] = heights.min() - 5                                                       # nothing raised except new cells
+        if t == 3:                                                                               # non-finite heights: a NaN pixel
+            heights[rng.uniform(size=(H, W)) < 0.1] = np.nan                                     # neither raises a cell nor shadows finite ones;
+            heights[rng.uniform(size=(H, W)) < 0.02] = np.inf                                    # +inf wins like any maximum, -inf never does
+            heights[rng.uniform(size=(H, W)) < 0.02] = -np.inf
         feat = rng.standard_normal((H, W, C)).astype(np.float32)
         state, observed, hmap, arg, m = R.smnet_heightmax_frame(state, observed, hmap, torch.from_numpy(feat), torch.from_numpy(w2m),
                                                                 torch.from_numpy(inl), torch.from_numpy(heights), mw, stride)
