@@ -178,6 +178,11 @@ class EpisodeBatch:
         """A10-A12 fused: [L0 (E,C,H/8,W/8), L1, L2] fp16 (channels_last memory)."""
         return self._timed("read", ops.read_pool, self.norm16, None, self.idx, out=self.levels)
 
+    def read_roi(self, boxes: torch.Tensor, batch_idx: torch.Tensor, pooled: int = 7) -> torch.Tensor:
+        """Per-proposal map features of the CURRENT frame's levels (call after ``step`` / ``read``): boxes (R,4) f32 XYXY in image
+        pixels, batch_idx (R) i32 slot of each box -> logical (R,C,pooled,pooled) f32 (see ops.read_roi / eod_read_roi)."""
+        return ops.read_roi([l.permute(0, 3, 1, 2) for l in self.levels], boxes, batch_idx, pooled)
+
     def _count(self, samp: Optional[torch.Tensor], active: Optional[torch.Tensor] = None) -> None:
         self._timed("count", ops.frame_count, self.idx, samp, self.frame_cnt, active)
         if self.variant != WRITE_DET and self.layout == LAYOUT_CHW:      # only the TMA-staged CHW kernel takes per-pixel divisors

@@ -18,7 +18,7 @@ launch_count = 0
 _LAUNCHES = {"eod_backproject_quantize": 1, "eod_quantize_world": 1, "eod_sample_mask": 1, "eod_frame_count": 1, "eod_expand_counts": 1, "eod_write_mean": 1, "eod_write_mean_det": 9,
              "eod_finalize_counts": 1, "eod_box_to_image_features": 1, "eod_masks_observed": 1, "eod_paste_masks": 1, "eod_write_objects_pasted": 1, "eod_bilinear_lattice": 1, "eod_write_objects": 1, "eod_flush_slots": 2, "eod_write_max": 2, "eod_read_pool": 2,
              "eod_fuse": 1, "eod_project_split_weights": 1, "eod_project_fuse": 1, "eod_project_fuse_levels": 1, "eod_normalize_memory": 1, "eod_reset_touched": 1, "eod_semmap_update": 1, "eod_semmap_decode": 2,
-             "eod_reset_episodes": 1, "eod_refresh_norm16": 1, "eod_check_indices": 1}
+             "eod_reset_episodes": 1, "eod_refresh_norm16": 1, "eod_check_indices": 1, "eod_read_roi": 1}
 
 
 def _call(name: str, *args) -> None:
@@ -446,6 +446,43 @@ def read_pool(table: torch.Tensor, counts: Optional[torch.Tensor], idx: torch.Te
           int(idx.dtype == torch.int64), E, C, H, W, n_cells, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
           _stream())
     return [o.permute(0, 3, 1, 2) for o in out]
+
+
+def read_roi(levels: Sequence[torch.Tensor], boxes: torch.Tensor, batch_idx: Optional[torch.Tensor] = None, pooled: int = 7,
+             strides: Sequence[int] = (8, 16, 32), sampling_ratio: int = 0, min_level: int = 3, canonical_size: float = 224.0,
+             canonical_level: int = 4, want_levels: bool = False):
+    """Per-ROI map features: ROIAlign (aligned, detectron2 ROIAlignV2) of the pooled memory levels over the proposals' boxes with
+    the FPN level assignment (detic_roi_heads.py:331-334 applied to the memory levels; see eod_read_roi).
+    levels: what read_pool returns - logical (E,C,h,w) fp16 tensors in channels-last memory; boxes (R,4) f32 XYXY image pixels;
+    batch_idx (R) i32.  Returns logical (R,C,pooled,pooled) f32 in channels-last memory [, assigned level (R) i32]."""
+    import ctypes
+    n = len(levels)
+    if not (1 <= n <= 4) or len(strides) != n:
+        raise ValueError("read_roi: 1..4 levels with one stride each")
+    _dev(boxes, torch.float32, "boxes")
+    if boxes.dim() != 2 or boxes.shape[1] != 4:
+        raise ValueError("boxes must be (R,4) XYXY")
+    R = boxes.shape[0]
+    C = levels[0].shape[1]
+    dims = [_level_dims(lv, C) for lv in levels]
+    E = dims[0][0]
+    if any(d[0] != E for d in dims):
+        raise ValueError("all levels must share the episode dimension")
+    if batch_idx is not None:
+        _dev(batch_idx, torch.int32, "batch_idx")
+        if batch_idx.numel() != R:
+            raise ValueError("batch_idx must hold one int32 per box")
+    elif E != 1:
+        raise ValueError("batch_idx is required when the levels hold more than one episode")
+    out = torch.empty((R, pooled, pooled, C), dtype=torch.float32, device=boxes.device)
+    lvl = torch.empty((R,), dtype=torch.int32, device=boxes.device) if want_levels else None
+    if R:
+        _call("eod_read_roi", n, (ctypes.c_void_p * n)(*[lv.data_ptr() for lv in levels]), (ctypes.c_int * n)(*[d[1] for d in dims]),
+              (ctypes.c_int * n)(*[d[2] for d in dims]), (ctypes.c_float * n)(*[1.0 / float(s) for s in strides]), E, C, boxes.data_ptr(),
+              _ptr(batch_idx), R, int(pooled), int(sampling_ratio), int(min_level), float(canonical_size), int(canonical_level),
+              out.data_ptr(), _ptr(lvl), _stream())
+    out = out.permute(0, 3, 1, 2)
+    return (out, lvl) if want_levels else out
 
 
 def fuse(res: Optional[torch.Tensor], mem: Optional[torch.Tensor], weight: float, mode: int,

@@ -229,6 +229,23 @@ int eod_read_pool(const void *table, int mem_is_f16, const float *counts, const 
                   eod_stream_t stream);
 
 
+/* Per-ROI read (north star subsystem 3): ROIAlign of the pooled memory levels over each proposal's box - the pooling the
+ * reference's ROI heads apply to the FUSED levels (detic_roi_heads.py:331-334, self.box_pooler = detectron2 ROIPooler:
+ * ROIAlignV2 (aligned, half-pixel offset), sampling_ratio 0 (adaptive ceil(roi / pooled)), 7x7 bins, scales 1/8, 1/16, 1/32,
+ * FPN level assignment floor(canonical_level + log2(sqrt(area) / canonical_size + eps)) clamped to the available levels).
+ * ROIAlign is linear, so pooling the memory levels with the proposals' boxes yields the per-ROI map feature that the fused
+ * path carries implicitly: pool(res + w (conv(L) + b)) = pool(res) + w (conv(pool(L)) + b).
+ *   levels / level_h / level_w / level_scale: HOST arrays of n_levels (<= 4) entries; levels[l] = device pointer of an
+ *     (E, h_l, w_l, C) fp16 channels-last level exactly as eod_read_pool stores it; level_scale[l] = 1 / stride
+ *   boxes (R,4) f32 XYXY in image pixels, batch_idx (R) i32 episode of each box (nullable = 0)
+ *   out (R, pooled, pooled, C) f32 channels-last (logical (R, C, pooled, pooled)); out_level (R) i32 nullable: assigned level
+ * Sample points, clamping and summation order of torchvision's CPU ROIAlign (ops/cpu/roi_align_kernel.cpp); accumulated fp32:
+ * within 1e-5 of scale of the executed reference op, level assignments exact.  min_level: index of levels[0] in the pyramid
+ * (3 for p3); canonical_size 224, canonical_level 4 in detectron2. */
+int eod_read_roi(int n_levels, const void *const *levels, const int *level_h, const int *level_w, const float *level_scale,
+                 int n_episodes, int C, const float *boxes, const int32_t *batch_idx, int n_rois, int pooled, int sampling_ratio,
+                 int min_level, float canonical_size, int canonical_level, float *out, int32_t *out_level, eod_stream_t stream);
+
 /* Stand-alone create_implicit_memory (custom_rcnn.py:764-774, and the half cast of :1036 when out_is_f16):
  * out[row] = sums[row] / counts[row] where counts[row] > 1 else sums[row].  n_rows = E*cells.  Only for
  * callers that need the normalised table itself; eod_read_pool fuses this step. */

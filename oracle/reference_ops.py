@@ -339,6 +339,34 @@ def project_and_fuse(levels: Sequence[torch.Tensor], results: Sequence[torch.Ten
     return out
 
 
+def assign_boxes_to_levels(boxes: torch.Tensor, min_level: int = 3, max_level: int = 5, canonical_box_size: int = 224,
+                           canonical_level: int = 4) -> torch.Tensor:
+    """detectron2 modeling/poolers.py assign_boxes_to_levels (published source restated; detectron2 is not under /root/reference):
+    floor(canonical_level + log2(sqrt(area) / canonical_box_size + eps)) clamped to [min_level, max_level], minus min_level."""
+    import sys
+    box_sizes = torch.sqrt((boxes[:, 2] - boxes[:, 0]) * (boxes[:, 3] - boxes[:, 1]))
+    lvl = torch.floor(canonical_level + torch.log2(box_sizes / canonical_box_size + sys.float_info.epsilon))
+    lvl = torch.clamp(lvl, min=min_level, max=max_level)
+    return lvl.to(torch.int64) - min_level
+
+
+def roi_read(levels: Sequence[torch.Tensor], boxes_per_image: Sequence[torch.Tensor], pooled: int = 7, strides=(8, 16, 32)):
+    """The box pooling of detic_roi_heads.py:331-334 (detectron2 ROIPooler, ROIAlignV2 = torchvision roi_align(aligned=True),
+    sampling_ratio 0) applied to the pooled MEMORY levels: levels[l] (B,C,h,w) -> (sum n_i, C, pooled, pooled) f32, levels (sum n_i).
+    torchvision's CPU ROIAlign is EXECUTED here; the level assignment is the restatement above."""
+    from torchvision.ops import roi_align
+    boxes = torch.cat(list(boxes_per_image), 0).float()
+    bidx = torch.cat([torch.full((b.shape[0], 1), float(i)) for i, b in enumerate(boxes_per_image)], 0)
+    rois = torch.cat([bidx, boxes], 1)
+    lvl = assign_boxes_to_levels(boxes, 3, 3 + len(levels) - 1)
+    out = torch.zeros(boxes.shape[0], levels[0].shape[1], pooled, pooled)
+    for k, (x, s) in enumerate(zip(levels, strides)):
+        sel = (lvl == k).nonzero().squeeze(1)
+        if sel.numel():
+            out[sel] = roi_align(x.float().contiguous(), rois[sel], (pooled, pooled), 1.0 / s, 0, True)
+    return out, lvl
+
+
 def read_frame(sums, counts, proj) -> List[torch.Tensor]:
     """A10 -> A11 -> A12 for one frame."""
     return read_pool(create_implicit_memory(sums, counts).to(torch.half), proj)

@@ -341,9 +341,13 @@ def test_memory_fusion_tensor_core_and_library_paths_agree(eod, cuda):
     before = eod.ops.launch_count
     with torch.no_grad():
         a = tc(res, [mem16], [idx], [None])
-        assert eod.ops.launch_count - before == 2 + 3 + 1        # read (L0/L1 + L2 pooling) + 3 weight splits + ONE fused projection launch
+        assert eod.ops.launch_count - before == 1 + 2 + 3 + 1    # index range check + read (L0/L1 + L2 pooling) + 3 weight splits + ONE fused projection launch
         a2 = tc(res, [mem16], [idx], [None])                     # weights unchanged: split cached
-        assert eod.ops.launch_count - before == 2 + 3 + 1 + 2 + 1
+        assert eod.ops.launch_count - before == 1 + 2 + 3 + 1 + 1 + 2 + 1
+        tc.validate_indices = False                              # planes that eod_backproject_quantize produced for this grid need no check
+        tc(res, [mem16], [idx], [None])
+        assert eod.ops.launch_count - before == 1 + 2 + 3 + 1 + 1 + 2 + 1 + 2 + 1
+        tc.validate_indices = True
         b = lib(res, [mem16], [idx], [None])
     for k in range(3):
         assert torch.equal(a[k], a2[k])
@@ -1221,3 +1225,90 @@ def test_edge_frames_through_step(eod, cuda):
     batch.reset()
     torch.cuda.synchronize()
     assert not batch.sums.any() and not batch.counts.any() and not batch.norm16.any()
+
+
+# --------------------------------------------------------------------------------------------------------
+# per-ROI read (north star subsystem 3; detic_roi_heads.py:331-334 applied to the memory levels)
+# --------------------------------------------------------------------------------------------------------
+def _roi_boxes(rng, n, H, W):
+    """Proposal-like boxes: all three FPN levels, fractional corners, boxes on the image border, a degenerate and a full-image one,
+    and sizes on the level-assignment knife edges (sqrt(area) = 112, 224, 448 up to an ulp)."""
+    cx, cy = rng.uniform(0, W, n), rng.uniform(0, H, n)
+    s = np.exp(rng.uniform(np.log(8), np.log(min(H, W)), n))
+    ar = np.exp(rng.uniform(-1, 1, n))
+    bw, bh = s * np.sqrt(ar), s / np.sqrt(ar)
+    b = np.stack([cx - bw / 2, cy - bh / 2, cx + bw / 2, cy + bh / 2], 1)
+    b[:, [0, 2]] = np.clip(b[:, [0, 2]], 0, W)
+    b[:, [1, 3]] = np.clip(b[:, [1, 3]], 0, H)                         # _create_proposals_from_boxes clips to the image (:314)
+    b = b.astype(np.float32)
+    extra = [[0, 0, W, H], [10, 10, 10, 40], [3.25, 7.5, 3.25 + 224, 7.5 + 224], [0, 0, 112, 112], [1, 1, 1 + 448, 1 + 448 * 0.999999],
+             [5, 5, 5 + np.nextafter(np.float32(224), np.float32(0)), 5 + 224], [W - 9.5, H - 7.25, W, H], [0, 0, 0.5, 0.5]]
+    return np.concatenate([b, np.asarray(extra, np.float32)], 0)
+
+
+@pytest.mark.parametrize("C,E", [(128, 1), (256, 3), (512, 2)])
+def test_read_roi_matches_executed_roi_align(eod, cuda, C, E):
+    """eod_read_roi against torchvision's CPU ROIAlign (executed) over the oracle's pooled levels, with detectron2's level
+    assignment: levels assigned exactly, pooled features within 1e-5 of scale."""
+    rng = np.random.default_rng(C + E)
+    H, W, cells = 480, 640, 3000
+    table = _t((rng.standard_normal((E, cells, C)) * 3).astype(np.float16), cuda)
+    idx = _t((rng.integers(0, cells, (E, H // 8, W // 8)).repeat(8, 1).repeat(8, 2)).astype(np.int32), cuda)
+    levels = eod.ops.read_pool(table, None, idx)
+    boxes = [_roi_boxes(rng, 40, H, W) for _ in range(E)]
+    bx = _t(np.concatenate(boxes), cuda)
+    bi = _t(np.concatenate([np.full(len(b), e, np.int32) for e, b in enumerate(boxes)]), cuda)
+    got, lvl = eod.ops.read_roi(levels, bx, bi, 7, want_levels=True)
+    torch.cuda.synchronize()
+    assert got.shape == (bx.shape[0], C, 7, 7)
+    ref, ref_lvl = R.roi_read([l.cpu() for l in levels], [torch.from_numpy(b) for b in boxes])
+    assert np.array_equal(lvl.cpu().numpy(), ref_lvl.numpy())                     # ROI -> level assignment: exact
+    assert len(set(ref_lvl.tolist())) == 3                                         # the case exercises all three levels
+    err = (got.cpu() - ref).abs().max().item()
+    assert err <= SUM_TOL * ref.abs().max().item(), err
+    # linearity, i.e. why this IS the reference's per-ROI memory term: pooling the fused level == pooled res + w * conv(pooled memory)
+    from torchvision.ops import roi_align
+    k = 1
+    sel = (ref_lvl == k).nonzero().squeeze(1)
+    conv = torch.nn.Conv2d(C, 32, 1).double()
+    res = torch.randn(E, 32, H // 16, W // 16, dtype=torch.float64)
+    fused = res + 5.0 * conv(levels[k].cpu().double())
+    rois = torch.cat([bi.cpu().double()[:, None], bx.cpu().double()], 1)[sel]
+    lhs = roi_align(fused, rois, (7, 7), 1 / 16, 0, True)
+    pooled_mem = got.cpu().double()[sel]
+    rhs = roi_align(res, rois, (7, 7), 1 / 16, 0, True) + 5.0 * conv(pooled_mem)
+    inside = (rois[:, 3] - rois[:, 1] > 0) & (rois[:, 4] - rois[:, 2] > 0)        # an empty box pools nothing: the bias has no weight there
+    assert (lhs - rhs)[inside].abs().max().item() <= 1e-4 * lhs.abs().max().item()
+
+
+def test_memory_fusion_read_roi_and_episode_batch_read_roi(eod, cuda):
+    """The module-level entry points: MemoryFusion.read_roi (reference-facing, lists per image; project=True returns the memory
+    term of box_pooler(fused levels)) and EpisodeBatch.read_roi (levels of the current frame)."""
+    rng = np.random.default_rng(5)
+    C, CO, H, W, cells = 256, 128, 96, 128, 500
+    fusion = eod.MemoryFusion("implicit_memory", "sum", 5, mem_feat_dim=C, ego_feat_dim=CO).to(cuda)
+    mem16 = [_t((rng.standard_normal((cells, C)) * 2).astype(np.float16), cuda) for _ in range(2)]
+    idx = [_t(rng.integers(0, cells, (H // 4, W // 4)).repeat(4, 0).repeat(4, 1).astype(np.int64), cuda) for _ in range(2)]
+    boxes = [torch.from_numpy(_roi_boxes(rng, 12, H, W)[:14]).clamp(0, W) for _ in range(2)]
+    for b in boxes:
+        b[:, [1, 3]] = b[:, [1, 3]].clamp(0, H)
+    roi = fusion.read_roi(mem16, idx, boxes)
+    levels = fusion.read(mem16, idx, [None, None])
+    ref, ref_lvl = R.roi_read([l.cpu() for l in levels], boxes)
+    assert (roi.cpu() - ref).abs().max().item() <= SUM_TOL * ref.abs().max().item()
+    with torch.no_grad():
+        proj = fusion.read_roi(mem16, idx, boxes, project=True).cpu()
+        want = torch.zeros_like(proj)
+        for k, conv in enumerate(fusion.merge_map_projections):
+            sel = (ref_lvl == k).nonzero().squeeze(1)
+            if sel.numel():
+                want[sel] = 5.0 * torch.nn.functional.conv2d(ref[sel], conv.weight.cpu(), conv.bias.cpu())
+    assert (proj - want).abs().max().item() <= 1e-4 * want.abs().max().item()
+    batch = eod.EpisodeBatch(2, 25, 20, C, H, W, cuda)
+    batch.norm16.copy_(torch.stack(mem16))
+    batch.set_indices(torch.stack(idx))
+    batch.read()
+    bx = torch.cat(boxes).to(cuda)
+    bi = torch.cat([torch.full((len(b),), i, dtype=torch.int32) for i, b in enumerate(boxes)]).to(cuda)
+    got = batch.read_roi(bx, bi)
+    assert (got.cpu() - ref).abs().max().item() <= SUM_TOL * ref.abs().max().item()
