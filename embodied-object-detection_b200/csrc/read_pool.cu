@@ -130,33 +130,38 @@ template <int V> struct RawOf<__half, V> { using type = RawF16<V>; };
 // Warp-autonomous read: a work item = one 16x16-pixel quadrant (4 L0 pixels, 1 L1 pixel) x all C channels, owned by ONE
 // warp (lane = group of V = C/32 consecutive channels: the per-run bookkeeping below is scalar work that every lane
 // repeats, so wider lanes amortise it over more channels - V = 4 -> 8 took C=256 from 0.40 to 0.27 ms, V = 8 -> 16 took
-// C=512 from 0.51 to 0.40 ms at E=64).  The warp stages the quadrant's 256 cell ids in its private
-// slice of shared memory, classifies its 16 windows itself (lanes 0-15) and walks them - no CTA barrier anywhere, and the
-// ids of the NEXT item are already in flight (registers) while the current one is processed.  Level 2 needs four L1
-// pixels of different quadrants; it is pooled from the stored L1 by pool_level2_kernel instead of through a CTA-wide
-// exchange.  (The CTA-per-32x32-block version spent 35 % of its stall samples on the index staging latency and on two
-// barriers per block.)
+// C=512 from 0.51 to 0.40 ms at E=64).  No CTA barrier anywhere; the ids of the NEXT item are already in flight (registers)
+// while the current one is processed.  Level 2 needs four L1 pixels of different quadrants; it is pooled from the stored L1
+// by pool_level2_kernel instead of through a CTA-wide exchange.
+//
+// v3 (round 2) - the kernel is issue-bound, so this version removes instructions, not bytes:
+//  * the run structure of the 16 4x4 windows is derived IN PARALLEL: lane -> (window, half) loads its two 4-pixel row
+//    segments straight from global memory, compares neighbours in summation order (8 compares + one shuffle) and the
+//    pair of lanes of a window combines its 16-bit "run head" mask with one more shuffle.  v2 had lanes 0-15 walk their
+//    window serially and write run lists to shared memory (~200 warp instructions per item, half of them predicated off);
+//  * windows are numbered L0-block-major, so the four masks / first cells an L0 pixel needs come back with one LDS each;
+//    runs are then enumerated from the mask in registers (ffs) and only a run's cell id is read from shared memory;
+//  * item -> (episode, quadrant) is stepped incrementally in 32-bit arithmetic (v2 decoded every item - and the
+//    prefetched one - with 64-bit divisions: six software-division calls per item).
 //
 // Summation order == ATen CPU avg_pool2d: fp32, start from 0, row-major over the window, then / k^2; the fp16 roundings
 // between levels (timm.py:168) are reproduced, so outputs are bit-identical.
 constexpr int kReadWarps = 8;
 
-struct QuadIdx { int v[8]; };
+struct QuadIdx { int a[4], b[4]; };      // two 4-pixel row segments of this lane's window half
 
 template <typename IdxT>
-__device__ __forceinline__ QuadIdx load_quad_idx(const IdxT *idx_e, int W, int qy, int qx, unsigned lane)
+__device__ __forceinline__ QuadIdx load_quad_idx(const IdxT *src, int W)
 {
-    // lane -> row lane>>1 of the quadrant, columns (lane&1)*8 .. +7
-    const IdxT *src = idx_e + (size_t)(qy * 16 + (lane >> 1)) * W + qx * 16 + (lane & 1) * 8;
     QuadIdx q;
     if (sizeof(IdxT) == 4) {
-        const int4 a = __ldg(reinterpret_cast<const int4 *>(src)), b = __ldg(reinterpret_cast<const int4 *>(src) + 1);
-        q.v[0] = a.x; q.v[1] = a.y; q.v[2] = a.z; q.v[3] = a.w; q.v[4] = b.x; q.v[5] = b.y; q.v[6] = b.z; q.v[7] = b.w;
+        const int4 a = __ldg(reinterpret_cast<const int4 *>(src)), b = __ldg(reinterpret_cast<const int4 *>(src + W));
+        q.a[0] = a.x; q.a[1] = a.y; q.a[2] = a.z; q.a[3] = a.w; q.b[0] = b.x; q.b[1] = b.y; q.b[2] = b.z; q.b[3] = b.w;
     } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const longlong2 a = __ldg(reinterpret_cast<const longlong2 *>(src) + k);
-            q.v[2 * k] = (int)a.x; q.v[2 * k + 1] = (int)a.y;
+        for (int k = 0; k < 2; ++k) {
+            const longlong2 a = __ldg(reinterpret_cast<const longlong2 *>(src) + k), b = __ldg(reinterpret_cast<const longlong2 *>(src + W) + k);
+            q.a[2 * k] = (int)a.x; q.a[2 * k + 1] = (int)a.y; q.b[2 * k] = (int)b.x; q.b[2 * k + 1] = (int)b.y;
         }
     }
     return q;
@@ -168,142 +173,126 @@ __global__ void __launch_bounds__(kReadWarps * 32, (C >= 512 ? 2 : (C >= 256 ? 3
                                                                                         __half *__restrict__ L0, __half *__restrict__ L1)
 {
     constexpr int V = C >= 512 ? 16 : (C >= 256 ? 8 : 4);      // channels per lane
-    constexpr int NC = C / (32 * V);         // channel chunks per quadrant
+    static_assert(C == 32 * V, "one warp covers all channels of a quadrant");
     using Raw = typename RawOf<TableT, V>::type;
-    __shared__ __align__(16) int s_idx[kReadWarps][16 * 16];
-    __shared__ int s_wcell[kReadWarps][16];                    // per 4x4 window: the cell id if all 16 pixels agree, else -1
-    __shared__ int s_run_cell[kReadWarps][16][16];             // mixed windows: runs of equal cell id in row-major (= summation) order ...
-    __shared__ __align__(16) unsigned char s_run_len[kReadWarps][16][16];   // ... their lengths ...
-    __shared__ int s_nruns[kReadWarps][16];                    // ... and how many there are
+    __shared__ __align__(16) int s_idx[kReadWarps][16 * 16];                 // window-major: [window][pixel in summation order]
+    __shared__ __align__(16) int s_wc[kReadWarps][16];                       // first cell of each window
+    __shared__ __align__(16) unsigned short s_wm[kReadWarps][16];            // run-head mask of each window (bit p: pixel p starts a run)
 
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nqy = H / 16, nqx = W / 16;
-    const int64_t n_items = (int64_t)E * nqy * nqx * NC;
-    const int64_t stride = (int64_t)gridDim.x * kReadWarps;
+    const int nqy = H / 16, nqx = W / 16, per_ep = nqy * nqx;
+    const int n_items = E * per_ep;                                          // the host guarantees it fits 31 bits
+    const int stride = (int)gridDim.x * kReadWarps;
     const int h0 = H / 8, w0 = W / 8, h1 = H / 16, w1 = W / 16;
 
-    auto decode = [&](int64_t item, int &e, int &qy, int &qx, int &chunk) {
-        chunk = (int)(item % NC);
-        int64_t q = item / NC;
-        qx = (int)(q % nqx); q /= nqx;
-        qy = (int)(q % nqy);
-        e = (int)(q / nqy);
-    };
-
-    int64_t item = (int64_t)blockIdx.x * kReadWarps + warp;
+    int item = (int)blockIdx.x * kReadWarps + (int)warp;
     if (item >= n_items) return;
-    int e, qy, qx, chunk;
-    decode(item, e, qy, qx, chunk);
-    QuadIdx nxt = load_quad_idx<IdxT>(idx + (size_t)e * H * W, W, qy, qx, lane);
+    // item -> (episode, quadrant row, quadrant column), then stepped with carries: no division inside the loop
+    int e = item / per_ep, qy = (item - e * per_ep) / nqx, qx = item - e * per_ep - qy * nqx;
+    const int se = stride / per_ep, sqy = (stride - se * per_ep) / nqx, sqx = stride - se * per_ep - sqy * nqx;
+    // this lane's share of a quadrant: window w = lane >> 1 in L0-block-major order (w = l0 * 4 + win), rows 2h, 2h+1 of the window
+    const int w = lane >> 1, hh = lane & 1;
+    const int lane_off = (((w >> 3) * 8 + ((w >> 1) & 1) * 4 + 2 * hh) * W) + ((w >> 2) & 1) * 8 + (w & 1) * 4;
+    auto src_of = [&](int e_, int qy_, int qx_) { return idx + ((size_t)e_ * H + (size_t)qy_ * 16) * W + qx_ * 16 + lane_off; };
+    QuadIdx nxt = load_quad_idx<IdxT>(src_of(e, qy, qx), W);
 
     for (; item < n_items; item += stride) {
-        decode(item, e, qy, qx, chunk);
-        // stage this item's ids, start the next item's loads
+        const QuadIdx q = nxt;
+        const int ce = e, cqy = qy, cqx = qx;
+        // advance to the next item of this warp and start its loads
+        qx += sqx; if (qx >= nqx) { qx -= nqx; ++qy; }
+        qy += sqy; if (qy >= nqy) { qy -= nqy; ++e; }
+        e += se;
+        if (item + stride < n_items) nxt = load_quad_idx<IdxT>(src_of(e, qy, qx), W);
+        // stage the ids window-major; derive the window's run heads in summation (row-major) order
         {
-            int4 *dst = reinterpret_cast<int4 *>(&s_idx[warp][(lane >> 1) * 16 + (lane & 1) * 8]);
-            dst[0] = make_int4(nxt.v[0], nxt.v[1], nxt.v[2], nxt.v[3]);
-            dst[1] = make_int4(nxt.v[4], nxt.v[5], nxt.v[6], nxt.v[7]);
+            int4 *dst = reinterpret_cast<int4 *>(&s_idx[warp][w * 16 + hh * 8]);
+            dst[0] = make_int4(q.a[0], q.a[1], q.a[2], q.a[3]);
+            dst[1] = make_int4(q.b[0], q.b[1], q.b[2], q.b[3]);
         }
-        if (item + stride < n_items) {
-            int e2, qy2, qx2, c2;
-            decode(item + stride, e2, qy2, qx2, c2);
-            nxt = load_quad_idx<IdxT>(idx + (size_t)e2 * H * W, W, qy2, qx2, lane);
-        }
-        __syncwarp();
-        if (lane < 16) {                                   // classify window (lane>>2, lane&3) of the quadrant
-            const int wy = lane >> 2, wx = lane & 3;
-            const int4 r0 = *reinterpret_cast<const int4 *>(&s_idx[warp][(wy * 4 + 0) * 16 + wx * 4]);
-            const int4 r1 = *reinterpret_cast<const int4 *>(&s_idx[warp][(wy * 4 + 1) * 16 + wx * 4]);
-            const int4 r2 = *reinterpret_cast<const int4 *>(&s_idx[warp][(wy * 4 + 2) * 16 + wx * 4]);
-            const int4 r3 = *reinterpret_cast<const int4 *>(&s_idx[warp][(wy * 4 + 3) * 16 + wx * 4]);
-            const int c0 = r0.x;
-            const bool u = (r0.y == c0) & (r0.z == c0) & (r0.w == c0) & (r1.x == c0) & (r1.y == c0) & (r1.z == c0) & (r1.w == c0) &
-                           (r2.x == c0) & (r2.y == c0) & (r2.z == c0) & (r2.w == c0) & (r3.x == c0) & (r3.y == c0) & (r3.z == c0) & (r3.w == c0);
-            s_wcell[warp][lane] = u ? c0 : -1;
-            if (!u) {
-                // a mixed window is typically an edge between two or three cells: 2-8 runs instead of 16 pixels; the walk below
-                // pays the fetch / fp16->fp32 conversion / bookkeeping per RUN and V/2 packed adds per pixel
-                const int cells[16] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w};
-                int prev = c0, len = 1, nr = 0;
-#pragma unroll
-                for (int k = 1; k < 16; ++k) {
-                    if (cells[k] != prev) {
-                        s_run_cell[warp][lane][nr] = prev;
-                        s_run_len[warp][lane][nr] = (unsigned char)len;
-                        ++nr;
-                        prev = cells[k];
-                        len = 1;
-                    } else {
-                        ++len;
-                    }
-                }
-                s_run_cell[warp][lane][nr] = prev;
-                s_run_len[warp][lane][nr] = (unsigned char)len;
-                s_nruns[warp][lane] = nr + 1;
-            }
+        const int prev = __shfl_up_sync(0xffffffffu, q.b[3], 1);             // last pixel of the window's second row (for hh == 1)
+        unsigned m8 = (hh == 0 || q.a[0] != prev) ? 1u : 0u;
+        m8 |= (q.a[1] != q.a[0]) << 1 | (q.a[2] != q.a[1]) << 2 | (q.a[3] != q.a[2]) << 3 | (q.b[0] != q.a[3]) << 4 | (q.b[1] != q.b[0]) << 5 |
+              (q.b[2] != q.b[1]) << 6 | (q.b[3] != q.b[2]) << 7;
+        const unsigned other = __shfl_xor_sync(0xffffffffu, m8, 1);
+        if (hh == 0) {
+            s_wc[warp][w] = q.a[0];
+            s_wm[warp][w] = (unsigned short)(m8 | (other << 8));
         }
         __syncwarp();
 
-        const int g = chunk * 32 + (int)lane;               // group of V channels
-        const TableT *table_e = table + (size_t)e * n_cells * C;
-        const float *counts_e = counts ? counts + (size_t)e * n_cells : nullptr;
+        const int g = (int)lane;                            // group of V channels
+        const TableT *table_e = table + (size_t)ce * n_cells * C;
+        const float *counts_e = counts ? counts + (size_t)ce * n_cells : nullptr;
         int cur_cell = -1;
         Vec<V> cur = vzero<V>();
         Vec<V> l1acc = vzero<V>();
 #pragma unroll 1
         for (int l0 = 0; l0 < 4; ++l0) {                   // L0 pixels of the quadrant, row-major
-            const int l0y = l0 >> 1, l0x = l0 & 1;
             // The four 4x4 windows of this L0 pixel.  A window whose 16 pixels hit ONE cell needs no additions: the
             // gathered value x is an fp16 number, so the sequential fp32 sum 0+x+x+...+x is exact at every step
             // (k*x, k <= 16, has at most 15 significant bits) and avg_pool2d(4) returns x itself - except that -0.0
-            // becomes +0.0 (0 + -0 = +0), which the shortcuts reproduce by adding +0 (found by profiles/stress_read.py).
-            const int wbase = (l0y * 2) * 4 + l0x * 2;
-            const int w00 = s_wcell[warp][wbase];
+            // becomes +0.0 (0 + -0 = +0), which the shortcuts reproduce by adding +0 (found by the read stress sweep).
+            const int4 wc4 = *reinterpret_cast<const int4 *>(&s_wc[warp][l0 * 4]);
+            const uint2 wm2 = *reinterpret_cast<const uint2 *>(&s_wm[warp][l0 * 4]);
             Vec<V> v0;
-            if (w00 >= 0 && w00 == s_wcell[warp][wbase + 1] && w00 == s_wcell[warp][wbase + 4] && w00 == s_wcell[warp][wbase + 5]) {
+            if (wm2.x == 0x00010001u && wm2.y == 0x00010001u && wc4.x == wc4.y && wc4.x == wc4.z && wc4.x == wc4.w) {
                 // whole 8x8 block in one cell: pool(4), pool(2) and the fp16 rounding all return the gathered value
-                if (w00 != cur_cell) cur = finish<V>(load_raw<V>(table_e, counts_e, (size_t)w00, C, g));
-                cur_cell = w00;
+                if (wc4.x != cur_cell) cur = finish<V>(load_raw<V>(table_e, counts_e, (size_t)wc4.x, C, g));
+                cur_cell = wc4.x;
                 v0 = vadd<V>(cur, vzero<V>());               // the reference's sums start from +0: a gathered -0.0 comes out as +0.0
-
             } else {
                 Vec<V> s2 = vzero<V>();
-#pragma unroll 1
-                for (int win = 0; win < 4; ++win) {        // 4x4 windows of the avg_pool2d(4) (timm.py:152)
-                    const int wi = wbase + (win >> 1) * 4 + (win & 1);
-                    const int wc = s_wcell[warp][wi];
-                    if (wc >= 0) {
-                        if (wc != cur_cell) cur = finish<V>(load_raw<V>(table_e, counts_e, (size_t)wc, C, g));
-                        cur_cell = wc;
+                const int wcs[4] = {wc4.x, wc4.y, wc4.z, wc4.w};
+                const unsigned wms[4] = {wm2.x & 0xffffu, wm2.x >> 16, wm2.y & 0xffffu, wm2.y >> 16};
+#pragma unroll
+                for (int win = 0; win < 4; ++win) {        // 4x4 windows of the avg_pool2d(4) (timm.py:152), row-major
+                    const int wc = wcs[win];
+                    unsigned rest = wms[win] & ~1u;          // run heads after the first pixel
+                    if (wc != cur_cell) cur = finish<V>(load_raw<V>(table_e, counts_e, (size_t)wc, C, g));
+                    cur_cell = wc;
+                    if (rest == 0u) {                        // one cell for the whole window
                         s2 = vadd<V>(s2, cur);
                         continue;
                     }
-                    const int nr = s_nruns[warp][wi];
+                    // a mixed window is typically an edge between two or three cells: 2-8 runs instead of 16 pixels; the walk pays
+                    // the fetch / fp16->fp32 conversion / bookkeeping per RUN and V/2 packed adds per pixel.  (A straight-line
+                    // per-pixel walk with a head-bit test per pixel was tried in r2: the compiler if-converts it into predicated
+                    // copies, 52.6 M instead of 40.0 M warp instructions per E=16 launch.)
+                    const int *cells = &s_idx[warp][(l0 * 4 + win) * 16];
                     Vec<V> s4 = vzero<V>();
-                    Raw raw = load_raw<V>(table_e, counts_e, (size_t)s_run_cell[warp][wi][0], C, g);
+                    int p = 0;
 #pragma unroll 1
-                    for (int r = 0; r < nr; ++r) {
-                        cur = finish<V>(raw);
-                        if (r + 1 < nr) raw = load_raw<V>(table_e, counts_e, (size_t)s_run_cell[warp][wi][r + 1], C, g);   // next run's row in flight under the adds
-                        int len = s_run_len[warp][wi][r];   // 1..15, warp-uniform
-                        // sequential fp32 sum: `len` times + cur
+                    while (true) {
+                        const int pn = rest ? (__ffs(rest) - 1) : 16;
+                        rest &= rest - 1;
+                        Raw raw;
+                        int ncell = cur_cell;
+                        if (pn < 16) {                       // next run's row in flight under the adds
+                            ncell = cells[pn];
+                            raw = load_raw<V>(table_e, counts_e, (size_t)ncell, C, g);
+                        }
+                        int len = pn - p;                    // 1..15, warp-uniform; sequential fp32 sum: `len` times + cur
 #pragma unroll 1
                         for (; len >= 4; len -= 4) { s4 = vadd<V>(s4, cur); s4 = vadd<V>(s4, cur); s4 = vadd<V>(s4, cur); s4 = vadd<V>(s4, cur); }
                         if (len & 2) { s4 = vadd<V>(s4, cur); s4 = vadd<V>(s4, cur); }
                         if (len & 1) s4 = vadd<V>(s4, cur);
+                        if (pn >= 16) break;
+                        cur = finish<V>(raw);
+                        cur_cell = ncell;
+                        p = pn;
                     }
-                    cur_cell = s_run_cell[warp][wi][nr - 1];
                     s2 = vadd<V>(s2, vscale<V>(s4, 0.0625f));    // / 16 (exact)
                 }
                 v0 = vround_half<V>(vscale<V>(s2, 0.25f));      // avg_pool2d(2) -> half (timm.py:168, level 0)
             }
-            const int y0 = qy * 2 + l0y, x0 = qx * 2 + l0x;
-            vstore_half<V>(L0 + (((size_t)e * h0 + y0) * w0 + x0) * C + V * g, v0);
+            const int y0 = cqy * 2 + (l0 >> 1), x0 = cqx * 2 + (l0 & 1);
+            vstore_half<V>(L0 + (((size_t)ce * h0 + y0) * w0 + x0) * C + V * g, v0);
             l1acc = vadd<V>(l1acc, v0);
         }
         const Vec<V> v1 = vround_half<V>(vscale<V>(l1acc, 0.25f));  // level 1
-        vstore_half<V>(L1 + (((size_t)e * h1 + qy) * w1 + qx) * C + V * g, v1);
-        __syncwarp();                                       // the slice is rewritten by the next item
+        vstore_half<V>(L1 + (((size_t)ce * h1 + cqy) * w1 + cqx) * C + V * g, v1);
+        __syncwarp();                                       // the slices are rewritten by the next item
     }
 }
 
@@ -352,6 +341,7 @@ int launch(const void *table, int mem_is_f16, const float *counts, const void *i
            int64_t n_cells, void *L0, void *L1, void *L2, cudaStream_t st)
 {
     const int64_t n_items = (int64_t)E * (H / 16) * (W / 16);      // C in {128, 256, 512}: one warp covers all channels of a quadrant (V = C / 32 per lane)
+    EOD_REQUIRE(n_items < (1ll << 31) - (1ll << 24), EOD_ERR_BADARG, "eod_read_pool: too many quadrants for one launch");
     int64_t blocks = (n_items + kReadWarps - 1) / kReadWarps;
     const int64_t cap = (int64_t)eod_num_sms() * 4 * 4;          // 3-4 resident CTAs per SM, a few waves: each warp walks several items with prefetch
     if (blocks > cap) blocks = cap;

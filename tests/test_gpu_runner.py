@@ -123,7 +123,7 @@ def test_runner_matches_serial_reference_loop(eod, cuda, tmp_path, test_type, re
         semmap1, mem, obs = eod.formats.load_memory(str(tmp_path / "memory" / name))
         assert np.array_equal(obs, c_ref.numpy()), name                 # visibility counts: exact
         assert np.abs(mem - s_ref.numpy()).max() <= SUM_TOL * max(float(s_ref.abs().max()), 1e-30), name
-        assert np.array_equal(mem != 0, s_ref.numpy() != 0), name       # touched-cell set: exact
+        assert np.array_equal((mem != 0).any(1), (s_ref.numpy() != 0).any(1)), name      # touched-cell set (rows): exact; single elements may cancel to 0
         assert (semmap1 == 0).all()                                     # no classifier given: semmap stays -1 (+1 on load, loader.py:221)
 
 
