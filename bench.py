@@ -163,17 +163,17 @@ def measured_traffic(E: int):
         return None
 
 
-def write_launch_bytes(E: int, touched_per_launch: float) -> float:
+def write_launch_bytes(E: int, touched_per_launch: float, c: int = C) -> float:
     """Algorithmic bytes of ONE eod_write_mean launch over E episodes (DESIGN.md 'Roofline accounting'):
     features read once + index plane + touched grid rows read-modify-written + per-cell sample counts."""
-    return E * (N_PIX * C * 4 + N_PIX * 4) + touched_per_launch * (C * 4 * 2 + 4)
+    return E * (N_PIX * c * 4 + N_PIX * 4) + touched_per_launch * (c * 4 * 2 + 4)
 
 
-def frame_bytes(visible_per_frame: float) -> float:
+def frame_bytes(visible_per_frame: float, c: int = C) -> float:
     """Whole-path algorithmic bytes per frame (SURVEY 8d / BASELINE.md 5), M = V (every pixel sampled)."""
     v = visible_per_frame
-    write = N_PIX * 4 + 64 + N_PIX * C * 4 + v * (C * 4 * 2 + 8)
-    read = N_PIX * 4 + v * (C * 4 + 4) + 6300 * C * 2
+    write = N_PIX * 4 + 64 + N_PIX * c * 4 + v * (c * 4 * 2 + 8)
+    read = N_PIX * 4 + v * (c * 4 + 4) + 6300 * c * 2
     return write + read
 
 
@@ -433,6 +433,87 @@ def main_gpu(args, rank, local_rank, world):
                                    "sample": f"{args.cpu_frames} frames of episode 0 ({sec:.1f} s): C back-projection + torch-CPU read chain "
                                              f"+ sparse-equivalent (index_add_) write; the literal one-hot matmul of the reference needs "
                                              f"{N_PIX * MAP_W * MAP_H / 1e9:.0f} GB at stride 1"}
+        print(json.dumps(out))
+
+
+def main_cfg5(args, rank, local_rank, world):
+    """BASELINE configs[4]: 512 synthetic episodes x 100 frames, 512-d dense features, 1000x1000 grid, sharded by episode over
+    the ranks (STRONG scaling: the job is fixed).  Each rank keeps --slots grids resident and streams its share of the
+    episodes through them in waves (EpisodeRunner); no collective on the hot path, one all_reduce of counters at the end."""
+    eod = importlib.import_module("embodied-object-detection_b200")
+    sharding = eod.sharding
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    eod._lib.lib()
+    n_ep, T_, Cc, mw, mh, R = args.cfg5_episodes, args.cfg5_frames, 512, 1000, 1000, args.slots
+    intr = eod.compute_intrinsics(W, H, math.radians(67.5))
+    provider = eod.runner.PooledSyntheticProvider(n_ep, T_, Cc, R, dev, H, W, mw, mh, float(CELL), pool=64)
+    runner = eod.EpisodeRunner(provider, mw, mh, Cc, R, height=H, width=W, device=dev, test_type="episodic", rank=rank, world=world,
+                               intr=intr, cell=float(CELL))
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    runner.run(max_steps=max(3, args.warmup) * 4)                      # warm-up: a dozen frame-steps of the first wave
+    barrier()
+    runner.batch.profile(True)
+    frames = steps_run = 0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        st = runner.run()
+        frames += st["frames"]
+        steps_run += st["steps"]
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = sharding.max_over_ranks(ev0.elapsed_time(ev1), dev)
+    stage_ms = runner.batch.stage_ms()
+    runner.batch.profile(False)
+    totals = sharding.gather_counters({"frames": float(frames), "steps": float(steps_run)}, dev)
+    value = totals["frames"] / (ms_total / 1e3)
+    # size-independent check at the full size: the first slot's first episode, replayed alone through a one-episode batch,
+    # must land in the same state as inside the lock-step batch (counts exact, sums to reduction-order noise)
+    check = None
+    if rank == 0 and not args.no_parity:
+        n_chk = 4
+        runner.run(max_steps=n_chk)
+        torch.cuda.synchronize()
+        e0 = runner.schedule.streams[0][0]
+        solo = eod.EpisodeBatch(1, mw, mh, Cc, H, W, dev)
+        traj = e0 % provider.pool
+        for t in range(n_chk):
+            solo.step(provider.depth[traj, t][None], provider.pose[traj, t][None], provider.shifts[traj][None], intr, float(CELL),
+                      provider.feat[(provider._k - n_chk + t) & 1][0:1].contiguous())
+        torch.cuda.synchronize()
+        scale = float(solo.sums.abs().max())
+        check = {"frames": n_chk, "counts_equal": bool(torch.equal(solo.counts[0], runner.batch.counts[0])),
+                 "sums_max_diff_over_scale": float((solo.sums[0] - runner.batch.sums[0]).abs().max()) / max(scale, 1e-30),
+                 "norm16_equal_up_to_1ulp": bool(((solo.norm16[0].view(torch.int16).int() - runner.batch.norm16[0].view(torch.int16).int()).abs() <= 1).all())}
+        check["ok"] = check["counts_equal"] and check["sums_max_diff_over_scale"] <= 1e-6
+        del solo
+    peak, peak_src = measured_peak_gbs()
+    wbytes = write_launch_bytes(R, 0.0, Cc)
+    achieved = wbytes / stage_ms["write"] / 1e6 if stage_ms.get("write") else None
+    out = {"metric": "memory write+read frames/sec (480x640, C=512)", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"configs[4]: {n_ep} episodes x {T_} frames, 480x640 RGB-D, dense per-pixel C=512 fp32 features (CHW), 1000x1000 grid "
+                                  f"@0.2 m, sharded by episode over {world} GPU(s), {R} resident grids per GPU refilled in waves (EpisodeRunner, "
+                                  f"TEST_TYPE episodic); 64 distinct ray-cast trajectories replayed by the {n_ep} episodes",
+                      "episodes": n_ep, "frames_per_episode": T_, "grid": [mw, mh], "channels": Cc, "slots_per_gpu": R,
+                      "parallelism": f"episode-sharded x{world}, no hot-path collective",
+                      "l2_policy": f"inputs larger than L2 ({R * Cc * N_PIX * 4 / 1e9:.1f} GB of features per frame-step, two alternating slabs)"},
+           "clocks": clocks, "frames": totals["frames"], "frame_steps_per_rank": int(totals["steps"] / world / max(1, args.steps)),
+           "roofline": {"bound": "hbm", "kernel": "write_mean_chw_tma_kernel<512>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": achieved / peak if achieved else None, "peak_source": peak_src, "bytes_per_launch": wbytes,
+                        "launch_ms": stage_ms.get("write"), "stage_ms": stage_ms, "note": "feature + index bytes of a full wave (touched grid rows not counted)"},
+           "self_check": check}
+    if rank == 0:
         print(json.dumps(out))
 
 
@@ -729,6 +810,11 @@ def main():
     ap.add_argument("--write-variant", type=int, default=0, help="diagnostics: 0 auto, 1 LDG, 2 TMA, 3 TMA dry (no result)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the post-run oracle check of the benchmarked path")
+    ap.add_argument("--workload", default="cfg1", choices=["cfg1", "cfg5"], help="cfg1: BASELINE configs[1] (default, the driver's line); "
+                    "cfg5: configs[4], 512 episodes x 100 frames, C=512, 1000x1000, strong scaling over --gpus")
+    ap.add_argument("--slots", type=int, default=32, help="cfg5: resident grids per GPU")
+    ap.add_argument("--cfg5-episodes", type=int, default=512)
+    ap.add_argument("--cfg5-frames", type=int, default=100)
     ap.add_argument("--no-extras", action="store_true", help="skip the projection+fusion and object-regime stage timings")
     ap.add_argument("--no-numa", action="store_true", help="diagnostics: do not bind the rank to its GPU's NUMA node")
     ap.add_argument("--no-pipeline", action="store_true", help="diagnostics: stream-ordered EpisodeBatch.step (no cross-frame overlap)")
@@ -741,7 +827,10 @@ def main():
         torch.cuda.set_device(local_rank)
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        main_gpu(args, rank, local_rank, world)
+        if args.workload == "cfg5":
+            main_cfg5(args, rank, local_rank, world)
+        else:
+            main_gpu(args, rank, local_rank, world)
     finally:
         if world > 1:
             torch.distributed.destroy_process_group()

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_void_p
 
 from .build import SO_PATH
 
@@ -24,6 +24,8 @@ SIGNATURES = {
     "eod_last_error": [],
     "eod_backproject_quantize": [_P, _P, _P, c_int, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_int,
                                  c_int, c_int, c_float, _P, _P, _P, _P, _P, _P],
+    "eod_backproject_quantize_u16": [_P, c_double, _P, _P, c_int, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_int,
+                                     c_int, c_int, c_float, _P, _P, _P, _P, _P, _P],
     "eod_quantize_world": [_P, c_int64, c_float, c_float, c_float, c_int, c_int, c_int, _P, _P],
     "eod_sample_mask": [_P, c_int, c_int, c_int, _P, _P, _P],
     "eod_frame_count": [_P, _P, _P, c_int, c_int, c_int64, _P, _P, _P, _P, c_int, _P],

@@ -19,8 +19,18 @@ __device__ __forceinline__ int clip_cell(float q, int n)
     return q_overflows(q) ? 0 : (int)fminf(fmaxf(q, 0.0f), (float)(n - 1));
 }
 
+// Depth as the sensor delivers it: fp32 metres (habitat: build_data.py:205-207), or uint16 sensor units divided by `depth_div`
+// (robot_demo.py:515: depth_image / 1000 - numpy true division in fp64, then torch.FloatTensor rounds to fp32).
+template <bool U16>
+__device__ __forceinline__ float load_depth(const void *depth, double div, size_t g)
+{
+    if (U16) return __double2float_rn(__ddiv_rn((double)__ldg(reinterpret_cast<const uint16_t *>(depth) + g), div));
+    return __ldg(reinterpret_cast<const float *>(depth) + g);
+}
+
 struct BackprojectParams {
-    const float *depth;
+    const void *depth;
+    double depth_div;
     const float *pose;
     const float *shifts;
     int32_t *idx;
@@ -33,6 +43,7 @@ struct BackprojectParams {
     int map_w, map_h, order;
 };
 
+template <bool U16>
 __global__ void __launch_bounds__(256) backproject_quantize_kernel(const BackprojectParams P)
 {
     const int e = blockIdx.y;
@@ -47,7 +58,7 @@ __global__ void __launch_bounds__(256) backproject_quantize_kernel(const Backpro
     const float xs = __fdiv_rn(__fsub_rn(__fadd_rn((float)u, 0.5f), P.cx), P.fx);
     const float ys = __fdiv_rn(__fsub_rn(__fadd_rn((float)v, 0.5f), P.cy), P.fy);
     const size_t g = (size_t)e * HW + p;
-    const float z = __ldg(P.depth + g);
+    const float z = load_depth<U16>(P.depth, P.depth_div, g);
     const float x = __fmul_rn(z, xs);
     const float y = __fmul_rn(z, ys);
 
@@ -85,6 +96,7 @@ __global__ void __launch_bounds__(256) backproject_quantize_kernel(const Backpro
 // Same arithmetic, four consecutive pixels of one image row per thread (W % 4 == 0, 16-byte aligned planes): 128-bit depth loads
 // and index stores, the pose / shift scalars and the row's y_scale are fetched and computed once per thread instead of
 // once per pixel (the scalar kernel issued 18 uniform loads and 4 IEEE divides per pixel).
+template <bool U16>
 __global__ void __launch_bounds__(256) backproject_quantize_vec4_kernel(const BackprojectParams P)
 {
     const int e = blockIdx.y;
@@ -103,8 +115,16 @@ __global__ void __launch_bounds__(256) backproject_quantize_vec4_kernel(const Ba
     const float ys = __fdiv_rn(__fsub_rn(__fadd_rn((float)v, 0.5f), P.cy), P.fy);
     const float thr = __fadd_rn(t[7], P.z_clip);
     const size_t g = (size_t)e * HW + p;
-    const float4 d4 = __ldg(reinterpret_cast<const float4 *>(P.depth + g));
-    const float zz[4] = {d4.x, d4.y, d4.z, d4.w};
+    float zz[4];
+    if (U16) {
+        const uint2 d = __ldg(reinterpret_cast<const uint2 *>(reinterpret_cast<const uint16_t *>(P.depth) + g));
+        const uint32_t raw[4] = {d.x & 0xffffu, d.x >> 16, d.y & 0xffffu, d.y >> 16};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) zz[k] = __double2float_rn(__ddiv_rn((double)raw[k], P.depth_div));
+    } else {
+        const float4 d4 = __ldg(reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(P.depth) + g));
+        zz[0] = d4.x; zz[1] = d4.y; zz[2] = d4.z; zz[3] = d4.w;
+    }
     int idx4[4], q2v[8];
     uint32_t out4 = 0;
     float h4[4], w12[12];
@@ -176,10 +196,10 @@ extern "C" int eod_quantize_world(const float *world, int64_t n_points, float sh
     return eod_check_launch("eod_quantize_world");
 }
 
-extern "C" int eod_backproject_quantize(const float *depth, const float *pose, const float *shifts, int n_episodes,
-                                        int H, int W, float fx, float fy, float cx, float cy, float cell, int map_w,
-                                        int map_h, int order, float z_clip, int32_t *idx, int32_t *q2,
-                                        uint8_t *outlier, float *height, float *world, eod_stream_t stream)
+static int backproject_launch(const void *depth, bool u16, double depth_div, const float *pose, const float *shifts, int n_episodes,
+                              int H, int W, float fx, float fy, float cx, float cy, float cell, int map_w,
+                              int map_h, int order, float z_clip, int32_t *idx, int32_t *q2,
+                              uint8_t *outlier, float *height, float *world, eod_stream_t stream)
 {
     EOD_REQUIRE(depth && pose && shifts, EOD_ERR_BADARG, "eod_backproject_quantize: null input");
     EOD_REQUIRE(n_episodes > 0 && H > 0 && W > 0 && map_w > 0 && map_h > 0, EOD_ERR_BADARG,
@@ -188,15 +208,36 @@ extern "C" int eod_backproject_quantize(const float *depth, const float *pose, c
     EOD_REQUIRE(cell > 0.0f && fx != 0.0f && fy != 0.0f, EOD_ERR_BADARG, "eod_backproject_quantize: bad cell/intrinsics");
     EOD_REQUIRE((int64_t)map_w * map_h < (int64_t)INT32_MAX, EOD_ERR_BADARG, "eod_backproject_quantize: map too large");
     EOD_REQUIRE(n_episodes <= 65535, EOD_ERR_BADARG, "eod_backproject_quantize: n_episodes > 65535");
-    BackprojectParams P{depth, pose, shifts, idx, q2, outlier, height, world, H, W, fx, fy, cx, cy, cell, z_clip, map_w, map_h, order};
+    BackprojectParams P{depth, depth_div, pose, shifts, idx, q2, outlier, height, world, H, W, fx, fy, cx, cy, cell, z_clip, map_w, map_h, order};
     const bool vec = W % 4 == 0 && eod_aligned16(depth) && (!idx || eod_aligned16(idx)) && (!q2 || eod_aligned16(q2)) &&
                      (!outlier || (reinterpret_cast<uintptr_t>(outlier) & 3u) == 0) && (!height || eod_aligned16(height)) && (!world || eod_aligned16(world));
     if (vec) {
         dim3 grid((H * W / 4 + 255) / 256, n_episodes);
-        backproject_quantize_vec4_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+        if (u16) backproject_quantize_vec4_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+        else backproject_quantize_vec4_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(P);
     } else {
         dim3 grid((H * W + 255) / 256, n_episodes);
-        backproject_quantize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+        if (u16) backproject_quantize_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+        else backproject_quantize_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(P);
     }
     return eod_check_launch("eod_backproject_quantize");
+}
+
+extern "C" int eod_backproject_quantize(const float *depth, const float *pose, const float *shifts, int n_episodes,
+                                        int H, int W, float fx, float fy, float cx, float cy, float cell, int map_w,
+                                        int map_h, int order, float z_clip, int32_t *idx, int32_t *q2,
+                                        uint8_t *outlier, float *height, float *world, eod_stream_t stream)
+{
+    return backproject_launch(depth, false, 1.0, pose, shifts, n_episodes, H, W, fx, fy, cx, cy, cell, map_w, map_h, order, z_clip, idx, q2,
+                              outlier, height, world, stream);
+}
+
+extern "C" int eod_backproject_quantize_u16(const uint16_t *depth, double depth_div, const float *pose, const float *shifts, int n_episodes,
+                                            int H, int W, float fx, float fy, float cx, float cy, float cell, int map_w,
+                                            int map_h, int order, float z_clip, int32_t *idx, int32_t *q2,
+                                            uint8_t *outlier, float *height, float *world, eod_stream_t stream)
+{
+    EOD_REQUIRE(depth_div > 0.0, EOD_ERR_BADARG, "eod_backproject_quantize_u16: depth_div must be positive");
+    return backproject_launch(depth, true, depth_div, pose, shifts, n_episodes, H, W, fx, fy, cx, cy, cell, map_w, map_h, order, z_clip, idx, q2,
+                              outlier, height, world, stream);
 }

@@ -24,6 +24,7 @@
 #include <string.h>
 
 #include "eod_common.cuh"
+#include "tmap_cache.cuh"
 
 namespace {
 
@@ -444,9 +445,7 @@ int pf_make_tmap(const void *ptr, int64_t rows, int K, int box_rows, CUtensorMap
     const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     const cuuint64_t gstr[1] = {(cuuint64_t)K * 2};
     const cuuint32_t box[2] = {PF_BK, (cuuint32_t)box_rows};
-    const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUresult r = eod_encode_tmap_cached(enc, tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ptr, gdim, gstr, box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
     EOD_REQUIRE(r == CUDA_SUCCESS, EOD_ERR_LAUNCH, "eod_project_fuse: cuTensorMapEncodeTiled failed (%d)", (int)r);
     return EOD_OK;
 }
@@ -459,9 +458,7 @@ int p2_make_tmap_a(const void *ptr, int E, int hw, int K, CUtensorMap *tm)
     const cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)hw, (cuuint64_t)E};
     const cuuint64_t gstr[2] = {(cuuint64_t)K * 2, (cuuint64_t)hw * K * 2};
     const cuuint32_t box[3] = {PF_BK, P2_BM, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUresult r = eod_encode_tmap_cached(enc, tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, ptr, gdim, gstr, box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
     EOD_REQUIRE(r == CUDA_SUCCESS, EOD_ERR_LAUNCH, "eod_project_fuse: cuTensorMapEncodeTiled(level) failed (%d)", (int)r);
     return EOD_OK;
 }
@@ -474,9 +471,8 @@ int p2_make_tmap_r(const float *ptr, int E, int hw, int N, CUtensorMap *tm)
     const cuuint64_t gdim[3] = {(cuuint64_t)hw, (cuuint64_t)N, (cuuint64_t)E};
     const cuuint64_t gstr[2] = {(cuuint64_t)hw * 4, (cuuint64_t)hw * N * 4};
     const cuuint32_t box[3] = {P2_BM, P2_RCH, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUresult r = eod_encode_tmap_cached(enc, tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ptr, gdim, gstr, box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                              CU_TENSOR_MAP_SWIZZLE_NONE);
     EOD_REQUIRE(r == CUDA_SUCCESS, EOD_ERR_LAUNCH, "eod_project_fuse: cuTensorMapEncodeTiled(res) failed (%d)", (int)r);
     return EOD_OK;
 }

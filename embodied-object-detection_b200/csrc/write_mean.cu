@@ -22,6 +22,7 @@
 #include <stdlib.h>
 
 #include "eod_common.cuh"
+#include "tmap_cache.cuh"
 
 namespace {
 
@@ -863,12 +864,10 @@ int make_feature_tmap(const float *feat, int E, int HW, CUtensorMap *tmap)
     const cuuint64_t gdim[3] = {(cuuint64_t)HW, (cuuint64_t)C, (cuuint64_t)E};
     const cuuint64_t gstr[2] = {(cuuint64_t)HW * 4, (cuuint64_t)HW * C * 4};
     const cuuint32_t box[3] = {TILE_PX, (cuuint32_t)Cfg::kChanBlk, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
     static const int promo_env = [] { const char *v = getenv("EOD_TMA_L2_PROMOTION"); return v ? atoi(v) : 256; }();   // tuning knob: 0 | 128 | 256
     const CUtensorMapL2promotion promo = promo_env == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
                                          : (promo_env == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
-    const CUresult r = enc(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(feat), gdim, gstr, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUresult r = eod_encode_tmap_cached(enc, tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, feat, gdim, gstr, box, promo);
     EOD_REQUIRE(r == CUDA_SUCCESS, EOD_ERR_LAUNCH, "eod_write_mean: cuTensorMapEncodeTiled failed (%d)", (int)r);
     return EOD_OK;
 }

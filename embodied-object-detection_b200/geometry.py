@@ -63,7 +63,8 @@ class Projector:
 
     def __init__(self, vfov: float, batch_size: int, feature_map_height: int, feature_map_width: int, output_height: int,
                  output_width: int, gridcellsize: float, world_shift_origin, z_clip_threshold: float,
-                 device: torch.device = torch.device("cuda"), intrinsics: Optional[Sequence[float]] = None):
+                 device: torch.device = torch.device("cuda"), intrinsics: Optional[Sequence[float]] = None, depth_div: float = 1000.0):
+        self.depth_div = float(depth_div)                        # divisor of uint16 depth inputs (robot_demo.py:515: millimetres)
         self.vfov, self.batch_size = vfov, batch_size
         self.fmh, self.fmw = feature_map_height, feature_map_width
         self.output_height, self.output_width = output_height, output_width
@@ -77,13 +78,14 @@ class Projector:
 
     def _run(self, depth: torch.Tensor, T: torch.Tensor, map_world_shift=None, order: int = ORDER_ZX, **want):
         assert depth.shape[2] == self.fmh and depth.shape[3] == self.fmw
-        d = depth[:, 0].to(self.device, torch.float32).contiguous()
+        # raw uint16 sensor depth stays uint16 (divided by depth_div inside the kernel: robot_demo.py:515-517)
+        d = depth[:, 0].to(self.device).contiguous() if depth.dtype == torch.uint16 else depth[:, 0].to(self.device, torch.float32).contiguous()
         B = d.shape[0]
         pose = T.detach().to("cpu", torch.float32)[:, :3, :].reshape(B, 12)
         s1 = torch.zeros(3) if map_world_shift is None else torch.as_tensor(map_world_shift, dtype=torch.float32).reshape(3).cpu()
         shifts = torch.cat([self.world_shift_origin, s1]).unsqueeze(0).repeat(B, 1)
         return ops.backproject_quantize(d, pose.to(self.device), shifts.to(self.device), self.intrinsics, self.gridcellsize,
-                                        self.output_width, self.output_height, order, self.z_clip_threshold, **want)
+                                        self.output_width, self.output_height, order, self.z_clip_threshold, depth_div=self.depth_div, **want)
 
     def forward(self, depth: torch.Tensor, T: torch.Tensor, obs_per_map: int = 1, return_heights: bool = False):
         r = self._run(depth, T, want_idx=False, want_q2=True, want_outlier=True, want_height=return_heights)

@@ -58,9 +58,11 @@ def _stream(ref: Optional[torch.Tensor] = None) -> int:
 def backproject_quantize(depth: torch.Tensor, pose: torch.Tensor, shifts: torch.Tensor, intr: Sequence[float], cell: float,
                          map_w: int, map_h: int, order: int = ORDER_ZX, z_clip: float = 0.5, *, want_idx: bool = True,
                          want_q2: bool = False, want_outlier: bool = False, want_height: bool = False,
-                         want_world: bool = False, out: Optional[dict] = None) -> dict:
-    """depth (E,H,W) f32, pose (E,12) f32, shifts (E,6) f32 -> dict(idx, q2, outlier, height, world)."""
-    _dev(depth, torch.float32, "depth"), _dev(pose, torch.float32, "pose"), _dev(shifts, torch.float32, "shifts")
+                         want_world: bool = False, out: Optional[dict] = None, depth_div: float = 1000.0) -> dict:
+    """depth (E,H,W) f32 metres - or uint16 sensor units, divided by ``depth_div`` in the kernel as robot_demo.py:515-517 does on
+    the host - pose (E,12) f32, shifts (E,6) f32 -> dict(idx, q2, outlier, height, world)."""
+    raw = depth.dtype == torch.uint16
+    _dev(depth, torch.uint16 if raw else torch.float32, "depth"), _dev(pose, torch.float32, "pose"), _dev(shifts, torch.float32, "shifts")
     E, H, W = depth.shape
     if pose.shape != (E, 12) or shifts.shape != (E, 6):
         raise ValueError("pose must be (E,12) and shifts (E,6)")
@@ -80,9 +82,12 @@ def backproject_quantize(depth: torch.Tensor, pose: torch.Tensor, shifts: torch.
     height = buf("height", want_height, (E, H, W), torch.float32)
     world = buf("world", want_world, (E, H, W, 3), torch.float32)
     fx, fy, cx, cy = (float(v) for v in intr)
-    _call("eod_backproject_quantize", depth.data_ptr(), pose.data_ptr(), shifts.data_ptr(), E, H, W, fx, fy, cx, cy,
-          float(cell), int(map_w), int(map_h), int(order), float(z_clip), _ptr(idx), _ptr(q2), _ptr(outlier),
-          _ptr(height), _ptr(world), _stream())
+    tail = (pose.data_ptr(), shifts.data_ptr(), E, H, W, fx, fy, cx, cy, float(cell), int(map_w), int(map_h), int(order), float(z_clip),
+            _ptr(idx), _ptr(q2), _ptr(outlier), _ptr(height), _ptr(world), _stream())
+    if raw:
+        _call("eod_backproject_quantize_u16", depth.data_ptr(), float(depth_div), *tail)
+    else:
+        _call("eod_backproject_quantize", depth.data_ptr(), *tail)
     return out
 
 

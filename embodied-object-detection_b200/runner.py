@@ -271,6 +271,7 @@ class EpisodeRunner:
         """Process this rank's share of the dataset.  on_levels(step, levels): consumer hook, called after every frame-step
         with the three pooled fp16 levels (R,C,h,w) ordered on the caller's stream (idle slots hold stale values)."""
         b = self.batch
+        self.stats = {k: 0 for k in self.stats}                  # per run() call
         with torch.cuda.device(self.device):
             for k, step in enumerate(self.schedule):
                 if max_steps is not None and k >= max_steps:
@@ -307,3 +308,55 @@ class EpisodeRunner:
                             self._save(s, self.provider.name(a[0]))
             b.join()
         return dict(self.stats)
+
+
+class PooledSyntheticProvider:
+    """Synthetic dense-regime episodes for workloads too large to hold as depth maps (BASELINE configs[4]: 512 episodes x 100
+    frames = 63 GB of fp32 depth): ``pool`` distinct trajectories are ray-cast once on the device (episodes.DeviceEpisodes) and
+    episode e replays trajectory e % pool into ITS OWN grid; every episode starts with memory_reset (independent episodes,
+    TEST_TYPE episodic).  Features: two resident random (R,C,H,W) slabs used alternately (>> L2), as in bench.py.  Input
+    generation only - nothing here is on the measured path except one gather of the step's depth / pose rows."""
+    trusted_indices = True
+
+    def __init__(self, n_episodes: int, n_frames: int, channels: int, n_slots: int, device, height: int = 480, width: int = 640,
+                 map_w: int = 1000, map_h: int = 1000, cell: float = 0.2, pool: int = 64, seed0: int = 1234, lengths=None):
+        from . import episodes as E_
+        from .geometry import transform3d
+        self.device = torch.device(device)
+        self.n_episodes, self.T, self.pool = int(n_episodes), int(n_frames), int(min(pool, n_episodes))
+        self.lengths = None if lengths is None else [int(x) for x in lengths]
+        dev_eps = E_.DeviceEpisodes(self.pool, n_frames, self.device, height, width, map_w, map_h, cell, seed0)
+        self.depth = torch.empty((self.pool, n_frames, height, width), dtype=torch.float32, device=self.device)
+        for t in range(n_frames):
+            dev_eps.render(list(range(self.pool)), [t] * self.pool, out=self.depth[:, t])
+        T = transform3d(torch.from_numpy(dev_eps.xyzhe.reshape(-1, 5))).reshape(self.pool, n_frames, 4, 4)
+        self.T_host = T.numpy()
+        self.shift_host = dev_eps.shift
+        self.pose = T[:, :, :3, :].reshape(self.pool, n_frames, 12).contiguous().to(self.device)
+        self.shifts = torch.from_numpy(np.concatenate([np.zeros_like(dev_eps.shift), dev_eps.shift], 1)).to(self.device)
+        gen = torch.Generator(device=self.device).manual_seed(seed0)
+        self.feat = [torch.randn((n_slots, channels, height, width), device=self.device, generator=gen) for _ in range(2)]
+        self._st = _Staging(self.device)
+        self._keep: List[dict] = []
+        self._k = 0
+
+    def n_frames(self, i: int) -> int:
+        return self.T if self.lengths is None else self.lengths[i]
+
+    def name(self, i: int) -> str:
+        return f"synthetic_{i % self.pool}_{i}"
+
+    def reset_flag(self, i: int, f: int) -> bool:
+        return f == 0
+
+    def stage(self, assign: Sequence[Optional[Tuple[int, int]]]) -> dict:
+        self._st.next()
+        R = len(assign)
+        pin, dev = self._st.buf("sel", (2, R), torch.int64)
+        pin.copy_(torch.tensor([[0 if a is None else a[0] % self.pool for a in assign], [0 if a is None else a[1] for a in assign]], dtype=torch.int64))
+        dev.copy_(pin, non_blocking=True)
+        self._st.commit()
+        out = {"depth": self.depth[dev[0], dev[1]], "pose": self.pose[dev[0], dev[1]], "shifts": self.shifts[dev[0]], "feat": self.feat[self._k & 1]}
+        self._k += 1
+        self._keep = (self._keep + [out])[-3:]            # gathered rows stay alive until the steps that read them have been ordered
+        return out

@@ -75,6 +75,15 @@ int eod_backproject_quantize(const float *depth, const float *pose, const float 
                              int order, float z_clip, int32_t *idx, int32_t *q2, uint8_t *outlier, float *height,
                              float *world, eod_stream_t stream);
 
+/* Same launch on RAW sensor depth: uint16 sensor units divided by depth_div (1000 for millimetres) exactly as
+ * robot_demo.py:515-517 does it on the host (numpy true division in fp64, then torch.FloatTensor rounds to fp32), so the
+ * online robot path uploads 2 bytes per pixel and no host-side conversion remains.  Bit-exact with the float entry point
+ * fed `FloatTensor(depth_u16 / depth_div)`. */
+int eod_backproject_quantize_u16(const uint16_t *depth, double depth_div, const float *pose, const float *shifts, int n_episodes,
+                                 int H, int W, float fx, float fy, float cx, float cy, float cell, int map_w, int map_h,
+                                 int order, float z_clip, int32_t *idx, int32_t *q2, uint8_t *outlier, float *height,
+                                 float *world, eod_stream_t stream);
+
 /* Offline builder's quantise step on STORED world coordinates (sensor_data/*.h5 'projection_indices'):
  * SMNet/build_memory_data.py:135-143.  world (n_points,3) f32 -> idx (n_points) i32, clipped, bit-exact. */
 int eod_quantize_world(const float *world, int64_t n_points, float shift_x, float shift_z, float cell, int map_w, int map_h,

@@ -76,6 +76,28 @@ def test_robot_demo_geometry_matches_reference_golden(eod, cuda, golden):
         flat = proj.flat_indices(depth, T, g["map_world_shift"], order="xz")
         assert flat.shape == (1, H, W, 1) and flat.dtype == torch.int32
         assert np.array_equal(flat[0, ..., 0].cpu().numpy(), g["flat"][t])
+        # raw sensor words straight to the device: the kernel does robot_demo.py:515's fp64 division and fp32 rounding itself
+        raw = torch.from_numpy(g["depth_mm"][t].astype(np.uint16))[None, None]
+        flat_raw = proj.flat_indices(raw, T, g["map_world_shift"], order="xz")
+        assert np.array_equal(flat_raw[0, ..., 0].cpu().numpy(), g["flat"][t])
+
+
+def test_backproject_u16_depth_every_sensor_word(eod, cuda):
+    """All 65 536 uint16 depth words, several divisors, scalar and 4-px kernels: the in-kernel conversion must equal
+    torch.FloatTensor(depth_u16 / div) (numpy fp64 true division, then fp32 rounding) bit for bit - checked on the heights / world
+    coordinates, which expose the converted depth."""
+    words = np.arange(65536, dtype=np.uint16)
+    T = eod.transform3d(torch.from_numpy(np.array([[0.3, 0.65, -0.2, 0.4, math.pi + 0.06]], np.float32)), axis_swap=True)
+    sh = _t(np.zeros((1, 6), np.float32), cuda)
+    pose = T[:, :3].reshape(1, 12).to(cuda)
+    for (H, W), div in (((128, 512), 1000.0), ((128, 512), 255.0), ((256, 256), 6553.5), ((65536 // 127 + 1, 127), 1000.0)):
+        d = np.resize(words, (H, W))
+        intr = eod.compute_intrinsics(W, H, math.radians(58))
+        a = eod.ops.backproject_quantize(_t(d[None], cuda), pose, sh, intr, 0.05, 200, 200, 1, want_world=True, want_height=True, depth_div=div)
+        ref_depth = torch.FloatTensor(d / div)[None].to(cuda)
+        b = eod.ops.backproject_quantize(ref_depth, pose, sh, intr, 0.05, 200, 200, 1, want_world=True, want_height=True)
+        for k in ("idx", "world", "height"):
+            assert torch.equal(a[k].view(torch.int32), b[k].view(torch.int32)), (H, W, div, k)
 
 
 def test_backproject_non_finite_depths_follow_torch(eod, cuda):

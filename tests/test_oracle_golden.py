@@ -1,5 +1,7 @@
 """The oracle (oracle/geometry.c + oracle/reference_ops.py) against fixtures produced by running the reference's own
 source (tests/golden/make_golden.py).  CPU only."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -7,6 +9,7 @@ import torch
 import oracle
 from oracle import reference_ops as R
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 INTR_480 = (320.0, 359.1853942871094, 320.0, 240.0)
 
 
@@ -214,3 +217,33 @@ def test_paste_masks_c_oracle_vs_torch_on_threshold_knife_edges():
         for thr in (0.5, 0.25):
             ref = R.paste_masks_in_image(torch.from_numpy(probs), torch.from_numpy(boxes), (H, W), thr).numpy()
             assert np.array_equal(oracle.paste_masks(probs, boxes, H, W, thr), ref), (case, thr)
+
+
+def test_bytecode_listings_pin_the_unsourced_write_variants(tmp_path):
+    """SURVEY 8a rows A7' / A7'' / A14 exist only as bytecode.  oracle/pyc_disasm.py (own marshal reader: the 3.12 interpreter cannot
+    load 3.9 / 3.10 code objects) produced the listings under oracle/disasm/ that the restatements cite; this test pins the
+    facts the canonical rules rest on, and - where /root/reference is present - that the committed listings regenerate."""
+    import re
+    from oracle import pyc_disasm
+    d = os.path.join(ROOT, "oracle", "disasm")
+    enc = open(os.path.join(d, "smnet_encode_model_test_py39.txt")).read()
+    # height_map, idx = scatter_max(height + 1000, flat[inliers], dim=0, out=height_map); m = idx >= 0; observed += m
+    assert re.search(r"LOAD_GLOBAL\s+\d+\s+\(scatter_max\)", enc) and "('dim', 'out')" in enc
+    assert re.search(r"LOAD_CONST\s+\d+\s+\(1000\)\n\s+\d+ INPLACE_ADD", enc)
+    i = enc.index("(scatter_max)")
+    tail = enc[i:i + 1500]
+    assert re.search(r"STORE_FAST\s+\d+\s+\(height_map\)\n\s+\d+ STORE_FAST\s+\d+\s+\(highest_height_indices\)", tail)
+    assert re.search(r"\(highest_height_indices\)\n\s+\d+ LOAD_CONST\s+\d+\s+\(0\)\n\s+\d+ COMPARE_OP\s+\d+\s+\(>=\)", tail)
+    assert "('size', 'mode', 'align_corners')" in enc and "((480, 640))" in enc and "('bilinear')" in enc
+    assert "(rnn)" in enc and "(linlayer)" not in enc                      # model_test: GRU / LSTM update only
+    enc310 = open(os.path.join(d, "smnet_encode_model_py310.txt")).read()
+    assert "('replace')" in enc310 and "(linlayer)" in enc310              # model.py (3.10): state[m] = linlayer(winners)
+    fpn = open(os.path.join(d, "custommapfpn_forward_timm_py39.txt")).read()
+    assert "(interpolate)" in fpn and "(map_merge_forward_projection)" in fpn or "(map_merge_memory_projection)" in fpn
+    exp = open(os.path.join(d, "create_explicit_memory_custom_rcnn_py39.txt")).read()
+    assert "(zs_weight)" in exp or "(semmap)" in exp
+    if os.path.isdir("/root/reference/Detic"):
+        made = pyc_disasm.emit("/root/reference", str(tmp_path))
+        assert len(made) == 4
+        for f in made:
+            assert open(os.path.join(tmp_path, f)).read() == open(os.path.join(d, f)).read(), f
