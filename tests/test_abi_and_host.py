@@ -30,6 +30,9 @@ def test_library_exports_every_declared_symbol(eod):
     # the ctypes table binds exactly the declared set
     assert sorted(eod._lib.SIGNATURES) == declared
     assert eod._lib.lib().eod_version() == 100
+    # every entry point that launches kernels is in the launch-count table ops._call consults (a missing key raised only on the GPU)
+    no_launch = {"eod_version", "eod_last_error", "eod_write_mean_det_workspace_bytes", "eod_write_mean_det_status_offset"}
+    assert set(eod.ops._LAUNCHES) == set(declared) - no_launch
 
 
 def test_library_is_sm100a_only(eod):
