@@ -52,6 +52,7 @@ SIGNATURES = {
     "eod_reset_episodes": [_P, _P, _P, _P, c_int, c_int64, c_int, _P],
     "eod_refresh_norm16": [_P, _P, _P, _P, c_int, c_int64, c_int, _P],
     "eod_check_indices": [_P, c_int, c_int64, c_int64, _P, _P, _P],
+    "eod_remap_indices": [_P, c_int, c_int64, _P, c_int, c_int64, c_int, c_int64, _P, _P, _P],
     "eod_project_split_weights": [_P, c_int, c_int, _P, _P],
     "eod_project_fuse_levels": [c_int, _P, _P, _P, _P, _P, _P, c_float, c_int, c_int, c_int, c_int, c_int, _P],
     "eod_project_fuse": [_P, _P, _P, _P, c_float, c_int, c_int, c_int, c_int, c_int, _P, _P],

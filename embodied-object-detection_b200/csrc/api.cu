@@ -37,5 +37,32 @@ int eod_num_sms()
     return n;
 }
 
+// Work tickets for persistent kernels that claim their tiles dynamically: a pool of zeroed {next, done} int pairs per device.
+// A launch takes the next pair of the pool; the kernel's last CTA re-arms it (both words back to 0), so a pair is reusable as
+// soon as its launch has finished.  64 pairs per device: two launches could only meet on one pair if more than 64 ticketed
+// launches of this library were in flight on the device at once.  The pool is allocated at the first call on a device (do not
+// make that first call inside a CUDA graph capture); nullptr = allocation failed (callers fall back to static partitioning).
+int *eod_work_tickets()
+{
+    constexpr int kPairs = 64;
+    static int *pool[64] = {nullptr};
+    static unsigned next[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    int *p = __atomic_load_n(&pool[dev & 63], __ATOMIC_ACQUIRE);
+    if (!p) {
+        int *fresh = nullptr;
+        if (cudaMalloc(&fresh, kPairs * 2 * sizeof(int)) != cudaSuccess || cudaMemset(fresh, 0, kPairs * 2 * sizeof(int)) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        int *expected = nullptr;
+        if (__atomic_compare_exchange_n(&pool[dev & 63], &expected, fresh, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE)) p = fresh;
+        else { cudaFree(fresh); p = expected; }
+    }
+    const unsigned k = __atomic_fetch_add(&next[dev & 63], 1u, __ATOMIC_RELAXED) % kPairs;
+    return p + 2 * k;
+}
+
 extern "C" int eod_version(void) { return 100; /* 0.1.0 */ }
 extern "C" const char *eod_last_error(void) { return g_err; }

@@ -12,6 +12,7 @@
 void eod_set_error(const char *fmt, ...);
 int eod_check_launch(const char *what);
 int eod_num_sms();
+int *eod_work_tickets();      // zeroed {next, done} pair for one dynamically scheduled launch (api.cu)
 
 #define EOD_REQUIRE(cond, code, ...)      \
     do {                                  \

@@ -70,6 +70,33 @@ __device__ __forceinline__ void vstore_half(__half *dst, const Vec<V> &a)
     }
 }
 
+// Four pixels of a two-cell window in summation order: s += (bit k of pat ? b : a) for k = 0..3.  pat is warp-uniform; one
+// indexed jump to one of 16 straight-line variants (no predicated-off additions, no per-run bookkeeping).
+template <int V>
+__device__ __forceinline__ void vadd_row2(Vec<V> &s, const Vec<V> &a, const Vec<V> &b, unsigned pat)
+{
+#define EOD_R4(x0, x1, x2, x3) s = vadd<V>(s, x0); s = vadd<V>(s, x1); s = vadd<V>(s, x2); s = vadd<V>(s, x3); break;
+    switch (pat & 15u) {
+    case 0: EOD_R4(a, a, a, a)
+    case 1: EOD_R4(b, a, a, a)
+    case 2: EOD_R4(a, b, a, a)
+    case 3: EOD_R4(b, b, a, a)
+    case 4: EOD_R4(a, a, b, a)
+    case 5: EOD_R4(b, a, b, a)
+    case 6: EOD_R4(a, b, b, a)
+    case 7: EOD_R4(b, b, b, a)
+    case 8: EOD_R4(a, a, a, b)
+    case 9: EOD_R4(b, a, a, b)
+    case 10: EOD_R4(a, b, a, b)
+    case 11: EOD_R4(b, b, a, b)
+    case 12: EOD_R4(a, a, b, b)
+    case 13: EOD_R4(b, a, b, b)
+    case 14: EOD_R4(a, b, b, b)
+    default: EOD_R4(b, b, b, b)
+    }
+#undef EOD_R4
+}
+
 // Split row fetch: the global load of a row is issued (load_raw) before its consumer (finish: normalise + fp16
 // rounding) runs, so the next run's row is in flight under the current run's adds.
 template <int V> struct RawF32 { float4 v[V / 4]; float n; };
@@ -167,6 +194,37 @@ __device__ __forceinline__ QuadIdx load_quad_idx(const IdxT *src, int W)
     return q;
 }
 
+// shared memory by 32-bit shared-window address (inline PTX): the compiler keeps ONE base register per warp instead of
+// re-deriving `&array[warp][...]` from %tid / %cluster_ctaid inside the loops (v4a: ~10 uniform-datapath instructions per window)
+__device__ __forceinline__ int4 rp_lds128(uint32_t a)
+{
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int2 rp_lds64(uint32_t a)
+{
+    int2 v;
+    asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int rp_lds32(uint32_t a)
+{
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void rp_sts128(uint32_t a, int x, int y, int z, int w)
+{
+    asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ void rp_sts32(uint32_t a, int x) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(x) : "memory"); }
+__device__ __forceinline__ void rp_sts16(uint32_t a, unsigned x) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)x) : "memory"); }
+
+// per-warp slice: ids window-major (1024 B) | window descriptors {first cell, second cell or -1, run-head mask, 0} (16 x 16 B) |
+// first cells (16 x 4 B) | run-head masks (16 x 2 B)
+constexpr int kRpIdx = 0, kRpDesc = 1024, kRpWc = 1280, kRpWm = 1344, kRpSlice = 1376;
+
 template <int C, typename TableT, typename IdxT>
 __global__ void __launch_bounds__(kReadWarps * 32, (C >= 512 ? 2 : (C >= 256 ? 3 : 4))) read_pool_kernel(const TableT *__restrict__ table, const float *__restrict__ counts,
                                                                                         const IdxT *__restrict__ idx, int H, int W, int64_t n_cells, int E,
@@ -175,11 +233,10 @@ __global__ void __launch_bounds__(kReadWarps * 32, (C >= 512 ? 2 : (C >= 256 ? 3
     constexpr int V = C >= 512 ? 16 : (C >= 256 ? 8 : 4);      // channels per lane
     static_assert(C == 32 * V, "one warp covers all channels of a quadrant");
     using Raw = typename RawOf<TableT, V>::type;
-    __shared__ __align__(16) int s_idx[kReadWarps][16 * 16];                 // window-major: [window][pixel in summation order]
-    __shared__ __align__(16) int s_wc[kReadWarps][16];                       // first cell of each window
-    __shared__ __align__(16) unsigned short s_wm[kReadWarps][16];            // run-head mask of each window (bit p: pixel p starts a run)
+    __shared__ __align__(16) unsigned char s_raw[kReadWarps * kRpSlice];
 
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t sm = smem_u32(s_raw) + warp * kRpSlice;                   // this warp's slice
     const int nqy = H / 16, nqx = W / 16, per_ep = nqy * nqx;
     const int n_items = E * per_ep;                                          // the host guarantees it fits 31 bits
     const int stride = (int)gridDim.x * kReadWarps;
@@ -195,6 +252,9 @@ __global__ void __launch_bounds__(kReadWarps * 32, (C >= 512 ? 2 : (C >= 256 ? 3
     const int lane_off = (((w >> 3) * 8 + ((w >> 1) & 1) * 4 + 2 * hh) * W) + ((w >> 2) & 1) * 8 + (w & 1) * 4;
     auto src_of = [&](int e_, int qy_, int qx_) { return idx + ((size_t)e_ * H + (size_t)qy_ * 16) * W + qx_ * 16 + lane_off; };
     QuadIdx nxt = load_quad_idx<IdxT>(src_of(e, qy, qx), W);
+    const int g = (int)lane;                                // group of V channels
+    const uint32_t sm_ids = sm + kRpIdx + (w * 16 + hh * 8) * 4;
+    const size_t ep_rows = (size_t)n_cells * C;
 
     for (; item < n_items; item += stride) {
         const QuadIdx q = nxt;
@@ -205,27 +265,39 @@ __global__ void __launch_bounds__(kReadWarps * 32, (C >= 512 ? 2 : (C >= 256 ? 3
         e += se;
         if (item + stride < n_items) nxt = load_quad_idx<IdxT>(src_of(e, qy, qx), W);
         // stage the ids window-major; derive the window's run heads in summation (row-major) order
-        {
-            int4 *dst = reinterpret_cast<int4 *>(&s_idx[warp][w * 16 + hh * 8]);
-            dst[0] = make_int4(q.a[0], q.a[1], q.a[2], q.a[3]);
-            dst[1] = make_int4(q.b[0], q.b[1], q.b[2], q.b[3]);
-        }
+        rp_sts128(sm_ids, q.a[0], q.a[1], q.a[2], q.a[3]);
+        rp_sts128(sm_ids + 16, q.b[0], q.b[1], q.b[2], q.b[3]);
         const int prev = __shfl_up_sync(0xffffffffu, q.b[3], 1);             // last pixel of the window's second row (for hh == 1)
         unsigned m8 = (hh == 0 || q.a[0] != prev) ? 1u : 0u;
         m8 |= (q.a[1] != q.a[0]) << 1 | (q.a[2] != q.a[1]) << 2 | (q.a[3] != q.a[2]) << 3 | (q.b[0] != q.a[3]) << 4 | (q.b[1] != q.b[0]) << 5 |
               (q.b[2] != q.b[1]) << 6 | (q.b[3] != q.b[2]) << 7;
         const unsigned other = __shfl_xor_sync(0xffffffffu, m8, 1);
+        // two-cell windows (an edge between two map cells: 89 % of the mixed windows of the synthetic episodes, typically 8 runs
+        // A A B B / A A B B / ...): the pixels take one of TWO rows, so the walk below keeps both in registers and pays nothing per
+        // run.  B = any id != A; valid iff every id of the window is A or B.
+        const int cA = __shfl_sync(0xffffffffu, q.a[0], lane & ~1u);
+        int bsel = cA;
+        bsel = q.b[3] != cA ? q.b[3] : bsel; bsel = q.b[2] != cA ? q.b[2] : bsel; bsel = q.b[1] != cA ? q.b[1] : bsel; bsel = q.b[0] != cA ? q.b[0] : bsel;
+        bsel = q.a[3] != cA ? q.a[3] : bsel; bsel = q.a[2] != cA ? q.a[2] : bsel; bsel = q.a[1] != cA ? q.a[1] : bsel; bsel = q.a[0] != cA ? q.a[0] : bsel;
+        const int bsel_o = __shfl_xor_sync(0xffffffffu, bsel, 1);
+        const int b_first = hh == 0 ? bsel : bsel_o, b_second = hh == 0 ? bsel_o : bsel;
+        const int cB = b_first != cA ? b_first : b_second;
+        const bool in2 = (q.a[0] == cA || q.a[0] == cB) && (q.a[1] == cA || q.a[1] == cB) && (q.a[2] == cA || q.a[2] == cB) && (q.a[3] == cA || q.a[3] == cB) &&
+                         (q.b[0] == cA || q.b[0] == cB) && (q.b[1] == cA || q.b[1] == cB) && (q.b[2] == cA || q.b[2] == cB) && (q.b[3] == cA || q.b[3] == cB);
+        const bool in2_o = __shfl_xor_sync(0xffffffffu, (int)in2, 1) != 0;
         if (hh == 0) {
-            s_wc[warp][w] = q.a[0];
-            s_wm[warp][w] = (unsigned short)(m8 | (other << 8));
+            const unsigned m16 = m8 | (other << 8);
+            rp_sts128(sm + kRpDesc + w * 16, cA, (in2 && in2_o && cB != cA) ? cB : -1, (int)m16, 0);
+            rp_sts32(sm + kRpWc + w * 4, cA);
+            rp_sts16(sm + kRpWm + w * 2, m16);
         }
         __syncwarp();
 
-        const int g = (int)lane;                            // group of V channels
-        const TableT *table_e = table + (size_t)ce * n_cells * C;
+        const char *rows = reinterpret_cast<const char *>(table + (size_t)ce * ep_rows + (size_t)g * V);   // this lane's channel group of row 0
         const float *counts_e = counts ? counts + (size_t)ce * n_cells : nullptr;
-        int cur_cell = -1;
-        Vec<V> cur = vzero<V>();
+        auto fetch = [&](int cell) { return load_raw<V>(reinterpret_cast<const TableT *>(rows), counts_e, (size_t)cell, C, 0); };
+        int cur_cell = -1, oth_cell = -1;
+        Vec<V> cur = vzero<V>(), oth = vzero<V>();
         Vec<V> l1acc = vzero<V>();
 #pragma unroll 1
         for (int l0 = 0; l0 < 4; ++l0) {                   // L0 pixels of the quadrant, row-major
@@ -233,54 +305,68 @@ __global__ void __launch_bounds__(kReadWarps * 32, (C >= 512 ? 2 : (C >= 256 ? 3
             // gathered value x is an fp16 number, so the sequential fp32 sum 0+x+x+...+x is exact at every step
             // (k*x, k <= 16, has at most 15 significant bits) and avg_pool2d(4) returns x itself - except that -0.0
             // becomes +0.0 (0 + -0 = +0), which the shortcuts reproduce by adding +0 (found by the read stress sweep).
-            const int4 wc4 = *reinterpret_cast<const int4 *>(&s_wc[warp][l0 * 4]);
-            const uint2 wm2 = *reinterpret_cast<const uint2 *>(&s_wm[warp][l0 * 4]);
+            const int4 wc4 = rp_lds128(sm + kRpWc + l0 * 16);
+            const int2 wm2 = rp_lds64(sm + kRpWm + l0 * 8);
             Vec<V> v0;
-            if (wm2.x == 0x00010001u && wm2.y == 0x00010001u && wc4.x == wc4.y && wc4.x == wc4.z && wc4.x == wc4.w) {
+            if (wm2.x == 0x00010001 && wm2.y == 0x00010001 && wc4.x == wc4.y && wc4.x == wc4.z && wc4.x == wc4.w) {
                 // whole 8x8 block in one cell: pool(4), pool(2) and the fp16 rounding all return the gathered value
-                if (wc4.x != cur_cell) cur = finish<V>(load_raw<V>(table_e, counts_e, (size_t)wc4.x, C, g));
+                if (wc4.x != cur_cell) cur = finish<V>(fetch(wc4.x));
                 cur_cell = wc4.x;
                 v0 = vadd<V>(cur, vzero<V>());               // the reference's sums start from +0: a gathered -0.0 comes out as +0.0
             } else {
                 Vec<V> s2 = vzero<V>();
-                const int wcs[4] = {wc4.x, wc4.y, wc4.z, wc4.w};
-                const unsigned wms[4] = {wm2.x & 0xffffu, wm2.x >> 16, wm2.y & 0xffffu, wm2.y >> 16};
-#pragma unroll
-                for (int win = 0; win < 4; ++win) {        // 4x4 windows of the avg_pool2d(4) (timm.py:152), row-major
-                    const int wc = wcs[win];
-                    unsigned rest = wms[win] & ~1u;          // run heads after the first pixel
-                    if (wc != cur_cell) cur = finish<V>(load_raw<V>(table_e, counts_e, (size_t)wc, C, g));
+                // NOT unrolled: the window body holds the 16 row variants of vadd_row2 and the generic run walk; four copies of it
+                // (r2 v4a) ran slower than v3 despite fewer instructions - the warps of an SM sit in different windows and the
+                // instruction cache could not hold the unrolled body.  One LDS.128 brings the window's descriptor.
+                uint32_t dsc = sm + kRpDesc + l0 * 64;
+#pragma unroll 1
+                for (int win = 0; win < 4; ++win, dsc += 16) {   // 4x4 windows of the avg_pool2d(4) (timm.py:152), row-major
+                    const int4 d = rp_lds128(dsc);
+                    const int wc = d.x, wb = d.y;
+                    unsigned rest = (unsigned)d.z & ~1u;        // run heads after the first pixel
+                    if (wc != cur_cell) cur = finish<V>(fetch(wc));
                     cur_cell = wc;
                     if (rest == 0u) {                        // one cell for the whole window
                         s2 = vadd<V>(s2, cur);
                         continue;
                     }
-                    // a mixed window is typically an edge between two or three cells: 2-8 runs instead of 16 pixels; the walk pays
-                    // the fetch / fp16->fp32 conversion / bookkeeping per RUN and V/2 packed adds per pixel.  (A straight-line
-                    // per-pixel walk with a head-bit test per pixel was tried in r2: the compiler if-converts it into predicated
-                    // copies, 52.6 M instead of 40.0 M warp instructions per E=16 launch.)
-                    const int *cells = &s_idx[warp][(l0 * 4 + win) * 16];
                     Vec<V> s4 = vzero<V>();
-                    int p = 0;
+                    if (wb >= 0) {
+                        // exactly two cells: cur = row of A (first pixel), oth = row of B
+                        if (wb != oth_cell) oth = finish<V>(fetch(wb));
+                        oth_cell = wb;
+                        // bit p of bm: pixel p belongs to B = parity of the run heads in (0, p] (prefix xor over the 16-bit head mask)
+                        unsigned bm = rest;
+                        bm ^= bm << 1; bm ^= bm << 2; bm ^= bm << 4; bm ^= bm << 8;
 #pragma unroll 1
-                    while (true) {
-                        const int pn = rest ? (__ffs(rest) - 1) : 16;
-                        rest &= rest - 1;
-                        Raw raw;
-                        int ncell = cur_cell;
-                        if (pn < 16) {                       // next run's row in flight under the adds
-                            ncell = cells[pn];
-                            raw = load_raw<V>(table_e, counts_e, (size_t)ncell, C, g);
+                        for (int r = 0; r < 4; ++r, bm >>= 4) vadd_row2<V>(s4, cur, oth, bm);
+                    } else {
+                        // three or more cells in the window: 2-8 runs instead of 16 pixels; the walk pays the fetch / fp16->fp32
+                        // conversion / bookkeeping per RUN and V/2 packed adds per pixel.  (A straight-line per-pixel walk with a
+                        // head-bit test per pixel was tried in r2: the compiler if-converts it into predicated copies, 52.6 M
+                        // instead of 40.0 M warp instructions per E=16 launch.)
+                        const uint32_t cells = sm + kRpIdx + (uint32_t)(l0 * 4 + win) * 64;
+                        int p = 0;
+#pragma unroll 1
+                        while (true) {
+                            const int pn = rest ? (__ffs(rest) - 1) : 16;
+                            rest &= rest - 1;
+                            Raw raw;
+                            int ncell = cur_cell;
+                            if (pn < 16) {                   // next run's row in flight under the adds
+                                ncell = rp_lds32(cells + pn * 4);
+                                raw = fetch(ncell);
+                            }
+                            int len = pn - p;                // 1..15, warp-uniform; sequential fp32 sum: `len` times + cur
+#pragma unroll 1
+                            for (; len >= 4; len -= 4) { s4 = vadd<V>(s4, cur); s4 = vadd<V>(s4, cur); s4 = vadd<V>(s4, cur); s4 = vadd<V>(s4, cur); }
+                            if (len & 2) { s4 = vadd<V>(s4, cur); s4 = vadd<V>(s4, cur); }
+                            if (len & 1) s4 = vadd<V>(s4, cur);
+                            if (pn >= 16) break;
+                            cur = finish<V>(raw);
+                            cur_cell = ncell;
+                            p = pn;
                         }
-                        int len = pn - p;                    // 1..15, warp-uniform; sequential fp32 sum: `len` times + cur
-#pragma unroll 1
-                        for (; len >= 4; len -= 4) { s4 = vadd<V>(s4, cur); s4 = vadd<V>(s4, cur); s4 = vadd<V>(s4, cur); s4 = vadd<V>(s4, cur); }
-                        if (len & 2) { s4 = vadd<V>(s4, cur); s4 = vadd<V>(s4, cur); }
-                        if (len & 1) s4 = vadd<V>(s4, cur);
-                        if (pn >= 16) break;
-                        cur = finish<V>(raw);
-                        cur_cell = ncell;
-                        p = pn;
                     }
                     s2 = vadd<V>(s2, vscale<V>(s4, 0.0625f));    // / 16 (exact)
                 }

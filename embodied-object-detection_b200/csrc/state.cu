@@ -87,6 +87,26 @@ __global__ void __launch_bounds__(256) check_indices_kernel(const IdxT *__restri
     if ((threadIdx.x & 31) == 0 && bad) atomicAdd(err, bad);
 }
 
+// explicit_map read mode (SMNet/loader.py:233-246, create_explicit_memory in the 3.9 bytecode of custom_rcnn): the projection index of a
+// pixel is replaced by the class of the cell it falls into, shifted by `add` (-1 "empty" -> row 0 of the [zeros; class table] memory).
+// A bad cell id or a class outside [0, n_rows) is counted in err[0] and clamped, as in check_indices_kernel.
+template <typename IdxT, typename LutT>
+__global__ void __launch_bounds__(256) remap_indices_kernel(const IdxT *__restrict__ idx, int64_t n, const LutT *__restrict__ lut, int64_t n_cells,
+                                                            int add, int64_t n_rows, int32_t *__restrict__ out32, int32_t *__restrict__ err)
+{
+    int bad = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const long long c = (long long)idx[i];
+        const bool ok_c = c >= 0 && c < (long long)n_cells;
+        const long long v = (long long)__ldg(lut + (ok_c ? c : 0)) + add;
+        const bool ok = ok_c && v >= 0 && v < (long long)n_rows;
+        bad += ok ? 0 : 1;
+        out32[i] = (int32_t)(ok ? v : 0);
+    }
+    bad = __reduce_add_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(err, bad);
+}
+
 int launch_touched(bool refresh, float *counts, float *sums, void *norm16, const int32_t *mask, int64_t n_rows, int64_t n_cells, int C,
                    cudaStream_t st, const char *what)
 {
@@ -137,4 +157,20 @@ extern "C" int eod_check_indices(const void *idx, int idx_is_i64, int64_t n, int
     if (idx_is_i64) check_indices_kernel<int64_t><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const int64_t *)idx, n, n_cells, idx32_out, err);
     else check_indices_kernel<int32_t><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const int32_t *)idx, n, n_cells, idx32_out, err);
     return eod_check_launch("eod_check_indices");
+}
+
+extern "C" int eod_remap_indices(const void *idx, int idx_is_i64, int64_t n, const void *lut, int lut_is_i64, int64_t n_cells, int add, int64_t n_rows,
+                                 int32_t *out32, int32_t *err, eod_stream_t stream)
+{
+    EOD_REQUIRE(idx && lut && out32 && err, EOD_ERR_BADARG, "eod_remap_indices: null pointer");
+    EOD_REQUIRE(n > 0 && n_cells > 0 && n_rows > 0 && n_rows <= 0x7fffffffll, EOD_ERR_BADARG, "eod_remap_indices: bad sizes");
+    int64_t blocks = (n + 255) / 256;
+    const int64_t cap = (int64_t)eod_num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (idx_is_i64 && lut_is_i64) remap_indices_kernel<int64_t, int64_t><<<(int)blocks, 256, 0, st>>>((const int64_t *)idx, n, (const int64_t *)lut, n_cells, add, n_rows, out32, err);
+    else if (idx_is_i64) remap_indices_kernel<int64_t, int32_t><<<(int)blocks, 256, 0, st>>>((const int64_t *)idx, n, (const int32_t *)lut, n_cells, add, n_rows, out32, err);
+    else if (lut_is_i64) remap_indices_kernel<int32_t, int64_t><<<(int)blocks, 256, 0, st>>>((const int32_t *)idx, n, (const int64_t *)lut, n_cells, add, n_rows, out32, err);
+    else remap_indices_kernel<int32_t, int32_t><<<(int)blocks, 256, 0, st>>>((const int32_t *)idx, n, (const int32_t *)lut, n_cells, add, n_rows, out32, err);
+    return eod_check_launch("eod_remap_indices");
 }

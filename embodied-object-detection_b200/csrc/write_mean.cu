@@ -498,8 +498,8 @@ struct TmaCfg {
     static constexpr int kStages = 12;                                    // ring depth == consumer warps
     static constexpr int kThreads = 32 * (kStages + 1);
     static constexpr int kUnitBytes = kChanBlk * TILE_PX * 4;             // 16 KB, keeps every stage 1 KB aligned (SWIZZLE_128B)
-    // aux area per stage: cells (128 B) | samp (32 B) | pad | per-pixel 1/n (128 B)
-    static constexpr int kAuxCells = 0, kAuxSamp = 128, kAuxPixN = 256, kAuxBytes = 512;
+    // aux area per stage: cells (128 B) | samp (32 B) | pad | per-pixel 1/n (128 B) | unit descriptor {tile, channel block} (8 B)
+    static constexpr int kAuxCells = 0, kAuxSamp = 128, kAuxPixN = 256, kAuxUnit = 384, kAuxBytes = 512;
     static constexpr int kSmemBytes = kStages * (kUnitBytes + kAuxBytes) + 1024 /*align slack*/ + 256 /*barriers*/;
     static_assert(C % kChanBlk == 0, "C must be a multiple of 128");
     static_assert(kSmemBytes <= 232448, "exceeds 227 KB of shared memory");
@@ -538,6 +538,22 @@ __device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity)
         "r"(parity)
         : "memory");
 }
+// same wait with a suspend-time hint (ns): the warp sleeps in hardware instead of re-issuing the poll
+__device__ __forceinline__ void mbar_wait_hint(uint32_t bar, uint32_t parity, uint32_t hint_ns)
+{
+    if (hint_ns == 0) { mbar_wait_s(bar, parity); return; }
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP_H:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra DONE_H;\n\t"
+        "bra WAIT_LOOP_H;\n\t"
+        "DONE_H:\n\t"
+        "}" ::"r"(bar),
+        "r"(parity), "r"(hint_ns)
+        : "memory");
+}
 __device__ __forceinline__ float4 lds128(uint32_t addr)
 {
     float4 v;
@@ -549,6 +565,10 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr)
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
+}
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b)
+{
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
 }
 __device__ __forceinline__ uint32_t lds8(uint32_t addr)
 {
@@ -576,7 +596,8 @@ template <int C, bool kDry, bool kPixN, bool kDet>
 __global__ void __launch_bounds__(TmaCfg<C>::kThreads, 1)
 write_mean_chw_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t *__restrict__ idx, const uint8_t *__restrict__ samp,
                           const uint32_t *__restrict__ frame_cnt, const float *__restrict__ pix_n, const int32_t *__restrict__ active, int HW,
-                          int64_t n_cells, int tiles_per_ep, int n_tiles, int group, float *__restrict__ sums, const DetArgs det)
+                          int64_t n_cells, int tiles_per_ep, int n_tiles, int group, float *__restrict__ sums, const DetArgs det,
+                          int *__restrict__ work, int chunk, uint32_t wait_hint)
 {
     using Cfg = TmaCfg<C>;
     extern __shared__ unsigned char smem_dyn[];
@@ -598,20 +619,17 @@ write_mean_chw_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int32_
     }
     __syncthreads();
 
-    // Tiles are handed out in GROUPS of `group` raster neighbours (group q -> CTA q % gridDim.x) and a group's units
-    // are issued channel-block-major: the 128-byte row segments of neighbouring tiles are requested back to back, so
-    // they share one 256-byte L2 line fill (no second DRAM fetch by some other CTA at some other time) and fall into
-    // the same open DRAM page.
+    // Tiles are handed out in GROUPS of `group` raster neighbours and a group's units are issued channel-block-major: the
+    // 128-byte row segments of neighbouring tiles are requested back to back, so they share one 256-byte L2 line fill (no
+    // second DRAM fetch by some other CTA at some other time) and fall into the same open DRAM page.
+    // Groups are CLAIMED, not pre-assigned: the producer takes the next group from a global ticket (`work[0]`; the first one is
+    // the CTA's own index), so a CTA that starts late or shares its SM with the read / count kernels of the neighbouring frames
+    // simply takes fewer groups instead of stretching the launch (static q -> CTA q % G measured 3.19 ms alone but 3.4-3.9 ms
+    // next to the other stages).  The unit's {tile, channel block} travels to the owning consumer warp in the stage's aux area;
+    // a negative tile ends the consumer.  work == nullptr keeps the static round-robin (comparator).
     const int G = (int)gridDim.x, b = (int)blockIdx.x;
     const int n_groups = n_tiles / group;                        // host guarantees n_tiles % group == 0
-    const int my_groups = (n_groups - b + G - 1) / G;
     const int units_per_group = group * Cfg::kBlocks;
-    const int my_units = my_groups * units_per_group;
-    auto unit_of = [&](int u, int &t, int &cb) {
-        const int q = u / units_per_group, k = u - q * units_per_group;
-        cb = k / group;
-        t = group * (b + q * G) + (k - cb * group);
-    };
 
     if (warp == Cfg::kStages) {
         // ===== producer warp: one elected lane issues all copies =====
@@ -620,23 +638,51 @@ write_mean_chw_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int32_
             const uint32_t tx = Cfg::kUnitBytes + TILE_PX * 4 + (has_samp ? TILE_PX : 0) + (kPixN ? TILE_PX * 4 : 0);
             int stage = 0;
             uint32_t phase = 0;
-            for (int u = 0; u < my_units; ++u) {
-                int t, cb;
-                unit_of(u, t, cb);
-                const int e = t / tiles_per_ep, p0 = (t - e * tiles_per_ep) * TILE_PX;
-                const uint32_t fullb = full0 + 8 * stage, aux = aux0 + stage * Cfg::kAuxBytes;
-                mbar_wait_s(empty0 + 8 * stage, phase ^ 1);
-                if (active && __ldg(active + e) <= 0) {
-                    // idle slot of the batch: the stage is handed over empty (keeps the unit -> stage mapping), nothing is fetched
-                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fullb) : "memory");
-                } else {
-                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fullb), "r"(tx) : "memory");
-                    tma_load_3d_hint(base + stage * Cfg::kUnitBytes, &tmap, p0, cb * Cfg::kChanBlk, e, fullb, pol);
-                    bulk_load_1d_s(aux + Cfg::kAuxCells, idx + (size_t)e * HW + p0, TILE_PX * 4, fullb);
-                    if (has_samp) bulk_load_1d_s(aux + Cfg::kAuxSamp, samp + (size_t)e * HW + p0, TILE_PX, fullb);
-                    if (kPixN) bulk_load_1d_s(aux + Cfg::kAuxPixN, pix_n + (size_t)e * HW + p0, TILE_PX * 4, fullb);
+            // a ticket = `chunk` consecutive groups; the next ticket is drawn one chunk ahead (the round trip of an atomic under a
+            // saturated memory system is several microseconds - longer than one group lasts)
+            int c = b;
+            int c_next = work ? G + atomicAdd(work, 1) : c + G;
+            while (c * chunk < n_groups) {
+              const int c_next2 = work ? G + atomicAdd(work, 1) : c_next + G;
+              const int q_end = min(n_groups, (c + 1) * chunk);
+              for (int q = c * chunk; q < q_end; ++q) {
+                for (int k = 0; k < units_per_group; ++k) {
+                    const int cb = k / group, t = group * q + (k - cb * group);
+                    const int e = t / tiles_per_ep, p0 = (t - e * tiles_per_ep) * TILE_PX;
+                    const uint32_t fullb = full0 + 8 * stage, aux = aux0 + stage * Cfg::kAuxBytes;
+                    mbar_wait_hint(empty0 + 8 * stage, phase ^ 1, wait_hint);
+                    const bool idle = active && __ldg(active + e) <= 0;
+                    sts64(aux + Cfg::kAuxUnit, (uint32_t)t, (uint32_t)cb | (idle ? 0x100u : 0u));
+                    if (idle) {
+                        // idle slot of the batch: the stage is handed over empty, nothing is fetched
+                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fullb) : "memory");
+                    } else {
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fullb), "r"(tx) : "memory");
+                        tma_load_3d_hint(base + stage * Cfg::kUnitBytes, &tmap, p0, cb * Cfg::kChanBlk, e, fullb, pol);
+                        bulk_load_1d_s(aux + Cfg::kAuxCells, idx + (size_t)e * HW + p0, TILE_PX * 4, fullb);
+                        if (has_samp) bulk_load_1d_s(aux + Cfg::kAuxSamp, samp + (size_t)e * HW + p0, TILE_PX, fullb);
+                        if (kPixN) bulk_load_1d_s(aux + Cfg::kAuxPixN, pix_n + (size_t)e * HW + p0, TILE_PX * 4, fullb);
+                    }
+                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
+              }
+              c = c_next;
+              c_next = c_next2;
+            }
+            for (int s = 0; s < Cfg::kStages; ++s) {                          // one end marker per consumer warp
+                mbar_wait_hint(empty0 + 8 * stage, phase ^ 1, wait_hint);
+                sts64(aux0 + stage * Cfg::kAuxBytes + Cfg::kAuxUnit, 0xffffffffu, 0u);
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full0 + 8 * stage) : "memory");
                 if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+            }
+            if (work) {
+                // every CTA has drawn its last ticket before it counts itself done: the last one re-arms the pair for the next launch
+                __threadfence();
+                if (atomicAdd(work + 1, 1) == G - 1) {
+                    work[0] = 0;
+                    work[1] = 0;
+                    __threadfence();
+                }
             }
         }
         return;
@@ -647,13 +693,14 @@ write_mean_chw_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int32_
     const uint32_t aux = aux0 + warp * Cfg::kAuxBytes;
     const uint32_t fullb = full0 + 8 * warp, emptyb = empty0 + 8 * warp;
     const uint32_t sw = lane & 7;                                                  // rows l + 32k share the swizzle phase
-    uint32_t phase = 0;
-    for (int u = warp; u < my_units; u += Cfg::kStages, phase ^= 1) {
-        int t, cb;
-        unit_of(u, t, cb);
-        int run_pos = kDet ? __ldg(det.tile_off + t) : 0;          // issued before the wait: its latency hides behind the TMA load
-        const bool idle = active && __ldg(active + t / tiles_per_ep) <= 0;
-        mbar_wait_s(fullb, phase);
+    for (uint32_t phase = 0;; phase ^= 1) {
+        mbar_wait_hint(fullb, phase, wait_hint);
+        const int t = (int)lds32(aux + Cfg::kAuxUnit);
+        if (t < 0) break;                                          // end marker: no more units for this stage
+        const uint32_t cbw = lds32(aux + Cfg::kAuxUnit + 4);
+        const int cb = (int)(cbw & 0xffu);
+        const bool idle = (cbw & 0x100u) != 0;
+        int run_pos = kDet ? __ldg(det.tile_off + t) : 0;
         if (!kDry && !idle) {
             const int e = t / tiles_per_ep;
             // run structure of the tile: lane p looks at pixel p
@@ -851,7 +898,15 @@ int launch_tma_kernel(const CUtensorMap &tmap, const int32_t *idx, const uint8_t
     while (group > 1 && n_tiles % group) group >>= 1;
     const int n_groups = n_tiles / group;
     const int grid = n_groups < eod_num_sms() ? n_groups : eod_num_sms();
-    write_mean_chw_tma_kernel<C, kDry, kPixN, kDet><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmap, idx, samp, frame_cnt, pix_n, active, HW, n_cells, tiles_per_ep, n_tiles, group, sums, det);
+    static const int static_env = [] { const char *v = getenv("EOD_TMA_STATIC_TILES"); return v ? atoi(v) : 0; }();   // comparator: pre-assigned groups
+    int *work = static_env ? nullptr : eod_work_tickets();
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (work && (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone))
+        work = nullptr;      // a captured launch would pin its ticket pair for the graph's lifetime while eager launches keep rotating through the pool
+    static const int chunk_env = [] { const char *v = getenv("EOD_TMA_CHUNK"); return v ? atoi(v) : 8; }();        // groups per ticket
+    static const int hint_env = [] { const char *v = getenv("EOD_TMA_WAIT_HINT_NS"); return v ? atoi(v) : 0; }();   // suspend-time hint of the barrier waits
+    const int chunk = work ? (chunk_env > 0 ? chunk_env : 8) : 1;
+    write_mean_chw_tma_kernel<C, kDry, kPixN, kDet><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmap, idx, samp, frame_cnt, pix_n, active, HW, n_cells, tiles_per_ep, n_tiles, group, sums, det, work, chunk, (uint32_t)hint_env);
     return eod_check_launch("eod_write_mean[tma]");
 }
 

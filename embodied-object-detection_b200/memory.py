@@ -459,6 +459,33 @@ class SpatialFeatureMemory:
         obs = torch.as_tensor(frame["observations"]).to(self.device, torch.float32).contiguous()
         return ops.normalize_memory(mem, obs), frame["proj_indices"]
 
+    def create_explicit_memory(self, frame: Dict, clip_embeddings: torch.Tensor, semmap: Optional[torch.Tensor] = None
+                               ) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
+        """MODEL.MEMORY_TYPE 'explicit_map' (SMNet/loader.py:233-246,298; ``create_explicit_memory`` of the older custom_rcnn revision,
+        bytecode listing create_explicit_memory_custom_rcnn_py39.txt, src lines 1400-1411): the memory the read gathers from is the class
+        table with a zero row in front, ``memory = [0; clip_embeddings]`` (K+1, C), and a pixel's index is the class of the cell it
+        falls into, ``proj_indices := (semmap + 1)[proj_indices]`` (-1 'empty' -> row 0).  semmap: (cells,) int class map (-1 = empty);
+        default = the live explicit map of this memory (A14, ``self.semmap``).  Returns (memory fp32 (K+1,C), proj_indices int32
+        (H,W), ego_observations = observations[proj_indices] or None) - feed the first two to ``read_levels`` / ``MemoryFusion``
+        exactly like an implicit memory."""
+        table = torch.as_tensor(clip_embeddings).to(self.device, torch.float32)
+        memory = torch.cat([torch.zeros((1, table.shape[1]), dtype=torch.float32, device=self.device), table], 0).contiguous()
+        sm = self.semmap if semmap is None else torch.as_tensor(semmap).to(self.device)
+        if sm is None:
+            raise EodError("create_explicit_memory: no semantic map (pass semmap= or construct the memory with zs_weight)")
+        if sm.dtype not in (torch.int32, torch.int64):
+            sm = sm.to(torch.int64)
+        idx = torch.as_tensor(frame["proj_indices"]).to(self.device)
+        if idx.dim() == 3 and idx.shape[-1] == 1:
+            idx = idx.squeeze(2)
+        if idx.dtype not in (torch.int32, torch.int64):
+            idx = idx.to(torch.int64)
+        idx = idx.contiguous()
+        proj = ops.remap_indices(idx, sm.reshape(-1).contiguous(), memory.shape[0], add=1)
+        obs = frame.get("observations")
+        ego_obs = None if obs is None else torch.as_tensor(obs).to(self.device).reshape(-1)[idx.long()]
+        return memory, proj, ego_obs
+
     def preprocess_spatial_memory(self, batched_inputs: Sequence[Dict]):
         """custom_rcnn.py:1019-1042: lists of (memory f16, proj_indices int64, observations)."""
         memory, projection, observations = [], [], []

@@ -18,7 +18,7 @@ launch_count = 0
 _LAUNCHES = {"eod_backproject_quantize": 1, "eod_backproject_quantize_u16": 1, "eod_quantize_world": 1, "eod_sample_mask": 1, "eod_frame_count": 1, "eod_expand_counts": 1, "eod_write_mean": 1, "eod_write_mean_det": 9,
              "eod_finalize_counts": 1, "eod_box_to_image_features": 1, "eod_masks_observed": 1, "eod_paste_masks": 1, "eod_write_objects_pasted": 1, "eod_bilinear_lattice": 1, "eod_write_objects": 1, "eod_flush_slots": 2, "eod_write_max": 2, "eod_read_pool": 2,
              "eod_fuse": 1, "eod_project_split_weights": 1, "eod_project_fuse": 1, "eod_project_fuse_levels": 1, "eod_normalize_memory": 1, "eod_reset_touched": 1, "eod_semmap_update": 1, "eod_semmap_decode": 2,
-             "eod_reset_episodes": 1, "eod_refresh_norm16": 1, "eod_check_indices": 1, "eod_read_roi": 1}
+             "eod_reset_episodes": 1, "eod_refresh_norm16": 1, "eod_check_indices": 1, "eod_remap_indices": 1, "eod_read_roi": 1}
 
 
 def _call(name: str, *args) -> None:
@@ -246,6 +246,25 @@ def check_indices(idx: torch.Tensor, n_cells: int, want_i32: bool = False) -> Op
     bad = int(err.item())
     if bad:
         raise IndexError(f"{bad} cell indices are outside [0, {int(n_cells)}): proj_indices do not belong to this map")
+    return out
+
+
+def remap_indices(idx: torch.Tensor, lut: torch.Tensor, n_rows: int, add: int = 1) -> torch.Tensor:
+    """explicit_map read mode (loader.py:233-246): int32 plane ``lut[idx] + add`` of the same shape as idx - the rows of the
+    (n_rows, C) [zeros; class table] memory.  Raises IndexError, like the reference's numpy / torch gathers, if a cell id is outside
+    the map or a class outside the table.  Synchronises (one 4-byte read-back)."""
+    for t, name in ((idx, "idx"), (lut, "lut")):
+        if t.dtype not in (torch.int32, torch.int64):
+            raise TypeError(f"{name} must be int32 or int64")
+        _dev(t, t.dtype, name)
+    err = torch.zeros((1,), dtype=torch.int32, device=idx.device)
+    out = torch.empty(idx.shape, dtype=torch.int32, device=idx.device)
+    if idx.numel():
+        _call("eod_remap_indices", idx.data_ptr(), int(idx.dtype == torch.int64), idx.numel(), lut.data_ptr(), int(lut.dtype == torch.int64),
+              lut.numel(), int(add), int(n_rows), out.data_ptr(), err.data_ptr(), _stream())
+    bad = int(err.item())
+    if bad:
+        raise IndexError(f"{bad} pixels map outside the semantic map / the {int(n_rows)}-row class table")
     return out
 
 

@@ -299,6 +299,14 @@ int eod_refresh_norm16(const float *counts, const float *sums, void *norm16, con
 int eod_check_indices(const void *idx, int idx_is_i64, int64_t n, int64_t n_cells, int32_t *idx32_out, int32_t *err,
                       eod_stream_t stream);
 
+/* explicit_map read mode (SMNet/loader.py:233-246: `proj_indices = semmap_real[proj_indices]` with `semmap_real = semmap + 1`, memory =
+ * [zero row; class-embedding table]; consumed by create_explicit_memory of the older custom_rcnn revision, bytecode listing
+ * oracle/disasm/create_explicit_memory_custom_rcnn_py39.txt): out32[i] = lut[idx[i]] + add, the row of the (n_rows, C) table
+ * that eod_read_pool then gathers.  idx: n cell ids (int32 / int64), lut: n_cells class ids (int32 / int64).  err[0] (device int32,
+ * caller zeroes it) += number of ids outside [0, n_cells) or rows outside [0, n_rows); those come out as row 0. */
+int eod_remap_indices(const void *idx, int idx_is_i64, int64_t n, const void *lut, int lut_is_i64, int64_t n_cells, int add, int64_t n_rows,
+                      int32_t *out32, int32_t *err, eod_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * (4) Fusion epilogue, timm.py:177-189: out = res + weight*mem | weight*mem | res (two roundings, no
  * FMA contraction, as torch computes it).  n elements, fp32. */

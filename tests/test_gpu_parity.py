@@ -230,6 +230,47 @@ def test_read_pool_signed_zeros_and_adversarial_patterns(eod, cuda):
                     assert np.array_equal(got[k][e].contiguous().cpu().numpy().view(np.uint16), ref[k].view(np.uint16)), (C, e, k)
 
 
+def test_explicit_map_read_mode(eod, cuda):
+    """MODEL.MEMORY_TYPE 'explicit_map' (SMNet/loader.py:233-246,298): memory = [zero row; (20,512) class table], proj_indices =
+    (semmap + 1)[proj_indices].  The composed index plane must equal numpy's, and the read of the 21-row table (both as an fp16
+    table and as fp32 without counts, through SpatialFeatureMemory.read_levels and MemoryFusion.read) must be bit-identical to
+    timm.py:147-168 executed by torch-CPU on the same table (oracle R.read_pool); bad ids raise like the reference's gathers."""
+    rng = np.random.default_rng(21)
+    H, W, mw, mh, C, K = 96, 128, 70, 50, 512, 20
+    clip = rng.standard_normal((K, C)).astype(np.float32)
+    clip /= np.linalg.norm(clip, axis=1, keepdims=True)
+    semmap = rng.integers(-1, K, (mw * mh,)).astype(np.int64)
+    semmap[rng.random(mw * mh) < 0.5] = -1                                            # half the map is unobserved
+    yy, xx = np.mgrid[0:H, 0:W]
+    proj = ((yy // 5) * mw // 3 + xx // 3) % (mw * mh)
+    proj[::9, ::7] = rng.integers(0, mw * mh, proj[::9, ::7].shape)
+    obs = rng.integers(0, 5, (mw * mh,)).astype(np.float32)
+    mem = eod.SpatialFeatureMemory(C, cuda)
+    for idx_dtype, sm_dtype in ((np.int32, np.int64), (np.int64, np.int32), (np.int64, np.int64), (np.int32, np.int32)):
+        frame = {"proj_indices": proj.astype(idx_dtype)[..., None], "observations": obs}
+        memory, pidx, ego_obs = mem.create_explicit_memory(frame, torch.from_numpy(clip), torch.from_numpy(semmap.astype(sm_dtype)))
+        ref_mem = np.insert(clip, 0, np.zeros((1, C)), axis=0).astype(np.float32)      # loader.py:233-235
+        ref_idx = (semmap + 1)[proj]                                                  # loader.py:222,242
+        assert memory.shape == (K + 1, C) and np.array_equal(memory.cpu().numpy(), ref_mem)
+        assert pidx.dtype == torch.int32 and np.array_equal(pidx.cpu().numpy(), ref_idx)
+        assert np.array_equal(ego_obs.cpu().numpy(), obs[proj])
+    ref = R.read_pool(torch.from_numpy(ref_mem).half(), torch.from_numpy(ref_idx))
+    fus = eod.MemoryFusion("implicit_memory", "sum", 5, mem_feat_dim=C, ego_feat_dim=256).to(cuda)
+    for name, levels in (("read_levels f16", mem.read_levels(pidx, memory.half())),
+                         ("read_levels f32 no counts", mem.read_levels(pidx, memory)),
+                         ("MemoryFusion.read", fus.read([memory.half()], [pidx]))):
+        for k in range(3):
+            assert np.array_equal(levels[k][0].contiguous().cpu().numpy().view(np.uint16), ref[k][0].numpy().view(np.uint16)), (name, k)
+    bad = semmap.copy()
+    bad[proj[3, 3]] = K + 5                                                           # class outside the table
+    with pytest.raises(IndexError):
+        mem.create_explicit_memory({"proj_indices": proj}, torch.from_numpy(clip), torch.from_numpy(bad))
+    badp = proj.copy()
+    badp[0, 0] = mw * mh                                                              # cell outside the map
+    with pytest.raises(IndexError):
+        mem.create_explicit_memory({"proj_indices": badp}, torch.from_numpy(clip), torch.from_numpy(semmap))
+
+
 def test_fuse_bit_exact(eod, cuda):
     rng = np.random.default_rng(1)
     for n in (1, 3, 4, 1000, 256 * 60 * 80 + 3):
