@@ -705,23 +705,32 @@ write_mean_chw_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int32_
             const int e = t / tiles_per_ep;
             // run structure of the tile: lane p looks at pixel p
             const int cell = (int)lds32(aux + Cfg::kAuxCells + 4 * lane);
+            // kDet: runs of equal cell id (the deterministic reduce orders RUNS).  Default: all pixels of the tile that fall into one
+            // cell form ONE group, contiguous or not (MATCH.ANY) - with noisy depth or fine cells a tile alternates between a few
+            // cells (A B A A B ...) and every extra run would cost four more L2 reductions (profiles/r2: run-length sweep).
             const int prev = __shfl_up_sync(0xffffffffu, cell, 1);
-            unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || prev != cell);
+            const unsigned grp = kDet ? 0u : __match_any_sync(0xffffffffu, cell);
+            unsigned heads = __ballot_sync(0xffffffffu, kDet ? (lane == 0 || prev != cell) : ((unsigned)(__ffs(grp) - 1) == lane));
             const unsigned samps = has_samp ? __ballot_sync(0xffffffffu, lds8(aux + Cfg::kAuxSamp + lane) != 0) : 0xffffffffu;
             const float my_inv = kPixN ? __uint_as_float(lds32(aux + Cfg::kAuxPixN + 4 * lane)) : 0.f;
             float *dst = sums + ((size_t)e * n_cells) * C + cb * Cfg::kChanBlk + lane;
             const uint32_t *cnt_e = frame_cnt + (size_t)e * n_cells;
 
             while (heads) {
-                const int p0 = __ffs(heads) - 1;
+                const int p0 = __ffs(heads) - 1;                       // first pixel of the run / group
                 heads &= heads - 1;
-                const int p1 = heads ? (__ffs(heads) - 1) : TILE_PX;
-                const unsigned m = samps & (0xffffffffu >> (32 - p1)) & (0xffffffffu << p0);
-                if (m == 0) continue;                                  // no sampled pixel in this run
+                unsigned m;
+                if (kDet) {
+                    const int p1 = heads ? (__ffs(heads) - 1) : TILE_PX;
+                    m = samps & (0xffffffffu >> (32 - p1)) & (0xffffffffu << p0);
+                } else {
+                    m = samps & __shfl_sync(0xffffffffu, grp, p0);
+                }
+                if (m == 0) continue;                                  // no sampled pixel in this run / group
                 float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-                const int j1 = (p1 - 1) >> 2;
+                const int j1 = (31 - __clz(m)) >> 2;
 #pragma unroll 1
-                for (int j = p0 >> 2; j <= j1; ++j) {
+                for (int j = (__ffs(m) - 1) >> 2; j <= j1; ++j) {
                     const unsigned mj = (m >> (4 * j)) & 15u;
                     if (mj == 0) continue;
                     const uint32_t a = tile + (((uint32_t)j ^ sw) << 4);

@@ -362,12 +362,72 @@ class EpisodeBatch:
             self._finalize()
             e_fin = torch.cuda.Event()
             e_fin.record()
-            for t in (observed, samp):
-                t.record_stream(self._wr)
+            if not torch.cuda.is_current_stream_capturing():
+                for t in (observed, samp):
+                    t.record_stream(self._wr)
         self._e_read, self._e_fin = e_read, e_fin
         s0.wait_event(e_read)
         s0.wait_event(e_fin)
         return levels
+
+    def capture_step_detections(self, depth, pose, shifts, intr, cell, box_features, mask_probs, boxes, n_obj=None, **kw) -> "GraphedDetections":
+        """Capture ``step_detections`` for this shape into ONE CUDA graph (the online single-robot loop, robot_demo.py:559-566: a frame
+        is ~10 small launches on two streams, so one episode is bound by launch overhead, not by the kernels).  The arguments are
+        example inputs of the shapes / dtypes every later frame will have; they are copied into static buffers owned by the returned
+        object, whose ``__call__(depth, pose, shifts, box_features, mask_probs, boxes, n_obj)`` copies a frame's inputs in and replays
+        the graph.  Results are identical to the eager call (same kernels, same order)."""
+        return GraphedDetections(self, depth, pose, shifts, intr, cell, box_features, mask_probs, boxes, n_obj, kw)
+
+
+class GraphedDetections:
+    """``EpisodeBatch.step_detections`` of one fixed shape as a CUDA graph (see ``capture_step_detections``).  The three pooled
+    levels returned by a call live in static buffers: they are valid until the next call."""
+
+    _KEYS = ("depth", "pose", "shifts", "box_features", "mask_probs", "boxes", "n_obj")
+
+    def __init__(self, batch: "EpisodeBatch", depth, pose, shifts, intr, cell, box_features, mask_probs, boxes, n_obj, kw):
+        self.batch = batch
+        given = dict(zip(self._KEYS, (depth, pose, shifts, box_features, mask_probs, boxes, n_obj)))
+        self.static = {k: (None if v is None else v.detach().to(batch.device).clone().contiguous()) for k, v in given.items()}
+        st = self.static
+        args = (st["depth"], st["pose"], st["shifts"], intr, cell, st["box_features"], st["mask_probs"], st["boxes"], st["n_obj"])
+        with torch.cuda.device(batch.device):
+            batch.join()
+            torch.cuda.current_stream().synchronize()
+            # everything the step allocates lazily (slot workspace, the library's per-device state) must exist before the capture; the
+            # warm-up frame runs with n_obj = 0, which writes nothing and leaves the grid as it is
+            zero_obj = torch.zeros((batch.E,), dtype=torch.int32, device=batch.device)
+            batch.step_detections(*args[:8], zero_obj, **kw)
+            batch.join()
+            torch.cuda.current_stream().synchronize()
+            batch._t -= 1                                   # the warm-up frame does not count
+            batch._e_fin = batch._e_read = None             # no dependency on work recorded outside the capture
+            self.graph = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream()
+            with torch.cuda.graph(self.graph, stream=side):
+                self.levels = batch.step_detections(*args, **kw)
+            batch._t -= 1                                   # capturing enqueues nothing
+            batch._e_fin = batch._e_read = None             # replays are ordered by the stream they are launched on
+        self._k = batch._k                                  # the double-buffer half the graph was captured on
+
+    def __call__(self, depth, pose, shifts, box_features, mask_probs, boxes, n_obj=None):
+        b = self.batch
+        for k, v in zip(self._KEYS, (depth, pose, shifts, box_features, mask_probs, boxes, n_obj)):
+            dst = self.static[k]
+            if dst is None:
+                if v is not None:
+                    raise ValueError(f"{k}: the graph was captured without this input")
+                continue
+            if v is None:
+                raise ValueError(f"{k}: the graph was captured with this input")
+            if v.data_ptr() != dst.data_ptr():
+                dst.copy_(v, non_blocking=True)
+        b.join()                                            # an eager step before this replay may still be running on the side streams
+        b._e_fin = b._e_read = None
+        b._k = self._k
+        b._t += 1
+        self.graph.replay()
+        return self.levels
 
 
 class SpatialFeatureMemory:

@@ -913,6 +913,54 @@ def test_step_detections_two_streams_matches_serial(eod, cuda):
     assert b.counts.max().item() >= 2 and b.sums.abs().max().item() > 0
 
 
+def test_graphed_step_detections_matches_eager(eod, cuda):
+    """capture_step_detections (one CUDA graph per frame: the online single-robot loop) against the eager step_detections on a twin
+    batch, frame by frame, with an eager frame interleaved: identical indices, fp16 levels, counts and touched sets, sums within the
+    reduction-order tolerance; a frame without detections (n_obj = 0) writes nothing in either."""
+    C, H, W, mw, mh, Kmax, T = 128, 96, 128, 60, 45, 6, 6
+    cell = 0.2
+    for E in (1, 2):
+        rng = np.random.default_rng(78 + E)
+        eps = [eod.episodes.make_episode(600 + e, T, H, W, mw, mh, cell) for e in range(E)]
+        intr = eod.compute_intrinsics(W, H, math.radians(67.5))
+        shifts = _t(np.stack([np.concatenate([np.zeros(3, np.float32), ep.map_world_shift]) for ep in eps]), cuda)
+        a = eod.EpisodeBatch(E, mw, mh, C, H, W, cuda)
+        b = eod.EpisodeBatch(E, mw, mh, C, H, W, cuda)
+        graphed = None
+        for t in range(T):
+            Tm = eod.transform3d(torch.from_numpy(np.stack([ep.xyzhe[t] for ep in eps])))
+            pose = Tm[:, :3].reshape(E, 12).to(cuda)
+            depth = _t(np.stack([ep.depth[t] for ep in eps]), cuda)
+            n_obj = np.array([0 if t == 2 else Kmax - (t % 3)] + [3] * (E - 1), np.int32)
+            bf = np.zeros((E, Kmax, C), np.float32); pr = np.zeros((E, Kmax, 28, 28), np.float32); bx = np.zeros((E, Kmax, 4), np.float32)
+            for e in range(E):
+                if n_obj[e]:
+                    f, p, bb = eod.episodes.make_mask_head_detections(rng, H, W, C, (int(n_obj[e]), int(n_obj[e])), 28)
+                    bf[e, : n_obj[e]], pr[e, : n_obj[e]], bx[e, : n_obj[e]] = f, p, bb
+            args = (_t(bf, cuda), _t(pr, cuda), _t(bx, cuda), _t(n_obj, cuda))
+            if graphed is None:
+                graphed = a.capture_step_detections(depth, pose, shifts, intr, cell, *args)
+                assert float(a.sums.abs().max()) == 0.0 and float(a.counts.max()) == 0.0     # capturing wrote nothing
+            if t == 3:
+                la = [l.clone() for l in a.step_detections(depth, pose, shifts, intr, cell, *args)]      # eager frame in between
+            else:
+                la = [l.clone() for l in graphed(depth, pose, shifts, *args)]
+            lb = [l.clone() for l in b.step_detections(depth, pose, shifts, intr, cell, *args)]
+            torch.cuda.synchronize()
+            assert torch.equal(a.idx, b.idx), (E, t)
+            # the two batches accumulate with fp32 reductions in scheduling order, so their sums - and with them a few fp16 rows of
+            # the read table - may differ in the last bit: levels equal up to one fp16 ulp, and exactly wherever the tables agree
+            same_table = torch.equal(a.norm16, b.norm16) if t == 0 else None
+            for x, y in zip(la, lb):
+                d = (x.contiguous().view(torch.int16).int() - y.contiguous().view(torch.int16).int()).abs()
+                assert int(d.max()) <= 1 and float((d != 0).float().mean()) < 1e-3, (E, t)
+                if same_table:
+                    assert torch.equal(x, y), (E, t)
+            assert torch.equal(a.counts, b.counts) and torch.equal(a.sums == 0, b.sums == 0), (E, t)
+            assert (a.sums - b.sums).abs().max().item() <= SUM_TOL * max(b.sums.abs().max().item(), 1e-30)
+        assert b.counts.max().item() >= 2 and b.sums.abs().max().item() > 0
+
+
 def test_object_write_more_than_128_objects(eod, cuda):
     """Above 128 kept objects per frame the write takes its one-pixel-at-a-time path (the bitmask phase holds 128):
     both the byte-mask and the pasted variant against the oracle chain."""
