@@ -28,6 +28,26 @@ from ._lib import FUSE_IMAGE_ONLY, FUSE_MEM_ONLY, FUSE_SUM
 _FUSE_MODES = {"sum": FUSE_SUM, "mem_only": FUSE_MEM_ONLY, "image_only": FUSE_IMAGE_ONLY}
 
 
+class _LinearFn(torch.autograd.Function):
+    """y = x @ W^T + b on the tensor cores with fp32 accuracy (eod_linear_rows, 3xTF32) and its backward: the forward and both gradient
+    GEMMs are the same kernel fed with transposed VIEWS (the kernel takes any strides), the bias gradient is a column sum."""
+
+    @staticmethod
+    def forward(ctx, x2d, weight, bias):
+        ctx.save_for_backward(x2d, weight)
+        ctx.has_bias = bias is not None
+        return ops.linear_rows(x2d, weight, bias)
+
+    @staticmethod
+    def backward(ctx, g):
+        x2d, weight = ctx.saved_tensors
+        g = g.contiguous()
+        g_x = ops.linear_rows(g, weight.t()) if ctx.needs_input_grad[0] else None                    # (M,N) @ (N,K)
+        g_w = ops.linear_rows(g.t(), x2d.t()) if ctx.needs_input_grad[1] else None                    # (N,M) @ (M,K)
+        g_b = g.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return g_x, g_w, g_b
+
+
 class _FuseFn(torch.autograd.Function):
     """eod_fuse with its backward: out = res + w * mem | w * mem  =>  d res = g (sum only), d mem = w * g."""
 
@@ -103,11 +123,11 @@ class MemoryFusion(nn.Module):
         for k, conv in enumerate(self.merge_map_projections):
             sel = (lvl == k).nonzero().squeeze(1)
             if sel.numel():
-                x = roi[sel].permute(0, 2, 3, 1)                                              # (n, 7, 7, C) contiguous
-                y = torch.matmul(x, conv.weight.view(conv.weight.shape[0], -1).t())
-                if conv.bias is not None:
-                    y = y + conv.bias
-                out[sel] = (y * float(self.map_feature_weight)).permute(0, 3, 1, 2)
+                x = roi[sel].permute(0, 2, 3, 1)                                              # (n, 7, 7, C)
+                w2 = conv.weight.detach().to(torch.float32).reshape(conv.weight.shape[0], -1)
+                b2 = None if conv.bias is None else conv.bias.detach().to(torch.float32).contiguous()
+                y = ops.linear_rows(x.reshape(-1, x.shape[-1]), w2, b2, float(self.map_feature_weight))   # (bias + x.W) * MAP_FEATURE_WEIGHT
+                out[sel] = y.view(x.shape[0], pooled, pooled, -1).permute(0, 3, 1, 2)
         return out
 
     def forward(self, results: Sequence[torch.Tensor], map_memory, proj_indices, observations=None) -> List[torch.Tensor]:
@@ -137,9 +157,9 @@ class MemoryFusion(nn.Module):
         for k, (lvl, res, conv) in enumerate(zip(levels, results, convs)):
             # timm.py:174: 1x1 conv in fp32 (eval, no autocast) == per-pixel GEMM on the channels-last level
             x = lvl.permute(0, 2, 3, 1).to(torch.float32)                             # (B, h, w, C) contiguous
-            mem = torch.matmul(x, conv.weight.view(conv.weight.shape[0], -1).t())
-            if conv.bias is not None:
-                mem = mem + conv.bias
+            w2 = conv.weight.to(torch.float32).reshape(conv.weight.shape[0], -1)
+            b2 = None if conv.bias is None else conv.bias.to(torch.float32)
+            mem = _LinearFn.apply(x.reshape(-1, x.shape[-1]), w2, b2).view(x.shape[0], x.shape[1], x.shape[2], -1)
             mem = mem.permute(0, 3, 1, 2).contiguous()                               # NCHW like res
             res32 = res.to(torch.float32).contiguous()
             fused = _FuseFn.apply(res32, mem, float(self.map_feature_weight), mode)

@@ -695,7 +695,7 @@ class SpatialFeatureMemory:
                              weight: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None, step: int = 8):
         """Dense backbone-feature write (SURVEY 8a row A7'', bytecode-only older CustomMapFPN.forward): p3 (1,C,h,w) ->
         bilinear (H,W) align_corners=True -> [::step, ::step] -> optional 1x1 projection (map_merge_forward_projection,
-        library GEMM) -> per-cell mean with proj_indices[::step, ::step]; returns (memory (cells,C') f32 with the mean in the
+        eod_linear_rows) -> per-cell mean with proj_indices[::step, ::step]; returns (memory (cells,C') f32 with the mean in the
         observed cells and zeros elsewhere - the reference REPLACES the memory - and observed_mem (cells,) bool)."""
         idx_full = proj_indices.to(self.device)
         if idx_full.dim() == 3 and idx_full.shape[-1] == 1:
@@ -704,12 +704,11 @@ class SpatialFeatureMemory:
         f = ops.bilinear_lattice(p3.to(self.device, torch.float32).contiguous(), (H, W), step)
         layout = LAYOUT_CHW
         C = f.shape[1]
-        if weight is not None:                             # 1x1 conv == per-sample GEMM (fp32 library matmul, no TF32), output HWC
+        if weight is not None:                             # 1x1 conv == per-sample row GEMM on the tensor cores (fp32 accuracy), output HWC
             w2 = weight.to(self.device, torch.float32).reshape(weight.shape[0], -1)
-            f = torch.matmul(f[0].reshape(C, -1).t().contiguous(), w2.t())
-            if bias is not None:
-                f = f + bias.to(self.device, torch.float32)
-            f, C, layout = f.unsqueeze(0).contiguous(), w2.shape[0], LAYOUT_HWC
+            b2 = None if bias is None else bias.to(self.device, torch.float32).contiguous()
+            f = ops.linear_rows(f[0].reshape(C, -1).t(), w2, b2)          # the CHW lattice is read through a transposed view
+            f, C, layout = f.unsqueeze(0), w2.shape[0], LAYOUT_HWC
         else:
             f = f.reshape(1, C, -1).contiguous()
         idx = self._idx32(idx_full[::step, ::step].contiguous(), n_cells)

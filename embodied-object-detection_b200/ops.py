@@ -18,7 +18,7 @@ launch_count = 0
 _LAUNCHES = {"eod_backproject_quantize": 1, "eod_backproject_quantize_u16": 1, "eod_quantize_world": 1, "eod_sample_mask": 1, "eod_frame_count": 1, "eod_expand_counts": 1, "eod_write_mean": 1, "eod_write_mean_det": 9,
              "eod_finalize_counts": 1, "eod_box_to_image_features": 1, "eod_masks_observed": 1, "eod_paste_masks": 1, "eod_write_objects_pasted": 1, "eod_bilinear_lattice": 1, "eod_write_objects": 1, "eod_flush_slots": 2, "eod_write_max": 2, "eod_read_pool": 2,
              "eod_fuse": 1, "eod_project_split_weights": 1, "eod_project_fuse": 1, "eod_project_fuse_levels": 1, "eod_normalize_memory": 1, "eod_reset_touched": 1, "eod_semmap_update": 1, "eod_semmap_decode": 2,
-             "eod_reset_episodes": 1, "eod_refresh_norm16": 1, "eod_check_indices": 1, "eod_remap_indices": 1, "eod_read_roi": 1}
+             "eod_reset_episodes": 1, "eod_refresh_norm16": 1, "eod_check_indices": 1, "eod_remap_indices": 1, "eod_max_winner_list": 1, "eod_linear_rows": 1, "eod_read_roi": 1}
 
 
 def _call(name: str, *args) -> None:
@@ -447,6 +447,84 @@ def write_max(height: torch.Tensor, idx: torch.Tensor, outlier: Optional[torch.T
     _call("eod_write_max", height.data_ptr(), idx.data_ptr(), _ptr(outlier), _ptr(feat), int(layout), E, C, H, W,
           int(pix_stride), height_map.shape[1], height_map.data_ptr(), key64.data_ptr(), arg_pix.data_ptr(),
           _ptr(observed), _ptr(state), _stream())
+
+
+def write_max_linear(height: torch.Tensor, idx: torch.Tensor, outlier: Optional[torch.Tensor], feat: torch.Tensor, height_map: torch.Tensor,
+                     key64: torch.Tensor, arg_pix: torch.Tensor, observed: Optional[torch.Tensor], state: torch.Tensor, weight: torch.Tensor,
+                     bias: Optional[torch.Tensor], layout: int = LAYOUT_HWC, pix_stride: int = 1) -> torch.Tensor:
+    """SMNet 'replace' update with the linear layer (model.py of the 3.10 bytecode, src lines 104-128): the height-max contest of
+    write_max, then ``state[raised cells] = linlayer(feature[winner pixels])`` as ONE tensor-core row GEMM over the winners only
+    (eod_max_winner_list + eod_linear_rows).  feat (E,H,W,C_in) [HWC] or (E,C_in,H,W) [CHW]; weight (C_mem,C_in), bias (C_mem,);
+    state (E,cells,C_mem).  Returns the device-side winner count (1,) i32."""
+    _dev(feat, torch.float32, "feat"), _dev(state, torch.float32, "state"), _dev(weight, torch.float32, "weight")
+    E, H, W = height.shape
+    c_in = weight.shape[1]
+    if tuple(feat.shape) != ((E, H, W, c_in) if layout == LAYOUT_HWC else (E, c_in, H, W)):
+        raise ValueError("write_max_linear: feat does not match (E,H,W,C_in) / (E,C_in,H,W)")
+    if state.shape[2] != weight.shape[0]:
+        raise ValueError("write_max_linear: state channels must equal weight.shape[0]")
+    write_max(height, idx, outlier, None, height_map, key64, arg_pix, observed, None, layout, pix_stride)
+    lattice = -(-H // pix_stride) * -(-W // pix_stride)
+    src, dst, count = max_winner_list(arg_pix, H, W, c_in, layout, capacity=min(arg_pix.numel(), E * lattice))
+    linear_rows(feat, weight, bias, 1.0, out=state.view(-1, state.shape[2]), a_off=src, a_k_stride=1 if layout == LAYOUT_HWC else H * W,
+                m_count=count, n_rows=src.numel(), y_dst=dst)
+    return count
+
+
+def linear_rows(a: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, scale: float = 1.0, *,
+                out: Optional[torch.Tensor] = None, a_off: Optional[torch.Tensor] = None, a_k_stride: int = 1, m_count: Optional[torch.Tensor] = None,
+                n_rows: Optional[int] = None, y_dst: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Y = scale * (A @ weight^T + bias) in fp32 accuracy on the tensor cores (eod_linear_rows, 3xTF32).
+    a: (M,K) f32, ANY strides (a transposed view costs nothing) - or, with ``a_off`` (M_max,) int64 element offsets, the flat f32
+    buffer the rows are gathered from (element l of row i at a_off[i] + l * a_k_stride; K = weight.shape[1]; ``m_count`` (1,) i32 on
+    the device bounds the rows, ``n_rows`` = M_max).  weight: (N,K) f32, any strides; bias (N,) f32.  out: (rows,N') f32 with unit
+    column stride, written at row i or y_dst[i] (int64); default a fresh (M,N)."""
+    _devs = [a, weight] + [t for t in (bias, out, a_off, m_count, y_dst) if t is not None]
+    for t in _devs:
+        if not t.is_cuda or t.device != a.device:
+            raise EodError("linear_rows: all tensors must live on one CUDA device (no CPU fallback)")
+    if a.dtype != torch.float32 or weight.dtype != torch.float32 or weight.dim() != 2:
+        raise TypeError("linear_rows: a and weight must be float32, weight (N,K)")
+    N, K = weight.shape
+    if a_off is None:
+        if a.dim() != 2 or a.shape[1] != K:
+            raise ValueError("linear_rows: a must be (M,K)")
+        M, a_rs, a_ks = a.shape[0], a.stride(0), a.stride(1)
+    else:
+        if a_off.dtype != torch.int64 or not a_off.is_contiguous():
+            raise TypeError("linear_rows: a_off must be contiguous int64")
+        M, a_rs, a_ks = int(a_off.numel() if n_rows is None else n_rows), 0, int(a_k_stride)
+    if bias is not None:
+        _dev(bias, torch.float32, "bias")
+    if out is None:
+        if y_dst is not None:
+            raise ValueError("linear_rows: scattered rows need an explicit out")
+        out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    if out.dtype != torch.float32 or out.dim() != 2 or out.stride(1) != 1 or out.shape[1] < N:
+        raise ValueError("linear_rows: out must be (rows, >= N) float32 with unit column stride")
+    if m_count is not None:
+        _dev(m_count, torch.int32, "m_count")
+    if y_dst is not None and (y_dst.dtype != torch.int64 or not y_dst.is_contiguous()):
+        raise TypeError("linear_rows: y_dst must be contiguous int64")
+    if a.device.index != torch.cuda.current_device():
+        raise EodError("linear_rows: tensors are not on the current CUDA device")
+    _call("eod_linear_rows", a.data_ptr(), int(a_rs), int(a_ks), _ptr(a_off), weight.data_ptr(), int(weight.stride(0)), int(weight.stride(1)),
+          _ptr(bias), float(scale), int(M), _ptr(m_count), int(N), int(K), out.data_ptr(), int(out.stride(0)), _ptr(y_dst), _stream())
+    return out
+
+
+def max_winner_list(arg_pix: torch.Tensor, H: int, W: int, C: int, layout: int = LAYOUT_HWC, capacity: Optional[int] = None):
+    """arg_pix (E,cells) i32 of write_max -> (src_off (cap,) i64, dst_row (cap,) i64, count (1,) i32) for linear_rows (the 'replace'
+    update: state[dst_row] = linlayer(feat[src_off ...])).  capacity defaults to the number of pixels, the most winners a frame can have."""
+    _dev(arg_pix, torch.int32, "arg_pix")
+    E, n_cells = arg_pix.shape
+    cap = int(min(E * n_cells, E * H * W) if capacity is None else capacity)
+    src = torch.empty((cap,), dtype=torch.int64, device=arg_pix.device)
+    dst = torch.empty((cap,), dtype=torch.int64, device=arg_pix.device)
+    count = torch.empty((1,), dtype=torch.int32, device=arg_pix.device)
+    _call("eod_max_winner_list", arg_pix.data_ptr(), E, n_cells, int(H), int(W), int(C), int(layout), src.data_ptr(), dst.data_ptr(),
+          count.data_ptr(), cap, _stream())
+    return src, dst, count
 
 
 def read_pool(table: torch.Tensor, counts: Optional[torch.Tensor], idx: torch.Tensor, out: Optional[Sequence[torch.Tensor]] = None):

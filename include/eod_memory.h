@@ -222,6 +222,25 @@ int eod_write_max(const float *height, const int32_t *idx, const uint8_t *outlie
                   int n_episodes, int C, int H, int W, int pix_stride, int64_t n_cells, float *height_map,
                   uint64_t *key64, int32_t *arg_pix, uint8_t *observed, float *state, eod_stream_t stream);
 
+/* 'replace' update of the SMNet encoder (SMNet/__pycache__/model.cpython-310.pyc, bytecode listing smnet_encode_model_py310.txt src
+ * lines 104-128: tmp_memory = feature[proj_index[m]]; state[m] = linlayer(tmp_memory)): the raised cells of eod_write_max as a
+ * compact list - src_off[i] = element offset of the winner pixel's feature vector inside feat (E,H,W,C) [HWC: channels contiguous]
+ * or (E,C,H,W) [CHW: channel stride H*W], dst_row[i] = e * n_cells + cell - in arbitrary order; count[0] (device int32) = number of
+ * winners.  capacity = entries src_off / dst_row can hold (winners beyond it are counted but not listed). */
+int eod_max_winner_list(const int32_t *arg_pix, int n_episodes, int64_t n_cells, int H, int W, int C, int layout, int64_t *src_off,
+                        int64_t *dst_row, int32_t *count, int capacity, eod_stream_t stream);
+
+/* Row GEMM with fp32 accuracy on tcgen05 tensor cores (3xTF32 split, fp32 accumulation in TMEM):
+ *   Y[dst(i) * y_row_stride + j] = scale * ( sum_l A(i,l) * B(j,l) + bias[j] ),  i < min(M, *m_count), j < N, l < K
+ *   A(i,l) = A[(a_off ? a_off[i] : i * a_row_stride) + l * a_k_stride]      B(j,l) = B[j * b_row_stride + l * b_k_stride]
+ *   dst(i) = y_dst ? y_dst[i] : i ;  a_off, bias, m_count, y_dst nullable ;  N % 16 == 0.
+ * Replaces the nn.Linear of the 'replace' update above (with the lists of eod_max_winner_list), the 1x1 forward projection of the
+ * dense backbone-feature write (A7''), the projection of per-ROI memory features and the fp32 conv1x1 of timm.py:174 on the
+ * training path (forward and, through the strides, both gradients).  |error| <= 1e-5 * scale of the result vs fp64. */
+int eod_linear_rows(const float *A, int64_t a_row_stride, int64_t a_k_stride, const int64_t *a_off, const float *B, int64_t b_row_stride,
+                    int64_t b_k_stride, const float *bias, float scale, int M, const int32_t *m_count, int N, int K, float *Y,
+                    int64_t y_row_stride, const int64_t *y_dst, eod_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * (3) Read.  Replaces create_implicit_memory (custom_rcnn.py:764-774), the fp16 cast (:1036) and
  * timm.py:147-168 (gather to the image plane, avg-pool 4, then per level avg-pool 2 -> half) in one

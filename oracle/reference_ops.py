@@ -278,7 +278,7 @@ def scatter_max_canonical(src: torch.Tensor, index: torch.Tensor, out: torch.Ten
 
 
 def smnet_heightmax_frame(state, observed, height_map, feat_hwc, w2m, inliers, heights, map_w: int,
-                          downsample: int = 1):
+                          downsample: int = 1, linlayer=None):
     """One frame of SMNet.encode (model_test.pyc src lines 62-163, 'replace'-without-linear update):
     returns new (state, observed, height_map, arg, m).  feat_hwc (H,W,C) f32 already interpolated."""
     if downsample > 1:
@@ -290,7 +290,9 @@ def smnet_heightmax_frame(state, observed, height_map, feat_hwc, w2m, inliers, h
     observed = observed | m
     state = state.clone()
     if m.any():
-        state[m] = feat_hwc[inliers][arg[m]]
+        rows = feat_hwc[inliers][arg[m]]
+        # model.py (3.10 bytecode, src lines 126-128): mem_update == 'replace' -> state[m] = self.linlayer(tmp_memory)
+        state[m] = rows if linlayer is None else F.linear(rows, linlayer[0], linlayer[1])
     return state, observed, height_map, arg, m
 
 

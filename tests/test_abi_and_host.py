@@ -35,6 +35,20 @@ def test_library_exports_every_declared_symbol(eod):
     assert set(eod.ops._LAUNCHES) == set(declared) - no_launch
 
 
+def test_no_library_gemm_in_product_code():
+    """Every dense contraction of the path runs on the in-tree tcgen05 kernels (csrc/project_fuse.cu, csrc/linear.cu): the package
+    holds no call into the library GEMMs (torch.matmul in the training path and the A7'' forward projection)."""
+    pat = re.compile(r"torch\.(matmul|mm|bmm|addmm|einsum|baddbmm)\s*\(|F\.(linear|conv2d|conv1d|bilinear)\s*\(|\.matmul\(")
+    bad = []
+    for f in os.listdir(PKG):
+        if f.endswith(".py"):
+            for n, line in enumerate(open(os.path.join(PKG, f)), 1):
+                code = line.split("#", 1)[0]
+                if pat.search(code):
+                    bad.append((f, n, line.strip()))
+    assert not bad, bad
+
+
 def test_library_is_sm100a_only(eod):
     out = subprocess.run(["cuobjdump", "--list-elf", eod.build.SO_PATH], capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_\d+a?", out))

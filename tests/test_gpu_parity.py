@@ -1056,6 +1056,86 @@ def test_write_max_vs_oracle(eod, cuda, layout, stride):
         assert int(d_key.abs().sum()) == 0
 
 
+@pytest.mark.parametrize("M,K,N", [(1, 64, 16), (127, 64, 256), (128, 96, 64), (300, 512, 256), (1000, 256, 512), (257, 20, 48)])
+def test_linear_rows_fp32_accuracy_on_tensor_cores(eod, cuda, M, K, N):
+    """eod_linear_rows (3xTF32 on tcgen05, fp32 accumulators in TMEM) against fp64: |error| <= 1e-5 of scale - and not worse than a few
+    times the error of the fp32 library GEMM it replaces - for contiguous, transposed (row stride 1) and padded operands, with and
+    without bias / scale, K not a multiple of the 32-wide chunk, N over one and two TMEM column blocks."""
+    g = torch.Generator(device=cuda).manual_seed(M * 7 + K)
+    a = torch.randn((M, K), device=cuda, generator=g) * torch.rand((M, 1), device=cuda, generator=g).mul(6).sub(3).exp()    # rows of very different scale
+    w = torch.randn((N, K), device=cuda, generator=g) / K ** 0.5
+    b = torch.randn((N,), device=cuda, generator=g)
+    ref = (a.double() @ w.double().t() + b.double()) * 0.75
+    scale = float(ref.abs().max())
+    lib_err = float(((a @ w.t() + b) * 0.75 - ref).abs().max()) / scale
+    a_t = a.t().contiguous().t()                                     # same values, row stride 1 / element stride M
+    w_pad = torch.zeros((N, K + 12), device=cuda)[:, 3:3 + K]        # unaligned rows, row stride K + 12
+    w_pad.copy_(w)
+    for name, (aa, ww) in {"contiguous": (a, w), "A transposed view": (a_t, w), "W padded / unaligned": (a, w_pad), "both": (a_t, w_pad)}.items():
+        got = eod.ops.linear_rows(aa, ww, b, 0.75)
+        err = float((got.double() - ref).abs().max()) / scale
+        assert err <= 1e-5 and err <= max(4 * lib_err, 2e-6), (name, err, lib_err)
+    nob = eod.ops.linear_rows(a, w)
+    assert float((nob.double() - a.double() @ w.double().t()).abs().max()) <= 1e-5 * float((a.double() @ w.double().t()).abs().max())
+    # gathered rows + scattered output + device-side row count (the 'replace' update's shape)
+    perm = torch.randperm(M, device=cuda, generator=g)
+    n_live = max(1, (2 * M) // 3)
+    out = torch.full((M + 5, N), 7.0, device=cuda)
+    eod.ops.linear_rows(a, w, b, 1.0, out=out, a_off=(perm * K).to(torch.int64), m_count=torch.tensor([n_live], dtype=torch.int32, device=cuda),
+                        n_rows=M, y_dst=(perm + 5).to(torch.int64))
+    ref2 = a.double() @ w.double().t() + b.double()
+    live = perm[:n_live]
+    assert float((out[live + 5].double() - ref2[live]).abs().max()) <= 1e-5 * float(ref2.abs().max())
+    untouched = torch.ones(M + 5, dtype=torch.bool, device=cuda)
+    untouched[live + 5] = False
+    assert bool((out[untouched] == 7.0).all())                       # rows beyond the count and unlisted rows are not written
+
+
+@pytest.mark.parametrize("layout", [0, 1])
+def test_write_max_replace_with_linlayer(eod, cuda, layout):
+    """SMNet 'replace' update with the linear layer (model.cpython-310.pyc src lines 104-128): state[raised cells] = linlayer(feature[
+    winner pixels]).  Contest results (argmax, height map, observed) exact vs the canonical-rule oracle; the raised cells' rows equal
+    F.linear of the winners' features (fp64 reference, 1e-5 of scale), every other row is left untouched bit for bit."""
+    rng = np.random.default_rng(31 + layout)
+    H, W, C_in, C_mem, mw, mh, T, stride = 48, 64, 64, 256, 23, 19, 3, 2
+    cells = mw * mh
+    lin_w = (rng.standard_normal((C_mem, C_in)) / 8).astype(np.float32)
+    lin_b = rng.standard_normal(C_mem).astype(np.float32)
+    state = torch.zeros(cells, C_mem, dtype=torch.float64)
+    observed = torch.zeros(cells, dtype=torch.bool)
+    hmap = torch.zeros(cells)
+    d_state = torch.zeros((1, cells, C_mem), device=cuda)
+    d_obs = torch.zeros((1, cells), dtype=torch.uint8, device=cuda)
+    d_hmap = torch.zeros((1, cells), device=cuda)
+    d_key = torch.zeros((1, cells), dtype=torch.int64, device=cuda)
+    d_arg = torch.zeros((1, cells), dtype=torch.int32, device=cuda)
+    for t in range(T):
+        w2m = np.stack([rng.integers(0, mw, (H // 4, W // 4)).repeat(4, 0).repeat(4, 1), rng.integers(0, mh, (H // 4, W // 4)).repeat(4, 0).repeat(4, 1)], -1)
+        inl = rng.uniform(size=(H, W)) < 0.7
+        heights = (np.round(rng.uniform(-1.5, 1.0, (H, W)) * 4) / 4).astype(np.float32)
+        if t == 2:
+            heights[:] = heights.min() - 5
+        feat = rng.standard_normal((H, W, C_in)).astype(np.float32)
+        prev = d_state.clone()
+        state, observed, hmap, arg, m = R.smnet_heightmax_frame(state, observed, hmap, torch.from_numpy(feat).double(), torch.from_numpy(w2m),
+                                                                torch.from_numpy(inl), torch.from_numpy(heights), mw, stride,
+                                                                linlayer=(torch.from_numpy(lin_w).double(), torch.from_numpy(lin_b).double()))
+        flat = (w2m[..., 1] * mw + w2m[..., 0]).astype(np.int32)
+        f_dev = _t(feat if layout == 1 else feat.transpose(2, 0, 1), cuda)[None].contiguous()
+        count = eod.ops.write_max_linear(_t(heights, cuda)[None], _t(flat, cuda)[None], _t((~inl).view(np.uint8), cuda)[None], f_dev, d_hmap, d_key,
+                                         d_arg, d_obs, d_state, _t(lin_w, cuda), _t(lin_b, cuda), layout, stride)
+        torch.cuda.synchronize()
+        assert int(count.item()) == int(m.sum())
+        assert np.array_equal(d_hmap[0].cpu().numpy(), hmap.numpy())
+        assert np.array_equal(d_obs[0].cpu().numpy().astype(bool), observed.numpy())
+        assert np.array_equal((d_arg[0] >= 0).cpu().numpy(), m.numpy())
+        got = d_state[0].cpu().double()
+        assert float((got - state).abs().max()) <= 1e-5 * float(state.abs().max())
+        assert torch.equal(d_state[0][~m.to(cuda)], prev[0][~m.to(cuda)])                       # cells that were not raised keep their rows
+        state = got.clone()                                                                     # carry the device rows (no drift between frames)
+        assert int(d_key.abs().sum()) == 0
+
+
 def test_write_max_config3_full_size(eod, cuda):
     """BASELINE configs[2]: SMNet-style height-max projection, 480x640, C=256, 0.02 m cells, 1000x1000 map.  Geometry
     (unclipped cell coordinates, outlier mask, heights) comes from the back-projection kernel exactly as
