@@ -163,6 +163,20 @@ def measured_traffic(E: int):
         return None
 
 
+def pcie_info(gpu: int):
+    """PCIe link of this rank's GPU (the e2e arm is bounded by it) and the box's topology matrix, for the record."""
+    info = {}
+    try:
+        q = subprocess.run(["nvidia-smi", "-i", str(gpu), "--query-gpu=pci.bus_id,pcie.link.gen.current,pcie.link.width.current,pcie.link.gen.max",
+                            "--format=csv,noheader"], capture_output=True, text=True, timeout=10).stdout.strip()
+        info["link"] = q
+        topo = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=10).stdout
+        info["topo"] = [l[:200] for l in topo.splitlines() if l.startswith("GPU")][:9]
+    except Exception as exc:
+        info["error"] = repr(exc)[:100]
+    return info
+
+
 def write_launch_bytes(E: int, touched_per_launch: float, c: int = C) -> float:
     """Algorithmic bytes of ONE eod_write_mean launch over E episodes (DESIGN.md 'Roofline accounting'):
     features read once + index plane + touched grid rows read-modify-written + per-cell sample counts."""
@@ -418,7 +432,7 @@ def main_gpu(args, rank, local_rank, world):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": workload_config(world), "clocks": clocks, "gpu_launches": int(launches),
         "e2e": e2e, "e2e_variants": e2e_variants, "value_with_fusion": with_fusion, "write_alone": write_alone, "parity_check": parity,
-        "roofline_1000": roofline_1000, "extras": extras, "host": {"numa_node": numa_node, "cpus": os.cpu_count()},
+        "roofline_1000": roofline_1000, "extras": extras, "host": {"numa_node": numa_node, "cpus": os.cpu_count(), "pcie": pcie_info(local_rank)},
         "roofline": {"bound": "hbm", "kernel": "write_mean_chw_tma_kernel<256>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "frac_of_nominal_8TBs": (achieved / 8000.0) if achieved else None,
                      "traffic": measured_traffic(E), "peak_source": peak_src, "bytes_per_launch": wbytes, "launch_ms": stage_ms.get("write"),
@@ -712,11 +726,14 @@ def run_e2e_variants(eod, batch, dev, depth_h, pose_h, shifts, intr, args, world
     ready = [torch.cuda.Event() for _ in range(2)]
     freed = [torch.cuda.Event() for _ in range(2)]
 
-    def run(upload_extra, step_fn, d2h_fn, n_frames):
+    def run(upload_extra, step_fn, d2h_fn, n_frames, depth_src=None, depth_dst=None):
+        depth_src = pin_depth if depth_src is None else depth_src
+        depth_dst = dev_depth if depth_dst is None else depth_dst
+
         def upload(t, b):
             with torch.cuda.stream(copy_s):
                 copy_s.wait_event(freed[b])
-                dev_depth[b].copy_(pin_depth[t % N_FRAMES], non_blocking=True)
+                depth_dst[b].copy_(depth_src[t % N_FRAMES], non_blocking=True)
                 dev_pose[b].copy_(pin_pose[t % N_FRAMES], non_blocking=True)
                 upload_extra(t, b)
                 ready[b].record(copy_s)
@@ -794,6 +811,28 @@ def run_e2e_variants(eod, batch, dev, depth_h, pose_h, shifts, intr, args, world
     out["object_regime"] = {"value": world * E * n_fr_obj * args.e2e_steps / sec, "unit": UNIT, "ms_per_frame_step": 1e3 * sec / (n_fr_obj * args.e2e_steps),
                             "h2d_bytes_per_step": int(h2d * n_fr_obj), "d2h_bytes_per_step": int(host_l2.numel() * 2 * n_fr_obj),
                             "shape": f"E={E}, C={C}, <= {Kmax} detections per frame; D2H = the coarsest pooled level (15x20) per frame-step"}
+    # ---- object regime with the depth in the sensor's own format: uint16 millimetres (robot_demo.py:515), divided inside the kernel ----
+    pin_depth16 = (torch.from_numpy(depth_h).permute(1, 0, 2, 3) * 1000.0).round().clamp_(0, 65535).to(torch.uint16).contiguous().pin_memory()
+    dev_depth16 = [torch.empty((E, H, W), dtype=torch.uint16, device=dev) for _ in range(2)]
+    sec = run(up_det, lambda b: batch.step_detections(dev_depth16[b], dev_pose[b], shifts, intr, float(CELL), *dev_det[b]),
+              lambda: host_l2.copy_(batch.levels[2], non_blocking=True), n_fr_obj, pin_depth16, dev_depth16)
+    h2d = E * (H * W * 2 + 48) + sum(int(x[0].numel() * x.element_size()) for x in pin_det)
+    out["object_regime_u16_depth"] = {"value": world * E * n_fr_obj * args.e2e_steps / sec, "unit": UNIT, "ms_per_frame_step": 1e3 * sec / (n_fr_obj * args.e2e_steps),
+                                      "h2d_bytes_per_step": int(h2d * n_fr_obj), "d2h_bytes_per_step": int(host_l2.numel() * 2 * n_fr_obj),
+                                      "shape": "as object_regime, depth uploaded as uint16 millimetres (eod_backproject_quantize_u16)"}
+    # ---- the same with the frame-step captured into one CUDA graph (EpisodeBatch.capture_step_detections): one launch per frame-step
+    # instead of ~12 launches on two streams; the uploaded buffers are copied device-to-device into the graph's static inputs ----
+    try:
+        graphed = batch.capture_step_detections(dev_depth16[0], dev_pose[0], shifts, intr, float(CELL), *dev_det[0])
+        sec = run(up_det, lambda b: graphed(dev_depth16[b], dev_pose[b], shifts, *dev_det[b]),
+                  lambda: host_l2.copy_(batch.levels[2], non_blocking=True), n_fr_obj, pin_depth16, dev_depth16)
+        out["object_regime_u16_depth_graph"] = {"value": world * E * n_fr_obj * args.e2e_steps / sec, "unit": UNIT,
+                                                "ms_per_frame_step": 1e3 * sec / (n_fr_obj * args.e2e_steps), "h2d_bytes_per_step": int(h2d * n_fr_obj),
+                                                "d2h_bytes_per_step": int(host_l2.numel() * 2 * n_fr_obj),
+                                                "shape": "as object_regime_u16_depth, one CUDA-graph launch per frame-step"}
+        del graphed
+    except Exception as exc:
+        out["object_regime_u16_depth_graph"] = {"error": repr(exc)[:300]}
     return out
 
 

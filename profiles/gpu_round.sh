@@ -7,7 +7,7 @@ mkdir -p $O
 python -m pytest tests -m gpu -x -q > $O/pytest_$TAG.log 2>&1; echo "pytest rc=$?"; tail -3 $O/pytest_$TAG.log
 python __graft_entry__.py --smoke > $O/smoke_$TAG.log 2>&1; echo "smoke rc=$?"; tail -1 $O/smoke_$TAG.log
 # adversarial / randomised sweeps against the oracle (bit-exact kernels) and kernel-vs-kernel (tcgen05 variants)
-python profiles/stress.py > $O/stress_$TAG.log 2>&1; echo "stress rc=$?"; grep "stress:" $O/stress_$TAG.log
+python profiles/prof_online.py > $O/online_$TAG.json 2>$O/online_$TAG.err; echo "online rc=$?"; tail -1 $O/online_$TAG.json
 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_ref_$TAG.log 2>$O/bench_ref_$TAG.err; echo "bench ref rc=$?"
 python bench.py > $O/bench_$TAG.log 2>$O/bench_$TAG.err; echo "bench rc=$?"; tail -c 600 $O/bench_$TAG.err
 cat $O/bench_$TAG.log
