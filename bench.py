@@ -730,9 +730,13 @@ def run_e2e_variants(eod, batch, dev, depth_h, pose_h, shifts, intr, args, world
         depth_src = pin_depth if depth_src is None else depth_src
         depth_dst = dev_depth if depth_dst is None else depth_dst
 
+        fin = [None, None]                               # finalize event of the last step that read buffer b (pipelined steps outlive the call)
+
         def upload(t, b):
             with torch.cuda.stream(copy_s):
                 copy_s.wait_event(freed[b])
+                if fin[b] is not None:
+                    copy_s.wait_event(fin[b])
                 depth_dst[b].copy_(depth_src[t % N_FRAMES], non_blocking=True)
                 dev_pose[b].copy_(pin_pose[t % N_FRAMES], non_blocking=True)
                 upload_extra(t, b)
@@ -747,8 +751,10 @@ def run_e2e_variants(eod, batch, dev, depth_h, pose_h, shifts, intr, args, world
                     upload(t + 1, b ^ 1)
                 comp_s.wait_event(ready[b])
                 step_fn(b)
+                fin[b] = batch._e_fin
                 d2h_fn()
                 freed[b].record(comp_s)
+            batch.join()
             torch.cuda.synchronize()
 
         for f in freed:
@@ -805,7 +811,8 @@ def run_e2e_variants(eod, batch, dev, depth_h, pose_h, shifts, intr, args, world
             d.copy_(p_[t % n_var], non_blocking=True)
 
     n_fr_obj = 5 * n_fr
-    sec = run(up_det, lambda b: batch.step_detections(dev_depth[b], dev_pose[b], shifts, intr, float(CELL), *dev_det[b]),
+    batch.pipeline = True          # the write side of frame t runs under the staging / geometry / paste of frame t+1; inputs are ordered on the
+    sec = run(up_det, lambda b: batch.step_detections(dev_depth[b], dev_pose[b], shifts, intr, float(CELL), *dev_det[b], inputs_ready=False),   # caller's stream
               lambda: host_l2.copy_(batch.levels[2], non_blocking=True), n_fr_obj)
     h2d = E * (H * W * 4 + 48) + sum(int(x[0].numel() * x.element_size()) for x in pin_det)
     out["object_regime"] = {"value": world * E * n_fr_obj * args.e2e_steps / sec, "unit": UNIT, "ms_per_frame_step": 1e3 * sec / (n_fr_obj * args.e2e_steps),
@@ -814,7 +821,7 @@ def run_e2e_variants(eod, batch, dev, depth_h, pose_h, shifts, intr, args, world
     # ---- object regime with the depth in the sensor's own format: uint16 millimetres (robot_demo.py:515), divided inside the kernel ----
     pin_depth16 = (torch.from_numpy(depth_h).permute(1, 0, 2, 3) * 1000.0).round().clamp_(0, 65535).to(torch.uint16).contiguous().pin_memory()
     dev_depth16 = [torch.empty((E, H, W), dtype=torch.uint16, device=dev) for _ in range(2)]
-    sec = run(up_det, lambda b: batch.step_detections(dev_depth16[b], dev_pose[b], shifts, intr, float(CELL), *dev_det[b]),
+    sec = run(up_det, lambda b: batch.step_detections(dev_depth16[b], dev_pose[b], shifts, intr, float(CELL), *dev_det[b], inputs_ready=False),
               lambda: host_l2.copy_(batch.levels[2], non_blocking=True), n_fr_obj, pin_depth16, dev_depth16)
     h2d = E * (H * W * 2 + 48) + sum(int(x[0].numel() * x.element_size()) for x in pin_det)
     out["object_regime_u16_depth"] = {"value": world * E * n_fr_obj * args.e2e_steps / sec, "unit": UNIT, "ms_per_frame_step": 1e3 * sec / (n_fr_obj * args.e2e_steps),
@@ -833,6 +840,8 @@ def run_e2e_variants(eod, batch, dev, depth_h, pose_h, shifts, intr, args, world
         del graphed
     except Exception as exc:
         out["object_regime_u16_depth_graph"] = {"error": repr(exc)[:300]}
+    batch.join()
+    batch.pipeline = False
     return out
 
 

@@ -78,6 +78,7 @@ class EpisodeBatch:
         with torch.cuda.device(self.device):
             self._geo = torch.cuda.Stream(priority=0)
             self._wr = torch.cuda.Stream(priority=-1)      # the HBM-bound stage gets the SMs first
+        self._pre: Optional[torch.cuda.Stream] = None      # paste / sample stream of the object regime, created on first use
         self._e_fin: Optional[torch.cuda.Event] = None
         self._e_read: Optional[torch.cuda.Event] = None
         self._sync_next = True
@@ -307,20 +308,31 @@ class EpisodeBatch:
 
     def step_detections(self, depth, pose, shifts, intr, cell, box_features, mask_probs, boxes, n_obj=None, sample_stride: int = 8,
                         mask_thresh: float = 0.5, order: int = ORDER_ZX, *, reset_mask: Optional[torch.Tensor] = None,
-                        refresh_mask: Optional[torch.Tensor] = None, proj_indices: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
+                        refresh_mask: Optional[torch.Tensor] = None, proj_indices: Optional[torch.Tensor] = None,
+                        inputs_ready: bool = True) -> List[torch.Tensor]:
         """One frame of the reference's LIVE regime for all E episodes (custom_rcnn.py:489-515 with :876-936): read of the
         state left by frame t-1, then the write of this frame's kept detections (un-pasted 28x28 mask probabilities + boxes).
-        Two streams, stream-ordered for the caller on entry and exit:
+        Three streams, stream-ordered for the caller on entry and exit:
 
-            geometry stream : project ----------------------------> read
-            write stream    : paste/observed -> sample -> (project) count -> write_objects -> flush -> (read) finalize
+            geometry stream : project ---------------------> read   (needs finalize of frame t-1)
+            paste stream    : paste/observed -> sample
+            write stream    : (project, sample) count -> write_objects -> flush -> (read) finalize
 
-        The mask pasting and the sampling scan do not depend on the geometry, and the issue-bound read runs next to the
-        latency-bound object write instead of in front of it.  Slots whose episode has ended pass n_obj == 0 (nothing is
-        written, :686); reset_mask / refresh_mask as in ``step``."""
+        The mask pasting and the sampling scan depend on neither the geometry nor the state, and the issue-bound read runs next to
+        the latency-bound object write instead of in front of it.  With ``pipeline=True`` the caller's stream is not made to wait for
+        this frame's finalize, so project / paste / sample of frame t+1 run under write / flush / finalize of frame t (index plane and
+        per-frame counts are double buffered); the state chain read(t) -> finalize(t) -> read(t+1) is what remains serial.  The
+        promise about inputs is the one of ``step`` (``inputs_ready=False`` drops it for one call).  Slots whose episode has ended
+        pass n_obj == 0 (nothing is written, :686); reset_mask / refresh_mask as in ``step``."""
         s0 = torch.cuda.current_stream(self.device)
+        capturing = torch.cuda.is_current_stream_capturing()
         self._k = self._t & 1
         self._t += 1
+        strict = (not self.pipeline) or self._sync_next or not inputs_ready or capturing
+        self._sync_next = False
+        if self._pre is None:
+            with torch.cuda.device(self.device):
+                self._pre = torch.cuda.Stream(priority=0)
         S = -(-self.H * self.W // sample_stride)
         if self._slots is None or self._slots.S < S:
             self._slots = ops.ObjectSlots(self.E, self.n_cells, self.C, S, self.device)
@@ -336,25 +348,33 @@ class EpisodeBatch:
                     ops.refresh_norm16(self.counts, self.sums, self.norm16, refresh_mask)
                 e_state = torch.cuda.Event()
                 e_state.record()
+        with torch.cuda.stream(self._pre):
+            if strict:
+                self._pre.wait_event(e_in)
+            _, observed = ops.paste_masks(mask_probs, boxes, (self.H, self.W), mask_thresh, n_obj, want_masks=False, want_observed=True)
+            samp = ops.sample_mask(observed, sample_stride)
+            e_samp = torch.cuda.Event()
+            e_samp.record()
         with torch.cuda.stream(self._geo):
-            self._geo.wait_event(e_in)
-            if self._e_fin is not None:
-                self._geo.wait_event(self._e_fin)
+            if strict:
+                self._geo.wait_event(e_in)
             self._geometry(depth, pose, shifts, intr, cell, order, proj_indices)
             e_geo = torch.cuda.Event()
             e_geo.record()
+            if not strict:
+                self._geo.wait_event(e_in)                 # the caller has consumed the previous frame's levels
+            if self._e_fin is not None:
+                self._geo.wait_event(self._e_fin)          # norm16 as finalised by frame t-1
             if e_state is not None:
                 self._geo.wait_event(e_state)
             levels = self.read()
             e_read = torch.cuda.Event()
             e_read.record()
         with torch.cuda.stream(self._wr):
-            self._wr.wait_event(e_in)
-            if self._e_fin is not None:
-                self._wr.wait_event(self._e_fin)
-            _, observed = ops.paste_masks(mask_probs, boxes, (self.H, self.W), mask_thresh, n_obj, want_masks=False, want_observed=True)
-            samp = ops.sample_mask(observed, sample_stride)
+            if strict:
+                self._wr.wait_event(e_in)
             self._wr.wait_event(e_geo)
+            self._wr.wait_event(e_samp)
             ops.frame_count(self.idx, samp, self.frame_cnt, n_obj, self._slots)
             ops.write_objects_pasted(box_features, mask_probs, boxes, n_obj, self.idx, samp, self._slots, mask_thresh)
             ops.flush_slots(self.frame_cnt, self._slots, self.sums)
@@ -362,12 +382,16 @@ class EpisodeBatch:
             self._finalize()
             e_fin = torch.cuda.Event()
             e_fin.record()
-            if not torch.cuda.is_current_stream_capturing():
+            if not capturing:
                 for t in (observed, samp):
                     t.record_stream(self._wr)
         self._e_read, self._e_fin = e_read, e_fin
         s0.wait_event(e_read)
-        s0.wait_event(e_fin)
+        if self.pipeline and not capturing:
+            for t in (box_features, mask_probs, boxes) + ((n_obj,) if n_obj is not None else ()):
+                t.record_stream(self._wr)
+        else:
+            s0.wait_event(e_fin)
         return levels
 
     def capture_step_detections(self, depth, pose, shifts, intr, cell, box_features, mask_probs, boxes, n_obj=None, **kw) -> "GraphedDetections":

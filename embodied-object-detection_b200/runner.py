@@ -295,7 +295,7 @@ class EpisodeRunner:
                 else:
                     n_obj = torch.where(dev[0] > 0, inp["n_obj"], torch.zeros_like(inp["n_obj"]))
                     levels = b.step_detections(depth, pose, shifts, self.intr, self.cell, inp["box_features"], inp["mask_probs"], inp["boxes"],
-                                               n_obj, self.sample_stride, self.mask_thresh, self.order, **masks, **geo)
+                                               n_obj, self.sample_stride, self.mask_thresh, self.order, inputs_ready=False, **masks, **geo)
                 self.stats["steps"] += 1
                 self.stats["slot_steps"] += self.R
                 self.stats["frames"] += sum(a is not None for a in step.assign)
