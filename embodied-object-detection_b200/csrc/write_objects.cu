@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(256) paste_masks_kernel(const float *__restric
                                                           uint8_t *__restrict__ masks, uint8_t *__restrict__ observed)
 {
     __shared__ PasteObj s_obj[kPasteChunk];
+    __shared__ uint32_t s_hit[kPasteChunk / 32];           // observed-only: objects whose row range meets this CTA's pixel rows
     const int e = blockIdx.y, HW = H * W;
     const int p0 = (blockIdx.x * 256 + threadIdx.x) * 4;
     const int K = n_obj ? max(0, min(__ldg(n_obj + e), Kmax)) : Kmax;
@@ -133,9 +134,46 @@ __global__ void __launch_bounds__(256) paste_masks_kernel(const float *__restric
     for (int k0 = 0; k0 < Kmax; k0 += kPasteChunk) {
         const int kn = min(kPasteChunk, Kmax - k0);
         __syncthreads();
-        if ((int)threadIdx.x < kn && k0 + (int)threadIdx.x < K) s_obj[threadIdx.x] = paste_prepare(boxes + ((size_t)e * Kmax + k0 + threadIdx.x) * 4, H, W, thr);
+        if ((int)threadIdx.x < kPasteChunk) {
+            bool hit = false;
+            if ((int)threadIdx.x < kn && k0 + (int)threadIdx.x < K) {
+                const PasteObj o = paste_prepare(boxes + ((size_t)e * Kmax + k0 + threadIdx.x) * 4, H, W, thr);
+                s_obj[threadIdx.x] = o;
+                const int row_lo = (int)(blockIdx.x * 1024) / W, row_hi = min(HW - 1, (int)(blockIdx.x * 1024) + 1023) / W;
+                hit = !(row_hi < o.ry0 || row_lo >= o.ry1);
+            }
+            const unsigned hits = __ballot_sync(0xffffffffu, hit);
+            if ((threadIdx.x & 31) == 0) s_hit[threadIdx.x >> 5] = hits;
+        }
         __syncthreads();
         if (p0 >= HW) continue;
+        if (!masks) {
+            // observed only (the fused object write never builds the masks): walk just the objects that reach this CTA's rows, and stop
+            // as soon as all four pixels are covered - overlapping detections are the rule
+            for (int w = 0; w < kPasteChunk / 32 && any != 0x01010101u; ++w) {
+                unsigned todo = s_hit[w];
+                while (todo && any != 0x01010101u) {
+                    const int j = w * 32 + __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const PasteObj o = s_obj[j];
+                    if (py[3] < o.ry0 || py[0] >= o.ry1 || (py[0] == py[3] && (px[3] < o.rx0 || px[0] >= o.rx1))) continue;
+                    const float *m = probs + ((size_t)e * Kmax + k0 + j) * S * S;
+                    if (py[0] == py[3]) {
+                        const PasteAxis ay = paste_axis(py[0], o.y0, o.dy, S);
+#pragma unroll
+                        for (int b = 0; b < 4; ++b)
+                            if (!((any >> (8 * b)) & 1u) && p0 + b < HW && px[b] >= o.rx0 && px[b] < o.rx1 &&
+                                paste_eval(m, S, paste_axis(px[b], o.x0, o.dx, S), ay, thr))
+                                any |= 1u << (8 * b);
+                    } else {
+#pragma unroll
+                        for (int b = 0; b < 4; ++b)
+                            if (!((any >> (8 * b)) & 1u) && p0 + b < HW && paste_covers(m, o, S, px[b], py[b], thr)) any |= 1u << (8 * b);
+                    }
+                }
+            }
+            continue;
+        }
         for (int j = 0; j < kn; ++j) {
             const int k = k0 + j;
             uint32_t bits = 0;
