@@ -56,7 +56,7 @@ class EpisodeBatch:
 
     def __init__(self, n_episodes: int, map_w: int, map_h: int, channels: int, height: int = 480, width: int = 640,
                  device: torch.device = torch.device("cuda"), layout: int = LAYOUT_CHW, variant: int = WRITE_AUTO,
-                 pipeline: bool = False):
+                 pipeline: bool = False, fp16_table: bool = True):
         if torch.device(device).type != "cuda":
             raise EodError("EpisodeBatch needs a CUDA device (no CPU fallback)")
         self.E, self.map_w, self.map_h, self.C, self.H, self.W = n_episodes, map_w, map_h, channels, height, width
@@ -67,7 +67,9 @@ class EpisodeBatch:
         self.counts = torch.zeros((self.E, self.n_cells), dtype=torch.float32, **z)
         # always-current normalised fp16 copy of the grid (what create_implicit_memory + .half() would return); only
         # the rows of the cells visible in a frame change, and the write's post-pass refreshes exactly those
-        self.norm16 = torch.zeros((self.E, self.n_cells, self.C), dtype=torch.float16, **z)
+        # fp16_table=False drops it (a third of the grid's footprint: 84 instead of 56 resident 1000x1000x512 grids in 180 GB): the read
+        # then normalises and rounds the fp32 rows it gathers (same bits, twice the gathered bytes); no longterm snapshot in that mode
+        self.norm16 = torch.zeros((self.E, self.n_cells, self.C), dtype=torch.float16, **z) if fp16_table else None
         # per-frame planes, double buffered (frame t uses buffer t & 1)
         self._idx2 = [torch.zeros((self.E, height, width), dtype=torch.int32, **z) for _ in range(2)]
         self._frame_cnt2 = [torch.zeros((self.E, self.n_cells), dtype=torch.int32, **z) for _ in range(2)]
@@ -137,7 +139,8 @@ class EpisodeBatch:
         elif full:
             self.sums.zero_()
             self.counts.zero_()
-            self.norm16.zero_()
+            if self.norm16 is not None:
+                self.norm16.zero_()
             for f in self._frame_cnt2:
                 f.zero_()
         else:
@@ -171,12 +174,18 @@ class EpisodeBatch:
     def refresh_read(self, mask: Optional[torch.Tensor] = None) -> None:
         """Bring the fp16 read table up to date with sums / counts for the slots with mask[e] != 0 (None = all): the
         'updated_memory = self.implicit_memory' of custom_rcnn.py:482-486 at the first frame of a sequence."""
+        if self.norm16 is None:
+            raise EodError("refresh_read: this batch keeps no fp16 read table (fp16_table=False)")
         self.join()
         ops.refresh_norm16(self.counts, self.sums, self.norm16, mask)
         self._sync_next = True
 
     def read(self) -> List[torch.Tensor]:
         """A10-A12 fused: [L0 (E,C,H/8,W/8), L1, L2] fp16 (channels_last memory)."""
+        if self.norm16 is None:
+            if self.read_frozen:
+                raise EodError("read_frozen (TEST_TYPE longterm) needs the fp16 read table: construct the batch with fp16_table=True")
+            return self._timed("read", ops.read_pool, self.sums, self.counts, self.idx, out=self.levels)
         return self._timed("read", ops.read_pool, self.norm16, None, self.idx, out=self.levels)
 
     def read_roi(self, boxes: torch.Tensor, batch_idx: torch.Tensor, pooled: int = 7) -> torch.Tensor:
@@ -202,7 +211,7 @@ class EpisodeBatch:
 
     def _finalize(self) -> None:
         # read_frozen (TEST_TYPE longterm): counts only - the fp16 table the read gathers from is a snapshot
-        if self.read_frozen:
+        if self.read_frozen or self.norm16 is None:
             self._timed("finalize", ops.finalize_counts, self.idx, self.frame_cnt, self.counts)
         else:
             self._timed("finalize", ops.finalize_counts, self.idx, self.frame_cnt, self.counts, None, self.sums, self.norm16)
@@ -269,7 +278,7 @@ class EpisodeBatch:
                 self._wr.wait_event(e_in)
                 if reset_mask is not None:
                     ops.reset_episodes(self.counts, self.sums, self.norm16, reset_mask)
-                if refresh_mask is not None:
+                if refresh_mask is not None and self.norm16 is not None:
                     ops.refresh_norm16(self.counts, self.sums, self.norm16, refresh_mask)
                 e_state = torch.cuda.Event()
                 e_state.record()
@@ -344,7 +353,7 @@ class EpisodeBatch:
                 self._wr.wait_event(e_in)
                 if reset_mask is not None:
                     ops.reset_episodes(self.counts, self.sums, self.norm16, reset_mask)
-                if refresh_mask is not None:
+                if refresh_mask is not None and self.norm16 is not None:
                     ops.refresh_norm16(self.counts, self.sums, self.norm16, refresh_mask)
                 e_state = torch.cuda.Event()
                 e_state.record()

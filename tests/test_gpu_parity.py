@@ -929,6 +929,39 @@ def test_step_detections_two_streams_matches_serial(eod, cuda):
             assert int(d.max()) <= 1 and float((d != 0).float().mean()) < 1e-3, t      # tables may differ in the last bit (reduction order)
 
 
+def test_batch_without_fp16_table_reads_the_same_bits(eod, cuda):
+    """EpisodeBatch(fp16_table=False) keeps only sums / counts (a third less memory per grid) and lets the read normalise + round the
+    fp32 rows it gathers: levels, counts and sums must equal the default batch bit for bit (same kernels feed both, one stream each,
+    deterministic write variant so that the two batches' sums agree exactly), incl. a per-slot reset in the middle."""
+    E, C, H, W, mw, mh, T = 2, 128, 96, 128, 60, 45, 4
+    cell = 0.2
+    eps = [eod.episodes.make_episode(700 + e, T, H, W, mw, mh, cell) for e in range(E)]
+    intr = eod.compute_intrinsics(W, H, math.radians(67.5))
+    shifts = _t(np.stack([np.concatenate([np.zeros(3, np.float32), ep.map_world_shift]) for ep in eps]), cuda)
+    a = eod.EpisodeBatch(E, mw, mh, C, H, W, cuda, variant=eod._lib.WRITE_DET)
+    b = eod.EpisodeBatch(E, mw, mh, C, H, W, cuda, variant=eod._lib.WRITE_DET, fp16_table=False)
+    assert b.norm16 is None
+    a.det_runs_per_episode = b.det_runs_per_episode = H * W      # room for every run: no fallback to order-dependent reductions
+    g = torch.Generator(device=cuda).manual_seed(3)
+    for t in range(T):
+        Tm = eod.transform3d(torch.from_numpy(np.stack([ep.xyzhe[t] for ep in eps])))
+        pose = Tm[:, :3].reshape(E, 12).to(cuda)
+        depth = _t(np.stack([ep.depth[t] for ep in eps]), cuda)
+        feat = torch.randn((E, C, H, W), device=cuda, generator=g)
+        mask = torch.tensor([0, 1 if t == 2 else 0], dtype=torch.int32, device=cuda) if t == 2 else None
+        la = [l.clone() for l in a.step(depth, pose, shifts, intr, cell, feat, reset_mask=mask)]
+        lb = [l.clone() for l in b.step(depth, pose, shifts, intr, cell, feat, reset_mask=mask)]
+        torch.cuda.synchronize()
+        for x, y in zip(la, lb):
+            assert torch.equal(x, y), t
+        assert torch.equal(a.counts, b.counts), t
+        assert torch.equal(a.sums, b.sums), (t, float((a.sums - b.sums).abs().max()), int((a.sums != b.sums).sum()))
+    assert float(a.counts.max()) >= 2
+    b.read_frozen = True
+    with pytest.raises(eod.EodError):
+        b.read()
+
+
 def test_graphed_step_detections_matches_eager(eod, cuda):
     """capture_step_detections (one CUDA graph per frame: the online single-robot loop) against the eager step_detections on a twin
     batch, frame by frame, with an eager frame interleaved: identical indices, fp16 levels, counts and touched sets, sums within the
