@@ -235,8 +235,11 @@ __global__ void __launch_bounds__(kReadWarps * 32, (C >= 512 ? 2 : (C >= 256 ? 3
     using Raw = typename RawOf<TableT, V>::type;
     __shared__ __align__(16) unsigned char s_raw[kReadWarps * kRpSlice];
 
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t sm = smem_u32(s_raw) + warp * kRpSlice;                   // this warp's slice
+    unsigned lane = threadIdx.x & 31;
+    const unsigned warp = threadIdx.x >> 5;
+    asm volatile("" : "+r"(lane));
+    uint32_t sm = smem_u32(s_raw) + warp * kRpSlice;                         // this warp's slice
+    asm volatile("" : "+r"(sm));                                             // opaque: one register, not a %tid / %cluster_ctaid recomputation per use
     const int nqy = H / 16, nqx = W / 16, per_ep = nqy * nqx;
     const int n_items = E * per_ep;                                          // the host guarantees it fits 31 bits
     const int stride = (int)gridDim.x * kReadWarps;
@@ -253,7 +256,8 @@ __global__ void __launch_bounds__(kReadWarps * 32, (C >= 512 ? 2 : (C >= 256 ? 3
     auto src_of = [&](int e_, int qy_, int qx_) { return idx + ((size_t)e_ * H + (size_t)qy_ * 16) * W + qx_ * 16 + lane_off; };
     QuadIdx nxt = load_quad_idx<IdxT>(src_of(e, qy, qx), W);
     const int g = (int)lane;                                // group of V channels
-    const uint32_t sm_ids = sm + kRpIdx + (w * 16 + hh * 8) * 4;
+    uint32_t sm_ids = sm + kRpIdx + (w * 16 + hh * 8) * 4;
+    asm volatile("" : "+r"(sm_ids));
     const size_t ep_rows = (size_t)n_cells * C;
 
     for (; item < n_items; item += stride) {
@@ -294,6 +298,7 @@ __global__ void __launch_bounds__(kReadWarps * 32, (C >= 512 ? 2 : (C >= 256 ? 3
         __syncwarp();
 
         const char *rows = reinterpret_cast<const char *>(table + (size_t)ce * ep_rows + (size_t)g * V);   // this lane's channel group of row 0
+        asm volatile("" : "+l"(rows));      // opaque: keep the pointer in registers (the compiler re-derived it - 12 instructions - before every fetch)
         const float *counts_e = counts ? counts + (size_t)ce * n_cells : nullptr;
         auto fetch = [&](int cell) { return load_raw<V>(reinterpret_cast<const TableT *>(rows), counts_e, (size_t)cell, C, 0); };
         int cur_cell = -1, oth_cell = -1;
