@@ -70,12 +70,15 @@ __device__ __forceinline__ void vstore_half(__half *dst, const Vec<V> &a)
     }
 }
 
-// Four pixels of a two-cell window in summation order: s += (bit k of pat ? b : a) for k = 0..3.  pat is warp-uniform; one
-// indexed jump to one of 16 straight-line variants (no predicated-off additions, no per-run bookkeeping).
+// Rows of a two-cell window in summation order: for each of `reps` rows, s += (bit k of pat ? b : a) for k = 0..3.  pat and reps are
+// warp-uniform; one dispatch to one of 16 straight-line variants (no predicated-off additions, no per-run bookkeeping).  reps = 4
+// serves the commonest mixed window - a vertical edge, all four rows alike - with a single dispatch.
 template <int V>
-__device__ __forceinline__ void vadd_row2(Vec<V> &s, const Vec<V> &a, const Vec<V> &b, unsigned pat)
+__device__ __forceinline__ void vadd_row2(Vec<V> &s, const Vec<V> &a, const Vec<V> &b, unsigned pat, int reps)
 {
-#define EOD_R4(x0, x1, x2, x3) s = vadd<V>(s, x0); s = vadd<V>(s, x1); s = vadd<V>(s, x2); s = vadd<V>(s, x3); break;
+#define EOD_R4(x0, x1, x2, x3)                                                                                         \
+    _Pragma("unroll 1") for (int r = 0; r < reps; ++r) { s = vadd<V>(s, x0); s = vadd<V>(s, x1); s = vadd<V>(s, x2); s = vadd<V>(s, x3); } \
+    break;
     switch (pat & 15u) {
     case 0: EOD_R4(a, a, a, a)
     case 1: EOD_R4(b, a, a, a)
@@ -343,8 +346,13 @@ __global__ void __launch_bounds__(kReadWarps * 32, (C >= 512 ? 2 : (C >= 256 ? 3
                         // bit p of bm: pixel p belongs to B = parity of the run heads in (0, p] (prefix xor over the 16-bit head mask)
                         unsigned bm = rest;
                         bm ^= bm << 1; bm ^= bm << 2; bm ^= bm << 4; bm ^= bm << 8;
+                        bm &= 0xffffu;
+                        if (bm == (bm & 15u) * 0x1111u) {
+                            vadd_row2<V>(s4, cur, oth, bm, 4);      // all four rows alike
+                        } else {
 #pragma unroll 1
-                        for (int r = 0; r < 4; ++r, bm >>= 4) vadd_row2<V>(s4, cur, oth, bm);
+                            for (int r = 0; r < 4; ++r, bm >>= 4) vadd_row2<V>(s4, cur, oth, bm, 1);
+                        }
                     } else {
                         // three or more cells in the window: 2-8 runs instead of 16 pixels; the walk pays the fetch / fp16->fp32
                         // conversion / bookkeeping per RUN and V/2 packed adds per pixel.  (A straight-line per-pixel walk with a
