@@ -85,13 +85,20 @@ __device__ __forceinline__ float tf32_big(float x)
     return __uint_as_float(r);
 }
 
+// second half of the split; a non-finite x has no remainder (inf - inf would turn an infinite product into NaN)
+__device__ __forceinline__ float tf32_small(float x, float big)
+{
+    const float d = __fsub_rn(x, big);
+    return (__float_as_uint(big) & 0x7f800000u) == 0x7f800000u ? 0.f : tf32_big(d);
+}
+
 // one 16-byte chunk (4 consecutive k) of row `r` of a chunk tile -> its swizzled place in the big / small halves
 __device__ __forceinline__ void ln_store4(uint32_t big_base, uint32_t small_base, int r, int c, float4 x)
 {
     const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
     float4 b, s;
     b.x = tf32_big(x.x); b.y = tf32_big(x.y); b.z = tf32_big(x.z); b.w = tf32_big(x.w);
-    s.x = tf32_big(__fsub_rn(x.x, b.x)); s.y = tf32_big(__fsub_rn(x.y, b.y)); s.z = tf32_big(__fsub_rn(x.z, b.z)); s.w = tf32_big(__fsub_rn(x.w, b.w));
+    s.x = tf32_small(x.x, b.x); s.y = tf32_small(x.y, b.y); s.z = tf32_small(x.z, b.z); s.w = tf32_small(x.w, b.w);
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(big_base + off), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(small_base + off), "f"(s.x), "f"(s.y), "f"(s.z), "f"(s.w) : "memory");
 }
