@@ -236,7 +236,8 @@ int eod_max_winner_list(const int32_t *arg_pix, int n_episodes, int64_t n_cells,
  *   dst(i) = y_dst ? y_dst[i] : i ;  a_off, bias, m_count, y_dst nullable ;  N % 16 == 0.
  * Replaces the nn.Linear of the 'replace' update above (with the lists of eod_max_winner_list), the 1x1 forward projection of the
  * dense backbone-feature write (A7''), the projection of per-ROI memory features and the fp32 conv1x1 of timm.py:174 on the
- * training path (forward and, through the strides, both gradients).  |error| <= 1e-5 * scale of the result vs fp64. */
+ * training path (forward and, through the strides, both gradients).  |error| <= 1e-5 * scale of the result vs fp64.  A non-finite
+ * operand makes its output row non-finite (inf or NaN - the operand split can turn inf * 0 into NaN), never another row. */
 int eod_linear_rows(const float *A, int64_t a_row_stride, int64_t a_k_stride, const int64_t *a_off, const float *B, int64_t b_row_stride,
                     int64_t b_k_stride, const float *bias, float scale, int M, const int32_t *m_count, int N, int K, float *Y,
                     int64_t y_row_stride, const int64_t *y_dst, eod_stream_t stream);

@@ -1124,6 +1124,14 @@ def test_linear_rows_fp32_accuracy_on_tensor_cores(eod, cuda, M, K, N):
         got = eod.ops.linear_rows(aa, ww, b, 0.75)
         err = float((got.double() - ref).abs().max()) / scale
         assert err <= 1e-5 and err <= max(4 * lib_err, 2e-6), (name, err, lib_err)
+    if M > 2:                                    # a non-finite input poisons ITS row (inf or NaN: the split turns inf * 0-remainder into NaN), no other
+        a_inf = a.clone()
+        a_inf[1, 0], a_inf[2, K - 1] = float("inf"), float("nan")
+        got = eod.ops.linear_rows(a_inf, w, b, 0.75)
+        assert not bool(torch.isfinite(got[1:3]).any())
+        keep = torch.ones(M, dtype=torch.bool, device=cuda)
+        keep[1:3] = False
+        assert float((got[keep].double() - ref[keep]).abs().max()) <= 1e-5 * scale
     nob = eod.ops.linear_rows(a, w)
     assert float((nob.double() - a.double() @ w.double().t()).abs().max()) <= 1e-5 * float((a.double() @ w.double().t()).abs().max())
     # gathered rows + scattered output + device-side row count (the 'replace' update's shape)
