@@ -81,6 +81,7 @@ class EpisodeBatch:
             self._geo = torch.cuda.Stream(priority=0)
             self._wr = torch.cuda.Stream(priority=-1)      # the HBM-bound stage gets the SMs first
         self._pre: Optional[torch.cuda.Stream] = None      # paste / sample stream of the object regime, created on first use
+        self._obs2 = self._samp2 = None                    # its per-frame observed / sampled-pixel planes (E, H*W) u8, double buffered
         self._e_fin: Optional[torch.cuda.Event] = None
         self._e_read: Optional[torch.cuda.Event] = None
         self._sync_next = True
@@ -360,8 +361,17 @@ class EpisodeBatch:
         with torch.cuda.stream(self._pre):
             if strict:
                 self._pre.wait_event(e_in)
-            _, observed = ops.paste_masks(mask_probs, boxes, (self.H, self.W), mask_thresh, n_obj, want_masks=False, want_observed=True)
-            samp = ops.sample_mask(observed, sample_stride)
+            # per-frame planes owned by the batch (double buffered like the index plane): tensors allocated here on the paste stream
+            # and consumed on the write stream would make the caching allocator defer their reuse and fall back to cudaMalloc
+            if self._obs2 is None:
+                self._obs2 = [torch.empty((self.E, self.H * self.W), dtype=torch.uint8, device=self.device) for _ in range(2)]
+                self._samp2 = [torch.empty((self.E, self.H * self.W), dtype=torch.uint8, device=self.device) for _ in range(2)]
+                self._fin2 = [None, None]
+            if self._fin2[self._k] is not None and not capturing:
+                self._pre.wait_event(self._fin2[self._k])      # the write side of frame t-2 has finished with this half
+            _, observed = ops.paste_masks(mask_probs, boxes, (self.H, self.W), mask_thresh, n_obj, want_masks=False, want_observed=True,
+                                          observed_out=self._obs2[self._k])
+            samp = ops.sample_mask(observed, sample_stride, self._samp2[self._k])
             e_samp = torch.cuda.Event()
             e_samp.record()
         with torch.cuda.stream(self._geo):
@@ -391,10 +401,8 @@ class EpisodeBatch:
             self._finalize()
             e_fin = torch.cuda.Event()
             e_fin.record()
-            if not capturing:
-                for t in (observed, samp):
-                    t.record_stream(self._wr)
         self._e_read, self._e_fin = e_read, e_fin
+        self._fin2[self._k] = None if capturing else e_fin
         s0.wait_event(e_read)
         if self.pipeline and not capturing:
             for t in (box_features, mask_probs, boxes) + ((n_obj,) if n_obj is not None else ()):

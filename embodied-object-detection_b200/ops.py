@@ -376,14 +376,19 @@ def _paste_args(mask_probs: torch.Tensor, boxes: torch.Tensor, n_obj: Optional[t
 
 
 def paste_masks(mask_probs: torch.Tensor, boxes: torch.Tensor, image_shape: Tuple[int, int], threshold: float = 0.5,
-                n_obj: Optional[torch.Tensor] = None, want_masks: bool = True, want_observed: bool = False):
+                n_obj: Optional[torch.Tensor] = None, want_masks: bool = True, want_observed: bool = False,
+                observed_out: Optional[torch.Tensor] = None):
     """paste_masks_in_image (detectron2 mask_ops.py, custom_rcnn.py:880) for E episodes: mask_probs (E,Kmax,S,S) f32,
     boxes (E,Kmax,4) f32 -> masks (E,Kmax,H,W) bool and / or observed (E,H*W) u8 (OR over the episode's objects)."""
     E, Kmax, S = _paste_args(mask_probs, boxes, n_obj)
     H, W = int(image_shape[0]), int(image_shape[1])
     dev = mask_probs.device
     masks = torch.empty((E, Kmax, H, W), dtype=torch.uint8, device=dev) if want_masks else None
-    observed = torch.empty((E, H * W), dtype=torch.uint8, device=dev) if want_observed else None
+    observed = None
+    if want_observed:
+        observed = torch.empty((E, H * W), dtype=torch.uint8, device=dev) if observed_out is None else _dev(observed_out, torch.uint8, "observed_out")
+        if observed.numel() != E * H * W:
+            raise ValueError("observed_out must hold E*H*W bytes")
     if Kmax == 0:
         return (masks.view(torch.bool) if want_masks else None), (observed.zero_() if want_observed else None)
     _call("eod_paste_masks", mask_probs.data_ptr(), boxes.data_ptr(), _ptr(n_obj), E, Kmax, S, H, W, float(threshold),
