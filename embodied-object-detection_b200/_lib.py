@@ -47,7 +47,7 @@ SIGNATURES = {
     "eod_linear_rows": [_P, c_int64, c_int64, _P, _P, c_int64, c_int64, _P, c_float, c_int, _P, c_int, c_int, _P, c_int64, _P, _P],
     "eod_read_pool": [_P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int64, _P, _P, _P, _P],
     "eod_normalize_memory": [_P, _P, c_int64, c_int, _P, c_int, _P],
-    "eod_read_roi": [c_int, _P, _P, _P, _P, c_int, c_int, _P, _P, c_int, c_int, c_int, c_int, c_float, c_int, _P, _P, _P],
+    "eod_read_roi": [c_int, _P, _P, _P, _P, c_int, c_int, _P, _P, c_int, c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P],
     "eod_semmap_update": [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int64, _P, _P, _P],
     "eod_semmap_decode": [_P, _P, c_int, c_int64, c_float, _P, _P, _P],
     "eod_reset_touched": [_P, _P, _P, c_int64, c_int, _P],

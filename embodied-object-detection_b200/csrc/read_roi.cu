@@ -66,7 +66,7 @@ __device__ __forceinline__ int assign_level(float x1, float y1, float x2, float 
 template <int C>
 __global__ void __launch_bounds__(256) read_roi_kernel(RoiLevels L, const float *__restrict__ boxes, const int32_t *__restrict__ batch_idx, int R, int P,
                                                        int sampling_ratio, int min_level, float canonical_size, int canonical_level,
-                                                       float *__restrict__ out, int32_t *__restrict__ out_level)
+                                                       float *__restrict__ out, int32_t *__restrict__ out_level, float *__restrict__ out_valid)
 {
     constexpr int V = C / 32;
     const int r = blockIdx.x;
@@ -92,12 +92,14 @@ __global__ void __launch_bounds__(256) read_roi_kernel(RoiLevels L, const float 
         float acc[V];
 #pragma unroll
         for (int k = 0; k < V; ++k) acc[k] = 0.f;
+        int n_valid = 0;
         for (int iy = 0; iy < gh; ++iy) {
             const float yy = __fadd_rn(__fadd_rn(rsh, __fmul_rn((float)ph, bin_h)), __fdiv_rn(__fmul_rn(__fadd_rn((float)iy, 0.5f), bin_h), (float)gh));
             for (int ix = 0; ix < gw; ++ix) {
                 const float xx = __fadd_rn(__fadd_rn(rsw, __fmul_rn((float)pw, bin_w)), __fdiv_rn(__fmul_rn(__fadd_rn((float)ix, 0.5f), bin_w), (float)gw));
                 float y = yy, x = xx;
                 if (y < -1.0f || y > (float)h || x < -1.0f || x > (float)w) continue;        // empty sample: contributes 0
+                ++n_valid;
                 if (y <= 0.f) y = 0.f;
                 if (x <= 0.f) x = 0.f;
                 int y_low = (int)y, x_low = (int)x, y_high, x_high;
@@ -118,6 +120,9 @@ __global__ void __launch_bounds__(256) read_roi_kernel(RoiLevels L, const float 
                 }
             }
         }
+        // what ROIAlign makes of a constant-1 plane: the share of this bin's sample points that fall on the level (the bias of a 1x1
+        // projection applied BEFORE the pooling survives it with exactly this factor; 0 for empty / inverted boxes)
+        if (out_valid && lane == 0) out_valid[(size_t)r * P * P + bin] = __fdiv_rn((float)n_valid, count);
         float *dst = out + ((size_t)r * P * P + bin) * C + (size_t)lane * V;
 #pragma unroll
         for (int k = 0; k < V; k += 4)
@@ -130,7 +135,7 @@ __global__ void __launch_bounds__(256) read_roi_kernel(RoiLevels L, const float 
 
 extern "C" int eod_read_roi(int n_levels, const void *const *levels, const int *level_h, const int *level_w, const float *level_scale,
                             int n_episodes, int C, const float *boxes, const int32_t *batch_idx, int n_rois, int pooled, int sampling_ratio,
-                            int min_level, float canonical_size, int canonical_level, float *out, int32_t *out_level, eod_stream_t stream)
+                            int min_level, float canonical_size, int canonical_level, float *out, int32_t *out_level, float *out_valid, eod_stream_t stream)
 {
     EOD_REQUIRE(levels && level_h && level_w && level_scale && boxes && out, EOD_ERR_BADARG, "eod_read_roi: null pointer");
     EOD_REQUIRE(n_levels >= 1 && n_levels <= 4 && n_episodes > 0 && n_rois >= 0 && pooled > 0 && pooled <= 32 && sampling_ratio >= 0,
@@ -148,9 +153,9 @@ extern "C" int eod_read_roi(int n_levels, const void *const *levels, const int *
     EOD_REQUIRE(eod_aligned16(out), EOD_ERR_ALIGN, "eod_read_roi: out must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     switch (C) {
-    case 128: read_roi_kernel<128><<<n_rois, 256, 0, st>>>(L, boxes, batch_idx, n_rois, pooled, sampling_ratio, min_level, canonical_size, canonical_level, out, out_level); break;
-    case 256: read_roi_kernel<256><<<n_rois, 256, 0, st>>>(L, boxes, batch_idx, n_rois, pooled, sampling_ratio, min_level, canonical_size, canonical_level, out, out_level); break;
-    case 512: read_roi_kernel<512><<<n_rois, 256, 0, st>>>(L, boxes, batch_idx, n_rois, pooled, sampling_ratio, min_level, canonical_size, canonical_level, out, out_level); break;
+    case 128: read_roi_kernel<128><<<n_rois, 256, 0, st>>>(L, boxes, batch_idx, n_rois, pooled, sampling_ratio, min_level, canonical_size, canonical_level, out, out_level, out_valid); break;
+    case 256: read_roi_kernel<256><<<n_rois, 256, 0, st>>>(L, boxes, batch_idx, n_rois, pooled, sampling_ratio, min_level, canonical_size, canonical_level, out, out_level, out_valid); break;
+    case 512: read_roi_kernel<512><<<n_rois, 256, 0, st>>>(L, boxes, batch_idx, n_rois, pooled, sampling_ratio, min_level, canonical_size, canonical_level, out, out_level, out_valid); break;
     default:
         eod_set_error("eod_read_roi: C=%d not compiled in (128, 256, 512)", C);
         return EOD_ERR_UNSUPPORTED;

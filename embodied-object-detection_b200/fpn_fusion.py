@@ -116,7 +116,7 @@ class MemoryFusion(nn.Module):
         dev = levels[0].device
         bx = torch.cat([b.to(dev, torch.float32) for b in boxes], 0).contiguous()
         bi = torch.cat([torch.full((b.shape[0],), i, dtype=torch.int32, device=dev) for i, b in enumerate(boxes)], 0)
-        roi, lvl = ops.read_roi(levels, bx, bi, pooled, want_levels=True)
+        roi, lvl, valid = ops.read_roi(levels, bx, bi, pooled, want_levels=True, want_valid=True)
         if not project:
             return roi
         out = torch.empty((roi.shape[0], self.merge_map_projections[0].weight.shape[0], pooled, pooled), dtype=torch.float32, device=dev)
@@ -126,9 +126,29 @@ class MemoryFusion(nn.Module):
                 x = roi[sel].permute(0, 2, 3, 1)                                              # (n, 7, 7, C)
                 w2 = conv.weight.detach().to(torch.float32).reshape(conv.weight.shape[0], -1)
                 b2 = None if conv.bias is None else conv.bias.detach().to(torch.float32).contiguous()
-                y = ops.linear_rows(x.reshape(-1, x.shape[-1]), w2, b2, float(self.map_feature_weight))   # (bias + x.W) * MAP_FEATURE_WEIGHT
+                y = ops.linear_rows(x.reshape(-1, x.shape[-1]), w2, None, float(self.map_feature_weight))   # x.W * MAP_FEATURE_WEIGHT
+                if b2 is not None:
+                    # the reference adds the bias per level pixel BEFORE the pooling, so it survives with the bin's share of sample points
+                    # that lie on the level (1 for boxes inside the image, 0 for an empty box - whose pooled features are all zero)
+                    y.addcmul_(valid[sel].reshape(-1, 1), b2.view(1, -1), value=float(self.map_feature_weight))
                 out[sel] = y.view(x.shape[0], pooled, pooled, -1).permute(0, 3, 1, 2)
         return out
+
+    def fuse_roi(self, box_features: torch.Tensor, map_memory, proj_indices, boxes: Sequence[torch.Tensor], observations=None) -> torch.Tensor:
+        """North-star subsystem (4) at the ROI level: the ROI box-head input with the memory fused in.  box_features (sum n_i, C_ego, P, P)
+        = ``box_pooler(image-only levels, boxes)`` (detic_roi_heads.py:331-334 on the un-fused FPN output); returns what the reference's
+        ``box_pooler(fused levels, boxes)`` holds: by linearity of ROIAlign, box_features + MAP_FEATURE_WEIGHT * (conv1x1_l(pool(L_l)) + b_l)
+        ('sum'), the memory term alone ('mem_only'), or box_features unchanged ('image_only' / no memory)."""
+        if self.memory_type != "implicit_memory" or self.feat_fusion == "image_only":
+            return box_features
+        if self.feat_fusion not in _FUSE_MODES:
+            raise UnboundLocalError("new_res")
+        P = box_features.shape[-1]
+        mem = self.read_roi(map_memory, proj_indices, boxes, observations, pooled=P, project=True)         # already times MAP_FEATURE_WEIGHT
+        if self.feat_fusion == "mem_only":
+            return mem.to(box_features.dtype)
+        res = box_features.to(mem.device, torch.float32).contiguous()
+        return ops.fuse(res, mem.contiguous(), 1.0, FUSE_SUM).to(box_features.dtype)
 
     def forward(self, results: Sequence[torch.Tensor], map_memory, proj_indices, observations=None) -> List[torch.Tensor]:
         """results = [p3, p4, p5] -> fused [p3, p4, p5] (timm.py:142-192)."""

@@ -557,11 +557,12 @@ def read_pool(table: torch.Tensor, counts: Optional[torch.Tensor], idx: torch.Te
 
 def read_roi(levels: Sequence[torch.Tensor], boxes: torch.Tensor, batch_idx: Optional[torch.Tensor] = None, pooled: int = 7,
              strides: Sequence[int] = (8, 16, 32), sampling_ratio: int = 0, min_level: int = 3, canonical_size: float = 224.0,
-             canonical_level: int = 4, want_levels: bool = False):
+             canonical_level: int = 4, want_levels: bool = False, want_valid: bool = False):
     """Per-ROI map features: ROIAlign (aligned, detectron2 ROIAlignV2) of the pooled memory levels over the proposals' boxes with
     the FPN level assignment (detic_roi_heads.py:331-334 applied to the memory levels; see eod_read_roi).
     levels: what read_pool returns - logical (E,C,h,w) fp16 tensors in channels-last memory; boxes (R,4) f32 XYXY image pixels;
-    batch_idx (R) i32.  Returns logical (R,C,pooled,pooled) f32 in channels-last memory [, assigned level (R) i32]."""
+    batch_idx (R) i32.  Returns logical (R,C,pooled,pooled) f32 in channels-last memory [, assigned level (R) i32] [, valid (R,pooled,
+    pooled) f32: the share of each bin's sample points that lie on the level = ROIAlign of a constant-1 plane]."""
     import ctypes
     n = len(levels)
     if not (1 <= n <= 4) or len(strides) != n:
@@ -583,13 +584,15 @@ def read_roi(levels: Sequence[torch.Tensor], boxes: torch.Tensor, batch_idx: Opt
         raise ValueError("batch_idx is required when the levels hold more than one episode")
     out = torch.empty((R, pooled, pooled, C), dtype=torch.float32, device=boxes.device)
     lvl = torch.empty((R,), dtype=torch.int32, device=boxes.device) if want_levels else None
+    valid = torch.empty((R, pooled, pooled), dtype=torch.float32, device=boxes.device) if want_valid else None
     if R:
         _call("eod_read_roi", n, (ctypes.c_void_p * n)(*[lv.data_ptr() for lv in levels]), (ctypes.c_int * n)(*[d[1] for d in dims]),
               (ctypes.c_int * n)(*[d[2] for d in dims]), (ctypes.c_float * n)(*[1.0 / float(s) for s in strides]), E, C, boxes.data_ptr(),
               _ptr(batch_idx), R, int(pooled), int(sampling_ratio), int(min_level), float(canonical_size), int(canonical_level),
-              out.data_ptr(), _ptr(lvl), _stream())
+              out.data_ptr(), _ptr(lvl), _ptr(valid), _stream())
     out = out.permute(0, 3, 1, 2)
-    return (out, lvl) if want_levels else out
+    ret = (out,) + ((lvl,) if want_levels else ()) + ((valid,) if want_valid else ())
+    return ret if len(ret) > 1 else out
 
 
 def fuse(res: Optional[torch.Tensor], mem: Optional[torch.Tensor], weight: float, mode: int,

@@ -270,10 +270,12 @@ int eod_read_pool(const void *table, int mem_is_f16, const float *counts, const 
  *   out (R, pooled, pooled, C) f32 channels-last (logical (R, C, pooled, pooled)); out_level (R) i32 nullable: assigned level
  * Sample points, clamping and summation order of torchvision's CPU ROIAlign (ops/cpu/roi_align_kernel.cpp); accumulated fp32:
  * within 1e-5 of scale of the executed reference op, level assignments exact.  min_level: index of levels[0] in the pyramid
- * (3 for p3); canonical_size 224, canonical_level 4 in detectron2. */
+ * (3 for p3); canonical_size 224, canonical_level 4 in detectron2.  out_valid (nullable, (R,P,P) f32): per bin, the share of its sample
+ * points that lie on the level = ROIAlign of a constant-1 plane (1 for boxes inside the image, 0 for empty / inverted boxes): the factor
+ * with which the bias of a 1x1 projection applied before the pooling survives it. */
 int eod_read_roi(int n_levels, const void *const *levels, const int *level_h, const int *level_w, const float *level_scale,
                  int n_episodes, int C, const float *boxes, const int32_t *batch_idx, int n_rois, int pooled, int sampling_ratio,
-                 int min_level, float canonical_size, int canonical_level, float *out, int32_t *out_level, eod_stream_t stream);
+                 int min_level, float canonical_size, int canonical_level, float *out, int32_t *out_level, float *out_valid, eod_stream_t stream);
 
 /* Stand-alone create_implicit_memory (custom_rcnn.py:764-774, and the half cast of :1036 when out_is_f16):
  * out[row] = sums[row] / counts[row] where counts[row] > 1 else sums[row].  n_rows = E*cells.  Only for

@@ -1421,6 +1421,30 @@ def test_new_kernels_stay_inside_their_output_buffers(eod, cuda):
         eod.ops.project_fuse_levels([lvl], [ws], [None], [res], 5.0, 0, outs=[ov], variant=variant)
         torch.cuda.synchronize()
         assert intact(ob, op_), (variant, h, w)
+    # row GEMM: ragged last tile, strided output rows (guard bytes between rows too), scattered rows, K tail
+    for M, K, N in ((130, 40, 48), (5, 512, 256), (257, 64, 272)):
+        a = _t(rng.standard_normal((M, K)).astype(np.float32), cuda)
+        w = _t(rng.standard_normal((N, K)).astype(np.float32), cuda)
+        ob, ov, op_ = window((M + 3, N + 8), torch.float32)
+        dst = torch.randperm(M + 3, device=cuda)[:M].to(torch.int64).contiguous()
+        eod.ops.linear_rows(a, w, None, 1.0, out=ov, y_dst=dst, a_off=(torch.arange(M, device=cuda) * K).to(torch.int64), n_rows=M)
+        torch.cuda.synchronize()
+        assert intact(ob, op_), (M, K, N)
+        pad_cols = ov[:, N:].contiguous().view(torch.uint8)
+        assert bool((pad_cols == 0xA5).all()), (M, K, N)                                       # the 8 floats behind every output row
+        free = torch.ones(M + 3, dtype=torch.bool, device=cuda)
+        free[dst] = False
+        assert bool((ov[free].contiguous().view(torch.uint8) == 0xA5).all())
+        assert float((ov[dst][:, :N].double() - a.double() @ w.double().t()).abs().max()) <= 1e-5 * float((a.double() @ w.double().t()).abs().max())
+    # explicit-map index composition
+    lut = _t(rng.integers(-1, 20, (999,)).astype(np.int32), cuda)
+    src = _t(rng.integers(0, 999, (3, 41, 53)).astype(np.int64), cuda)
+    rb, rv, rp = window((3, 41, 53), torch.int32)
+    err = torch.zeros(1, dtype=torch.int32, device=cuda)
+    eod._lib.check(eod._lib.lib().eod_remap_indices(src.data_ptr(), 1, src.numel(), lut.data_ptr(), 0, lut.numel(), 1, 21, rv.data_ptr(), err.data_ptr(),
+                                                    torch.cuda.current_stream().cuda_stream), "eod_remap_indices")
+    torch.cuda.synchronize()
+    assert intact(rb, rp) and int(err.item()) == 0 and torch.equal(rv.long(), lut.long()[src] + 1)
     # sampling scan: vectorised (HW % 16 == 0) and scalar planes
     for hw in (16 * 1025, 47 * 81):
         obs = _t((rng.uniform(size=(2, hw)) < 0.3).astype(np.uint8), cuda)
@@ -1547,11 +1571,22 @@ def test_memory_fusion_read_roi_and_episode_batch_read_roi(eod, cuda):
     with torch.no_grad():
         proj = fusion.read_roi(mem16, idx, boxes, project=True).cpu()
         want = torch.zeros_like(proj)
+        # the bias is added per level pixel before the pooling (timm.py:174), so it survives with ROIAlign(constant 1): executed here
+        ones, _ = R.roi_read([torch.ones((2, 1) + tuple(l.shape[2:])) for l in levels], boxes)
         for k, conv in enumerate(fusion.merge_map_projections):
             sel = (ref_lvl == k).nonzero().squeeze(1)
             if sel.numel():
-                want[sel] = 5.0 * torch.nn.functional.conv2d(ref[sel], conv.weight.cpu(), conv.bias.cpu())
+                want[sel] = 5.0 * (torch.nn.functional.conv2d(ref[sel], conv.weight.cpu()) + conv.bias.cpu().view(1, -1, 1, 1) * ones[sel])
     assert (proj - want).abs().max().item() <= 1e-4 * want.abs().max().item()
+    # fusion at the ROI level (north star (4)): box_pooler(fused levels) == fuse_roi(box_pooler(image-only levels)) by linearity of ROIAlign
+    with torch.no_grad():
+        res = [torch.randn((2, CO, H >> s_, W >> s_), device=cuda) for s_ in (3, 4, 5)]
+        fused = fusion(res, mem16, idx, [None, None])
+        pooled_res, _ = R.roi_read([r.cpu() for r in res], boxes)
+        pooled_fused, _ = R.roi_read([f.cpu() for f in fused], boxes)
+        got_roi = fusion.fuse_roi(pooled_res.to(cuda), mem16, idx, boxes).cpu()
+    err_roi = (got_roi - pooled_fused).abs().max().item() / pooled_fused.abs().max().item()
+    assert err_roi <= 1e-4, err_roi
     batch = eod.EpisodeBatch(2, 25, 20, C, H, W, cuda)
     batch.norm16.copy_(torch.stack(mem16))
     batch.set_indices(torch.stack(idx))
