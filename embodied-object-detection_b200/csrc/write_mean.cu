@@ -597,7 +597,7 @@ __global__ void __launch_bounds__(TmaCfg<C>::kThreads, 1)
 write_mean_chw_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t *__restrict__ idx, const uint8_t *__restrict__ samp,
                           const uint32_t *__restrict__ frame_cnt, const float *__restrict__ pix_n, const int32_t *__restrict__ active, int HW,
                           int64_t n_cells, int tiles_per_ep, int n_tiles, int group, float *__restrict__ sums, const DetArgs det,
-                          int *__restrict__ work, int chunk, uint32_t wait_hint)
+                          int *__restrict__ work, int chunk, uint32_t wait_hint, int n_stages, int no_red)
 {
     using Cfg = TmaCfg<C>;
     extern __shared__ unsigned char smem_dyn[];
@@ -663,17 +663,17 @@ write_mean_chw_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int32_
                         if (has_samp) bulk_load_1d_s(aux + Cfg::kAuxSamp, samp + (size_t)e * HW + p0, TILE_PX, fullb);
                         if (kPixN) bulk_load_1d_s(aux + Cfg::kAuxPixN, pix_n + (size_t)e * HW + p0, TILE_PX * 4, fullb);
                     }
-                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                    if (++stage == n_stages) { stage = 0; phase ^= 1; }
                 }
               }
               c = c_next;
               c_next = c_next2;
             }
-            for (int s = 0; s < Cfg::kStages; ++s) {                          // one end marker per consumer warp
+            for (int s = 0; s < n_stages; ++s) {                              // one end marker per consumer warp
                 mbar_wait_hint(empty0 + 8 * stage, phase ^ 1, wait_hint);
                 sts64(aux0 + stage * Cfg::kAuxBytes + Cfg::kAuxUnit, 0xffffffffu, 0u);
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full0 + 8 * stage) : "memory");
-                if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                if (++stage == n_stages) { stage = 0; phase ^= 1; }
             }
             if (work) {
                 // every CTA has drawn its last ticket before it counts itself done: the last one re-arms the pair for the next launch
@@ -688,6 +688,7 @@ write_mean_chw_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int32_
         return;
     }
 
+    if (warp >= n_stages) return;                                  // diagnostics: a shallower ring (EOD_TMA_STAGES)
     // ===== consumer warp `warp`: owns ring stage `warp`, lane l owns channels l, l+32, l+64, l+96 of the block =====
     const uint32_t tile = base + warp * Cfg::kUnitBytes + lane * (TILE_PX * 4);   // row `lane` of the box
     const uint32_t aux = aux0 + warp * Cfg::kAuxBytes;
@@ -762,6 +763,7 @@ write_mean_chw_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int32_
                 float inv = __shfl_sync(0xffffffffu, my_inv, p0);
                 if (!kPixN) inv = __frcp_rn((float)(__ldg(cnt_e + rc) & 0x7fffffffu));
                 float *d = dst + (size_t)rc * C;
+                if (no_red) continue;                                  // diagnostics (EOD_TMA_NO_RED): everything but the reductions
                 red_add_f32(d, __fmul_rn(a0, inv));
                 red_add_f32(d + 32, __fmul_rn(a1, inv));
                 red_add_f32(d + 64, __fmul_rn(a2, inv));
@@ -914,8 +916,10 @@ int launch_tma_kernel(const CUtensorMap &tmap, const int32_t *idx, const uint8_t
         work = nullptr;      // a captured launch would pin its ticket pair for the graph's lifetime while eager launches keep rotating through the pool
     static const int chunk_env = [] { const char *v = getenv("EOD_TMA_CHUNK"); return v ? atoi(v) : 8; }();        // groups per ticket
     static const int hint_env = [] { const char *v = getenv("EOD_TMA_WAIT_HINT_NS"); return v ? atoi(v) : 0; }();   // suspend-time hint of the barrier waits
+    static const int stages_env = [] { const char *v = getenv("EOD_TMA_STAGES"); const int n = v ? atoi(v) : Cfg::kStages; return n >= 2 && n <= Cfg::kStages ? n : Cfg::kStages; }();
+    static const int nored_env = [] { const char *v = getenv("EOD_TMA_NO_RED"); return v ? atoi(v) : 0; }();   // profiling only: wrong results
     const int chunk = work ? (chunk_env > 0 ? chunk_env : 8) : 1;
-    write_mean_chw_tma_kernel<C, kDry, kPixN, kDet><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmap, idx, samp, frame_cnt, pix_n, active, HW, n_cells, tiles_per_ep, n_tiles, group, sums, det, work, chunk, (uint32_t)hint_env);
+    write_mean_chw_tma_kernel<C, kDry, kPixN, kDet><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tmap, idx, samp, frame_cnt, pix_n, active, HW, n_cells, tiles_per_ep, n_tiles, group, sums, det, work, chunk, (uint32_t)hint_env, stages_env, nored_env);
     return eod_check_launch("eod_write_mean[tma]");
 }
 
