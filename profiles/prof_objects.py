@@ -72,4 +72,21 @@ ms_sorted = sorted(x.elapsed_time(y) for x, y in ov[2:])
 res["step_detections_ms"] = ms_sorted[len(ms_sorted) // 2]                    # median: a single slow step (allocator, clock ramp) does not move it
 res["step_detections_ms_mean"] = sum(ms_sorted) / len(ms_sorted)
 res["step_detections_frames_per_s"] = E / res["step_detections_ms"] * 1e3
+# pipelined: frame t's write side under frame t+1's projection / paste / sample (inputs resident, as the mode requires); throughput over the loop
+pb = eod.EpisodeBatch(E, mw, mh, C, H, W, dev, pipeline=True)
+for t in range(4):
+    bf, pr, bx, n = dets[t & 1]
+    pb.step_detections(depth[t % 4], pose[t % 4], shifts, intr, cell, bf, pr, bx, n)
+pb.join()
+torch.cuda.synchronize()
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+for t in range(2 * T):
+    bf, pr, bx, n = dets[t & 1]
+    pb.step_detections(depth[t % 4], pose[t % 4], shifts, intr, cell, bf, pr, bx, n)
+pb.join()
+b.record()
+torch.cuda.synchronize()
+res["step_detections_pipelined_ms"] = a.elapsed_time(b) / (2 * T)
+res["step_detections_pipelined_frames_per_s"] = E / res["step_detections_pipelined_ms"] * 1e3
 print(json.dumps({"E": E, "Kmax": Kmax, "C": C, **res}))
