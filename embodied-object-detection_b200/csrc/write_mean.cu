@@ -31,6 +31,8 @@ constexpr int TILE_PX = 32;
 // ------------------------------------------------------------------------------------------------------
 // pre-pass / post-pass: one thread per pixel, warp-level run aggregation of the cell id
 // ------------------------------------------------------------------------------------------------------
+constexpr int kCountSpan = 4;
+
 __global__ void __launch_bounds__(256) frame_count_kernel(const int32_t *__restrict__ idx, const uint8_t *__restrict__ samp,
                                                           const int32_t *__restrict__ active, int HW, int64_t n_cells,
                                                           uint32_t *__restrict__ frame_cnt, int32_t *__restrict__ slot_of_cell,
@@ -38,33 +40,45 @@ __global__ void __launch_bounds__(256) frame_count_kernel(const int32_t *__restr
 {
     const int e = blockIdx.y;
     if (active && __ldg(active + e) <= 0) return;      // episode without a kept detection: no write, no visibility (custom_rcnn.py:686)
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31;
-    const bool valid = p < HW;
-    const size_t g = (size_t)e * HW + (valid ? p : 0);
-    const int cell = valid ? __ldg(idx + g) : -1;
-    const bool s = valid && (samp ? __ldg(samp + g) != 0 : true);
-    const int prev = __shfl_up_sync(0xffffffffu, cell, 1);
-    const bool head = valid && (lane == 0 || prev != cell);
-    const unsigned heads = __ballot_sync(0xffffffffu, head);
-    const unsigned samps = __ballot_sync(0xffffffffu, s);
-    const unsigned valids = __ballot_sync(0xffffffffu, valid);
-    if (head) {
-        const unsigned above = heads & ~((2u << lane) - 1u);               // heads strictly after this lane
-        const unsigned end = above ? (unsigned)(__ffs(above) - 1) : 32u;   // run = [lane, end)
-        const unsigned run = ((end >= 32u) ? 0xffffffffu : ((1u << end) - 1u)) & ~((1u << lane) - 1u) & valids;
-        const unsigned n = __popc(samps & run);
-        uint32_t *dst = frame_cnt + (size_t)e * n_cells + cell;
-        if (n) {
-            const uint32_t old = atomicAdd(dst, n);
-            if (slot_of_cell && (old & 0x7fffffffu) == 0u) {               // first samples of this cell in this frame: claim a slot
-                const int sl = atomicAdd(n_slots + e, 1);
-                if (sl < S) {
-                    slot_of_cell[(size_t)e * n_cells + cell] = sl + 1;
-                    slot_cell[(size_t)e * S + sl] = cell;
+    // kCountSpan consecutive 256-pixel spans per CTA, all loads issued first: a quarter of the CTAs (the launch was bound by block
+    // scheduling: 77 k CTAs of a dozen instructions at E=64) and four independent loads in flight per thread
+    int cellv[kCountSpan];
+    bool sv[kCountSpan], validv[kCountSpan];
+#pragma unroll
+    for (int it = 0; it < kCountSpan; ++it) {
+        const int p = (blockIdx.x * kCountSpan + it) * (int)blockDim.x + (int)threadIdx.x;
+        validv[it] = p < HW;
+        const size_t g = (size_t)e * HW + (validv[it] ? p : 0);
+        cellv[it] = validv[it] ? __ldg(idx + g) : -1;
+        sv[it] = validv[it] && (samp ? __ldg(samp + g) != 0 : true);
+    }
+#pragma unroll
+    for (int it = 0; it < kCountSpan; ++it) {
+        const int cell = cellv[it];
+        const bool valid = validv[it];
+        const int prev = __shfl_up_sync(0xffffffffu, cell, 1);
+        const bool head = valid && (lane == 0 || prev != cell);
+        const unsigned heads = __ballot_sync(0xffffffffu, head);
+        const unsigned samps = __ballot_sync(0xffffffffu, sv[it]);
+        const unsigned valids = __ballot_sync(0xffffffffu, valid);
+        if (head) {
+            const unsigned above = heads & ~((2u << lane) - 1u);               // heads strictly after this lane
+            const unsigned end = above ? (unsigned)(__ffs(above) - 1) : 32u;   // run = [lane, end)
+            const unsigned run = ((end >= 32u) ? 0xffffffffu : ((1u << end) - 1u)) & ~((1u << lane) - 1u) & valids;
+            const unsigned n = __popc(samps & run);
+            uint32_t *dst = frame_cnt + (size_t)e * n_cells + cell;
+            if (n) {
+                const uint32_t old = atomicAdd(dst, n);
+                if (slot_of_cell && (old & 0x7fffffffu) == 0u) {               // first samples of this cell in this frame: claim a slot
+                    const int sl = atomicAdd(n_slots + e, 1);
+                    if (sl < S) {
+                        slot_of_cell[(size_t)e * n_cells + cell] = sl + 1;
+                        slot_cell[(size_t)e * S + sl] = cell;
+                    }
                 }
-            }
-        } else atomicOr(dst, 0x80000000u);
+            } else atomicOr(dst, 0x80000000u);
+        }
     }
 }
 
@@ -220,6 +234,22 @@ __global__ void __launch_bounds__(256) expand_counts_kernel(const int32_t *__res
     const size_t g = (size_t)e * HW + p;
     const uint32_t n = __ldg(frame_cnt + (size_t)e * n_cells + __ldg(idx + g)) & 0x7fffffffu;
     pix_n[g] = n ? __frcp_rn((float)n) : 0.f;
+}
+
+// four pixels per thread (HW % 4 == 0, 16-byte aligned planes): 128-bit index load and divisor store, four gathers in flight
+__global__ void __launch_bounds__(256) expand_counts_vec4_kernel(const int32_t *__restrict__ idx, const uint32_t *__restrict__ frame_cnt,
+                                                                 int HW, int64_t n_cells, float *__restrict__ pix_n)
+{
+    const int e = blockIdx.y;
+    const int p = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (p >= HW) return;
+    const size_t g = (size_t)e * HW + p;
+    const int4 c = __ldg(reinterpret_cast<const int4 *>(idx + g));
+    const uint32_t *cnt = frame_cnt + (size_t)e * n_cells;
+    const uint32_t n0 = __ldg(cnt + c.x) & 0x7fffffffu, n1 = __ldg(cnt + c.y) & 0x7fffffffu, n2 = __ldg(cnt + c.z) & 0x7fffffffu,
+                   n3 = __ldg(cnt + c.w) & 0x7fffffffu;
+    *reinterpret_cast<float4 *>(pix_n + g) = make_float4(n0 ? __frcp_rn((float)n0) : 0.f, n1 ? __frcp_rn((float)n1) : 0.f,
+                                                         n2 ? __frcp_rn((float)n2) : 0.f, n3 ? __frcp_rn((float)n3) : 0.f);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -1491,7 +1521,7 @@ extern "C" int eod_frame_count(const int32_t *idx, const uint8_t *samp, const in
 {
     EOD_REQUIRE(idx && frame_cnt, EOD_ERR_BADARG, "eod_frame_count: null pointer");
     EOD_REQUIRE(n_episodes > 0 && n_episodes <= 65535 && HW > 0 && n_cells > 0, EOD_ERR_BADARG, "eod_frame_count: bad sizes");
-    dim3 grid((HW + 255) / 256, n_episodes);
+    dim3 grid((HW + 256 * kCountSpan - 1) / (256 * kCountSpan), n_episodes);
     EOD_REQUIRE(!slot_of_cell || (slot_cell && n_slots && n_slots_max > 0), EOD_ERR_BADARG, "eod_frame_count: slot_of_cell needs slot_cell, n_slots and n_slots_max");
     frame_count_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(idx, samp, active, HW, n_cells, frame_cnt, slot_of_cell, slot_cell, n_slots, n_slots_max);
     return eod_check_launch("eod_frame_count");
@@ -1553,6 +1583,11 @@ extern "C" int eod_expand_counts(const int32_t *idx, const uint32_t *frame_cnt, 
 {
     EOD_REQUIRE(idx && frame_cnt && pix_inv_n, EOD_ERR_BADARG, "eod_expand_counts: null pointer");
     EOD_REQUIRE(n_episodes > 0 && n_episodes <= 65535 && HW > 0 && n_cells > 0, EOD_ERR_BADARG, "eod_expand_counts: bad sizes");
+    if (HW % 4 == 0 && eod_aligned16(idx) && eod_aligned16(pix_inv_n)) {
+        dim3 grid4((HW / 4 + 255) / 256, n_episodes);
+        expand_counts_vec4_kernel<<<grid4, 256, 0, (cudaStream_t)stream>>>(idx, frame_cnt, HW, n_cells, pix_inv_n);
+        return eod_check_launch("eod_expand_counts");
+    }
     dim3 grid((HW + 255) / 256, n_episodes);
     expand_counts_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(idx, frame_cnt, HW, n_cells, pix_inv_n);
     return eod_check_launch("eod_expand_counts");
