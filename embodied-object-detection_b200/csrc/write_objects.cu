@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(256) write_objects_kernel(const float *__restr
     constexpr int J = C / 32;
     __shared__ int s_list[kObjSpan];
     __shared__ int s_slot[256];
-    __shared__ uint32_t s_cover[256][kCoverObjs / 32];
+    __shared__ __align__(16) uint32_t s_cover[256][kCoverObjs / 32];
     __shared__ PasteObj s_obj[kPasted ? kCoverObjs : 1];
     __shared__ int s_wcnt[8];
     const int e = blockIdx.y;
@@ -354,43 +354,53 @@ __global__ void __launch_bounds__(256) write_objects_kernel(const float *__restr
                     for (int j = 0; j < J4; ++j) red_add_v4(dst + 128 * j, agg[j].x, agg[j].y, agg[j].z, agg[j].w);
                 }
             };
+            // The pixel's value depends only on WHICH objects cover it: consecutive samples (8 observed pixels apart in raster order)
+            // mostly sit inside the same objects, so the value is recomputed only when the cover set changes (bit-identical either way).
+            float4 acc[J4];
+            uint4 have = make_uint4(0u, 0u, 0u, 0u);                       // cover set `acc` was computed for (all-zero: none yet)
+            int cnt = 0;
             for (int i = i_beg; i < i_end; ++i) {
-                float4 acc[J4];
+                const uint4 cw = *reinterpret_cast<const uint4 *>(&s_cover[i][0]);
+                if (cw.x != have.x || cw.y != have.y || cw.z != have.z || cw.w != have.w) {
+                    have = cw;
 #pragma unroll
-                for (int j = 0; j < J4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                int cnt = 0;
-                for (int wd = 0; wd < n_words; ++wd) {
-                    unsigned todo = s_cover[i][wd];
-                    cnt += __popc(todo);
-                    while (todo) {                                         // ascending object index
-                        const int kk = wd * 32 + __ffs(todo) - 1;
-                        todo &= todo - 1;
-                        const float4 *row = reinterpret_cast<const float4 *>(f + (size_t)kk * C) + lane;
+                    for (int j = 0; j < J4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    cnt = 0;
+                    const unsigned words[4] = {cw.x, cw.y, cw.z, cw.w};
 #pragma unroll
-                        for (int j = 0; j < J4; ++j) {
-                            const float4 x = __ldg(row + 32 * j);
-                            acc[j].x = __fadd_rn(acc[j].x, x.x); acc[j].y = __fadd_rn(acc[j].y, x.y);
-                            acc[j].z = __fadd_rn(acc[j].z, x.z); acc[j].w = __fadd_rn(acc[j].w, x.w);
+                    for (int wd = 0; wd < 4; ++wd) {
+                        unsigned todo = words[wd];
+                        cnt += __popc(todo);
+                        while (todo) {                                     // ascending object index
+                            const int kk = wd * 32 + __ffs(todo) - 1;
+                            todo &= todo - 1;
+                            const float4 *row = reinterpret_cast<const float4 *>(f + (size_t)kk * C) + lane;
+#pragma unroll
+                            for (int j = 0; j < J4; ++j) {
+                                const float4 x = __ldg(row + 32 * j);
+                                acc[j].x = __fadd_rn(acc[j].x, x.x); acc[j].y = __fadd_rn(acc[j].y, x.y);
+                                acc[j].z = __fadd_rn(acc[j].z, x.z); acc[j].w = __fadd_rn(acc[j].w, x.w);
+                            }
+                        }
+                    }
+                    // / number of covering objects (custom_rcnn.py:899).  Almost always 1 or 2: a power of two divides exactly like the
+                    // multiplication by its (exact) reciprocal, so the 4*J4 IEEE divides are only paid for 3, 5, 6, 7, ... objects
+                    if (cnt > 1) {
+                        if ((cnt & (cnt - 1)) == 0) {
+                            const float r = 1.0f / (float)cnt;
+#pragma unroll
+                            for (int j = 0; j < J4; ++j)
+                                acc[j] = make_float4(__fmul_rn(acc[j].x, r), __fmul_rn(acc[j].y, r), __fmul_rn(acc[j].z, r), __fmul_rn(acc[j].w, r));
+                        } else {
+                            const float n_px = (float)cnt;
+#pragma unroll
+                            for (int j = 0; j < J4; ++j)
+                                acc[j] = make_float4(__fdiv_rn(acc[j].x, n_px), __fdiv_rn(acc[j].y, n_px), __fdiv_rn(acc[j].z, n_px), __fdiv_rn(acc[j].w, n_px));
                         }
                     }
                 }
                 const int slot = s_slot[i];
                 if (cnt == 0 || slot < 0 || slot >= S) continue;           // cnt == 0 cannot happen for a sampled pixel; slot overflow: caller error
-                // / number of covering objects (custom_rcnn.py:899).  Almost always 1 or 2: a power of two divides exactly like the
-                // multiplication by its (exact) reciprocal, so the 4*J4 IEEE divides are only paid for 3, 5, 6, 7, ... objects
-                if (cnt > 1) {
-                    if ((cnt & (cnt - 1)) == 0) {
-                        const float r = 1.0f / (float)cnt;
-#pragma unroll
-                        for (int j = 0; j < J4; ++j)
-                            acc[j] = make_float4(__fmul_rn(acc[j].x, r), __fmul_rn(acc[j].y, r), __fmul_rn(acc[j].z, r), __fmul_rn(acc[j].w, r));
-                    } else {
-                        const float n_px = (float)cnt;
-#pragma unroll
-                        for (int j = 0; j < J4; ++j)
-                            acc[j] = make_float4(__fdiv_rn(acc[j].x, n_px), __fdiv_rn(acc[j].y, n_px), __fdiv_rn(acc[j].z, n_px), __fdiv_rn(acc[j].w, n_px));
-                    }
-                }
                 if (slot != agg_slot) {
                     flush();
                     agg_slot = slot;
