@@ -910,7 +910,11 @@ def test_step_detections_two_streams_matches_serial(eod, cuda):
         keep.append((depth, pose) + args)                                   # the pipelined batch is fed after the loop, back to back
         assert torch.equal(a.idx, b.idx)
         for x, y in zip(la, lb):
-            assert torch.equal(x, y), t
+            # the two batches reduce in scheduling order: a few fp16 rows of their read tables may differ in the last bit
+            d = (x.contiguous().view(torch.int16).int() - y.contiguous().view(torch.int16).int()).abs()
+            assert int(d.max()) <= 1 and float((d != 0).float().mean()) < 1e-3, t
+            if t == 0:
+                assert torch.equal(x, y)                                       # both tables still empty
         assert torch.equal(a.counts, b.counts) and torch.equal(a.sums == 0, b.sums == 0)
         assert (a.sums - b.sums).abs().max().item() <= SUM_TOL * max(b.sums.abs().max().item(), 1e-30)
         lc_all.append(lb)
