@@ -1,5 +1,5 @@
 """Command-line front end of the adversarial sweeps (tests/stress_cases.py) for sweeps larger than the bounded ones the GPU test
-tier runs:  python profiles/stress.py [read|paste|geometry|dense_write|objects|fuse ...] [CASES=n]"""
+tier runs:  python profiles/stress.py [read|paste|geometry|dense_write|objects|fuse|linear ...] [CASES=n]"""
 import os
 import sys
 
@@ -10,7 +10,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import stress_cases as S  # noqa: E402
 
-DEFAULT = {"read": 36, "paste": 60, "geometry": 12, "dense_write": 300, "objects": 30, "fuse": 0}
+DEFAULT = {"read": 36, "paste": 60, "geometry": 12, "dense_write": 300, "objects": 30, "fuse": 0, "linear": 96}
 names = [a for a in sys.argv[1:] if a in DEFAULT] or list(DEFAULT)
 dev = torch.device("cuda:0")
 rc = 0

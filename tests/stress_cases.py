@@ -360,3 +360,46 @@ many tiles per CTA, all level combinations, bias on/off, sum / mem_only.  Found 
     return len(msgs), n_bad_total[0], msgs
 
 
+
+
+def stress_linear(dev, cases):
+    """Randomised sweep of the tcgen05 row GEMM (eod_linear_rows, 3xTF32) against fp64: shapes from one row to several tiles, K with and
+without a 32-wide tail, N over one and two TMEM column blocks, every stride combination (contiguous / transposed / padded / unaligned
+operands), gathered input rows, scattered output rows with a device-side row count, rows of very different scale.  |error| <= 1e-5 of
+the result's scale, and rows that must not be written keep their fill."""
+    msgs = []
+    rng = np.random.default_rng(515)
+    bad = 0
+    for case in range(cases):
+        M = int(rng.choice([1, 2, 31, 127, 128, 129, 300, 700]))
+        K = int(rng.choice([4, 20, 32, 36, 64, 96, 256, 500, 512]))
+        N = 16 * int(rng.integers(1, 33))
+        g = torch.Generator(device=dev).manual_seed(case)
+        a = torch.randn((M, K), device=dev, generator=g) * torch.rand((M, 1), device=dev, generator=g).mul(8).sub(4).exp()
+        w = torch.randn((N, K), device=dev, generator=g) / K ** 0.5
+        b = torch.randn((N,), device=dev, generator=g) if case % 3 else None
+        scale_f = float(rng.choice([1.0, 5.0, 0.125]))
+        ka, kw = case % 4, (case // 4) % 3
+        aa = a if ka == 0 else (a.t().contiguous().t() if ka == 1 else torch.zeros((M, K + 7), device=dev)[:, 5:5 + K].copy_(a) if ka == 2 else a)
+        ww = w if kw == 0 else (w.t().contiguous().t() if kw == 1 else torch.zeros((N, K + 12), device=dev)[:, 3:3 + K].copy_(w))
+        ref = (a.double() @ w.double().t() + (b.double() if b is not None else 0.0)) * scale_f
+        tol = 1e-5 * float(ref.abs().max())
+        if ka == 3:                                                         # gather + scatter + device-side count
+            perm = torch.randperm(M, device=dev, generator=g)
+            n_live = int(rng.integers(1, M + 1))
+            out = torch.full((M + 4, N + 4), 3.0, device=dev)
+            ops.linear_rows(a, ww, b, scale_f, out=out, a_off=(perm * K).to(torch.int64), m_count=torch.tensor([n_live], dtype=torch.int32, device=dev),
+                            n_rows=M, y_dst=(perm + 2).to(torch.int64))
+            live = perm[:n_live]
+            err = float((out[live + 2][:, :N].double() - ref[live]).abs().max())
+            keep = torch.ones(M + 4, dtype=torch.bool, device=dev)
+            keep[live + 2] = False
+            clean = bool((out[keep] == 3.0).all()) and bool((out[:, N:] == 3.0).all())
+        else:
+            got = ops.linear_rows(aa, ww, b, scale_f)
+            err = float((got.double() - ref).abs().max())
+            clean = True
+        ok = err <= tol and clean
+        bad += int(not ok)
+        msgs.append(f"{'ok' if ok else 'MISMATCH'} linear case {case}: M={M} K={K} N={N} a-kind {ka} w-kind {kw} bias {b is not None} err/scale {err / max(tol * 1e5, 1e-30):.2e} clean {clean}")
+    return cases, bad, msgs

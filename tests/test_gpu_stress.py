@@ -13,7 +13,7 @@ import stress_cases as S  # noqa: E402
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name,cases", [("geometry", 8), ("read", 24), ("paste", 24), ("dense_write", 150), ("objects", 24), ("fuse", 0)])
+@pytest.mark.parametrize("name,cases", [("geometry", 8), ("read", 24), ("paste", 24), ("dense_write", 150), ("objects", 24), ("fuse", 0), ("linear", 36)])
 def test_stress_sweep(cuda, name, cases):
     n, bad, msgs = getattr(S, "stress_" + name)(cuda, cases)
     assert n > 0
