@@ -84,7 +84,7 @@ int eod_backproject_quantize_u16(const uint16_t *depth, double depth_div, const 
                                  int order, float z_clip, int32_t *idx, int32_t *q2, uint8_t *outlier, float *height,
                                  float *world, eod_stream_t stream);
 
-/* Offline builder's quantise step on STORED world coordinates (sensor_data/*.h5 'projection_indices'):
+/* Offline builder's quantise step on STORED world coordinates (sensor_data/<name>.h5 'projection_indices'):
  * SMNet/build_memory_data.py:135-143.  world (n_points,3) f32 -> idx (n_points) i32, clipped, bit-exact. */
 int eod_quantize_world(const float *world, int64_t n_points, float shift_x, float shift_z, float cell, int map_w, int map_h,
                        int order, int32_t *idx, eod_stream_t stream);
@@ -314,7 +314,7 @@ int eod_reset_episodes(float *counts, float *sums, void *norm16, const int32_t *
 int eod_refresh_norm16(const float *counts, const float *sums, void *norm16, const int32_t *mask, int n_episodes, int64_t n_cells,
                        int C, eod_stream_t stream);
 
-/* Range check of an externally supplied index plane (proj_indices of memory_data/*.h5, SMNet/loader.py:185-186; the reference
+/* Range check of an externally supplied index plane (proj_indices of memory_data/<name>.h5, SMNet/loader.py:185-186; the reference
  * raises IndexError on a bad id, timm.py:147).  Every kernel here uses a cell id as a row offset, so ids outside [0, n_cells)
  * must not reach them: err[0] (device int32, caller zeroes it) += number of out-of-range ids; idx32_out (nullable, n int32)
  * receives the ids with out-of-range ones clamped into the grid.  idx: n ids, int32 or int64 (idx_is_i64). */

@@ -35,6 +35,16 @@ def test_library_exports_every_declared_symbol(eod):
     assert set(eod.ops._LAUNCHES) == set(declared) - no_launch
 
 
+def test_header_is_plain_c(tmp_path):
+    """include/eod_memory.h is the drop-in boundary: it must compile as C99 and as C++17 without warnings (no torch / CUDA types)."""
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "eod_memory.h"\nint probe(void) { return eod_version(); }\n')
+    inc = os.path.join(ROOT, "include")
+    for cmd in (["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only"], ["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++"]):
+        res = subprocess.run(cmd + ["-I", inc, str(src)], capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr
+
+
 def test_no_library_gemm_in_product_code():
     """Every dense contraction of the path runs on the in-tree tcgen05 kernels (csrc/project_fuse.cu, csrc/linear.cu): the package
     holds no call into the library GEMMs (torch.matmul in the training path and the A7'' forward projection)."""
