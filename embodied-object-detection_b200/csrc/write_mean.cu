@@ -851,59 +851,58 @@ __global__ void __launch_bounds__(256, 3) write_mean_hwc_kernel(const void *__re
         const unsigned samps = __ballot_sync(0xffffffffu, my_s);
         const uint32_t *cnt_e = frame_cnt + (size_t)e * n_cells;
         float *sums_e = sums + (size_t)e * n_cells * C;
-        float4 acc[V];
-#pragma unroll
-        for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-        int cur = -1;
-        bool any = false;
-        auto flush = [&]() {
-            if (cur >= 0 && any) {
-                const float n = (float)(__ldg(cnt_e + cur) & 0x7fffffffu);
-#pragma unroll
-                for (int v = 0; v < V; ++v)
-                    red_add_v4(sums_e + (size_t)cur * C + v * 128 + 4 * lane, __fdiv_rn(acc[v].x, n), __fdiv_rn(acc[v].y, n),
-                               __fdiv_rn(acc[v].z, n), __fdiv_rn(acc[v].w, n));
-            }
-        };
-        // batches of PB pixels: the batch's rows are requested first (32 registers of raw data per lane: 4 fp32 pixels or
-        // 8 sixteen-bit ones at C=256), then walked - the same bytes in flight whatever the feature type
+        // All sampled pixels of the strip that fall into one cell form ONE group, contiguous or not (MATCH.ANY, as in the CHW kernel: with
+        // noisy depth a strip alternates between a few cells and every extra run would cost V more 128-bit reductions).  Groups are
+        // served in the order of their first pixel; a group's pixels are walked in raster order, in batches of PB whose rows are all
+        // requested before the first one is added (32 registers of raw data per lane: 4 fp32 pixels or 8 sixteen-bit ones at C=256 -
+        // the same bytes in flight whatever the feature type).
+        const unsigned grp = __match_any_sync(0xffffffffu, my_cell);
+        unsigned leaders = __ballot_sync(0xffffffffu, (int)lane < pvalid && (unsigned)(__ffs(grp) - 1) == lane);
         constexpr int PB = (F == FEAT_F32 ? 8 : 16) / V > 0 ? (F == FEAT_F32 ? 8 : 16) / V : 1;
+        while (leaders) {
+            const int lead = __ffs(leaders) - 1;
+            leaders &= leaders - 1;
+            unsigned rem = __shfl_sync(0xffffffffu, grp, lead) & samps;          // sampled pixels of this cell
+            if (rem == 0u) continue;
+            const int cell = __shfl_sync(0xffffffffu, my_cell, lead);
+            float4 acc[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
-        for (int pb = 0; pb < pvalid; pb += PB) {
-            FeatRaw<F> raw[PB][V];
+            while (rem) {
+                FeatRaw<F> raw[PB][V];
+                unsigned batch = rem;
+                int nb = 0;
 #pragma unroll
-            for (int b = 0; b < PB; ++b) {
-                const int p = pb + b;
-                if (p < pvalid && ((samps >> p) & 1u)) {
-                    const char *row = reinterpret_cast<const char *>(feat) + (pix0 + p) * C * (F == FEAT_F32 ? 4 : 2);
+                for (int b = 0; b < PB; ++b) {
+                    if (batch) {
+                        const int p = __ffs(batch) - 1;
+                        batch &= batch - 1;
+                        ++nb;
+                        const char *row = reinterpret_cast<const char *>(feat) + (pix0 + p) * C * (F == FEAT_F32 ? 4 : 2);
 #pragma unroll
-                    for (int v = 0; v < V; ++v) raw[b][v] = load_feat_raw<F>(row, v * 32 + (int)lane);
+                        for (int v = 0; v < V; ++v) raw[b][v] = load_feat_raw<F>(row, v * 32 + (int)lane);
+                    }
                 }
-            }
+                rem = batch;
 #pragma unroll
-            for (int b = 0; b < PB; ++b) {
-                const int p = pb + b;
-                if (p >= pvalid) break;
-                const int cell = __shfl_sync(0xffffffffu, my_cell, p);
-                if (cell != cur) {
-                    flush();
-                    cur = cell;
-                    any = false;
+                for (int b = 0; b < PB; ++b) {
+                    if (b < nb) {
 #pragma unroll
-                    for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                if ((samps >> p) & 1u) {
-                    any = true;
-#pragma unroll
-                    for (int v = 0; v < V; ++v) {
-                        const float4 f = widen_feat<F>(raw[b][v]);
-                        acc[v].x = __fadd_rn(acc[v].x, f.x); acc[v].y = __fadd_rn(acc[v].y, f.y);
-                        acc[v].z = __fadd_rn(acc[v].z, f.z); acc[v].w = __fadd_rn(acc[v].w, f.w);
+                        for (int v = 0; v < V; ++v) {
+                            const float4 f = widen_feat<F>(raw[b][v]);
+                            acc[v].x = __fadd_rn(acc[v].x, f.x); acc[v].y = __fadd_rn(acc[v].y, f.y);
+                            acc[v].z = __fadd_rn(acc[v].z, f.z); acc[v].w = __fadd_rn(acc[v].w, f.w);
+                        }
                     }
                 }
             }
+            const float n = (float)(__ldg(cnt_e + cell) & 0x7fffffffu);
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+                red_add_v4(sums_e + (size_t)cell * C + v * 128 + 4 * lane, __fdiv_rn(acc[v].x, n), __fdiv_rn(acc[v].y, n), __fdiv_rn(acc[v].z, n),
+                           __fdiv_rn(acc[v].w, n));
         }
-        flush();
     }
 }
 
