@@ -404,7 +404,7 @@ def main_gpu(args, rank, local_rank, world):
         except Exception as exc:                                     # a failed check must be visible, never silently dropped
             parity = {"ok": False, "error": repr(exc)[:300]}
 
-    extras = run_extras(eod, batch, dev, depth, pose, shifts, intr) if (rank == 0 and not args.no_extras) else None
+    extras = run_extras(eod, batch, dev, depth, pose, shifts, intr, slabs) if (rank == 0 and not args.no_extras) else None
     if world > 1:
         torch.distributed.barrier()
     # ---- e2e through the plugin API with host buffers (rank-local, then max over ranks) ----
@@ -572,7 +572,7 @@ def run_grid_1000(eod, dev, depth, pose, shift_h, intr, slabs, depth_h, T_h, my_
     return out
 
 
-def run_extras(eod, batch, dev, depth, pose, shifts, intr):
+def run_extras(eod, batch, dev, depth, pose, shifts, intr, slabs=None):
     """Two more stages of the same path, timed on the bench batch after the headline loop (CUDA events, resident inputs; not part
     of `value`): the tensor-core projection + fusion of the three read levels and the reference's live object
     regime (kept detections as 28x28 mask probabilities + boxes; mask pasting folded into the write).  Best effort."""
@@ -620,6 +620,39 @@ def run_extras(eod, batch, dev, depth, pose, shifts, intr):
         ms = a.elapsed_time(b) / N_FRAMES
         out["object_regime"] = {"ms_per_frame_step": ms, "frames_per_s": E / ms * 1e3,
                                 "shape": f"E={E}, C={C}, <= {Kmax} detections per frame, 28x28 mask probabilities + boxes, every 8th observed pixel"}
+        if slabs is not None:
+            # the same dense frame loop with the features taken as channels-last fp32 (EOD_LAYOUT_HWC): the resident random slabs are
+            # simply read as (E,H,W,C) - what a backbone running in torch.channels_last hands over; one step = N_FRAMES frame-steps
+            layout0, pipe0 = batch.layout, batch.pipeline
+            try:
+                batch.join()
+                batch.layout, batch.pipeline = eod._lib.LAYOUT_HWC, True
+                hwc = [s_.view(E, H, W, C) for s_ in slabs]
+                batch.reset()
+                for t in range(3):
+                    batch.step(depth[t], pose[t], shifts, intr, float(CELL), hwc[t & 1])
+                batch.join()
+                batch.profile(True)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for t in range(N_FRAMES):
+                    batch.step(depth[t], pose[t], shifts, intr, float(CELL), hwc[t & 1])
+                batch.join()
+                b.record()
+                torch.cuda.synchronize()
+                st = batch.stage_ms()
+                batch.profile(False)
+                ms = a.elapsed_time(b) / N_FRAMES
+                peak, _ = measured_peak_gbs()
+                fb = E * (N_PIX * C * 4 + N_PIX * 4)
+                out["dense_hwc_f32"] = {"ms_per_frame_step": ms, "frames_per_s": E / ms * 1e3, "write_launch_ms": st.get("write"),
+                                        "write_GBps": fb / st["write"] / 1e6 if st.get("write") else None,
+                                        "write_frac_of_peak": fb / st["write"] / 1e6 / peak if st.get("write") else None,
+                                        "kernel": "write_mean_hwc_kernel<256, f32>", "note": "same loop as the headline, features read channels-last"}
+            finally:
+                batch.join()
+                batch.layout, batch.pipeline = layout0, pipe0
+                batch.reset()
     except Exception as exc:                                                          # never lose the headline line to an extra
         out["error"] = repr(exc)[:200]
     return out
