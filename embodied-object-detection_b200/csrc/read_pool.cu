@@ -11,6 +11,8 @@
 //
 // Summation order == ATen CPU avg_pool2d: fp32, start from 0, row-major over the window, then / k^2;
 // the fp16 roundings between levels (timm.py:168) are reproduced, so outputs are bit-identical.
+#include <stdlib.h>
+
 #include "eod_common.cuh"
 
 namespace {
@@ -442,7 +444,8 @@ int launch(const void *table, int mem_is_f16, const float *counts, const void *i
     const int64_t n_items = (int64_t)E * (H / 16) * (W / 16);      // C in {128, 256, 512}: one warp covers all channels of a quadrant (V = C / 32 per lane)
     EOD_REQUIRE(n_items < (1ll << 31) - (1ll << 24), EOD_ERR_BADARG, "eod_read_pool: too many quadrants for one launch");
     int64_t blocks = (n_items + kReadWarps - 1) / kReadWarps;
-    const int64_t cap = (int64_t)eod_num_sms() * 4 * 4;          // 3-4 resident CTAs per SM, a few waves: each warp walks several items with prefetch
+    static const int cap_env = [] { const char *v = getenv("EOD_READ_CTAS_PER_SM"); const int k = v ? atoi(v) : 16; return k > 0 ? k : 16; }();   // tuning knob
+    const int64_t cap = (int64_t)eod_num_sms() * cap_env;        // default 16: 3-4 resident CTAs per SM, a few waves: each warp walks several items with prefetch
     if (blocks > cap) blocks = cap;
     dim3 grid((unsigned)blocks), block(kReadWarps * 32);
     __half *l0 = (__half *)L0, *l1 = (__half *)L1, *l2 = (__half *)L2;
