@@ -19,6 +19,8 @@ read gathers from, refreshed per frame for the visible cells only.  State never 
 """
 from __future__ import annotations
 
+import os
+
 import math
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -73,7 +75,7 @@ class EpisodeBatch:
         # per-frame planes, double buffered (frame t uses buffer t & 1)
         self._idx2 = [torch.zeros((self.E, height, width), dtype=torch.int32, **z) for _ in range(2)]
         self._frame_cnt2 = [torch.zeros((self.E, self.n_cells), dtype=torch.int32, **z) for _ in range(2)]
-        self._pix_inv_n2 = [torch.zeros((self.E, height, width), dtype=torch.float32, **z) for _ in range(2)]
+        self._pix_inv_n2: Optional[List[torch.Tensor]] = None      # (E,H,W) f32 reciprocal divisors, created on first use (pixel_divisors mode)
         self.levels = [torch.empty((self.E, height >> s, width >> s, self.C), dtype=torch.float16, **z) for s in (3, 4, 5)]
         self._k = 0
         self._t = 0
@@ -88,6 +90,11 @@ class EpisodeBatch:
         self._slots: Optional[ops.ObjectSlots] = None      # workspace of write_objects, created on first use
         self._det_ws: Optional[ops.DetWorkspace] = None    # workspace of the deterministic write (variant=WRITE_DET)
         self.det_runs_per_episode = 0                      # 0: HW/4 runs per episode and frame
+        # CHW write: True = the divisors 1/n_cell travel with the tile (expand_counts pre-pass + 4 B per pixel); False = the consumer
+        # looks a group's divisor up in frame_cnt itself (one dependent L2 load per group, no pre-pass)
+        # (round 2: with the pixels of a tile grouped by cell there are few look-ups, and the pre-pass plus its 158 MB per 64-episode
+        # frame-step cost more than they saved: 16.8 k -> 17.6 k frames/s in the bench, same bits)
+        self.pixel_divisors = os.environ.get("EOD_PIXEL_DIVISORS", "0") == "1"
         self.read_frozen = False      # True: finalize leaves norm16 alone (longterm snapshot read); refresh_read() updates it
         self.stage_events = None      # dict(stage -> [(start, end) CUDA events]) when profiling is on
 
@@ -102,6 +109,8 @@ class EpisodeBatch:
 
     @property
     def pix_inv_n(self) -> torch.Tensor:
+        if self._pix_inv_n2 is None:
+            self._pix_inv_n2 = [torch.zeros((self.E, self.H, self.W), dtype=torch.float32, device=self.device) for _ in range(2)]
         return self._pix_inv_n2[self._k]
 
     def profile(self, on: bool = True) -> None:
@@ -196,7 +205,7 @@ class EpisodeBatch:
 
     def _count(self, samp: Optional[torch.Tensor], active: Optional[torch.Tensor] = None) -> None:
         self._timed("count", ops.frame_count, self.idx, samp, self.frame_cnt, active)
-        if self.variant != WRITE_DET and self.layout == LAYOUT_CHW:      # only the TMA-staged CHW kernel takes per-pixel divisors
+        if self.variant != WRITE_DET and self.layout == LAYOUT_CHW and self.pixel_divisors:      # only the TMA-staged CHW kernel takes per-pixel divisors
             self._timed("expand", ops.expand_counts, self.idx, self.frame_cnt, self.pix_inv_n)
 
     def _write(self, feat: torch.Tensor, samp: Optional[torch.Tensor], active: Optional[torch.Tensor] = None) -> None:
@@ -208,7 +217,7 @@ class EpisodeBatch:
             self._timed("write", ops.write_mean_det, feat, self.idx, samp, self.frame_cnt, self.sums, self._det_ws)
             return
         self._timed("write", ops.write_mean, feat, self.idx, samp, self.frame_cnt, self.sums, self.layout, self.variant,
-                    self.pix_inv_n if self.layout == LAYOUT_CHW else None, active)
+                    self.pix_inv_n if (self.layout == LAYOUT_CHW and self.pixel_divisors) else None, active)
 
     def _finalize(self) -> None:
         # read_frozen (TEST_TYPE longterm): counts only - the fp16 table the read gathers from is a snapshot

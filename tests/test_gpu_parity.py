@@ -966,6 +966,33 @@ def test_batch_without_fp16_table_reads_the_same_bits(eod, cuda):
         b.read()
 
 
+def test_divisor_lookup_and_divisor_plane_agree(eod, cuda):
+    """The CHW write takes a group's divisor 1/n_cell either from frame_cnt (default since round 2) or from the per-pixel plane that
+    eod_expand_counts prepares (``pixel_divisors = True``): same counts, same touched set, sums equal up to reduction order."""
+    E, C, H, W, mw, mh, T = 2, 256, 96, 128, 60, 45, 3
+    cell = 0.2
+    eps = [eod.episodes.make_episode(800 + e, T, H, W, mw, mh, cell) for e in range(E)]
+    intr = eod.compute_intrinsics(W, H, math.radians(67.5))
+    shifts = _t(np.stack([np.concatenate([np.zeros(3, np.float32), ep.map_world_shift]) for ep in eps]), cuda)
+    a = eod.EpisodeBatch(E, mw, mh, C, H, W, cuda)
+    b = eod.EpisodeBatch(E, mw, mh, C, H, W, cuda)
+    assert a.pixel_divisors is False and a._pix_inv_n2 is None
+    b.pixel_divisors = True
+    g = torch.Generator(device=cuda).manual_seed(4)
+    for t in range(T):
+        Tm = eod.transform3d(torch.from_numpy(np.stack([ep.xyzhe[t] for ep in eps])))
+        pose = Tm[:, :3].reshape(E, 12).to(cuda)
+        depth = _t(np.stack([ep.depth[t] for ep in eps]), cuda)
+        feat = torch.randn((E, C, H, W), device=cuda, generator=g)
+        samp = (torch.rand((E, H, W), device=cuda, generator=g) < 0.6).to(torch.uint8) if t == 1 else None
+        a.step(depth, pose, shifts, intr, cell, feat, samp)
+        b.step(depth, pose, shifts, intr, cell, feat, samp)
+    torch.cuda.synchronize()
+    assert b._pix_inv_n2 is not None and a._pix_inv_n2 is None
+    assert torch.equal(a.counts, b.counts) and torch.equal(a.sums == 0, b.sums == 0)
+    assert (a.sums - b.sums).abs().max().item() <= 1e-6 * b.sums.abs().max().item()
+
+
 def test_graphed_step_detections_matches_eager(eod, cuda):
     """capture_step_detections (one CUDA graph per frame: the online single-robot loop) against the eager step_detections on a twin
     batch, frame by frame, with an eager frame interleaved: identical indices, fp16 levels, counts and touched sets, sums within the
