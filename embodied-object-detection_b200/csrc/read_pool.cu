@@ -309,6 +309,8 @@ __global__ void __launch_bounds__(kReadWarps * 32, (C >= 512 ? 2 : (C >= 256 ? 3
         int cur_cell = -1, oth_cell = -1;
         Vec<V> cur = vzero<V>(), oth = vzero<V>();
         Vec<V> l1acc = vzero<V>();
+        __half *l0_dst = L0 + (((size_t)ce * h0 + cqy * 2) * w0 + cqx * 2) * C + V * g;     // L0 pixel (2 qy, 2 qx): the other three are at + C, + w0 * C, + (w0 + 1) * C
+        asm volatile("" : "+l"(l0_dst));
 #pragma unroll 1
         for (int l0 = 0; l0 < 4; ++l0) {                   // L0 pixels of the quadrant, row-major
             // The four 4x4 windows of this L0 pixel.  A window whose 16 pixels hit ONE cell needs no additions: the
@@ -336,12 +338,13 @@ __global__ void __launch_bounds__(kReadWarps * 32, (C >= 512 ? 2 : (C >= 256 ? 3
                     unsigned rest = (unsigned)d.z & ~1u;        // run heads after the first pixel
                     if (wc != cur_cell) cur = finish<V>(fetch(wc));
                     cur_cell = wc;
-                    if (rest == 0u) {                        // one cell for the whole window
-                        s2 = vadd<V>(s2, cur);
-                        continue;
-                    }
-                    Vec<V> s4 = vzero<V>();
-                    if (wb >= 0) {
+                    Vec<V> s4;
+                    if (rest == 0u) {
+                        // one cell for the whole window: 16 * x is exact for an fp16-valued x, so the common tail below adds exactly x
+                        // (one join point for s2: the separate `s2 += cur; continue` cost eight register moves per window)
+                        s4 = vscale<V>(cur, 16.0f);
+                    } else if (wb >= 0) {
+                        s4 = vzero<V>();
                         // exactly two cells: cur = row of A (first pixel), oth = row of B
                         if (wb != oth_cell) oth = finish<V>(fetch(wb));
                         oth_cell = wb;
@@ -356,6 +359,7 @@ __global__ void __launch_bounds__(kReadWarps * 32, (C >= 512 ? 2 : (C >= 256 ? 3
                             for (int r = 0; r < 4; ++r, bm >>= 4) vadd_row2<V>(s4, cur, oth, bm, 1);
                         }
                     } else {
+                        s4 = vzero<V>();
                         // three or more cells in the window: 2-8 runs instead of 16 pixels; the walk pays the fetch / fp16->fp32
                         // conversion / bookkeeping per RUN and V/2 packed adds per pixel.  (A straight-line per-pixel walk with a
                         // head-bit test per pixel was tried in r2: the compiler if-converts it into predicated copies, 52.6 M
@@ -387,8 +391,7 @@ __global__ void __launch_bounds__(kReadWarps * 32, (C >= 512 ? 2 : (C >= 256 ? 3
                 }
                 v0 = vround_half<V>(vscale<V>(s2, 0.25f));      // avg_pool2d(2) -> half (timm.py:168, level 0)
             }
-            const int y0 = cqy * 2 + (l0 >> 1), x0 = cqx * 2 + (l0 & 1);
-            vstore_half<V>(L0 + (((size_t)ce * h0 + y0) * w0 + x0) * C + V * g, v0);
+            vstore_half<V>(l0_dst + ((l0 >> 1) * w0 + (l0 & 1)) * C, v0);
             l1acc = vadd<V>(l1acc, v0);
         }
         const Vec<V> v1 = vround_half<V>(vscale<V>(l1acc, 0.25f));  // level 1
