@@ -754,16 +754,18 @@ def run_e2e_variants(eod, batch, dev, depth_h, pose_h, shifts, intr, args, world
     n_fr = args.e2e_frames
     pin_depth = torch.from_numpy(depth_h).permute(1, 0, 2, 3).contiguous().pin_memory()      # (T, E, H, W)
     pin_pose = pose_h.contiguous().pin_memory()
+    NB = 3                                               # input staging depth of the object-regime arms (the dense arms use two)
     dev_depth = [torch.empty((E, H, W), device=dev) for _ in range(2)]
-    dev_pose = [torch.empty((E, 12), device=dev) for _ in range(2)]
-    ready = [torch.cuda.Event() for _ in range(2)]
-    freed = [torch.cuda.Event() for _ in range(2)]
+    dev_pose = [torch.empty((E, 12), device=dev) for _ in range(NB)]
+    ready = [torch.cuda.Event() for _ in range(NB)]
+    freed = [torch.cuda.Event() for _ in range(NB)]
 
     def run(upload_extra, step_fn, d2h_fn, n_frames, depth_src=None, depth_dst=None):
         depth_src = pin_depth if depth_src is None else depth_src
         depth_dst = dev_depth if depth_dst is None else depth_dst
 
-        fin = [None, None]                               # finalize event of the last step that read buffer b (pipelined steps outlive the call)
+        nb = len(depth_dst)                              # 2: double buffered; 3: the upload of frame t+1 waits for frame t-2, not t-1
+        fin = [None] * nb                                # finalize event of the last step that read buffer b (pipelined steps outlive the call)
 
         def upload(t, b):
             with torch.cuda.stream(copy_s):
@@ -779,9 +781,9 @@ def run_e2e_variants(eod, batch, dev, depth_h, pose_h, shifts, intr, args, world
             batch.reset()
             upload(0, 0)
             for t in range(n_frames):
-                b = t & 1
+                b = t % nb
                 if t + 1 < n_frames:
-                    upload(t + 1, b ^ 1)
+                    upload(t + 1, (t + 1) % nb)
                 comp_s.wait_event(ready[b])
                 step_fn(b)
                 fin[b] = batch._e_fin
@@ -836,26 +838,49 @@ def run_e2e_variants(eod, batch, dev, depth_h, pose_h, shifts, intr, args, world
             f, p_, b_ = eod.episodes.make_mask_head_detections(rng, H, W, C, (4, Kmax), 28)
             n[v, e] = f.shape[0]; bf[v, e, : n[v, e]], pr[v, e, : n[v, e]], bx[v, e, : n[v, e]] = f, p_, b_
     pin_det = [torch.from_numpy(x).pin_memory() for x in (bf, pr, bx, n)]
-    dev_det = [[torch.empty(x.shape[1:], dtype=x.dtype, device=dev) for x in pin_det] for _ in range(2)]
+    dev_det = [[torch.empty(x.shape[1:], dtype=x.dtype, device=dev) for x in pin_det] for _ in range(NB)]
     host_l2 = torch.empty(batch.levels[2].shape, dtype=torch.float16).pin_memory()
 
     def up_det(t, b):
         for d, p_ in zip(dev_det[b], pin_det):
             d.copy_(p_[t % n_var], non_blocking=True)
 
+    # D2H of the coarsest pooled level off the compute stream: a device-to-device copy into a double-buffered staging tensor (6 us) is
+    # ordered behind the read; the copy to pinned host memory runs on its own stream, so the next frame-step's launches do not queue
+    # behind 0.18 ms of PCIe (the inline copy serialised frame-steps: profiles/diag_e2e_obj.py)
+    d2h_s = torch.cuda.Stream(device=dev)
+    stage_l2 = [torch.empty_like(batch.levels[2]) for _ in range(2)]
+    d2h_done = [torch.cuda.Event() for _ in range(2)]
+    for ev_ in d2h_done:
+        ev_.record(comp_s)
+    d2h_k = [0]
+
+    def d2h_l2():
+        k = d2h_k[0] & 1
+        d2h_k[0] += 1
+        comp_s.wait_event(d2h_done[k])                     # the staging half is free again
+        stage_l2[k].copy_(batch.levels[2])
+        ready_ev = torch.cuda.Event()
+        ready_ev.record(comp_s)
+        with torch.cuda.stream(d2h_s):
+            d2h_s.wait_event(ready_ev)
+            host_l2.copy_(stage_l2[k], non_blocking=True)
+            d2h_done[k].record(d2h_s)
+
     n_fr_obj = 5 * n_fr
     batch.pipeline = True          # the write side of frame t runs under the staging / geometry / paste of frame t+1; inputs are ordered on the
-    sec = run(up_det, lambda b: batch.step_detections(dev_depth[b], dev_pose[b], shifts, intr, float(CELL), *dev_det[b], inputs_ready=False),   # caller's stream
-              lambda: host_l2.copy_(batch.levels[2], non_blocking=True), n_fr_obj)
+    dev_depth3 = dev_depth + [torch.empty((E, H, W), device=dev) for _ in range(NB - 2)]
+    sec = run(up_det, lambda b: batch.step_detections(dev_depth3[b], dev_pose[b], shifts, intr, float(CELL), *dev_det[b], inputs_ready=False),   # caller's stream
+              d2h_l2, n_fr_obj, None, dev_depth3)
     h2d = E * (H * W * 4 + 48) + sum(int(x[0].numel() * x.element_size()) for x in pin_det)
     out["object_regime"] = {"value": world * E * n_fr_obj * args.e2e_steps / sec, "unit": UNIT, "ms_per_frame_step": 1e3 * sec / (n_fr_obj * args.e2e_steps),
                             "h2d_bytes_per_step": int(h2d * n_fr_obj), "d2h_bytes_per_step": int(host_l2.numel() * 2 * n_fr_obj),
                             "shape": f"E={E}, C={C}, <= {Kmax} detections per frame; D2H = the coarsest pooled level (15x20) per frame-step"}
     # ---- object regime with the depth in the sensor's own format: uint16 millimetres (robot_demo.py:515), divided inside the kernel ----
     pin_depth16 = (torch.from_numpy(depth_h).permute(1, 0, 2, 3) * 1000.0).round().clamp_(0, 65535).to(torch.uint16).contiguous().pin_memory()
-    dev_depth16 = [torch.empty((E, H, W), dtype=torch.uint16, device=dev) for _ in range(2)]
+    dev_depth16 = [torch.empty((E, H, W), dtype=torch.uint16, device=dev) for _ in range(NB)]
     sec = run(up_det, lambda b: batch.step_detections(dev_depth16[b], dev_pose[b], shifts, intr, float(CELL), *dev_det[b], inputs_ready=False),
-              lambda: host_l2.copy_(batch.levels[2], non_blocking=True), n_fr_obj, pin_depth16, dev_depth16)
+              d2h_l2, n_fr_obj, pin_depth16, dev_depth16)
     h2d = E * (H * W * 2 + 48) + sum(int(x[0].numel() * x.element_size()) for x in pin_det)
     out["object_regime_u16_depth"] = {"value": world * E * n_fr_obj * args.e2e_steps / sec, "unit": UNIT, "ms_per_frame_step": 1e3 * sec / (n_fr_obj * args.e2e_steps),
                                       "h2d_bytes_per_step": int(h2d * n_fr_obj), "d2h_bytes_per_step": int(host_l2.numel() * 2 * n_fr_obj),
@@ -865,7 +890,7 @@ def run_e2e_variants(eod, batch, dev, depth_h, pose_h, shifts, intr, args, world
     try:
         graphed = batch.capture_step_detections(dev_depth16[0], dev_pose[0], shifts, intr, float(CELL), *dev_det[0])
         sec = run(up_det, lambda b: graphed(dev_depth16[b], dev_pose[b], shifts, *dev_det[b]),
-                  lambda: host_l2.copy_(batch.levels[2], non_blocking=True), n_fr_obj, pin_depth16, dev_depth16)
+                  d2h_l2, n_fr_obj, pin_depth16, dev_depth16)
         out["object_regime_u16_depth_graph"] = {"value": world * E * n_fr_obj * args.e2e_steps / sec, "unit": UNIT,
                                                 "ms_per_frame_step": 1e3 * sec / (n_fr_obj * args.e2e_steps), "h2d_bytes_per_step": int(h2d * n_fr_obj),
                                                 "d2h_bytes_per_step": int(host_l2.numel() * 2 * n_fr_obj),
