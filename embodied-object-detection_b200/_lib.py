@@ -26,6 +26,8 @@ SIGNATURES = {
                                  c_int, c_int, c_float, _P, _P, _P, _P, _P, _P],
     "eod_backproject_quantize_u16": [_P, c_double, _P, _P, c_int, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_int,
                                      c_int, c_int, c_float, _P, _P, _P, _P, _P, _P],
+    "eod_backproject_count": [_P, c_int, c_double, _P, _P, c_int, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_int, c_int, c_int,
+                              _P, _P, _P, _P],
     "eod_quantize_world": [_P, c_int64, c_float, c_float, c_float, c_int, c_int, c_int, _P, _P],
     "eod_sample_mask": [_P, c_int, c_int, c_int, _P, _P, _P],
     "eod_frame_count": [_P, _P, _P, c_int, c_int, c_int64, _P, _P, _P, _P, c_int, _P],

@@ -41,6 +41,10 @@ struct BackprojectParams {
     int H, W;
     float fx, fy, cx, cy, cell, z_clip;
     int map_w, map_h, order;
+    // optional, 4-pixel kernel only: per-cell pixel counts of the frame (eod_frame_count without a sample mask) folded into this launch
+    uint32_t *frame_cnt;
+    const int32_t *active;
+    int64_t n_cells;
 };
 
 template <bool U16>
@@ -165,6 +169,30 @@ __global__ void __launch_bounds__(256) backproject_quantize_vec4_kernel(const Ba
     if (P.outlier) *reinterpret_cast<uint32_t *>(P.outlier + g) = out4;
     if (P.height) *reinterpret_cast<float4 *>(P.height + g) = make_float4(h4[0], h4[1], h4[2], h4[3]);
     if (P.idx) *reinterpret_cast<int4 *>(P.idx + g) = make_int4(idx4[0], idx4[1], idx4[2], idx4[3]);
+    if (P.frame_cnt && (!P.active || __ldg(P.active + e) > 0)) {
+        // Per-cell pixel counts over the warp's 128 consecutive pixels with ONE integer atomic per run of equal cell id (the host only
+        // asks for this when H * W % 128 == 0: warps are full).  A lane issues the atomics of the runs that START among its four pixels;
+        // a run that reaches the lane's last pixel also takes the pixels it continues into: four from every following lane it swallows
+        // whole, then the leading pixels of the first lane where it ends.  Equals frame_count_kernel without a sample mask (sums of 1).
+        const unsigned lane = threadIdx.x & 31;
+        const int c0 = idx4[0], c1 = idx4[1], c2 = idx4[2], c3 = idx4[3];
+        const int prev3 = __shfl_up_sync(0xffffffffu, c3, 1);
+        const bool h0 = lane == 0 || prev3 != c0, h1 = c1 != c0, h2 = c2 != c1, h3 = c3 != c2;
+        const int lead = h1 ? 1 : (h2 ? 2 : (h3 ? 3 : 4));                 // pixels before the lane's first internal run head
+        const unsigned cont_mask = __ballot_sync(0xffffffffu, !h0);        // lanes whose first pixel continues the previous lane's run
+        const unsigned full_mask = __ballot_sync(0xffffffffu, !h0 && lead == 4);
+        const unsigned above = lane == 31 ? 0u : (0xffffffffu << (lane + 1));
+        const unsigned stop = ~full_mask & above;
+        const int M = stop ? (__ffs(stop) - 1) : 32;                       // first following lane that is not swallowed whole
+        const int lead_m = __shfl_sync(0xffffffffu, lead, M & 31);
+        const int ext = 4 * (M - (int)lane - 1) + ((M < 32 && ((cont_mask >> M) & 1u)) ? lead_m : 0);
+        uint32_t *cnt = P.frame_cnt + (size_t)e * P.n_cells;
+        const int end1 = h2 ? 2 : (h3 ? 3 : 4), end2 = h3 ? 3 : 4;          // end of a run starting at pixel 1 / 2
+        if (h0) atomicAdd(cnt + c0, (uint32_t)(lead + (lead == 4 ? ext : 0)));
+        if (h1) atomicAdd(cnt + c1, (uint32_t)(end1 - 1 + (end1 == 4 ? ext : 0)));
+        if (h2) atomicAdd(cnt + c2, (uint32_t)(end2 - 2 + (end2 == 4 ? ext : 0)));
+        if (h3) atomicAdd(cnt + c3, (uint32_t)(1 + ext));
+    }
 }
 
 // World xyz (as stored in sensor_data/*.h5 'projection_indices', SMNet/build_data.py:209-213,280) -> flat clipped cell
@@ -199,7 +227,8 @@ extern "C" int eod_quantize_world(const float *world, int64_t n_points, float sh
 static int backproject_launch(const void *depth, bool u16, double depth_div, const float *pose, const float *shifts, int n_episodes,
                               int H, int W, float fx, float fy, float cx, float cy, float cell, int map_w,
                               int map_h, int order, float z_clip, int32_t *idx, int32_t *q2,
-                              uint8_t *outlier, float *height, float *world, eod_stream_t stream)
+                              uint8_t *outlier, float *height, float *world, eod_stream_t stream, uint32_t *frame_cnt = nullptr,
+                              const int32_t *active = nullptr)
 {
     EOD_REQUIRE(depth && pose && shifts, EOD_ERR_BADARG, "eod_backproject_quantize: null input");
     EOD_REQUIRE(n_episodes > 0 && H > 0 && W > 0 && map_w > 0 && map_h > 0, EOD_ERR_BADARG,
@@ -208,9 +237,12 @@ static int backproject_launch(const void *depth, bool u16, double depth_div, con
     EOD_REQUIRE(cell > 0.0f && fx != 0.0f && fy != 0.0f, EOD_ERR_BADARG, "eod_backproject_quantize: bad cell/intrinsics");
     EOD_REQUIRE((int64_t)map_w * map_h < (int64_t)INT32_MAX, EOD_ERR_BADARG, "eod_backproject_quantize: map too large");
     EOD_REQUIRE(n_episodes <= 65535, EOD_ERR_BADARG, "eod_backproject_quantize: n_episodes > 65535");
-    BackprojectParams P{depth, depth_div, pose, shifts, idx, q2, outlier, height, world, H, W, fx, fy, cx, cy, cell, z_clip, map_w, map_h, order};
+    BackprojectParams P{depth, depth_div, pose, shifts, idx, q2, outlier, height, world, H, W, fx, fy, cx, cy, cell, z_clip, map_w, map_h, order,
+                        frame_cnt, active, (int64_t)map_w * map_h};
     const bool vec = W % 4 == 0 && eod_aligned16(depth) && (!idx || eod_aligned16(idx)) && (!q2 || eod_aligned16(q2)) &&
                      (!outlier || (reinterpret_cast<uintptr_t>(outlier) & 3u) == 0) && (!height || eod_aligned16(height)) && (!world || eod_aligned16(world));
+    EOD_REQUIRE(!frame_cnt || (vec && (H * W) % 128 == 0), EOD_ERR_UNSUPPORTED,
+                "eod_backproject_count: the fused count needs W %% 4 == 0, H * W %% 128 == 0 and 16-byte aligned planes (run eod_frame_count instead)");
     if (vec) {
         dim3 grid((H * W / 4 + 255) / 256, n_episodes);
         if (u16) backproject_quantize_vec4_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(P);
@@ -240,4 +272,14 @@ extern "C" int eod_backproject_quantize_u16(const uint16_t *depth, double depth_
     EOD_REQUIRE(depth_div > 0.0, EOD_ERR_BADARG, "eod_backproject_quantize_u16: depth_div must be positive");
     return backproject_launch(depth, true, depth_div, pose, shifts, n_episodes, H, W, fx, fy, cx, cy, cell, map_w, map_h, order, z_clip, idx, q2,
                               outlier, height, world, stream);
+}
+
+extern "C" int eod_backproject_count(const void *depth, int depth_is_u16, double depth_div, const float *pose, const float *shifts, int n_episodes,
+                                     int H, int W, float fx, float fy, float cx, float cy, float cell, int map_w, int map_h, int order,
+                                     const int32_t *active, int32_t *idx, uint32_t *frame_cnt, eod_stream_t stream)
+{
+    EOD_REQUIRE(idx && frame_cnt, EOD_ERR_BADARG, "eod_backproject_count: null output");
+    EOD_REQUIRE(!depth_is_u16 || depth_div > 0.0, EOD_ERR_BADARG, "eod_backproject_count: depth_div must be positive");
+    return backproject_launch(depth, depth_is_u16 != 0, depth_is_u16 ? depth_div : 1.0, pose, shifts, n_episodes, H, W, fx, fy, cx, cy, cell, map_w, map_h,
+                              order, 0.5f, idx, nullptr, nullptr, nullptr, nullptr, stream, frame_cnt, active);
 }

@@ -95,6 +95,7 @@ class EpisodeBatch:
         # (round 2: with the pixels of a tile grouped by cell there are few look-ups, and the pre-pass plus its 158 MB per 64-episode
         # frame-step cost more than they saved: 16.8 k -> 17.6 k frames/s in the bench, same bits)
         self.pixel_divisors = os.environ.get("EOD_PIXEL_DIVISORS", "0") == "1"
+        self.fused_count = os.environ.get("EOD_FUSED_COUNT", "1") != "0"      # dense step: eod_backproject_count instead of project + count
         self.read_frozen = False      # True: finalize leaves norm16 alone (longterm snapshot read); refresh_read() updates it
         self.stage_events = None      # dict(stage -> [(start, end) CUDA events]) when profiling is on
 
@@ -295,8 +296,15 @@ class EpisodeBatch:
         with torch.cuda.stream(self._geo):
             if strict:
                 self._geo.wait_event(e_in)                 # inputs (and a preceding reset) are ordered on the caller's stream
-            self._geometry(depth, pose, shifts, intr, cell, order, proj_indices)
-            self._count(samp, active)
+            if samp is None and proj_indices is None and self.fused_count and ops.backproject_count_supported(self.H, self.W):
+                # dense frame, geometry computed here: the per-cell pixel counts are taken inside the back-projection launch
+                self._timed("project", ops.backproject_count, depth, pose, shifts, intr, cell, self.map_w, self.map_h, self.idx, self.frame_cnt,
+                            active, order)
+                if self.variant != WRITE_DET and self.layout == LAYOUT_CHW and self.pixel_divisors:
+                    self._timed("expand", ops.expand_counts, self.idx, self.frame_cnt, self.pix_inv_n)
+            else:
+                self._geometry(depth, pose, shifts, intr, cell, order, proj_indices)
+                self._count(samp, active)
             e_geo = torch.cuda.Event()
             e_geo.record()
             if not strict:

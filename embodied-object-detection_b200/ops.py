@@ -15,7 +15,7 @@ from ._lib import (FUSE_IMAGE_ONLY, FUSE_MEM_ONLY, FUSE_SUM, LAYOUT_CHW, LAYOUT_
 # kernels launched through this module since import (bench.py reports it as gpu_launches)
 launch_count = 0
 
-_LAUNCHES = {"eod_backproject_quantize": 1, "eod_backproject_quantize_u16": 1, "eod_quantize_world": 1, "eod_sample_mask": 1, "eod_frame_count": 1, "eod_expand_counts": 1, "eod_write_mean": 1, "eod_write_mean_det": 9,
+_LAUNCHES = {"eod_backproject_quantize": 1, "eod_backproject_quantize_u16": 1, "eod_backproject_count": 1, "eod_quantize_world": 1, "eod_sample_mask": 1, "eod_frame_count": 1, "eod_expand_counts": 1, "eod_write_mean": 1, "eod_write_mean_det": 9,
              "eod_finalize_counts": 1, "eod_box_to_image_features": 1, "eod_masks_observed": 1, "eod_paste_masks": 1, "eod_write_objects_pasted": 1, "eod_bilinear_lattice": 1, "eod_write_objects": 1, "eod_flush_slots": 2, "eod_write_max": 2, "eod_read_pool": 2,
              "eod_fuse": 1, "eod_project_split_weights": 1, "eod_project_fuse": 1, "eod_project_fuse_levels": 1, "eod_normalize_memory": 1, "eod_reset_touched": 1, "eod_semmap_update": 1, "eod_semmap_decode": 2,
              "eod_reset_episodes": 1, "eod_refresh_norm16": 1, "eod_check_indices": 1, "eod_remap_indices": 1, "eod_max_winner_list": 1, "eod_linear_rows": 1, "eod_read_roi": 1}
@@ -89,6 +89,28 @@ def backproject_quantize(depth: torch.Tensor, pose: torch.Tensor, shifts: torch.
     else:
         _call("eod_backproject_quantize", depth.data_ptr(), *tail)
     return out
+
+
+def backproject_count_supported(H: int, W: int) -> bool:
+    return W % 4 == 0 and (H * W) % 128 == 0
+
+
+def backproject_count(depth: torch.Tensor, pose: torch.Tensor, shifts: torch.Tensor, intr: Sequence[float], cell: float, map_w: int, map_h: int,
+                      idx: torch.Tensor, frame_cnt: torch.Tensor, active: Optional[torch.Tensor] = None, order: int = ORDER_ZX,
+                      depth_div: float = 1000.0) -> None:
+    """Back-projection to cell ids (idx (E,H,W) i32) AND the frame's per-cell pixel counts (frame_cnt (E,cells) i32, accumulated) in one
+    launch - eod_backproject_quantize + eod_frame_count(samp=None) of a dense frame-step.  depth f32 or uint16 (/ depth_div)."""
+    raw = depth.dtype == torch.uint16
+    _dev(depth, torch.uint16 if raw else torch.float32, "depth"), _dev(pose, torch.float32, "pose"), _dev(shifts, torch.float32, "shifts")
+    _dev(idx, torch.int32, "idx"), _dev(frame_cnt, torch.int32, "frame_cnt")
+    E, H, W = depth.shape
+    if pose.shape != (E, 12) or shifts.shape != (E, 6) or tuple(idx.shape) != (E, H, W) or tuple(frame_cnt.shape) != (E, map_w * map_h):
+        raise ValueError("backproject_count: pose (E,12), shifts (E,6), idx (E,H,W), frame_cnt (E, map_w*map_h)")
+    if active is not None:
+        _dev(active, torch.int32, "active")
+    fx, fy, cx, cy = (float(v) for v in intr)
+    _call("eod_backproject_count", depth.data_ptr(), int(raw), float(depth_div), pose.data_ptr(), shifts.data_ptr(), E, H, W, fx, fy, cx, cy,
+          float(cell), int(map_w), int(map_h), int(order), _ptr(active), idx.data_ptr(), frame_cnt.data_ptr(), _stream())
 
 
 def quantize_world(world: torch.Tensor, map_world_shift: Sequence[float], cell: float, map_w: int, map_h: int,

@@ -84,6 +84,15 @@ int eod_backproject_quantize_u16(const uint16_t *depth, double depth_div, const 
                                  int order, float z_clip, int32_t *idx, int32_t *q2, uint8_t *outlier, float *height,
                                  float *world, eod_stream_t stream);
 
+/* eod_backproject_quantize (idx only) and eod_frame_count without a sample mask in ONE launch: the dense frame-step's per-cell pixel
+ * counts are taken while the cell ids are still in registers (one integer atomic per run of equal id over 128 consecutive pixels)
+ * instead of in a second pass over the index plane.  depth: f32 metres, or uint16 sensor words / depth_div (depth_is_u16);
+ * active (E) nullable: episodes with active <= 0 get their idx but are not counted; frame_cnt (E, map_w*map_h) u32 accumulates.
+ * Needs W % 4 == 0, H*W % 128 == 0 and 16-byte aligned planes, else EOD_ERR_UNSUPPORTED (then call the two entry points). */
+int eod_backproject_count(const void *depth, int depth_is_u16, double depth_div, const float *pose, const float *shifts, int n_episodes,
+                          int H, int W, float fx, float fy, float cx, float cy, float cell, int map_w, int map_h, int order,
+                          const int32_t *active, int32_t *idx, uint32_t *frame_cnt, eod_stream_t stream);
+
 /* Offline builder's quantise step on STORED world coordinates (sensor_data/<name>.h5 'projection_indices'):
  * SMNet/build_memory_data.py:135-143.  world (n_points,3) f32 -> idx (n_points) i32, clipped, bit-exact. */
 int eod_quantize_world(const float *world, int64_t n_points, float shift_x, float shift_z, float cell, int map_w, int map_h,

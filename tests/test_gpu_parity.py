@@ -966,6 +966,40 @@ def test_batch_without_fp16_table_reads_the_same_bits(eod, cuda):
         b.read()
 
 
+def test_backproject_count_equals_project_then_count(eod, cuda):
+    """eod_backproject_count (cell ids + per-cell pixel counts in one launch, one atomic per run over 128 consecutive pixels) against the
+    two separate launches: identical idx and frame_cnt - on ray-cast depth, on noise (every pixel its own run), on a constant plane
+    (one run per warp), with uint16 depth and with an active mask; sizes it cannot take are refused."""
+    rng = np.random.default_rng(12)
+    H, W, mw, mh, cell, E = 96, 128, 60, 45, 0.2, 3
+    intr = eod.compute_intrinsics(W, H, math.radians(67.5))
+    eps = [eod.episodes.make_episode(900 + e, 1, H, W, mw, mh, cell) for e in range(E)]
+    Tm = eod.transform3d(torch.from_numpy(np.stack([ep.xyzhe[0] for ep in eps])))
+    pose = Tm[:, :3].reshape(E, 12).to(cuda)
+    shifts = _t(np.stack([np.concatenate([np.zeros(3, np.float32), ep.map_world_shift]) for ep in eps]), cuda)
+    depths = {"raycast": np.stack([ep.depth[0] for ep in eps]),
+              "noise": rng.uniform(0.3, 9.0, (E, H, W)).astype(np.float32),
+              "plane": np.full((E, H, W), 2.5, np.float32),
+              "no depth": np.zeros((E, H, W), np.float32)}
+    for name, d in depths.items():
+        for raw in (False, True):
+            dd = _t((d * 1000).round().clip(0, 65535).astype(np.uint16), cuda) if raw else _t(d, cuda)
+            for active in (None, _t(np.array([1, 0, 2], np.int32), cuda)):
+                ref_idx = eod.ops.backproject_quantize(dd, pose, shifts, intr, cell, mw, mh)["idx"]
+                ref_cnt = torch.zeros((E, mw * mh), dtype=torch.int32, device=cuda)
+                eod.ops.frame_count(ref_idx, None, ref_cnt, active)
+                idx = torch.empty((E, H, W), dtype=torch.int32, device=cuda)
+                cnt = torch.zeros((E, mw * mh), dtype=torch.int32, device=cuda)
+                eod.ops.backproject_count(dd, pose, shifts, intr, cell, mw, mh, idx, cnt, active)
+                assert torch.equal(idx, ref_idx), (name, raw)
+                assert torch.equal(cnt, ref_cnt), (name, raw, active is not None)
+                assert int(cnt.sum()) == (H * W * (E if active is None else 2))
+    assert not eod.ops.backproject_count_supported(30, 100)
+    with pytest.raises(eod.EodError):
+        eod.ops.backproject_count(_t(np.ones((1, 30, 100), np.float32), cuda), pose[:1], shifts[:1], intr, cell, mw, mh,
+                                  torch.empty((1, 30, 100), dtype=torch.int32, device=cuda), torch.zeros((1, mw * mh), dtype=torch.int32, device=cuda))
+
+
 def test_divisor_lookup_and_divisor_plane_agree(eod, cuda):
     """The CHW write takes a group's divisor 1/n_cell either from frame_cnt (default since round 2) or from the per-pixel plane that
     eod_expand_counts prepares (``pixel_divisors = True``): same counts, same touched set, sums equal up to reduction order."""
