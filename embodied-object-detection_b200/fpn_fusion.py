@@ -11,8 +11,8 @@ Mirrors the memory block of ``CustomRecurrentFPN`` (detic/modeling/backbone/timm
 The gather -> avg-pool 4 -> (avg-pool 2 -> half) x3 chain runs as ONE kernel (eod_read_pool).  In inference the
 1x1 projection, the ``* weight`` and the ``+ res`` run as ONE tensor-core kernel per level (eod_project_fuse: fp16
 levels x hi/lo-split fp32 weights on tcgen05, fp32-GEMM accuracy).  When gradients are needed (training un-freezes the
-``map_merge`` parameters, custom_rcnn.py:609-613) the projection is the library GEMM under autograd and the epilogue is
-eod_fuse with a hand-written backward.  The dense backbone itself is out of scope and supplied by the caller.
+``map_merge`` parameters, custom_rcnn.py:609-613) the projection is the tcgen05 row GEMM eod_linear_rows (3xTF32, fp32 accuracy) under
+autograd - its forward and both gradient GEMMs - and the epilogue is eod_fuse with a hand-written backward.  The dense backbone itself is out of scope and supplied by the caller.
 """
 from __future__ import annotations
 
@@ -69,7 +69,7 @@ class MemoryFusion(nn.Module):
                  memory_feature_weight: float = 100.0, merge_type: str = "", mem_feat_dim: int = 512,
                  ego_feat_dim: int = 256, tensor_core: bool = True):
         super().__init__()
-        self.tensor_core = tensor_core      # False: library fp32 GEMM + eod_fuse also in inference
+        self.tensor_core = tensor_core      # False: the row GEMM (eod_linear_rows, 3xTF32) + eod_fuse also in inference, instead of the fused fp16-split launch
         self.validate_indices = True        # range-check proj_indices against the memory table before the gather
         self._w_split = {}                  # level -> ((weight ptr, version), (2N,K) f16 hi/lo split)
         self.memory_type, self.feat_fusion, self.merge_type = memory_type, fusion, merge_type
