@@ -16,11 +16,10 @@ autograd - its forward and both gradient GEMMs - and the epilogue is eod_fuse wi
 """
 from __future__ import annotations
 
-from typing import Callable, Dict, List, Optional, Sequence
+from typing import Callable, List, Optional, Sequence
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import ops
 from ._lib import FUSE_IMAGE_ONLY, FUSE_MEM_ONLY, FUSE_SUM
