@@ -83,6 +83,14 @@ def test_cpu_tensors_are_refused(eod):
         eod.EpisodeBatch(1, 10, 10, 128, device="cpu")
     with pytest.raises(eod.EodError):
         eod.SpatialFeatureMemory(device="cpu")
+    # the round-2 entry points have no CPU path either
+    with pytest.raises(eod.EodError):
+        eod.ops.linear_rows(torch.zeros(4, 16), torch.zeros(16, 16))
+    with pytest.raises(eod.EodError):
+        eod.ops.remap_indices(torch.zeros(4, dtype=torch.int64), torch.zeros(9, dtype=torch.int64), 21)
+    with pytest.raises(eod.EodError):
+        eod.ops.backproject_count(torch.zeros(1, 32, 32), torch.zeros(1, 12), torch.zeros(1, 6), (1.0, 1.0, 16.0, 16.0), 0.2, 10, 10,
+                                  torch.zeros(1, 32, 32, dtype=torch.int32), torch.zeros(1, 100, dtype=torch.int32))
 
 
 def test_badarg_codes_without_gpu(eod):
