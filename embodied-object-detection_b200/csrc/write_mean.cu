@@ -8,16 +8,18 @@
 // bounds the whole path) and is written for HBM bandwidth:
 //   * CHW features (the reference's (1,C,480,640) layout): a persistent CTA per SM, 12 consumer warps + 1 producer
 //     warp.  Unit of work = (32-pixel tile, 128-channel block) = one 16 KB 3-D TMA box (128B-swizzled) plus bulk
-//     copies of the tile's cell ids / sample mask / reciprocal divisors; unit u lands in ring stage u % 12 and is
-//     consumed by warp u % 12 (every consumer warp owns one stage: the full/empty mbarrier pair of the stage is the
-//     only synchronisation).  Lane l sums channels l, l+32, l+64, l+96 over each run of equal cell id with
-//     conflict-free LDS.128 (neighbouring pixels fall into the same map cell) and the run leaves the SM as four
-//     warp-wide red.global.add.f32 (128 contiguous bytes of the cell row each) - one L2 reduction per run and
-//     channel instead of one per pixel.  Details and measurements: DESIGN.md 3.1.
-//   * an LDG-staged variant of the same algorithm (padded smem tile) handles shapes the TMA path does
+//     copies of the tile's cell ids / sample mask (/ reciprocal divisors in pixel_divisors mode); the producer CLAIMS chunks of
+//     tile groups from a global ticket (eod_work_tickets), the stage a unit lands in belongs to one consumer warp (the
+//     full/empty mbarrier pair of the stage is the only synchronisation; the unit's {tile, channel block} travels in the
+//     stage's aux area).  All pixels of the tile that fall into one cell form a group (MATCH.ANY; runs in the deterministic
+//     variant): lane l sums channels l, l+32, l+64, l+96 over the group's pixels with conflict-free LDS.128, scales by
+//     1/n_cell (looked up in frame_cnt) and the group leaves the SM as four warp-wide red.global.add.f32 (128 contiguous
+//     bytes of the cell row each) - one L2 reduction per (tile, cell, channel) instead of one per pixel.  DESIGN.md 3.1.
+//   * an LDG-staged variant of the same algorithm (padded smem tile, runs) handles shapes the TMA path does
 //     not (HW % 32 != 0) and is the bring-up comparator (variant = EOD_WRITE_LDG).
-//   * HWC features: a warp walks a strip of pixels, lanes own float4 channel groups, runs accumulate in
-//     registers and flush straight from registers.
+//   * HWC features (fp32 / bf16 / fp16): a warp owns a strip of 32 pixels, lanes own float4 channel groups; the strip's pixels
+//     are grouped by cell the same way, a group's rows are requested in batches before they are added, and the group is
+//     flushed straight from registers (red.global.add.v4.f32).
 #include <cuda.h>
 #include <stdlib.h>
 
