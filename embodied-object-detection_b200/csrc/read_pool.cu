@@ -176,6 +176,11 @@ template <int V> struct RawOf<__half, V> { using type = RawF16<V>; };
 //  * item -> (episode, quadrant) is stepped incrementally in 32-bit arithmetic (v2 decoded every item - and the
 //    prefetched one - with 64-bit divisions: six software-division calls per item).
 //
+// v4 (round 2): windows that hold exactly two cells (an edge: 89 % of the mixed windows) keep both rows in registers and are summed
+// row by row through one of 16 straight-line 4-pixel variants (vadd_row2), one dispatch when all four rows are alike; shared memory
+// is addressed through one opaque base register, the row pointer / L0 base / lane are opaque too (the compiler re-derived them inside
+// the loops); uniform windows enter the common tail as 16 * x (exact) so that the L0 accumulator has a single join point.
+//
 // Summation order == ATen CPU avg_pool2d: fp32, start from 0, row-major over the window, then / k^2; the fp16 roundings
 // between levels (timm.py:168) are reproduced, so outputs are bit-identical.
 constexpr int kReadWarps = 8;
