@@ -310,7 +310,59 @@ def gen_loader_order():
     print("loader order: longterm length", len(out["order_longterm"]))
 
 
+def gen_explicit_map():
+    """MODEL.MEMORY_TYPE explicit_map / map_gt with a generated semantic map: SMNet/loader.py:222 (`semmap_real = semmap_real + 1`) and
+    :232-246 (memory = [zero row; class embeddings], proj_indices = semmap_real[proj_indices]) exec'd verbatim; the pooled levels of
+    the resulting (21,512) table through timm.py:147-168 exec'd verbatim."""
+    lines = open(os.path.join(REF, "SMNet/loader.py")).read().splitlines()
+    rng = np.random.default_rng(21)
+    H, W, mw, mh, C, K = 96, 128, 70, 50, 512, 20
+    clip = rng.standard_normal((K, C)).astype(np.float32)
+    clip /= np.linalg.norm(clip, axis=1, keepdims=True)
+    semmap = rng.integers(-1, K, (mw * mh,)).astype(np.int64)
+    semmap[rng.random(mw * mh) < 0.5] = -1
+    yy, xx = np.mgrid[0:H, 0:W]
+    proj = ((yy // 5) * mw // 3 + xx // 3) % (mw * mh)
+    proj[::9, ::7] = rng.integers(0, mw * mh, proj[::9, ::7].shape)
+    self_ns = type("S", (), {})()
+    self_ns.clip_path, self_ns.clip_embeddings, self_ns.memory_type, self_ns.smnet_class_mapping = "clip.npy", clip, "map_gt", None
+    u = {"self": self_ns, "np": np, "semmap_real": semmap.copy(), "proj_indices": proj.copy(), "semmap_gt": None, "print": lambda *a, **k: None}
+    exec_lines(lines, 222, 222, u)
+    exec_lines(lines, 232, 246, u)
+    memory, idx = u["memory"], u["proj_indices"]
+    assert memory.shape == (K + 1, C) and idx.shape == (H, W)
+    # the read of that table: timm.py:142-192 exec'd verbatim (as gen_read does); the pooled fp16-valued levels are captured where
+    # they enter the 1x1 projections
+    patch_cpu()
+    tl = open(os.path.join(REF, "detic/modeling/backbone/timm.py")).read().splitlines()
+    captured = {}
+
+    class _Conv:
+        def __init__(self, k):
+            self.k = k
+
+        def __call__(self, x):
+            captured[self.k] = x.detach().clone()
+            return torch.zeros((x.shape[0], 8, x.shape[2], x.shape[3]))
+
+    fpn = type("S", (), {})()
+    fpn.memory_type, fpn.feat_fusion, fpn.map_feature_weight = "implicit_memory", "sum", 5
+    fpn.merge_map_projections = [_Conv(k) for k in range(3)]
+    ns = {"torch": torch, "F": F, "self": fpn, "map_memory": [torch.from_numpy(memory.astype(np.float32)).half()],
+          "proj_indices": [torch.from_numpy(idx).long()], "observations": [torch.zeros(memory.shape[0]).half()],
+          "results": [torch.zeros(1, 8, H >> s_, W >> s_) for s_ in (3, 4, 5)]}
+    with torch.no_grad():
+        exec_lines(tl, 142, 192, ns)
+    levels = [captured[k].to(torch.half).numpy() for k in range(3)]
+    np.savez_compressed(os.path.join(HERE, "explicit_map.npz"), clip=clip, semmap=semmap, proj=proj.astype(np.int64), memory=memory.astype(np.float32),
+                        idx=idx.astype(np.int64), level0=levels[0], level1=levels[1], level2=levels[2])
+    print("explicit_map:", memory.shape, idx.shape, [l.shape for l in levels])
+
+
 if __name__ == "__main__":
+    if "--only-explicit-map" in sys.argv:
+        gen_explicit_map()
+        sys.exit(0)
     if "--only-loader" in sys.argv:
         gen_loader_order()
         sys.exit(0)
@@ -330,6 +382,7 @@ if __name__ == "__main__":
     gen_paste()
     gen_robot()
     gen_loader_order()
+    gen_explicit_map()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

@@ -230,7 +230,7 @@ def test_read_pool_signed_zeros_and_adversarial_patterns(eod, cuda):
                     assert np.array_equal(got[k][e].contiguous().cpu().numpy().view(np.uint16), ref[k].view(np.uint16)), (C, e, k)
 
 
-def test_explicit_map_read_mode(eod, cuda):
+def test_explicit_map_read_mode(eod, cuda, golden):
     """MODEL.MEMORY_TYPE 'explicit_map' (SMNet/loader.py:233-246,298): memory = [zero row; (20,512) class table], proj_indices =
     (semmap + 1)[proj_indices].  The composed index plane must equal numpy's, and the read of the 21-row table (both as an fp16
     table and as fp32 without counts, through SpatialFeatureMemory.read_levels and MemoryFusion.read) must be bit-identical to
@@ -261,6 +261,13 @@ def test_explicit_map_read_mode(eod, cuda):
                          ("MemoryFusion.read", fus.read([memory.half()], [pidx]))):
         for k in range(3):
             assert np.array_equal(levels[k][0].contiguous().cpu().numpy().view(np.uint16), ref[k][0].numpy().view(np.uint16)), (name, k)
+    # the same inputs went through the reference's own source (tests/golden/make_golden.py --only-explicit-map): identical outputs
+    g = golden("explicit_map")
+    assert np.array_equal(g["semmap"], semmap) and np.array_equal(g["proj"], proj) and np.array_equal(g["clip"], clip)
+    assert np.array_equal(memory.cpu().numpy(), g["memory"]) and np.array_equal(pidx.cpu().numpy(), g["idx"])
+    got = mem.read_levels(pidx, memory.half())
+    for k in range(3):
+        assert np.array_equal(got[k].contiguous().cpu().numpy().view(np.uint16), g[f"level{k}"].view(np.uint16)), k
     bad = semmap.copy()
     bad[proj[3, 3]] = K + 5                                                           # class outside the table
     with pytest.raises(IndexError):

@@ -247,3 +247,15 @@ def test_bytecode_listings_pin_the_unsourced_write_variants(tmp_path):
         assert len(made) == 4
         for f in made:
             assert open(os.path.join(tmp_path, f)).read() == open(os.path.join(d, f)).read(), f
+
+
+def test_explicit_map_composition_and_read_match_reference(golden):
+    """MODEL.MEMORY_TYPE explicit_map: SMNet/loader.py:222,232-246 and timm.py:142-192 executed from source -> explicit_map.npz.  The
+    restated composition ((semmap + 1)[proj], zero row in front of the class table) and the oracle's read of the 21-row table must
+    equal the reference's outputs bit for bit."""
+    g = golden("explicit_map")
+    assert np.array_equal(np.insert(g["clip"], 0, np.zeros((1, g["clip"].shape[1])), axis=0).astype(np.float32), g["memory"])
+    assert np.array_equal((g["semmap"] + 1)[g["proj"]], g["idx"])
+    levels = R.read_pool(torch.from_numpy(g["memory"]).half(), torch.from_numpy(g["idx"]))
+    for k in range(3):
+        assert np.array_equal(levels[k].numpy().view(np.uint16), g[f"level{k}"].view(np.uint16)), k
